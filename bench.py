@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — PPG frames/s of the `ppgs.from_audio` hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): mel + default Transformer, batch = 64 x 10 s
+synthetic 16 kHz audio per GPU (weak scaling: utterances shard on the batch axis,
+no data-path collective; one weight-blob broadcast at load).  A "step" is one
+pass of the hot path (fused STFT+mel -> Transformer -> softmax) over one batch.
+
+  value  device-resident: the batch is already in HBM when the timed region
+         starts (CUDA events, max over ranks);
+  e2e    the same metric through the C-ABI `ppgs_from_audio_host` with pinned
+         HOST buffers: H2D + compute + D2H inside the timed region;
+  roofline    the dominant kernel (per-kernel CUDA events, a second timed pass
+         over the same steps with the library's launch profiling enabled);
+  cpu_baseline / --impl reference    the reference's CPU path as shipped (stock
+         torch modules under bf16 autocast, oracle.AsShipped — the reference
+         tree itself cannot travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH, SECONDS, SAMPLE_RATE, HOP = 64, 10, 16000, 160
+SAMPLES = SECONDS * SAMPLE_RATE
+FRAMES = SAMPLES // HOP
+METRIC, UNIT = 'ppg_frames_per_sec', 'frames/s'
+WORKLOAD = 'mel + default Transformer (5x256, 2 heads, FFN 2048), batch=64x10s synthetic 16 kHz'
+
+# Algorithmic FLOPs of the reference's chunked algorithm:
+# 1000 frames -> chunks of 500/500/250 computed frames.
+H, C_IN, F_FFN, O_OUT, KSIZE, LAYERS = 256, 80, 2048, 40, 5, 5
+CHUNKS = (500, 500, 250)
+COMPUTED_FRAMES = sum(CHUNKS)
+DENSE_PER_FRAME = 2 * (KSIZE * C_IN * H + LAYERS * (3 * H * H + H * H + 2 * H * F_FFN)
+                       + KSIZE * H * O_OUT)
+ATTN_PER_UTT = sum(LAYERS * 4 * H * s * s for s in CHUNKS)
+FLOPS_PER_UTT = DENSE_PER_FRAME * COMPUTED_FRAMES + ATTN_PER_UTT
+FFN_FLOPS_PER_LAUNCH_HALF = 2 * H * F_FFN     # per computed frame, one of linear1 / linear2
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        peaks = json.load(open(path))
+        return {'hbm_gbs': peaks['hbm_gbs'], 'tflops_burst': peaks['bf16_tflops'],
+                'tflops_sustained': peaks['bf16_tflops_sustained'], 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tflops_burst': 1590.0, 'tflops_sustained': 1400.0,
+            'source': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, sm_max, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                sm_max = float(parts[1])
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': sm_max,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_reference_rate(steps, warmup, utterances=None, budget_s=20.0):
+    """The reference's CPU path as shipped (oracle.AsShipped: stock torch layers,
+    bf16 autocast, inference_mode) on all host cores, on a bounded sample of the
+    workload: `utterances` x 10 s per step through mel.from_audios +
+    from_features (ppgs/core.py:333-352; from_audio itself fails for B>1)."""
+    import torch
+    from oracle import ppg_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = O.AsShipped(O.random_state_dict(0))
+    probe = O.synthetic_audio(2, SAMPLES, 0)
+    model.from_audios(probe)
+    t0 = time.perf_counter()
+    model.from_audios(probe)
+    per_utt = (time.perf_counter() - t0) / 2
+    if utterances is None:
+        utterances = int(max(2, min(BATCH, budget_s / max(steps + warmup, 1) / per_utt)))
+    audio = O.synthetic_audio(utterances, SAMPLES, 1)
+    for _ in range(warmup):
+        model.from_audios(audio)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        out = model.from_audios(audio)
+        times.append(time.perf_counter() - t0)
+    assert out.shape == (utterances, O_OUT, FRAMES)
+    mean = sum(times) / len(times)
+    return {'value': utterances * FRAMES / mean, 'unit': UNIT, 'cores': torch.get_num_threads(),
+            'kind': 'port',
+            'sample': f'{utterances}x10s utterances per step, {steps} steps (+{warmup} warm-up), '
+                      f'as-shipped bf16-autocast torch modules, dtype {out.dtype}'.replace('torch.', '')}, mean
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(args.steps, 1)
+    warmup = max(args.warmup, 1)
+    base, mean = cpu_reference_rate(steps, warmup, budget_s=90.0)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': mean * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16 (cpu autocast)', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'note': 'CPU reference arm: bounded sample of the workload'},
+        'cpu_baseline': base,
+        'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=20)
+    parser.add_argument('--warmup', type=int, default=5)
+    parser.add_argument('--impl', default='ppgs_b200', choices=['ppgs_b200', 'reference'])
+    parser.add_argument('--precision', default=os.environ.get('PPGS_B200_PRECISION', 'auto'))
+    parser.add_argument('--no-cpu-baseline', action='store_true')
+    args = parser.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ppgs_b200
+    from ppgs_b200 import parallel
+    from oracle import ppg_oracle as O   # synthetic inputs + CPU baseline only
+
+    steps, warmup = max(args.steps, 1), max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        parallel.init('nccl')
+
+    # weights: rank 0 owns the state dict; one blob broadcast, no per-step collective
+    state = O.random_state_dict(0, peaky=True) if rank == 0 else None
+    engine = parallel.broadcast_engine(state, 'mel', local_rank)
+    if args.precision == 'auto':
+        for name in ('f16x2', 'fp32'):
+            try:
+                engine.precision = name
+                break
+            except RuntimeError:
+                continue
+    else:
+        engine.precision = args.precision
+    precision = engine.precision
+
+    # inputs larger than L2: 4 rotating batches (4 x 41 MB of audio; the per-step
+    # activation traffic in the workspace is > 1 GB on top)
+    rotate = 4
+    host = [O.synthetic_audio(BATCH, SAMPLES, 100 + rank * rotate + i).squeeze(1).pin_memory()
+            for i in range(rotate)]
+    dev = [h.to(device) for h in host]
+    out_host = torch.empty(BATCH, O_OUT, FRAMES, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def timed(fn, n):
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record()
+        for i in range(n):
+            fn(i)
+        stop.record()
+        barrier()
+        ms = torch.tensor([start.elapsed_time(stop)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    device_step = lambda i: engine.from_audio(dev[i % rotate])                      # noqa: E731
+    host_step = lambda i: engine.from_audio_host(host[i % rotate], out=out_host)    # noqa: E731
+
+    for i in range(warmup):
+        device_step(i)
+        host_step(i)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches_before = engine.launches
+    device_ms = timed(device_step, steps)
+    launches = engine.launches - launches_before
+    e2e_ms = timed(host_step, steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # roofline pass: same steps with per-kernel CUDA events (library profiling)
+    engine.set_profiling(True)
+    timed(device_step, steps)
+    stats = engine.kernel_stats()
+    engine.set_profiling(False)
+
+    # parity of what was just timed (2 rows of the last batch vs the oracle, rank 0)
+    parity = None
+    if rank == 0:
+        last = (steps - 1) % rotate
+        got = engine.from_audio(dev[last][:2].contiguous()).cpu()
+        ref = O.from_audio(O.random_state_dict(0, peaky=True), host[last][:2].unsqueeze(1))
+        parity = (got - ref).abs().max().item()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+
+    peaks = load_peaks()
+    frames_total = BATCH * FRAMES * world
+    value = frames_total / (device_ms / steps / 1e3)
+    e2e_value = frames_total / (e2e_ms / steps / 1e3)
+
+    # dominant kernel = largest share of device time among the profiled kernels
+    total_kernel_ms = sum(ms for ms, _ in stats.values()) or 1.0
+    name, (kernel_ms, kernel_launches) = max(stats.items(), key=lambda kv: kv[1][0])
+    per_launch_ms = kernel_ms / max(kernel_launches, 1)
+    computed = BATCH * COMPUTED_FRAMES
+    flops_by_kernel = {
+        'ffn1': FFN_FLOPS_PER_LAUNCH_HALF * computed, 'ffn2': FFN_FLOPS_PER_LAUNCH_HALF * computed,
+        'ffn': 2 * FFN_FLOPS_PER_LAUNCH_HALF * computed, 'qkv': 2 * 3 * H * H * computed,
+        'out_proj': 2 * H * H * computed, 'conv_in': 2 * KSIZE * C_IN * H * computed,
+        'conv_out': 2 * KSIZE * H * O_OUT * computed, 'attention': BATCH * ATTN_PER_UTT / LAYERS}
+    roofline = {'kernel': name, 'share_of_step': kernel_ms / total_kernel_ms,
+                'ms_per_launch': per_launch_ms, 'traffic': None}
+    key = next((k for k in sorted(flops_by_kernel, key=len, reverse=True) if k in name), None)
+    if key is not None:
+        achieved = flops_by_kernel[key] / (per_launch_ms * 1e-3) / 1e12
+        peak = peaks['tflops_sustained']
+        roofline.update({'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': achieved / peak,
+                         'peak_source': f"{peaks['source']} bf16 cuBLAS sustained (kernel timed "
+                                        'inside a long step)',
+                         'algorithmic_flops_per_launch': flops_by_kernel[key]})
+    else:   # mel front-end
+        bytes_per_launch = BATCH * FRAMES * 800
+        achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+        roofline.update({'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
+                         'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
+                         'peak_source': peaks['source']})
+    whole = FLOPS_PER_UTT * BATCH / (device_ms / steps * 1e-3) / 1e12
+    roofline['whole_step'] = {'achieved_tflops': whole, 'frac': whole / peaks['tflops_sustained'],
+                              'algorithmic_flops_per_step': FLOPS_PER_UTT * BATCH}
+    mel_stat = stats.get('mel_stft_fbank')
+    if mel_stat:
+        mel_ms = mel_stat[0] / max(mel_stat[1], 1)
+        gbs = BATCH * FRAMES * 800 / (mel_ms * 1e-3) / 1e9
+        roofline['mel_frontend'] = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'],
+                                    'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'],
+                                    'ms_per_launch': mel_ms}
+    roofline['kernels_ms_per_step'] = {k: round(ms / steps, 4) for k, (ms, _) in sorted(stats.items())}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu, _ = cpu_reference_rate(steps=3, warmup=1, budget_s=20.0)
+
+    dtype = {'fp32': 'f32 (CUDA-core FFMA)', 'f16x2': 'f16x2-split tcgen05 MMA, f32 accumulate',
+             'f16': 'f16 tcgen05 MMA, f32 accumulate'}.get(precision, precision)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
+        'warmup': warmup, 'ms_per_step': device_ms / steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': dtype, 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'per_gpu_batch': BATCH, 'samples': SAMPLES,
+                   'frames_per_utterance': FRAMES, 'chunking': '500/400/50 (reference semantics)',
+                   'precision': precision, 'parallelism': f'dp{world} (utterance shards, no collective)',
+                   'l2': f'inputs larger than L2: {rotate} rotating batches + >1 GB activation traffic per step',
+                   'max_abs_vs_oracle': parity},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms / steps,
+                'h2d_bytes_per_step': BATCH * SAMPLES * 4 * world,
+                'd2h_bytes_per_step': BATCH * O_OUT * FRAMES * 4 * world,
+                'api': 'ppgs_from_audio_host (C ABI), pinned host buffers'},
+        'gpu_launches': launches,
+        'clocks': clocks,
+        'roofline': roofline,
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+if __name__ == '__main__':
+    main()

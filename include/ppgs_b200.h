@@ -1,0 +1,163 @@
+/*
+ * ppgs_b200 — C ABI of the B200-native PPG inference engine.
+ *
+ * Drop-in boundary for the forward path of interactiveaudiolab/ppgs
+ * (`ppgs.from_audio`: mel front-end -> Transformer encoder -> 40-way softmax).
+ * The reference has no native code and no FFI; each entry point
+ * below names the reference Python function whose arithmetic it replaces, and
+ * `INTEGRATION.md` shows the ctypes binding a maintainer of the reference would
+ * add at that call site.
+ *
+ * Conventions
+ *  - plain C types only; all `*_dev` pointers are CUDA device pointers on the
+ *    engine's device, all `*_host` pointers are host memory;
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default
+ *    stream); device entry points are asynchronous on that stream;
+ *  - every function returns 0 on success or a negative `PPGS_E_*` code and never
+ *    aborts; `ppgs_last_error()` returns a thread-local message for the last
+ *    failure;
+ *  - one engine per (device, checkpoint); calls on one engine must be serialised
+ *    by the caller (the reference's function-attribute caches are not
+ *    thread-safe either: ppgs/core.py:565);
+ *  - the engine owns the packed weights and a grow-only device workspace; the
+ *    caller owns every input / output buffer.
+ */
+#ifndef PPGS_B200_H_
+#define PPGS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPGS_ABI_VERSION 1
+
+/* error codes (mirrors of the reference's exception types are noted) */
+#define PPGS_OK 0
+#define PPGS_E_INVALID -1    /* ValueError: bad argument / shape / unknown name */
+#define PPGS_E_CUDA -2       /* RuntimeError: a CUDA call failed               */
+#define PPGS_E_STATE -3      /* RuntimeError: engine not finalised / missing weight */
+#define PPGS_E_TOO_LARGE -4  /* ValueError('size is too large'): transformer.py:103-104 */
+#define PPGS_E_UNSUPPORTED -5
+
+/* arithmetic of the dense contractions (GEMMs + attention) */
+#define PPGS_PRECISION_FP32 0       /* CUDA-core FFMA; validation mode               */
+#define PPGS_PRECISION_F16X2 1      /* tcgen05, split-fp16 operands, 3 MMA passes, fp32
+                                       accumulate in TMEM: the <=1e-4 parity mode    */
+#define PPGS_PRECISION_F16 2        /* tcgen05, single-pass fp16 operands (the
+                                       reference's own CUDA autocast numerics class) */
+
+/* Model hyper-parameters: ppgs/config/defaults.py:127-161, ppgs/config/w2v2fb.py:7-10,
+ * config/causal_transformer.py:18, torch.nn.TransformerEncoderLayer defaults. */
+typedef struct ppgs_model_config {
+    int32_t input_channels;   /* 80 (mel) / 768 (w2v2fb)  */
+    int32_t hidden_channels;  /* 256 / 512                */
+    int32_t num_layers;       /* 5                        */
+    int32_t num_heads;        /* 2                        */
+    int32_t ffn_channels;     /* 2048                     */
+    int32_t output_channels;  /* 40 = len(ppgs.PHONEMES)  */
+    int32_t kernel_size;      /* 5                        */
+    int32_t is_causal;        /* IS_CAUSAL                */
+    int32_t chunk_length;     /* 500                      */
+    int32_t chunk_overlap;    /* 50                       */
+    int32_t max_len;          /* 5000 (positional table)  */
+    float layer_norm_eps;     /* 1e-5                     */
+} ppgs_model_config;
+
+typedef struct ppgs_engine ppgs_engine;
+
+int ppgs_abi_version(void);
+const char* ppgs_last_error(void);
+
+/* Fills *cfg with the reference defaults for 'mel' (ppgs/config/defaults.py). */
+void ppgs_default_config(ppgs_model_config* cfg);
+
+/* ppgs.load.model (ppgs/load.py:33-81) + ppgs.Model (ppgs/model/core.py:9-25):
+ * build an engine for `cfg` on CUDA device `device`. */
+int ppgs_engine_create(const ppgs_model_config* cfg, int device, ppgs_engine** out);
+void ppgs_engine_destroy(ppgs_engine* engine);
+
+/* `model.load_state_dict` (ppgs/load.py:76-79): upload one fp32 tensor under its
+ * reference state-dict key, e.g. "input_layer.weight" (H,C,5),
+ * "model.layers.0.self_attn.in_proj_weight" (3H,H), "position.encoding" (L,1,H).
+ * Shapes are validated against `cfg`; unknown keys are an error (strict load). */
+int ppgs_engine_set_weight(ppgs_engine* engine, const char* name,
+                           const float* data_host, const int64_t* shape, int ndim);
+
+/* Strict-load check (every key present) + packing into kernel layouts (k-major
+ * conv weights, split-fp16 planes, power-of-two scales). */
+int ppgs_engine_finalize(ppgs_engine* engine);
+
+int ppgs_engine_set_precision(ppgs_engine* engine, int precision);
+int ppgs_engine_get_precision(const ppgs_engine* engine);
+
+/* Single NCCL-free hook for multi-GPU loading: size of / pointer to the packed
+ * weight blob on the device, so the host can `torch.distributed.broadcast` it
+ * from rank 0 before `ppgs_engine_adopt_blob`. */
+size_t ppgs_engine_blob_bytes(const ppgs_engine* engine);
+void* ppgs_engine_blob_dev(ppgs_engine* engine);
+/* After the blob bytes were overwritten in place (e.g. by a broadcast), mark the
+ * engine finalised without re-uploading from host tensors. */
+int ppgs_engine_adopt_blob(ppgs_engine* engine);
+
+/* ppgs.preprocess.mel.from_audios (ppgs/preprocess/mel.py:14-19) =
+ * spectrogram.from_audios (ppgs/preprocess/spectrogram.py:14-50) + linear_to_mel
+ * (mel.py:56-76), autocast off.
+ *   audio_dev : (batch, samples) fp32, row stride `audio_stride` elements
+ *   mel_dev   : (batch, 80, samples/160) fp16, contiguous
+ * Requires samples >= 433 (reflect padding of 432, as torch does). */
+int ppgs_mel_forward(ppgs_engine* engine, const float* audio_dev, int batch,
+                     int64_t samples, int64_t audio_stride, void* mel_dev,
+                     void* stream);
+
+/* ppgs.from_features -> ppgs.infer -> Transformer.forward (ppgs/core.py:72-128,
+ * 551-596; ppgs/model/transformer.py:45-81), including the 500/400/50 chunking
+ * unless `legacy_mode`, the key-padding (and causal) masks, and softmax(dim=1)
+ * when `softmax` != 0.
+ *   features_dev : (batch, input_channels, frames) fp16, contiguous
+ *   lengths_host : (batch,) int64 frame lengths; max must equal `frames`
+ *   out_dev      : (batch, output_channels, frames) fp32, contiguous */
+int ppgs_transformer_forward(ppgs_engine* engine, const void* features_dev,
+                             int batch, int frames, const int64_t* lengths_host,
+                             int softmax, int legacy_mode, float* out_dev,
+                             void* stream);
+
+/* ppgs.from_audio (ppgs/core.py:22-69) for a batch, device buffers:
+ * mel front-end + transformer in one call; the fp16 features stay in the
+ * engine workspace.  lengths_host are SAMPLE lengths (NULL = all `samples`),
+ * converted with `// 160` like ppgs/core.py:326. */
+int ppgs_from_audio(ppgs_engine* engine, const float* audio_dev, int batch,
+                    int64_t samples, int64_t audio_stride,
+                    const int64_t* lengths_host, int softmax, int legacy_mode,
+                    float* out_dev, void* stream);
+
+/* Same, HOST buffers (the reference-facing call timed as `e2e` in bench.py):
+ * H2D of the audio, compute, D2H of the posteriors, stream-synchronised on
+ * return.  Pinned host memory is used as-is; pageable memory works but is slower. */
+int ppgs_from_audio_host(ppgs_engine* engine, const float* audio_host, int batch,
+                         int64_t samples, const int64_t* lengths_host,
+                         int softmax, int legacy_mode, float* out_host,
+                         void* stream);
+
+/* Number of kernels this library launched since the engine was created
+ * (bench.py's `gpu_launches`). */
+int64_t ppgs_engine_launch_count(const ppgs_engine* engine);
+
+/* Per-kernel device timing for bench.py's roofline: when enabled, every launch is
+ * bracketed by CUDA events on its stream and accumulated under the kernel's
+ * name.  `ppgs_engine_kernel_stat(e, i, ...)` enumerates the names (returns
+ * PPGS_E_INVALID past the end; synchronises the pending events).  Enabling or
+ * disabling clears the statistics. */
+int ppgs_engine_set_profiling(ppgs_engine* engine, int enabled);
+int ppgs_engine_kernel_stat(ppgs_engine* engine, int index, char* name, size_t name_bytes,
+                            double* total_ms, int64_t* launches);
+
+/* Device bytes currently held by the engine's grow-only workspace. */
+size_t ppgs_engine_workspace_bytes(const ppgs_engine* engine);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPGS_B200_H_ */

@@ -1,0 +1,37 @@
+"""`python -m ppgs_b200` — the flags of `python -m ppgs` (ppgs/__main__.py:12-59)."""
+import argparse
+from pathlib import Path
+
+import ppgs_b200
+
+
+def parse_args(argv=None):
+    parser = argparse.ArgumentParser(description='Phonetic posteriorgram inference')
+    parser.add_argument('--audio_files', nargs='+', type=Path, required=True,
+                        help='Paths to audio files')
+    parser.add_argument('--output_files', nargs='+', type=Path, required=True,
+                        help='The one-to-one corresponding output files')
+    parser.add_argument('--representation', type=str, default=ppgs_b200.REPRESENTATION,
+                        help='Representation to use for inference')
+    parser.add_argument('--checkpoint', type=Path, help='The checkpoint file')
+    parser.add_argument('--num-workers', type=int, default=0,
+                        help='Number of CPU threads for reading / saving')
+    parser.add_argument('--gpu', type=int,
+                        help='The index of the GPU to use for inference (default: current)')
+    parser.add_argument('--max-frames', type=float, default=ppgs_b200.MAX_INFERENCE_FRAMES,
+                        help='Maximum number of frames in a batch')
+    parser.add_argument('--legacy-mode', action='store_true',
+                        help='Use legacy (unchunked) inference')
+    parser.add_argument('--config', type=Path, nargs='*',
+                        help='accepted for compatibility with yapecs; ignored')
+    return parser.parse_args(argv)
+
+
+def main(argv=None):
+    args = vars(parse_args(argv))
+    args.pop('config', None)
+    ppgs_b200.from_files_to_files(**args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,48 @@
+"""Constants of the reference configuration (ppgs/config/defaults.py:20-32,
+127-161, ppgs/config/static.py:22, ppgs/config/w2v2fb.py:7-10).  The reference
+freezes these at import time through yapecs; here they are plain module
+attributes re-exported from `ppgs_b200`."""
+
+# Audio parameters (defaults.py:20-32)
+HOPSIZE = 160
+NUM_FFT = 1024
+NUM_MELS = 80
+SAMPLE_RATE = 16000
+WINDOW_SIZE = 1024
+
+# Representations (defaults.py:43-53)
+ALL_REPRESENTATIONS = ['mel', 'w2v2fb']
+BEST_REPRESENTATION = 'mel'
+REPRESENTATION = BEST_REPRESENTATION
+REPRESENTATION_KIND = 'ppg'
+
+# Model parameters (defaults.py:127-161)
+LOCAL_CHECKPOINT = None
+ATTENTION_HEADS = 2
+IS_CAUSAL = False
+HIDDEN_CHANNELS = 256
+INPUT_CHANNELS = 80
+KERNEL_SIZE = 5
+MODEL = 'transformer'
+NUM_HIDDEN_LAYERS = 5
+OUTPUT_CHANNELS = 40
+CHUNK_OVERLAP = 50
+CHUNK_LENGTH = 500
+MAX_LEN = 5000                   # ppgs/model/transformer.py:24
+FFN_CHANNELS = 2048              # torch.nn.TransformerEncoderLayer default
+LAYER_NORM_EPS = 1e-5            # torch.nn.TransformerEncoderLayer default
+
+# Data parameters (defaults.py:170,185,202; static.py:22)
+BUCKETS = 1
+RANDOM_SEED = 1234
+MAX_INFERENCE_FRAMES = float('inf')
+
+# Per-representation model kwargs (ppgs/load.py:35-50, ppgs/config/w2v2fb.py:7-10)
+MODEL_KWARGS = {
+    'mel': {},
+    'w2v2fb': {'hidden_channels': 512, 'input_channels': 768},
+}
+
+# Hugging Face checkpoint names (ppgs/load.py:59-67)
+HF_REPO = 'CameronChurchwell/ppgs'
+HF_CHECKPOINTS = {'mel': 'mel-800k.pt', 'w2v2fb': 'w2v2fb-425k.pt'}

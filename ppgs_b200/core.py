@@ -1,0 +1,283 @@
+"""Inference API of ppgs_b200 — same names, argument order and defaults as
+ppgs/core.py:22-391 of the reference; the arithmetic runs in libppgs_b200.so.
+
+Differences from the reference that a caller can observe:
+* every function needs a CUDA device (`gpu=None` means the current CUDA device;
+  the reference would use the CPU) — there is no CPU / PyTorch fallback;
+* `from_audio` accepts batch > 1 (the reference builds a length tensor of shape
+  (1,) and fails for B > 1);
+* results are fp32 CUDA tensors; numerics are the reference's modules evaluated
+  in fp32 with autocast disabled (oracle mode O3), not bf16/fp16 autocast;
+* `gpu` may also be a list of ordinals in `from_files_to_files` to shard the file
+  list across GPUs of one box from a single process group (see parallel.py).
+"""
+import os
+import queue
+import threading
+from typing import Dict, List, Optional, Union
+
+import torch
+
+from . import config
+from . import data
+from . import load
+from . import preprocess
+
+###############################################################################
+# Application programming interface
+###############################################################################
+
+
+def from_audio(
+    audio: torch.Tensor,
+    sample_rate: Union[int, float],
+    representation: str = config.REPRESENTATION,
+    checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
+    gpu: Optional[int] = None,
+    legacy_mode: bool = False
+) -> torch.Tensor:
+    """Infer ppgs from audio (ppgs/core.py:22-69)
+
+    Arguments
+        audio: batched audio, shape=(batch, 1, samples) (or (1, samples))
+        sample_rate: audio sampling rate
+        representation: 'mel' (w2v2fb: not built yet)
+        checkpoint: the checkpoint file
+        gpu: CUDA ordinal
+        legacy_mode: use legacy (unchunked) inference
+
+    Returns
+        ppgs, shape=(batch, len(ppgs.PHONEMES), frames), fp32 on the GPU
+    """
+    if audio.dim() == 2:
+        audio = audio.unsqueeze(0)
+    audio = resample(audio, sample_rate)
+    engine = load.model(checkpoint, representation, gpu)
+    if _fused_frontend(representation):
+        # mel front-end + transformer in one C-ABI call; features stay on-chip
+        # in the engine workspace (ppgs_from_audio)
+        return engine.from_audio(audio, softmax=True, legacy_mode=legacy_mode)
+    features = preprocess.from_audio(
+        audio, representation=representation,
+        sample_rate=config.SAMPLE_RATE, gpu=gpu)
+    lengths = torch.full((features.shape[0],), features.shape[-1], dtype=torch.long)
+    return from_features(features, lengths, representation, checkpoint, gpu,
+                         legacy_mode=legacy_mode)
+
+
+def from_features(
+    features: torch.Tensor,
+    lengths: torch.Tensor,
+    representation: str = config.REPRESENTATION,
+    checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
+    gpu: Optional[int] = None,
+    softmax: bool = True,
+    legacy_mode: bool = False
+) -> torch.Tensor:
+    """Infer ppgs from input features (ppgs/core.py:72-128)
+
+    features: shape=(batch, channels, frames); lengths: shape=(batch,)
+    """
+    return infer(features, lengths, representation, checkpoint, softmax,
+                 legacy_mode, gpu=gpu)
+
+
+def from_file(
+    file: Union[str, bytes, os.PathLike],
+    representation: str = config.REPRESENTATION,
+    checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
+    gpu: Optional[int] = None,
+    legacy_mode: bool = False
+) -> torch.Tensor:
+    """Infer ppgs from an audio file (ppgs/core.py:131-168);
+    returns shape=(len(ppgs.PHONEMES), frames)"""
+    audio = load.audio(file)
+    return from_audio(
+        audio, config.SAMPLE_RATE, representation, checkpoint, gpu, legacy_mode
+    ).squeeze(0)
+
+
+def from_file_to_file(
+    audio_file: Union[str, bytes, os.PathLike],
+    output_file: Union[str, bytes, os.PathLike],
+    representation: str = config.REPRESENTATION,
+    checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
+    gpu: Optional[int] = None,
+    legacy_mode: bool = False
+) -> None:
+    """Infer ppg from an audio file and save to a torch tensor file
+    (ppgs/core.py:171-204)"""
+    result = from_file(audio_file, representation, checkpoint, gpu, legacy_mode)
+    torch.save(result.detach().cpu(), output_file)
+
+
+def from_files_to_files(
+    audio_files: List[Union[str, bytes, os.PathLike]],
+    output_files: List[Union[str, bytes, os.PathLike]],
+    representation: str = config.REPRESENTATION,
+    checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
+    num_workers: int = 0,
+    gpu: Optional[int] = None,
+    max_frames: int = config.MAX_INFERENCE_FRAMES,
+    legacy_mode: bool = False
+) -> None:
+    """Infer ppgs from audio files and save to torch tensor files
+    (ppgs/core.py:207-272).  `num_workers` == 0: one file per call like the
+    reference; > 0: frame-budget batches from `data.loader` (reader threads) and
+    `num_workers // 2` writer threads."""
+    if len(audio_files) != len(output_files):
+        raise ValueError('audio_files and output_files must have equal lengths')
+    if num_workers == 0:
+        for audio_file, output_file in zip(audio_files, output_files):
+            from_file_to_file(
+                audio_file, output_file, representation, checkpoint, gpu, legacy_mode)
+        return
+    dataloader = data.loader(
+        audio_files,
+        features=['audio', 'length', 'audio_file'],
+        num_workers=num_workers // 2,
+        max_frames=max_frames)
+    mapping = {
+        audio_file: output_file
+        for audio_file, output_file in zip(audio_files, output_files)}
+    from_dataloader(
+        dataloader, mapping, representation, checkpoint,
+        save_workers=num_workers // 2, gpu=gpu, legacy_mode=legacy_mode)
+
+
+###############################################################################
+# Batched file inference
+###############################################################################
+
+
+def from_dataloader(
+    dataloader,
+    output_files: Dict[
+        Union[str, bytes, os.PathLike],
+        Union[str, bytes, os.PathLike]],
+    representation: str = config.REPRESENTATION,
+    checkpoint: Union[str, bytes, os.PathLike] = None,
+    save_workers: int = 1,
+    gpu: Optional[int] = None,
+    legacy_mode: bool = False
+) -> None:
+    """Infer ppgs from a dataloader yielding (audio, length, audio_filename)
+    batches (ppgs/core.py:280-391).  The reference pickles every result to a
+    spawn Pool; here writer *threads* take (pinned host tensor, filename,
+    frames) items from a bounded queue, so the D2H copy of batch i overlaps the
+    kernels of batch i+1."""
+    engine = load.model(checkpoint, representation, gpu)
+    writer = _Writer(save_workers)
+    try:
+        for audios, lengths, audio_files in dataloader:
+            frame_lengths = lengths // config.HOPSIZE
+            if _fused_frontend(representation):
+                result = engine.from_audio(
+                    audios, lengths=lengths, softmax=True, legacy_mode=legacy_mode)
+            else:
+                features = preprocess.get(representation).from_audios(
+                    audios, lengths, gpu=gpu)
+                if features.requires_grad:
+                    raise ValueError('All representations should be detached')
+                result = engine.transformer(
+                    features, frame_lengths, softmax=True, legacy_mode=legacy_mode)
+            host = torch.empty(result.shape, dtype=result.dtype, pin_memory=True)
+            host.copy_(result, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(engine.device))
+            filenames = [output_files[file] for file in audio_files]
+            writer.put(done, host, filenames, frame_lengths.tolist())
+    finally:
+        writer.close()
+
+
+class _Writer:
+    """Bounded queue + `workers` saver threads (0 = save synchronously).
+    Replaces the spawn Pool + qsize back-pressure of ppgs/core.py:311-314,358-365."""
+
+    def __init__(self, workers):
+        self.workers = max(int(workers), 0)
+        self.errors = []
+        if self.workers:
+            self.queue = queue.Queue(maxsize=4 * self.workers)
+            self.threads = [
+                threading.Thread(target=self._run, daemon=True)
+                for _ in range(self.workers)]
+            for thread in self.threads:
+                thread.start()
+
+    @staticmethod
+    def _save(done, host, filenames, frames):
+        done.synchronize()
+        for ppg, filename, length in zip(host, filenames, frames):
+            preprocess.save_masked(ppg, filename, int(length))
+
+    def _run(self):
+        while True:
+            item = self.queue.get()
+            if item is None:
+                return
+            try:
+                self._save(*item)
+            except Exception as error:   # surfaced by close()
+                self.errors.append(error)
+
+    def put(self, done, host, filenames, frames):
+        if self.workers:
+            self.queue.put((done, host, filenames, frames))
+        else:
+            self._save(done, host, filenames, frames)
+
+    def close(self):
+        if self.workers:
+            for _ in self.threads:
+                self.queue.put(None)
+            for thread in self.threads:
+                thread.join()
+        if self.errors:
+            raise self.errors[0]
+
+
+###############################################################################
+# Inference
+###############################################################################
+
+
+def infer(
+    features,
+    lengths,
+    representation=config.REPRESENTATION,
+    checkpoint=None,
+    softmax=True,
+    legacy_mode=False,
+    gpu=None
+):
+    """Perform model inference (ppgs/core.py:551-596): cached engine per
+    (representation, checkpoint, device); logits -> softmax(dim=1) in-kernel."""
+    if gpu is None and features.is_cuda:
+        gpu = features.device.index
+    engine = load.model(checkpoint, representation, gpu)
+    return engine.transformer(features, lengths, softmax=softmax, legacy_mode=legacy_mode)
+
+
+def resample(audio, sample_rate, target_rate=config.SAMPLE_RATE):
+    """Perform audio resampling (ppgs/core.py:599-608)"""
+    if sample_rate == target_rate:
+        return audio
+    import torchaudio
+    resampler = torchaudio.transforms.Resample(sample_rate, target_rate)
+    return resampler.to(audio.device)(audio)
+
+
+def representation_file_extension():
+    """ppgs/core.py:611-621"""
+    if (config.REPRESENTATION == config.BEST_REPRESENTATION and
+            config.REPRESENTATION_KIND == 'ppg'):
+        return '-ppg.pt'
+    if config.REPRESENTATION_KIND == 'ppg':
+        return f'-{config.REPRESENTATION}-ppg.pt'
+    return f'-{config.REPRESENTATION}.pt'
+
+
+def _fused_frontend(representation):
+    return (representation if representation is not None else config.REPRESENTATION) == 'mel'

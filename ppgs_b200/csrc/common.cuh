@@ -1,0 +1,159 @@
+// Shared declarations of the ppgs_b200 CUDA library (not part of the C ABI).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ppgs_b200.h"
+
+namespace ppgs {
+
+constexpr int kHopSamples = 160;   // ppgs.HOPSIZE
+constexpr int kMelChannels = 80;   // ppgs.NUM_MELS
+
+void set_error(const char* fmt, ...);
+
+#define PPGS_CUDA(expr)                                                          \
+    do {                                                                         \
+        cudaError_t err__ = (expr);                                              \
+        if (err__ != cudaSuccess) {                                              \
+            ::ppgs::set_error("%s failed: %s (%s:%d)", #expr,                    \
+                              cudaGetErrorString(err__), __FILE__, __LINE__);    \
+            return PPGS_E_CUDA;                                                  \
+        }                                                                        \
+    } while (0)
+
+#define PPGS_CHECK(expr)                    \
+    do {                                    \
+        int rc__ = (expr);                  \
+        if (rc__ != PPGS_OK) return rc__;   \
+    } while (0)
+
+// One folded sequence = (chunk i, utterance b) of ppgs/model/transformer.py:56-63,
+// or the whole utterance when un-chunked.  Rows of every activation matrix are
+// time-major: sequence s owns rows [row0, row0 + pitch), of which the first
+// `tensor_len` are real frames of the chunk tensor and the rest are zero padding.
+struct SeqInfo {
+    int32_t row0;         // first activation row
+    int32_t tensor_len;   // Tc: frames of the chunk tensor (<= pitch - 2)
+    int32_t valid_len;    // chunk_lengths[b]: keys / frames that are not masked
+    int32_t batch;        // source utterance
+    int32_t src_start;    // frame of the utterance at local t=0 (may be negative:
+                          // replicate padding clamps to frame 0)
+    int32_t keep_begin;   // local frames [keep_begin, keep_end) are emitted ...
+    int32_t keep_end;
+    int32_t out_start;    // ... to output frames out_start + (t - keep_begin)
+};
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+struct MelTables {
+    float* window = nullptr;      // [1024] periodic hann
+    float2* tw512 = nullptr;      // [512] exp(-2 pi i m / 512)
+    float2* tw1024 = nullptr;     // [513] exp(-2 pi i k / 1024)
+    int32_t* band_meta = nullptr; // [80][3] first bin, count, weight offset
+    float* band_weights = nullptr;
+    int band_weight_count = 0;
+};
+
+// Split-fp16 operand planes: plane 0 = hi, plane 1 = lo (rows stacked).
+struct PlanePair {
+    __half* data = nullptr;   // [2][rows][cols]
+    int rows = 0, cols = 0;
+    float inv_scale = 1.f;    // multiply the accumulator by this (power of two)
+};
+
+struct LayerWeights {
+    float *in_w, *in_b, *out_w, *out_b, *l1_w, *l1_b, *l2_w, *l2_b;
+    float *n1_w, *n1_b, *n2_w, *n2_b;
+};
+
+}  // namespace ppgs
+
+struct ppgs_engine {
+    ppgs_model_config cfg;
+    int device = 0;
+    int precision = PPGS_PRECISION_FP32;
+    bool finalized = false;
+    int sm_count = 148;
+
+    // fp32 weights by reference state-dict key, held on the host until finalize
+    std::map<std::string, ppgs::HostTensor> weights;
+
+    // packed blob (one allocation; broadcastable)
+    void* blob = nullptr;
+    size_t blob_bytes = 0;
+    float* conv_in_w = nullptr;    // [H][5*C]   k = tap*C + c
+    float* conv_out_w = nullptr;   // [O][5*H]
+    float* pe = nullptr;           // [max_len][H]
+    std::vector<ppgs::LayerWeights> layers;
+    float *conv_in_b = nullptr, *conv_out_b = nullptr;
+
+    ppgs::MelTables mel;
+    std::vector<float> host_window;   // optional override ("frontend.window")
+
+    // grow-only workspace
+    void* workspace = nullptr;
+    size_t workspace_bytes = 0;
+    // pinned staging for per-call tables
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    // device staging for the host-buffer entry point
+    void* io_dev = nullptr;
+    size_t io_dev_bytes = 0;
+
+    int64_t launches = 0;
+
+    // optional per-kernel timing (ppgs_engine_set_profiling): CUDA events on the
+    // launch stream around every launch, accumulated per kernel name
+    bool profiling = false;
+    struct KernelStat {
+        double ms = 0.0;
+        int64_t launches = 0;
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    };
+    std::map<std::string, KernelStat> stats;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace ppgs {
+
+int ensure_workspace(ppgs_engine* e, size_t bytes);
+
+// Brackets one kernel launch: counts it, and when profiling records CUDA events
+// on `stream` around it.
+struct LaunchScope {
+    ppgs_engine* e;
+    cudaStream_t stream;
+    ppgs_engine::KernelStat* stat = nullptr;
+    cudaEvent_t start = nullptr;
+    LaunchScope(ppgs_engine* e, const char* name, cudaStream_t stream);
+    ~LaunchScope();
+};
+int ensure_pinned(ppgs_engine* e, size_t bytes);
+
+// mel.cu
+int build_mel_tables(ppgs_engine* e, const float* basis_host /* [80][513] or null */);
+int launch_mel(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+               int64_t stride, __half* mel, cudaStream_t stream);
+
+// transformer_fp32.cu
+struct ForwardPlan {
+    std::vector<SeqInfo> seqs;
+    int rows = 0;          // total activation rows (multiple of 128)
+    int max_pitch = 0;
+    int batch = 0, frames = 0;
+};
+int build_plan(const ppgs_engine* e, int batch, int frames, const int64_t* lengths,
+               int legacy_mode, ForwardPlan* plan);
+int transformer_forward_fp32(ppgs_engine* e, const __half* features, const ForwardPlan& plan,
+                             int softmax, float* out, cudaStream_t stream);
+
+}  // namespace ppgs

@@ -1,0 +1,621 @@
+// C ABI of libppgs_b200.so (include/ppgs_b200.h): engine lifetime, strict
+// state-dict loading (ppgs/load.py:76-79), weight packing, and the forward entry
+// points that replace ppgs.preprocess.mel.from_audios / ppgs.from_features /
+// ppgs.from_audio.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace ppgs {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int ensure_workspace(ppgs_engine* e, size_t bytes) {
+    if (bytes <= e->workspace_bytes) return PPGS_OK;
+    if (e->workspace) {
+        PPGS_CUDA(cudaDeviceSynchronize());   // earlier launches may still use the old block
+        PPGS_CUDA(cudaFree(e->workspace));
+        e->workspace = nullptr;
+        e->workspace_bytes = 0;
+    }
+    const size_t grown = bytes + bytes / 8;
+    PPGS_CUDA(cudaMalloc(&e->workspace, grown));
+    e->workspace_bytes = grown;
+    return PPGS_OK;
+}
+
+int ensure_pinned(ppgs_engine* e, size_t bytes) {
+    if (bytes <= e->pinned_bytes) return PPGS_OK;
+    if (e->pinned) {
+        PPGS_CUDA(cudaDeviceSynchronize());
+        PPGS_CUDA(cudaFreeHost(e->pinned));
+        e->pinned = nullptr;
+        e->pinned_bytes = 0;
+    }
+    const size_t grown = std::max<size_t>(bytes * 2, 1 << 16);
+    PPGS_CUDA(cudaMallocHost(&e->pinned, grown));
+    e->pinned_bytes = grown;
+    return PPGS_OK;
+}
+
+static cudaEvent_t take_event(ppgs_engine* e) {
+    if (!e->event_pool.empty()) {
+        cudaEvent_t ev = e->event_pool.back();
+        e->event_pool.pop_back();
+        return ev;
+    }
+    cudaEvent_t ev = nullptr;
+    cudaEventCreate(&ev);
+    return ev;
+}
+
+LaunchScope::LaunchScope(ppgs_engine* e_, const char* name, cudaStream_t stream_)
+    : e(e_), stream(stream_) {
+    e->launches += 1;
+    if (!e->profiling) return;
+    stat = &e->stats[name];
+    start = take_event(e);
+    cudaEventRecord(start, stream);
+}
+
+LaunchScope::~LaunchScope() {
+    if (!stat) return;
+    cudaEvent_t stop = take_event(e);
+    cudaEventRecord(stop, stream);
+    stat->pending.emplace_back(start, stop);
+    stat->launches += 1;
+}
+
+static void drain_stats(ppgs_engine* e) {
+    for (auto& kv : e->stats) {
+        for (auto& pr : kv.second.pending) {
+            cudaEventSynchronize(pr.second);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, pr.first, pr.second);
+            kv.second.ms += ms;
+            e->event_pool.push_back(pr.first);
+            e->event_pool.push_back(pr.second);
+        }
+        kv.second.pending.clear();
+    }
+}
+
+int upload_plan(ppgs_engine* e, const ForwardPlan& plan, SeqInfo* seqs_dev, int* tile_seq_dev,
+                cudaStream_t stream) {
+    const size_t seq_bytes = plan.seqs.size() * sizeof(SeqInfo);
+    const size_t tiles = plan.rows / 128;
+    // The staging buffer is reused by the next call: make sure the previous
+    // call's async copy has been consumed.
+    PPGS_CUDA(cudaStreamSynchronize(stream));
+    PPGS_CHECK(ensure_pinned(e, seq_bytes + tiles * sizeof(int)));
+    char* p = static_cast<char*>(e->pinned);
+    memcpy(p, plan.seqs.data(), seq_bytes);
+    int* tile_seq = reinterpret_cast<int*>(p + seq_bytes);
+    for (size_t s = 0; s < plan.seqs.size(); ++s) {
+        const int first = plan.seqs[s].row0 / 128;
+        const int last = (s + 1 < plan.seqs.size() ? plan.seqs[s + 1].row0 : plan.rows) / 128;
+        for (int t = first; t < last; ++t) tile_seq[t] = (int)s;
+    }
+    PPGS_CUDA(cudaMemcpyAsync(seqs_dev, p, seq_bytes, cudaMemcpyHostToDevice, stream));
+    PPGS_CUDA(cudaMemcpyAsync(tile_seq_dev, tile_seq, tiles * sizeof(int), cudaMemcpyHostToDevice,
+                              stream));
+    return PPGS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------
+struct KeySpec {
+    std::string name;
+    std::vector<int64_t> shape;
+};
+
+static std::vector<KeySpec> expected_keys(const ppgs_model_config& c) {
+    const int64_t H = c.hidden_channels, C = c.input_channels, F = c.ffn_channels;
+    const int64_t O = c.output_channels, k = c.kernel_size, L = c.max_len;
+    std::vector<KeySpec> keys;
+    keys.push_back({"position.encoding", {L, 1, H}});
+    keys.push_back({"input_layer.weight", {H, C, k}});
+    keys.push_back({"input_layer.bias", {H}});
+    for (int l = 0; l < c.num_layers; ++l) {
+        const std::string p = "model.layers." + std::to_string(l) + ".";
+        keys.push_back({p + "self_attn.in_proj_weight", {3 * H, H}});
+        keys.push_back({p + "self_attn.in_proj_bias", {3 * H}});
+        keys.push_back({p + "self_attn.out_proj.weight", {H, H}});
+        keys.push_back({p + "self_attn.out_proj.bias", {H}});
+        keys.push_back({p + "linear1.weight", {F, H}});
+        keys.push_back({p + "linear1.bias", {F}});
+        keys.push_back({p + "linear2.weight", {H, F}});
+        keys.push_back({p + "linear2.bias", {H}});
+        keys.push_back({p + "norm1.weight", {H}});
+        keys.push_back({p + "norm1.bias", {H}});
+        keys.push_back({p + "norm2.weight", {H}});
+        keys.push_back({p + "norm2.bias", {H}});
+    }
+    keys.push_back({"output_layer.weight", {O, H, k}});
+    keys.push_back({"output_layer.bias", {O}});
+    return keys;
+}
+
+// Packed blob: every tensor the kernels read, in one allocation whose layout is
+// a pure function of the config (so every rank carves identical pointers).
+struct BlobWriter {
+    std::vector<char>* host;   // null: only measure / carve
+    char* dev;
+    size_t off = 0;
+    template <typename T>
+    T* put(const T* src, size_t count) {
+        const size_t bytes = count * sizeof(T);
+        if (host) {
+            host->resize(off + ((bytes + 255) & ~size_t(255)), 0);
+            if (src) memcpy(host->data() + off, src, bytes);
+        }
+        T* p = dev ? reinterpret_cast<T*>(dev + off) : nullptr;
+        off += (bytes + 255) & ~size_t(255);
+        return p;
+    }
+};
+
+static std::vector<float> conv_k_major(const HostTensor* w) {
+    // (out, in, k) -> [out][tap * in + c]: the im2col row of frame t is then the
+    // contiguous run of k*in activations starting at row t - k/2.
+    std::vector<float> packed;
+    if (!w) return packed;
+    const int64_t O = w->shape[0], I = w->shape[1], K = w->shape[2];
+    packed.resize((size_t)(O * I * K));
+    for (int64_t o = 0; o < O; ++o)
+        for (int64_t c = 0; c < I; ++c)
+            for (int64_t t = 0; t < K; ++t)
+                packed[(size_t)((o * K + t) * I + c)] = w->data[(size_t)((o * I + c) * K + t)];
+    return packed;
+}
+
+// Walks the blob layout.  With `e->weights` populated and `host` set it also
+// serialises the data; otherwise it only assigns device pointers.
+static size_t layout_blob(ppgs_engine* e, std::vector<char>* host, char* dev) {
+    const ppgs_model_config& c = e->cfg;
+    const size_t H = c.hidden_channels, C = c.input_channels, F = c.ffn_channels;
+    const size_t O = c.output_channels, k = c.kernel_size, L = c.max_len;
+    BlobWriter w{host, dev};
+    auto get = [&](const std::string& name) -> const HostTensor* {
+        if (!host) return nullptr;
+        return &e->weights.at(name);
+    };
+    auto raw = [&](const std::string& name, size_t count) -> float* {
+        const HostTensor* t = get(name);
+        return w.put<float>(t ? t->data.data() : nullptr, count);
+    };
+    {
+        std::vector<float> packed = conv_k_major(get("input_layer.weight"));
+        e->conv_in_w = w.put<float>(host ? packed.data() : nullptr, H * C * k);
+    }
+    e->conv_in_b = raw("input_layer.bias", H);
+    e->pe = raw("position.encoding", L * H);
+    e->layers.resize(c.num_layers);
+    for (int l = 0; l < c.num_layers; ++l) {
+        const std::string p = "model.layers." + std::to_string(l) + ".";
+        LayerWeights& lw = e->layers[l];
+        lw.in_w = raw(p + "self_attn.in_proj_weight", 3 * H * H);
+        lw.in_b = raw(p + "self_attn.in_proj_bias", 3 * H);
+        lw.out_w = raw(p + "self_attn.out_proj.weight", H * H);
+        lw.out_b = raw(p + "self_attn.out_proj.bias", H);
+        lw.l1_w = raw(p + "linear1.weight", F * H);
+        lw.l1_b = raw(p + "linear1.bias", F);
+        lw.l2_w = raw(p + "linear2.weight", H * F);
+        lw.l2_b = raw(p + "linear2.bias", H);
+        lw.n1_w = raw(p + "norm1.weight", H);
+        lw.n1_b = raw(p + "norm1.bias", H);
+        lw.n2_w = raw(p + "norm2.weight", H);
+        lw.n2_b = raw(p + "norm2.bias", H);
+    }
+    {
+        std::vector<float> packed = conv_k_major(get("output_layer.weight"));
+        e->conv_out_w = w.put<float>(host ? packed.data() : nullptr, O * H * k);
+    }
+    e->conv_out_b = raw("output_layer.bias", O);
+    return w.off;
+}
+
+static int alloc_blob(ppgs_engine* e) {
+    if (e->blob) return PPGS_OK;
+    e->blob_bytes = layout_blob(e, nullptr, nullptr);
+    PPGS_CUDA(cudaMalloc(&e->blob, e->blob_bytes));
+    layout_blob(e, nullptr, static_cast<char*>(e->blob));
+    return PPGS_OK;
+}
+
+}  // namespace ppgs
+
+using namespace ppgs;
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) {
+            set_error("cannot select CUDA device %d: %s", device,
+                      cudaGetErrorString(cudaGetLastError()));
+            ok = false;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define PPGS_ENTER(e)                                     \
+    if (!(e)) {                                           \
+        set_error("engine is NULL");                      \
+        return PPGS_E_INVALID;                            \
+    }                                                     \
+    DeviceGuard guard__((e)->device);                     \
+    if (!guard__.ok) return PPGS_E_CUDA
+
+extern "C" {
+
+int ppgs_abi_version(void) { return PPGS_ABI_VERSION; }
+
+const char* ppgs_last_error(void) { return g_error; }
+
+void ppgs_default_config(ppgs_model_config* cfg) {
+    if (!cfg) return;
+    cfg->input_channels = 80;
+    cfg->hidden_channels = 256;
+    cfg->num_layers = 5;
+    cfg->num_heads = 2;
+    cfg->ffn_channels = 2048;
+    cfg->output_channels = 40;
+    cfg->kernel_size = 5;
+    cfg->is_causal = 0;
+    cfg->chunk_length = 500;
+    cfg->chunk_overlap = 50;
+    cfg->max_len = 5000;
+    cfg->layer_norm_eps = 1e-5f;
+}
+
+int ppgs_engine_create(const ppgs_model_config* cfg, int device, ppgs_engine** out) {
+    if (!cfg || !out) {
+        set_error("cfg and out must not be NULL");
+        return PPGS_E_INVALID;
+    }
+    const ppgs_model_config& c = *cfg;
+    if (c.input_channels <= 0 || c.hidden_channels <= 0 || c.num_layers <= 0 || c.num_heads <= 0 ||
+        c.ffn_channels <= 0 || c.output_channels <= 0 || c.kernel_size <= 0 ||
+        (c.kernel_size & 1) == 0 || c.hidden_channels % c.num_heads != 0 || c.max_len <= 0 ||
+        c.chunk_length <= 2 * c.chunk_overlap || c.chunk_overlap < 0 || c.output_channels > 64) {
+        set_error("invalid model config");
+        return PPGS_E_INVALID;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        set_error("no CUDA device available: %s", cudaGetErrorString(cudaGetLastError()));
+        return PPGS_E_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        set_error("device %d out of range (have %d)", device, count);
+        return PPGS_E_INVALID;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return PPGS_E_CUDA;
+    cudaDeviceProp prop;
+    PPGS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("ppgs_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
+                  prop.minor);
+        return PPGS_E_UNSUPPORTED;
+    }
+    ppgs_engine* e = new ppgs_engine();
+    e->cfg = c;
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    *out = e;
+    return PPGS_OK;
+}
+
+void ppgs_engine_destroy(ppgs_engine* e) {
+    if (!e) return;
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    cudaFree(e->blob);
+    cudaFree(e->workspace);
+    cudaFree(e->io_dev);
+    cudaFreeHost(e->pinned);
+    cudaFree(e->mel.window);
+    cudaFree(e->mel.tw512);
+    cudaFree(e->mel.tw1024);
+    cudaFree(e->mel.band_meta);
+    cudaFree(e->mel.band_weights);
+    drain_stats(e);
+    for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+    delete e;
+}
+
+int ppgs_engine_set_weight(ppgs_engine* e, const char* name, const float* data,
+                           const int64_t* shape, int ndim) {
+    if (!e || !name || !data || !shape || ndim < 0) {
+        set_error("set_weight: NULL argument");
+        return PPGS_E_INVALID;
+    }
+    std::vector<int64_t> shp(shape, shape + ndim);
+    size_t numel = 1;
+    for (int64_t d : shp) numel *= (size_t)d;
+    const std::string key(name);
+    if (key == "frontend.window") {
+        if (numel != 1024) {
+            set_error("frontend.window must have 1024 elements");
+            return PPGS_E_INVALID;
+        }
+        e->host_window.assign(data, data + numel);
+        return PPGS_OK;
+    }
+    if (key == "frontend.mel_basis") {
+        if (shp != std::vector<int64_t>{80, 513}) {
+            set_error("frontend.mel_basis must be (80, 513)");
+            return PPGS_E_INVALID;
+        }
+        HostTensor t;
+        t.data.assign(data, data + numel);
+        t.shape = shp;
+        e->weights[key] = std::move(t);
+        return PPGS_OK;
+    }
+    for (const KeySpec& spec : expected_keys(e->cfg)) {
+        if (spec.name != key) continue;
+        if (spec.shape != shp) {
+            set_error("size mismatch for %s", name);   // load_state_dict(strict) wording
+            return PPGS_E_INVALID;
+        }
+        HostTensor t;
+        t.data.assign(data, data + numel);
+        t.shape = shp;
+        e->weights[key] = std::move(t);
+        e->finalized = false;
+        return PPGS_OK;
+    }
+    set_error("unexpected key in state_dict: %s", name);
+    return PPGS_E_INVALID;
+}
+
+int ppgs_engine_finalize(ppgs_engine* e) {
+    PPGS_ENTER(e);
+    for (const KeySpec& spec : expected_keys(e->cfg)) {
+        if (!e->weights.count(spec.name)) {
+            set_error("missing key in state_dict: %s", spec.name.c_str());
+            return PPGS_E_STATE;
+        }
+    }
+    PPGS_CHECK(alloc_blob(e));
+    std::vector<char> host;
+    const size_t bytes = layout_blob(e, &host, static_cast<char*>(e->blob));
+    if (bytes != e->blob_bytes) {
+        set_error("internal error: blob layout mismatch");
+        return PPGS_E_STATE;
+    }
+    PPGS_CUDA(cudaMemcpy(e->blob, host.data(), bytes, cudaMemcpyHostToDevice));
+    const float* basis = nullptr;
+    auto it = e->weights.find("frontend.mel_basis");
+    if (it != e->weights.end()) basis = it->second.data.data();
+    PPGS_CHECK(build_mel_tables(e, basis));
+    // host copies are no longer needed (keep the optional front-end tables)
+    for (auto i = e->weights.begin(); i != e->weights.end();) {
+        if (i->first.rfind("frontend.", 0) == 0) ++i;
+        else i = e->weights.erase(i);
+    }
+    e->finalized = true;
+    return PPGS_OK;
+}
+
+size_t ppgs_engine_blob_bytes(const ppgs_engine* e) {
+    if (!e) return 0;
+    ppgs_engine tmp;
+    tmp.cfg = e->cfg;
+    return layout_blob(&tmp, nullptr, nullptr);
+}
+
+void* ppgs_engine_blob_dev(ppgs_engine* e) {
+    if (!e) return nullptr;
+    DeviceGuard guard(e->device);
+    if (!guard.ok || alloc_blob(e) != PPGS_OK) return nullptr;
+    return e->blob;
+}
+
+int ppgs_engine_adopt_blob(ppgs_engine* e) {
+    PPGS_ENTER(e);
+    if (!e->blob) {
+        set_error("adopt_blob: call ppgs_engine_blob_dev first");
+        return PPGS_E_STATE;
+    }
+    const float* basis = nullptr;
+    auto it = e->weights.find("frontend.mel_basis");
+    if (it != e->weights.end()) basis = it->second.data.data();
+    PPGS_CHECK(build_mel_tables(e, basis));
+    e->finalized = true;
+    return PPGS_OK;
+}
+
+int ppgs_engine_set_precision(ppgs_engine* e, int precision) {
+    if (!e) {
+        set_error("engine is NULL");
+        return PPGS_E_INVALID;
+    }
+    if (precision != PPGS_PRECISION_FP32) {
+        set_error("precision %d is not available in this build", precision);
+        return PPGS_E_UNSUPPORTED;
+    }
+    e->precision = precision;
+    return PPGS_OK;
+}
+
+int ppgs_engine_get_precision(const ppgs_engine* e) { return e ? e->precision : PPGS_E_INVALID; }
+
+int64_t ppgs_engine_launch_count(const ppgs_engine* e) { return e ? e->launches : 0; }
+
+int ppgs_engine_set_profiling(ppgs_engine* e, int enabled) {
+    PPGS_ENTER(e);
+    drain_stats(e);
+    e->stats.clear();
+    e->profiling = enabled != 0;
+    return PPGS_OK;
+}
+
+int ppgs_engine_kernel_stat(ppgs_engine* e, int index, char* name, size_t name_bytes,
+                            double* total_ms, int64_t* launches) {
+    PPGS_ENTER(e);
+    drain_stats(e);
+    if (index < 0 || index >= (int)e->stats.size()) return PPGS_E_INVALID;
+    auto it = e->stats.begin();
+    std::advance(it, index);
+    if (name && name_bytes) snprintf(name, name_bytes, "%s", it->first.c_str());
+    if (total_ms) *total_ms = it->second.ms;
+    if (launches) *launches = it->second.launches;
+    return PPGS_OK;
+}
+
+size_t ppgs_engine_workspace_bytes(const ppgs_engine* e) { return e ? e->workspace_bytes : 0; }
+
+static int require_ready(ppgs_engine* e) {
+    if (!e->finalized) {
+        set_error("engine has no weights: call ppgs_engine_finalize first");
+        return PPGS_E_STATE;
+    }
+    return PPGS_OK;
+}
+
+int ppgs_mel_forward(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                     int64_t stride, void* mel, void* stream) {
+    PPGS_ENTER(e);
+    PPGS_CHECK(require_ready(e));
+    if (!audio || !mel || batch < 0 || samples < 0 || stride < samples) {
+        set_error("mel_forward: bad argument");
+        return PPGS_E_INVALID;
+    }
+    return launch_mel(e, audio, batch, samples, stride, static_cast<__half*>(mel),
+                      static_cast<cudaStream_t>(stream));
+}
+
+static int run_transformer(ppgs_engine* e, const __half* features, const ForwardPlan& plan,
+                           int softmax, float* out, cudaStream_t stream) {
+    switch (e->precision) {
+        case PPGS_PRECISION_FP32:
+            return transformer_forward_fp32(e, features, plan, softmax, out, stream);
+        default:
+            set_error("precision %d is not available in this build", e->precision);
+            return PPGS_E_UNSUPPORTED;
+    }
+}
+
+int ppgs_transformer_forward(ppgs_engine* e, const void* features, int batch, int frames,
+                             const int64_t* lengths, int softmax, int legacy_mode, float* out,
+                             void* stream) {
+    PPGS_ENTER(e);
+    PPGS_CHECK(require_ready(e));
+    if (!features || !lengths || !out) {
+        set_error("transformer_forward: NULL argument");
+        return PPGS_E_INVALID;
+    }
+    ForwardPlan plan;
+    PPGS_CHECK(build_plan(e, batch, frames, lengths, legacy_mode, &plan));
+    return run_transformer(e, static_cast<const __half*>(features), plan, softmax, out,
+                           static_cast<cudaStream_t>(stream));
+}
+
+// features for the fused entry points live at the top of a separate allocation so
+// that the transformer's workspace growth cannot move them mid-call
+static int ensure_io(ppgs_engine* e, size_t bytes) {
+    if (bytes <= e->io_dev_bytes) return PPGS_OK;
+    if (e->io_dev) {
+        PPGS_CUDA(cudaDeviceSynchronize());
+        PPGS_CUDA(cudaFree(e->io_dev));
+        e->io_dev = nullptr;
+        e->io_dev_bytes = 0;
+    }
+    PPGS_CUDA(cudaMalloc(&e->io_dev, bytes));
+    e->io_dev_bytes = bytes;
+    return PPGS_OK;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static int from_audio_device(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                             int64_t stride, const int64_t* lengths, int softmax,
+                             int legacy_mode, float* out, __half* mel, cudaStream_t stream) {
+    const int frames = (int)(samples / kHopSamples);
+    if (frames <= 0) {
+        set_error("from_audio: need at least %d samples", kHopSamples);
+        return PPGS_E_INVALID;
+    }
+    std::vector<int64_t> frame_lengths(batch, frames);
+    if (lengths)
+        for (int b = 0; b < batch; ++b) frame_lengths[b] = lengths[b] / kHopSamples;
+    ForwardPlan plan;
+    PPGS_CHECK(build_plan(e, batch, frames, frame_lengths.data(), legacy_mode, &plan));
+    PPGS_CHECK(launch_mel(e, audio, batch, samples, stride, mel, stream));
+    return run_transformer(e, mel, plan, softmax, out, stream);
+}
+
+int ppgs_from_audio(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                    int64_t stride, const int64_t* lengths, int softmax, int legacy_mode,
+                    float* out, void* stream) {
+    PPGS_ENTER(e);
+    PPGS_CHECK(require_ready(e));
+    if (!audio || !out || batch <= 0 || samples <= 0 || stride < samples) {
+        set_error("from_audio: bad argument");
+        return PPGS_E_INVALID;
+    }
+    if (e->cfg.input_channels != kMelChannels) {
+        set_error("from_audio: the mel front-end feeds %d channels, model expects %d",
+                  kMelChannels, e->cfg.input_channels);
+        return PPGS_E_INVALID;
+    }
+    const size_t mel_bytes = align256((size_t)batch * kMelChannels * (samples / kHopSamples) * 2);
+    PPGS_CHECK(ensure_io(e, mel_bytes));
+    return from_audio_device(e, audio, batch, samples, stride, lengths, softmax, legacy_mode, out,
+                             static_cast<__half*>(e->io_dev), static_cast<cudaStream_t>(stream));
+}
+
+int ppgs_from_audio_host(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                         const int64_t* lengths, int softmax, int legacy_mode, float* out,
+                         void* stream_) {
+    PPGS_ENTER(e);
+    PPGS_CHECK(require_ready(e));
+    if (!audio || !out || batch <= 0 || samples <= 0) {
+        set_error("from_audio_host: bad argument");
+        return PPGS_E_INVALID;
+    }
+    if (e->cfg.input_channels != kMelChannels) {
+        set_error("from_audio_host: model does not take mel features");
+        return PPGS_E_INVALID;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int64_t frames = samples / kHopSamples;
+    const size_t audio_bytes = align256((size_t)batch * samples * 4);
+    const size_t mel_bytes = align256((size_t)batch * kMelChannels * frames * 2);
+    const size_t out_bytes = align256((size_t)batch * e->cfg.output_channels * frames * 4);
+    PPGS_CHECK(ensure_io(e, audio_bytes + mel_bytes + out_bytes));
+    char* io = static_cast<char*>(e->io_dev);
+    float* audio_dev = reinterpret_cast<float*>(io);
+    __half* mel_dev = reinterpret_cast<__half*>(io + audio_bytes);
+    float* out_dev = reinterpret_cast<float*>(io + audio_bytes + mel_bytes);
+    PPGS_CUDA(cudaMemcpyAsync(audio_dev, audio, (size_t)batch * samples * 4,
+                              cudaMemcpyHostToDevice, stream));
+    PPGS_CHECK(from_audio_device(e, audio_dev, batch, samples, samples, lengths, softmax,
+                                 legacy_mode, out_dev, mel_dev, stream));
+    PPGS_CUDA(cudaMemcpyAsync(out, out_dev, (size_t)batch * e->cfg.output_channels * frames * 4,
+                              cudaMemcpyDeviceToHost, stream));
+    PPGS_CUDA(cudaStreamSynchronize(stream));
+    return PPGS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,374 @@
+// K1: fused framed STFT + Slaney mel + log + fp16 kernel (HBM-bound stage).
+//
+// Replaces ppgs.preprocess.mel.from_audios (ppgs/preprocess/mel.py:14-19):
+//   spectrogram.from_audios  ppgs/preprocess/spectrogram.py:14-50
+//   linear_to_mel            ppgs/preprocess/mel.py:56-76
+// which in the reference is reflection_pad1d + as_strided framing + cuFFT R2C +
+// five elementwise passes over a complex (B,513,T) tensor + a batched GEMM +
+// clamp/log/half.  Here one persistent CTA stages the audio of a 32-frame tile
+// in shared memory with the bulk async-copy engine (cp.async.bulk -> UBLKCP,
+// mbarrier completion), each warp runs 1024-point real FFTs out of that tile and
+// only the (80, frames) fp16 mel leaves the SM: 640 B in + 160 B out per frame.
+//
+// Compiled with --fmad=false: the arithmetic is written with explicit fmaf so
+// that the CPU emulation harness (tests/csrc/mel_emul.cpp) replays it bit for bit.
+#include <math.h>
+
+#include "common.cuh"
+#include "mel_math.cuh"
+
+namespace ppgs {
+
+constexpr int kTileFrames = 32;
+constexpr int kMelWarps = 8;
+constexpr int kMelThreads = kMelWarps * 32;
+constexpr int kTileSamples = (kTileFrames - 1) * kHop + kNfft;   // 5984
+constexpr int kMaxBandWeights = 2048;
+
+struct MelSmem {
+    alignas(16) float audio[kTileSamples];
+    alignas(16) float window[kNfft];
+    alignas(16) cf tw512[kHalf];
+    alignas(16) cf tw1024[kBins + 3];
+    alignas(16) cf zb[kMelWarps][kZPad];
+    alignas(16) float band_weights[kMaxBandWeights];
+    int32_t band_meta[kMels * 3];
+    alignas(16) __half out[kMels][kTileFrames];
+    alignas(8) unsigned long long mbar;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes,
+                                              unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// One frame by one warp.  `a` points at the frame's first (padded-signal) sample
+// in the shared audio tile.
+__device__ __forceinline__ void frame_to_mel(const float* a, MelSmem& s, cf* zb, int lane,
+                                             int frame_in_tile) {
+    cf v0[8], v1[8];
+    // ---- pass 0: window + pack (z[n] = x[2n] + i x[2n+1]) + radix-8, Ns = 1
+    {
+        const float2* a2 = reinterpret_cast<const float2*>(a);
+        const float2* w2 = reinterpret_cast<const float2*>(s.window);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float2 x = a2[lane + 64 * r], w = w2[lane + 64 * r];
+            v0[r] = {x.x * w.x, x.y * w.y};
+            x = a2[lane + 32 + 64 * r];
+            w = w2[lane + 32 + 64 * r];
+            v1[r] = {x.x * w.x, x.y * w.y};
+        }
+        dft8(v0);
+        dft8(v1);
+        __syncwarp();   // previous frame's readers of zb are done
+        const int b0 = stockham_store_base<0>(lane), b1 = stockham_store_base<0>(lane + 32);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            zb[zpad(b0 + r)] = v0[r];
+            zb[zpad(b1 + r)] = v1[r];
+        }
+    }
+    // ---- pass 1: Ns = 8
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        v0[r] = zb[zpad(lane + 64 * r)];
+        v1[r] = zb[zpad(lane + 32 + 64 * r)];
+    }
+    stockham_twiddle<1>(v0, lane, s.tw512);
+    stockham_twiddle<1>(v1, lane + 32, s.tw512);
+    dft8(v0);
+    dft8(v1);
+    __syncwarp();
+    {
+        const int b0 = stockham_store_base<1>(lane), b1 = stockham_store_base<1>(lane + 32);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            zb[zpad(b0 + 8 * r)] = v0[r];
+            zb[zpad(b1 + 8 * r)] = v1[r];
+        }
+    }
+    // ---- pass 2: Ns = 64
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        v0[r] = zb[zpad(lane + 64 * r)];
+        v1[r] = zb[zpad(lane + 32 + 64 * r)];
+    }
+    stockham_twiddle<2>(v0, lane, s.tw512);
+    stockham_twiddle<2>(v1, lane + 32, s.tw512);
+    dft8(v0);
+    dft8(v1);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        zb[zpad(lane + 64 * r)] = v0[r];
+        zb[zpad(lane + 32 + 64 * r)] = v1[r];
+    }
+    __syncwarp();
+    // ---- unpack to 513 one-sided bins, magnitude, fp16 round
+    float mag[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+        int k = lane + 32 * i;
+        float m = 0.f;
+        if (k < kBins) m = __half2float(__float2half_rn(sqrtf(bin_power(zb, k, s.tw1024))));
+        mag[i] = m;
+    }
+    __syncwarp();
+    float* spec = reinterpret_cast<float*>(zb);   // reuse the FFT buffer: [513] floats
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+        int k = lane + 32 * i;
+        if (k < kBins) spec[k] = mag[i];
+    }
+    __syncwarp();
+    // ---- sparse triangular filterbank, ascending-k fmaf chain per band
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int m = lane + 32 * i;
+        if (m < kMels) {
+            int first = s.band_meta[3 * m], count = s.band_meta[3 * m + 1];
+            const float* w = s.band_weights + s.band_meta[3 * m + 2];
+            float acc = 0.f;
+            for (int j = 0; j < count; ++j) acc = fmaf(w[j], spec[first + j], acc);
+            s.out[m][frame_in_tile] = __float2half_rn(logf(fmaxf(acc, 1e-5f)));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMelThreads, 2)
+mel_kernel(const float* __restrict__ audio, int64_t samples, int64_t stride, int frames,
+           int tiles_per_row, int total_tiles, MelTables t, __half* __restrict__ mel,
+           int bulk_ok) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MelSmem& s = *reinterpret_cast<MelSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < kNfft; i += kMelThreads) s.window[i] = t.window[i];
+    for (int i = tid; i < kHalf; i += kMelThreads) s.tw512[i] = {t.tw512[i].x, t.tw512[i].y};
+    for (int i = tid; i < kBins; i += kMelThreads) s.tw1024[i] = {t.tw1024[i].x, t.tw1024[i].y};
+    for (int i = tid; i < kMels * 3; i += kMelThreads) s.band_meta[i] = t.band_meta[i];
+    for (int i = tid; i < t.band_weight_count; i += kMelThreads)
+        s.band_weights[i] = t.band_weights[i];
+    if (tid == 0) {
+        mbar_init(&s.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint32_t parity = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_row;
+        const int f0 = (tile - b * tiles_per_row) * kTileFrames;
+        const int nf = min(kTileFrames, frames - f0);
+        const int n_samples = (nf - 1) * kHop + kNfft;
+        const float* row = audio + (int64_t)b * stride;
+        const int64_t first = (int64_t)f0 * kHop - kReflect;   // source index of tile sample 0
+        const bool interior = first >= 0 && first + n_samples <= samples;
+
+        if (interior && bulk_ok) {
+            // TMA-class bulk copy: one elected thread, completion on the mbarrier.
+            if (tid == 0) {
+                uint32_t bytes = (uint32_t)n_samples * 4u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&s.mbar, bytes);
+                bulk_copy_g2s(s.audio, row + first, bytes, &s.mbar);
+            }
+            mbar_wait(&s.mbar, parity);
+            parity ^= 1;
+        } else {
+            for (int i = tid; i < n_samples; i += kMelThreads) {
+                int64_t src = first + i;
+                if (src < 0) src = -src;                               // reflect (no edge repeat)
+                if (src >= samples) src = 2 * (samples - 1) - src;
+                s.audio[i] = row[src];
+            }
+            __syncthreads();
+        }
+
+        for (int f = warp; f < nf; f += kMelWarps)
+            frame_to_mel(s.audio + f * kHop, s, s.zb[warp], lane, f);
+        __syncthreads();
+
+        // (80, nf) tile -> mel[b][m][f0 + f], contiguous along f
+        __half* dst = mel + ((int64_t)b * kMels) * frames + f0;
+        if (nf == kTileFrames && (frames & 1) == 0) {
+            for (int i = tid; i < kMels * (kTileFrames / 2); i += kMelThreads) {
+                int m = i / (kTileFrames / 2), p = i - m * (kTileFrames / 2);
+                *reinterpret_cast<__half2*>(dst + (int64_t)m * frames + 2 * p) =
+                    *reinterpret_cast<const __half2*>(&s.out[m][2 * p]);
+            }
+        } else {
+            for (int i = tid; i < kMels * kTileFrames; i += kMelThreads) {
+                int m = i / kTileFrames, f = i - m * kTileFrames;
+                if (f < nf) dst[(int64_t)m * frames + f] = s.out[m][f];
+            }
+        }
+        __syncthreads();   // s.audio / s.out reused by the next tile
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+
+// Slaney mel filterbank = librosa.filters.mel(sr=16000, n_fft=1024, n_mels=80)
+// (call site ppgs/preprocess/mel.py:61-64): triangles in fp64, stored in fp32,
+// scaled by 2/(f[m+2]-f[m]) in fp64 and rounded to fp32 again (librosa keeps the
+// weights array in float32).
+static void slaney_basis(std::vector<float>& basis) {
+    const int n_mels = kMels, n_bins = kBins;
+    const double sr = 16000.0, f_sp = 200.0 / 3, min_log_hz = 1000.0;
+    const double min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+    auto hz_to_mel = [&](double f) {
+        return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+    };
+    auto mel_to_hz = [&](double m) {
+        return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+    };
+    std::vector<double> mel_f(n_mels + 2), fft_f(n_bins);
+    const double m_lo = hz_to_mel(0.0), m_hi = hz_to_mel(sr / 2);
+    for (int i = 0; i < n_mels + 2; ++i) {
+        // numpy.linspace: start + i*step, last point exact
+        double m = (i == n_mels + 1) ? m_hi : m_lo + i * ((m_hi - m_lo) / (n_mels + 1));
+        mel_f[i] = mel_to_hz(m);
+    }
+    for (int k = 0; k < n_bins; ++k)
+        fft_f[k] = (k == n_bins - 1) ? sr / 2 : k * ((sr / 2) / (n_bins - 1));
+    basis.assign((size_t)n_mels * n_bins, 0.f);
+    for (int m = 0; m < n_mels; ++m) {
+        const double fd0 = mel_f[m + 1] - mel_f[m], fd1 = mel_f[m + 2] - mel_f[m + 1];
+        const double enorm = 2.0 / (mel_f[m + 2] - mel_f[m]);
+        for (int k = 0; k < n_bins; ++k) {
+            double lower = -(mel_f[m] - fft_f[k]) / fd0;
+            double upper = (mel_f[m + 2] - fft_f[k]) / fd1;
+            double tri = fmax(0.0, fmin(lower, upper));
+            float w32 = (float)tri;
+            basis[(size_t)m * n_bins + k] = (float)((double)w32 * enorm);
+        }
+    }
+}
+
+int build_mel_tables(ppgs_engine* e, const float* basis_host) {
+    std::vector<float> basis;
+    if (basis_host) basis.assign(basis_host, basis_host + (size_t)kMels * kBins);
+    else slaney_basis(basis);
+
+    std::vector<float> window(kNfft);
+    if (!e->host_window.empty()) window = e->host_window;
+    else
+        for (int n = 0; n < kNfft; ++n)
+            window[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / kNfft));
+    std::vector<float2> tw512(kHalf), tw1024(kBins);
+    for (int m = 0; m < kHalf; ++m) {
+        double a = -2.0 * M_PI * m / kHalf;
+        tw512[m] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (int k = 0; k < kBins; ++k) {
+        double a = -2.0 * M_PI * k / kNfft;
+        tw1024[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    std::vector<int32_t> meta(kMels * 3);
+    std::vector<float> weights;
+    for (int m = 0; m < kMels; ++m) {
+        int first = -1, last = -1;
+        for (int k = 0; k < kBins; ++k)
+            if (basis[(size_t)m * kBins + k] != 0.f) {
+                if (first < 0) first = k;
+                last = k;
+            }
+        int count = first < 0 ? 0 : last - first + 1;
+        meta[3 * m] = first < 0 ? 0 : first;
+        meta[3 * m + 1] = count;
+        meta[3 * m + 2] = (int32_t)weights.size();
+        for (int j = 0; j < count; ++j) weights.push_back(basis[(size_t)m * kBins + first + j]);
+    }
+    if ((int)weights.size() > kMaxBandWeights) {
+        set_error("mel basis has %zu non-zeros, more than the kernel's %d", weights.size(),
+                  kMaxBandWeights);
+        return PPGS_E_INVALID;
+    }
+    MelTables& t = e->mel;
+    auto upload = [&](void** dst, const void* src, size_t bytes) -> int {
+        if (*dst) cudaFree(*dst);
+        PPGS_CUDA(cudaMalloc(dst, bytes));
+        PPGS_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+        return PPGS_OK;
+    };
+    PPGS_CHECK(upload((void**)&t.window, window.data(), window.size() * 4));
+    PPGS_CHECK(upload((void**)&t.tw512, tw512.data(), tw512.size() * 8));
+    PPGS_CHECK(upload((void**)&t.tw1024, tw1024.data(), tw1024.size() * 8));
+    PPGS_CHECK(upload((void**)&t.band_meta, meta.data(), meta.size() * 4));
+    PPGS_CHECK(upload((void**)&t.band_weights, weights.data(), weights.size() * 4));
+    t.band_weight_count = (int)weights.size();
+    return PPGS_OK;
+}
+
+int launch_mel(ppgs_engine* e, const float* audio, int batch, int64_t samples, int64_t stride,
+               __half* mel, cudaStream_t stream) {
+    if (batch <= 0) return PPGS_OK;
+    if (samples <= kReflect) {
+        // torch reflection_pad1d: "padding size should be less than the input size"
+        set_error("mel front-end needs more than %d samples per utterance, got %lld", kReflect,
+                  (long long)samples);
+        return PPGS_E_INVALID;
+    }
+    const int frames = (int)(samples / kHop);
+    if (frames == 0) return PPGS_OK;
+    const int tiles_per_row = (frames + kTileFrames - 1) / kTileFrames;
+    const int64_t total = (int64_t)tiles_per_row * batch;
+    if (total > INT32_MAX) {
+        set_error("too many mel tiles");
+        return PPGS_E_TOO_LARGE;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        PPGS_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(MelSmem)));
+        attr_set = true;
+    }
+    // bulk copies need 16-byte aligned sources: base, row stride and tile offset
+    // (160*4 and 432*4 are multiples of 16).
+    const int bulk_ok = ((reinterpret_cast<uintptr_t>(audio) & 15) == 0) && (stride % 4 == 0);
+    const int grid = (int)std::min<int64_t>(total, 2 * (int64_t)e->sm_count);
+    {
+        LaunchScope scope(e, "mel_stft_fbank", stream);
+        mel_kernel<<<grid, kMelThreads, sizeof(MelSmem), stream>>>(
+            audio, samples, stride, frames, tiles_per_row, (int)total, e->mel, mel, bulk_ok);
+    }
+    PPGS_CUDA(cudaGetLastError());
+    return PPGS_OK;
+}
+
+}  // namespace ppgs

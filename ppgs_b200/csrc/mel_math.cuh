@@ -1,0 +1,109 @@
+// Per-frame arithmetic of the fused STFT + mel kernel, shared verbatim by the
+// CUDA kernel (mel.cu) and by the CPU emulation harness under tests/csrc that
+// checks it against the oracle without a GPU.
+//
+// Replaces ppgs/preprocess/spectrogram.py:14-50 (reflect pad 432, hann-windowed
+// 1024-point STFT hop 160, sqrt(re^2+im^2+1e-6), fp16 round) and
+// ppgs/preprocess/mel.py:56-76 (80x513 Slaney filterbank, log(clamp(.,1e-5)),
+// fp16 round).
+//
+// One warp transforms one frame: the 1024 real samples are packed into 512
+// complex points, transformed by a 3-pass radix-8 Stockham FFT (in place in a
+// padded shared-memory buffer, two butterflies per lane per pass), unpacked to
+// the 513 one-sided bins, and reduced by the sparse triangular filterbank.
+// All functions are written per (lane, butterfly) so that the host harness can
+// replay a warp with a plain loop.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define PPGS_HD __host__ __device__ __forceinline__
+#else
+#define PPGS_HD inline
+#endif
+
+namespace ppgs {
+
+constexpr int kHop = 160;
+constexpr int kNfft = 1024;
+constexpr int kHalf = 512;          // complex FFT length
+constexpr int kBins = 513;
+constexpr int kMels = 80;
+constexpr int kReflect = (kNfft - kHop) / 2;   // 432
+constexpr int kZPad = kHalf + kHalf / 8;       // padded complex buffer length (576)
+
+struct cf {
+    float x, y;
+};
+
+PPGS_HD int zpad(int i) { return i + (i >> 3); }
+
+PPGS_HD cf cadd(cf a, cf b) { return {a.x + b.x, a.y + b.y}; }
+PPGS_HD cf csub(cf a, cf b) { return {a.x - b.x, a.y - b.y}; }
+PPGS_HD cf cmul(cf a, cf b) {
+    return {fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)};
+}
+PPGS_HD cf mul_neg_i(cf a) { return {a.y, -a.x}; }
+
+// 4-point forward DFT, natural order in and out.
+PPGS_HD void dft4(cf a0, cf a1, cf a2, cf a3, cf& x0, cf& x1, cf& x2, cf& x3) {
+    cf t0 = cadd(a0, a2), t2 = csub(a0, a2);
+    cf t1 = cadd(a1, a3), t3 = mul_neg_i(csub(a1, a3));
+    x0 = cadd(t0, t1);
+    x2 = csub(t0, t1);
+    x1 = cadd(t2, t3);
+    x3 = csub(t2, t3);
+}
+
+// 8-point forward DFT (decimation in frequency), natural order in and out.
+PPGS_HD void dft8(cf* v) {
+    const float c = 0.70710678118654752440f;
+    cf u0 = cadd(v[0], v[4]), d0 = csub(v[0], v[4]);
+    cf u1 = cadd(v[1], v[5]), d1 = csub(v[1], v[5]);
+    cf u2 = cadd(v[2], v[6]), d2 = csub(v[2], v[6]);
+    cf u3 = cadd(v[3], v[7]), d3 = csub(v[3], v[7]);
+    d1 = {c * (d1.x + d1.y), c * (d1.y - d1.x)};      // * exp(-i pi/4)
+    d2 = mul_neg_i(d2);                               // * exp(-i pi/2)
+    d3 = {c * (d3.y - d3.x), -c * (d3.x + d3.y)};     // * exp(-3i pi/4)
+    dft4(u0, u1, u2, u3, v[0], v[2], v[4], v[6]);
+    dft4(d0, d1, d2, d3, v[1], v[3], v[5], v[7]);
+}
+
+// Butterfly `j` (0..63) of Stockham pass `pass` (0,1,2 <-> Ns = 1,8,64).
+// Load: v[r] = src[j + 64 r] (twiddled), store: dst[expand(j) + r Ns].
+template <int PASS>
+PPGS_HD void stockham_twiddle(cf* v, int j, const cf* tw512) {
+    if (PASS == 0) return;
+    constexpr int Ns = (PASS == 1) ? 8 : 64;
+    constexpr int step = 512 / (Ns * 8);
+    const int k = j & (Ns - 1);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], tw512[k * r * step]);
+}
+
+template <int PASS>
+PPGS_HD int stockham_store_base(int j) {
+    constexpr int Ns = (PASS == 0) ? 1 : (PASS == 1) ? 8 : 64;
+    return (j / Ns) * Ns * 8 + (j & (Ns - 1));
+}
+
+template <int PASS>
+PPGS_HD int stockham_store_stride() {
+    return (PASS == 0) ? 1 : (PASS == 1) ? 8 : 64;
+}
+
+// One-sided bin k (0..512) of the real transform from the packed complex FFT Z
+// (zb is the padded buffer), then magnitude as the reference computes it, rounded
+// through fp16 and returned as float.
+PPGS_HD float bin_power(const cf* zb, int k, const cf* tw1024) {
+    cf zk = zb[zpad(k & (kHalf - 1))];
+    cf zn = zb[zpad((kHalf - k) & (kHalf - 1))];
+    cf e = {0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y)};
+    cf o = {0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x)};
+    cf x = cadd(e, cmul(tw1024[k], o));
+    float p = x.x * x.x + x.y * x.y;   // compiled without fma contraction
+    return p + 1e-6f;
+}
+
+}  // namespace ppgs

@@ -1,0 +1,137 @@
+"""Batch scheduler for the file API — the host-side replacement of
+ppgs/data/{loader,dataset,sampler,collate}.py on the inference path
+(SURVEY.md §8 a11): file list -> frame lengths from the WAV headers ->
+frame-budget batches -> zero-padded (B,1,max_samples) pinned fp32 batches.
+
+Batch composition is part of the reference's semantics (a padded row's result
+depends on the batch's padded length, SURVEY.md §3.2 ii-iii), so the packing
+below reproduces the reference sampler's batches exactly (same seed, same
+greedy rule); only the machinery differs: reader *threads* decoding straight
+into a pinned batch buffer instead of DataLoader worker processes + collate.
+"""
+import concurrent.futures
+import warnings
+
+import numpy as np
+import torch
+
+from . import config
+from . import load
+
+
+class Metadata:
+    """Frame lengths of a list of audio files (ppgs/data/dataset.py:136-216,
+    list-of-files branch).  Files longer than `max_frames` are skipped with the
+    reference's warning."""
+
+    def __init__(self, audio_files, max_frames=config.MAX_INFERENCE_FRAMES):
+        self.audio_files, self.lengths = [], []
+        for audio_file in audio_files:
+            samples, sample_rate = load.wav_num_frames(audio_file)
+            length = int(samples * (config.SAMPLE_RATE / sample_rate)) // config.HOPSIZE
+            if length <= max_frames:
+                self.audio_files.append(audio_file)
+                self.lengths.append(length)
+            else:
+                warnings.warn(
+                    f'File {audio_file} of length {length} '
+                    f'exceeds max_frames of {max_frames}. Skipping.')
+
+    def __len__(self):
+        return len(self.audio_files)
+
+
+def frame_budget_batches(lengths, max_frames, seed=config.RANDOM_SEED, epoch=0,
+                         buckets=config.BUCKETS):
+    """Batches of file indices with (n+1)*max_len <= max_frames
+    (ppgs/data/sampler.py:46-82 over the buckets of ppgs/data/dataset.py:107-127).
+    Deterministic in (seed + epoch)."""
+    generator = torch.Generator()
+    generator.manual_seed(seed + epoch)
+    lengths = np.asarray(lengths)
+    order = np.argsort(lengths)
+    pairs = np.stack((order, lengths[order])).T if len(order) else np.zeros((0, 2), int)
+    size = max(len(pairs) // buckets, 1)
+    groups = [pairs[i * size:(i + 1) * size] for i in range(buckets)]
+    if len(pairs) > buckets * size:   # remainder joins the last bucket
+        groups[-1] = np.concatenate((groups[-1], pairs[buckets * size:]))
+    batches = []
+    for group in groups:
+        if not len(group):
+            continue
+        group = group[torch.randperm(len(group), generator=generator).tolist()]
+        batch, longest = [], 0
+        for index, length in group:
+            longest = max(longest, length)
+            if batch and (len(batch) + 1) * longest > max_frames:
+                batches.append(batch)
+                longest = length
+                batch = [int(index)]
+            else:
+                batch.append(int(index))
+        if batch:
+            batches.append(batch)
+    return [batches[i] for i in torch.randperm(len(batches), generator=generator).tolist()]
+
+
+def collate(audios, pin_memory=False):
+    """Zero-pad (1,samples_i) audios into (B,1,max_samples) fp32 + int64 sample
+    lengths (ppgs/data/collate.py:19-28)."""
+    lengths = torch.tensor([audio.shape[-1] for audio in audios], dtype=torch.long)
+    padded = torch.zeros(
+        len(audios), 1, int(lengths.max()), dtype=torch.float32, pin_memory=pin_memory)
+    for row, audio in zip(padded, audios):
+        row[:, :audio.shape[-1]] = audio[:1]
+    return padded, lengths
+
+
+class Loader:
+    """Iterable of (audio (B,1,max_samples) pinned fp32, lengths (B,) int64
+    samples, [audio_file]) — what `ppgs.data.loader(files, ['audio','length',
+    'audio_file'], num_workers, max_frames)` yields (ppgs/data/loader.py:20-43).
+    `num_workers` reader threads decode files; up to `prefetch` batches ahead."""
+
+    def __init__(self, audio_files, num_workers=0, max_frames=config.MAX_INFERENCE_FRAMES,
+                 prefetch=2, shard=None):
+        self.dataset = Metadata(audio_files, max_frames)
+        self.batches = frame_budget_batches(self.dataset.lengths, max_frames)
+        if shard is not None:
+            rank, world = shard
+            self.batches = self.batches[rank::world]
+        self.num_workers = max(int(num_workers), 0)
+        self.prefetch = prefetch
+        self.pin = torch.cuda.is_available()
+
+    def __len__(self):
+        return len(self.batches)
+
+    def _load(self, batch):
+        files = [self.dataset.audio_files[i] for i in batch]
+        audios = [load.audio(file) for file in files]
+        padded, lengths = collate(audios, self.pin)
+        return padded, lengths, files
+
+    def __iter__(self):
+        if self.num_workers == 0:
+            for batch in self.batches:
+                yield self._load(batch)
+            return
+        with concurrent.futures.ThreadPoolExecutor(self.num_workers) as pool:
+            pending = []
+            batches = iter(self.batches)
+            for batch in batches:
+                pending.append(pool.submit(self._load, batch))
+                if len(pending) > self.prefetch:
+                    yield pending.pop(0).result()
+            for future in pending:
+                yield future.result()
+
+
+def loader(audio_files, features=('audio', 'length', 'audio_file'), num_workers=0,
+           max_frames=config.MAX_INFERENCE_FRAMES, shard=None):
+    """ppgs.data.loader for the inference feature set."""
+    if list(features) != ['audio', 'length', 'audio_file']:
+        raise ValueError(
+            "ppgs_b200.data.loader serves the inference path only: "
+            "features must be ['audio', 'length', 'audio_file']")
+    return Loader(audio_files, num_workers, max_frames, shard=shard)

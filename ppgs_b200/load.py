@@ -1,0 +1,138 @@
+"""Loading utilities (ppgs/load.py:17-81)."""
+import os
+import threading
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import config
+from .engine import Engine
+
+_engines = {}
+_lock = threading.Lock()
+
+
+def audio(file):
+    """Load audio from disk as (channels, samples) fp32 at 16 kHz
+    (ppgs/load.py:17-30).  PCM / float WAV is decoded here with scipy
+    (torchaudio.load needs torchcodec); other containers go through
+    torchaudio when it can decode them."""
+    path = Path(file)
+    if path.suffix.lower() == '.wav':
+        from scipy.io import wavfile
+        sample_rate, data = wavfile.read(path)
+        if data.dtype == np.int16:
+            data = data.astype(np.float32) / 32768.0
+        elif data.dtype == np.int32:
+            data = data.astype(np.float32) / 2147483648.0
+        elif data.dtype == np.uint8:
+            data = (data.astype(np.float32) - 128.0) / 128.0
+        else:
+            data = data.astype(np.float32)
+        if data.ndim == 1:
+            data = data[None]
+        else:
+            data = data.T
+        waveform = torch.from_numpy(np.ascontiguousarray(data))
+    else:
+        import torchaudio
+        try:
+            if path.suffix.lower() == '.mp3':
+                waveform, sample_rate = torchaudio.load(path, format='mp3')
+            else:
+                waveform, sample_rate = torchaudio.load(file)
+        except RuntimeError:
+            if path.suffix.lower() == '.mp3':
+                raise RuntimeError(
+                    'Failed to load mp3 file, make sure ffmpeg<=4.3 is installed')
+            raise
+    from .core import resample
+    return resample(waveform, sample_rate)
+
+
+def wav_num_frames(file):
+    """(samples, sample_rate) from the header only (torchaudio.info at
+    ppgs/data/dataset.py:187)."""
+    import wave
+    try:
+        with wave.open(str(file), 'rb') as f:
+            return f.getnframes(), f.getframerate()
+    except (wave.Error, EOFError):
+        waveform = audio(file)
+        return waveform.shape[-1], config.SAMPLE_RATE
+
+
+def state_dict(checkpoint=None, representation=None):
+    """Resolve + read a checkpoint (ppgs/load.py:59-79).  Unlike the reference,
+    `checkpoint=` is honoured for w2v2fb too."""
+    if checkpoint is None:
+        checkpoint = config.LOCAL_CHECKPOINT
+    if checkpoint is None:
+        name = representation if representation is not None else config.REPRESENTATION
+        if name not in config.HF_CHECKPOINTS:
+            raise ValueError(
+                f'No default checkpoints exist for representation {name}')
+        try:
+            import huggingface_hub
+            checkpoint = huggingface_hub.hf_hub_download(
+                config.HF_REPO, config.HF_CHECKPOINTS[name])
+        except Exception as error:
+            raise RuntimeError(
+                f'No checkpoint given and {config.HF_CHECKPOINTS[name]} could not be '
+                f'fetched from {config.HF_REPO}: {error}') from error
+    state = torch.load(checkpoint, map_location='cpu')
+    if 'model' in state:
+        state = state['model']
+    return state
+
+
+def model_kwargs(representation):
+    """ppgs/load.py:35-50."""
+    if representation is None:
+        return {}
+    if representation not in config.MODEL_KWARGS:
+        raise ValueError(
+            'Supplying representation directly only supported for w2v2fb and mel')
+    return dict(config.MODEL_KWARGS[representation])
+
+
+def model(checkpoint=None, representation=None, gpu=None, is_causal=None):
+    """Build (or fetch the cached) engine for (representation, checkpoint, gpu)
+    — ppgs.load.model + the cache of ppgs/core.py:565-580."""
+    device = resolve_device(gpu)
+    causal = config.IS_CAUSAL if is_causal is None else bool(is_causal)
+    key = cache_key(representation, checkpoint, device.index, causal)
+    with _lock:
+        engine = _engines.get(key)
+        if engine is None:
+            kwargs = model_kwargs(representation)
+            state = state_dict(checkpoint, representation)
+            engine = Engine(device, is_causal=causal, **kwargs)
+            engine.load_state_dict(state)
+            precision = os.environ.get('PPGS_B200_PRECISION')
+            if precision:
+                engine.precision = precision
+            _engines[key] = engine
+    return engine
+
+
+def cache_key(representation, checkpoint, gpu, is_causal=None):
+    causal = config.IS_CAUSAL if is_causal is None else bool(is_causal)
+    return (str(representation), str(checkpoint), resolve_device(gpu).index, causal)
+
+
+def clear_cache():
+    with _lock:
+        _engines.clear()
+
+
+def resolve_device(gpu=None):
+    """`gpu` is a CUDA ordinal as in the reference; None means the current CUDA
+    device (the reference would run on the CPU — this engine has no CPU path)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            'ppgs_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    if gpu is None:
+        gpu = torch.cuda.current_device()
+    return torch.device('cuda', int(gpu))

@@ -1,0 +1,236 @@
+"""Parity tests proper: the CUDA library, called through the C ABI
+(ppgs_b200._lib / Engine), against the oracle and against the committed golden
+outputs of the reference's own modules.
+
+Tolerances
+* mel features: <= 1 fp16 ulp from the reference mel, mismatch rate <= 1e-3, and
+  BIT-EXACT against the CPU replay of the kernel arithmetic;
+* posteriorgrams: <= 1e-4 max-abs (BASELINE.json north_star) against the
+  reference modules evaluated in fp32 with autocast off (oracle mode O3).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import ppg_oracle as O
+from test_mel_emulation import emulate, ulp_distance
+from test_oracle_golden import MEL, PPG, mel_case_audio, ppg_case_inputs
+
+pytestmark = pytest.mark.gpu
+
+PPG_TOL = 1e-4
+PRECISIONS = ['fp32', 'f16x2']
+
+
+@pytest.fixture(scope='module')
+def ppgs_b200():
+    import ppgs_b200
+    return ppgs_b200
+
+
+def make_engine(ppgs_b200, sd, precision, **kwargs):
+    engine = ppgs_b200.Engine(0, **kwargs)
+    engine.load_state_dict(sd)
+    try:
+        engine.precision = precision
+    except RuntimeError as error:
+        if 'not available' in str(error):
+            pytest.skip(f'precision {precision} not built')
+        raise
+    return engine
+
+
+@pytest.fixture(scope='module')
+def frontend(ppgs_b200):
+    return make_engine(ppgs_b200, O.random_state_dict(0), 'fp32')
+
+
+# --------------------------------------------------------------------------- mel
+@pytest.mark.parametrize('name', MEL)
+def test_mel_vs_reference_golden(frontend, mel_emul_lib, name):
+    g = golden(name)
+    audio = mel_case_audio(g)
+    mel = frontend.mel(audio.cuda()).cpu().numpy()
+    assert mel.shape == g['mel'].shape and mel.dtype == np.float16
+    dist = ulp_distance(mel, g['mel'])
+    assert dist.max() <= 1
+    assert (dist > 0).mean() <= 1e-3
+    # the kernel and its CPU replay execute the same fp32 operations
+    assert np.array_equal(mel.view(np.uint16), emulate(mel_emul_lib, audio).view(np.uint16))
+
+
+@pytest.mark.parametrize('batch,samples', [(1, 433), (3, 160 * 33 + 7), (2, 160 * 64), (5, 48000)])
+def test_mel_edges_vs_oracle(frontend, batch, samples):
+    """Short inputs (everything is reflect padding), ragged tile tails, odd frame
+    counts (scalar store path) and unaligned rows (non-TMA load path)."""
+    audio = O.synthetic_audio(batch, samples, seed=batch)
+    ref = O.mel_from_audios(audio).numpy()
+    mel = frontend.mel(audio.cuda()).cpu().numpy()
+    assert ulp_distance(mel, ref).max() <= 1
+    # a view whose rows start at a 4-byte (not 16-byte) aligned address
+    wide = torch.zeros(batch, samples + 3, device='cuda')
+    wide[:, 1:samples + 1] = audio[:, 0].cuda()
+    mel2 = frontend.mel(wide[:, 1:samples + 1]).cpu().numpy()
+    assert np.array_equal(mel2.view(np.uint16), mel.view(np.uint16))
+
+
+def test_mel_rejects_too_short(frontend):
+    with pytest.raises(ValueError):
+        frontend.mel(torch.zeros(1, 1, 432, device='cuda'))
+
+
+# ------------------------------------------------------------------- transformer
+@pytest.mark.parametrize('precision', PRECISIONS)
+@pytest.mark.parametrize('name', PPG)
+def test_transformer_vs_reference_golden(ppgs_b200, name, precision):
+    g = golden(name)
+    sd, audio, lengths = ppg_case_inputs(g)
+    feats = O.mel_from_audios(audio)
+    engine = make_engine(ppgs_b200, sd, precision, is_causal=bool(g['causal']))
+    ppg = engine.transformer(feats.cuda(), lengths).cpu().numpy()
+    assert ppg.shape == g['ppg'].shape
+    err = np.abs(ppg - g['ppg']).max()
+    assert err <= PPG_TOL, f'{name} {precision}: max-abs {err:.3e}'
+    logits = engine.transformer(feats.cuda(), lengths, softmax=False).cpu().numpy()
+    assert np.abs(logits - g['logits']).max() <= 2e-3
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+@pytest.mark.parametrize('frames,lengths', [
+    (160, [160]), (400, [400, 399, 3]), (500, [500]), (501, [501, 500]),
+    (900, [900, 450, 451, 50, 49]), (1000, [1000] * 3), (1234, [1234, 2])])
+def test_from_audio_end_to_end_vs_oracle(ppgs_b200, frames, lengths, precision):
+    """T3: audio in, posteriors out, batched-vs-batched, equal and ragged lengths
+    around the 500/400/50 chunk boundaries."""
+    sd = O.random_state_dict(3, peaky=True)
+    audio = O.synthetic_audio(len(lengths), frames * 160, seed=frames)
+    sample_lengths = torch.tensor(lengths) * 160
+    ref = O.from_audio(sd, audio, lengths=sample_lengths).numpy()
+    engine = make_engine(ppgs_b200, sd, precision)
+    out = engine.from_audio(audio.cuda(), lengths=sample_lengths).cpu().numpy()
+    assert out.shape == ref.shape
+    for row, n in enumerate(lengths):      # valid frames (save_masked crops the rest)
+        err = np.abs(out[row, :, :n] - ref[row, :, :n]).max()
+        assert err <= PPG_TOL, f'row {row}: {err:.3e}'
+    pinned = audio.pin_memory()
+    host = engine.from_audio_host(pinned, lengths=sample_lengths).numpy()
+    assert np.array_equal(host, out)
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_legacy_mode_and_logits(ppgs_b200, precision):
+    sd = O.random_state_dict(5)
+    feats = O.mel_from_audios(O.synthetic_audio(2, 700 * 160, 9))
+    lengths = torch.tensor([700, 512])
+    engine = make_engine(ppgs_b200, sd, precision)
+    ref = O.from_features(sd, feats, lengths, legacy_mode=True).numpy()
+    out = engine.transformer(feats.cuda(), lengths, legacy_mode=True).cpu().numpy()
+    assert np.abs(out[0] - ref[0]).max() <= PPG_TOL
+    assert np.abs(out[1, :, :512] - ref[1, :, :512]).max() <= PPG_TOL
+    chunked = engine.transformer(feats.cuda(), lengths).cpu().numpy()
+    assert np.abs(chunked - out).max() > 1e-3      # chunking is semantics
+
+
+def test_error_conventions(ppgs_b200):
+    engine = make_engine(ppgs_b200, O.random_state_dict(0), 'fp32')
+    feats = torch.zeros(2, 80, 100, dtype=torch.float16, device='cuda')
+    with pytest.raises(ValueError):      # max(lengths) != T: reference fails at `* mask`
+        engine.transformer(feats, torch.tensor([90, 80]))
+    with pytest.raises(ValueError):      # F4: one length per row
+        engine.transformer(feats, torch.tensor([100]))
+    with pytest.raises(ValueError, match='size is too large'):
+        engine.transformer(torch.zeros(1, 80, 5001, dtype=torch.float16, device='cuda'),
+                           torch.tensor([5001]), legacy_mode=True)
+    bad = dict(O.random_state_dict(0))
+    bad.pop('output_layer.bias')
+    with pytest.raises(RuntimeError, match='missing key'):
+        ppgs_b200.Engine(0).load_state_dict(bad)
+    bad = dict(O.random_state_dict(0))
+    bad['input_layer.weight'] = torch.zeros(256, 81, 5)
+    with pytest.raises(ValueError, match='size mismatch'):
+        ppgs_b200.Engine(0).load_state_dict(bad)
+
+
+# ---------------------------------------------------------------- public API
+def test_public_api_and_files(ppgs_b200, tmp_path):
+    """from_audio / from_features / from_file / from_files_to_files with
+    `checkpoint=` (T4: .pt outputs cropped like save_masked)."""
+    from test_host_logic import write_wav
+    sd = O.random_state_dict(2)
+    ckpt = tmp_path / 'ckpt.pt'
+    torch.save({'model': sd}, ckpt)
+    audio = O.synthetic_audio(2, 64000, 1)
+    ref = O.from_audio(sd, audio).numpy()
+    out = ppgs_b200.from_audio(audio, 16000, checkpoint=ckpt, gpu=0)
+    assert out.is_cuda and out.dtype == torch.float32 and out.shape == (2, 40, 400)
+    assert np.abs(out.cpu().numpy() - ref).max() <= PPG_TOL
+    feats = ppgs_b200.preprocess.from_audio(audio, 'mel', 16000, gpu=0)
+    assert feats.dtype == torch.float16 and feats.shape == (2, 80, 400)
+    out2 = ppgs_b200.from_features(feats, torch.tensor([400, 400]), checkpoint=ckpt, gpu=0)
+    assert torch.equal(out, out2)
+    with pytest.raises(ValueError):
+        ppgs_b200.from_audio(audio, 16000, representation='dac', checkpoint=ckpt, gpu=0)
+
+    files, outputs, lengths = [], [], [16000, 40000, 90000, 8000, 16161]
+    for i, n in enumerate(lengths):
+        files.append(tmp_path / f'{i}.wav')
+        outputs.append(tmp_path / f'{i}-ppg.pt')
+        write_wav(files[-1], n, seed=10 + i)
+    ppgs_b200.from_files_to_files(files, outputs, checkpoint=ckpt, gpu=0)
+    single = [torch.load(o) for o in outputs]
+    for ppg, file, n in zip(single, files, lengths):
+        assert ppg.shape == (40, n // 160) and ppg.dtype == torch.float32
+        expect = O.from_audio(sd, ppgs_b200.load.audio(file)[None])[0].numpy()
+        assert np.abs(ppg.numpy() - expect).max() <= PPG_TOL
+    # batched path: same batches as the reference sampler -> batched-vs-batched parity
+    batched_out = [tmp_path / f'{i}-b.pt' for i in range(len(files))]
+    ppgs_b200.from_files_to_files(files, batched_out, checkpoint=ckpt, num_workers=4, gpu=0,
+                                  max_frames=1200)
+    for batch in ppgs_b200.data.frame_budget_batches([n // 160 for n in lengths], 1200):
+        audios = [ppgs_b200.load.audio(files[i]) for i in batch]
+        padded, sample_lengths = O.collate(audios)
+        expect = O.from_audio(sd, padded, lengths=sample_lengths).numpy()
+        for row, i in enumerate(batch):
+            got = torch.load(batched_out[i]).numpy()
+            assert got.shape == (40, lengths[i] // 160)
+            assert np.abs(got - expect[row, :, :got.shape[1]]).max() <= PPG_TOL
+
+
+# ------------------------------------------------------- full-size properties
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_config2_full_size_properties(ppgs_b200, precision):
+    """BASELINE config 2 (64 x 10 s): size-independent properties + an oracle
+    check of two rows (rows are independent when all lengths are equal)."""
+    sd = O.random_state_dict(0, peaky=True)
+    engine = make_engine(ppgs_b200, sd, precision)
+    audio = O.synthetic_audio(64, 160000, 0)
+    out = engine.from_audio(audio.cuda())
+    assert out.shape == (64, 40, 1000)
+    assert torch.isfinite(out).all() and (out >= 0).all()
+    assert (out.sum(1) - 1).abs().max() <= 1e-5
+    # batch-composition independence for equal-length rows
+    sub = engine.from_audio(audio[5:7].cuda())
+    assert (sub - out[5:7]).abs().max() <= 1e-6
+    ref = O.from_audio(sd, audio[5:7])
+    assert (out[5:7].cpu() - ref).abs().max() <= PPG_TOL
+    # launch accounting used by bench.py
+    before = engine.launches
+    engine.from_audio(audio.cuda())
+    assert engine.launches > before
+
+
+def test_weight_blob_roundtrip(ppgs_b200):
+    """The multi-GPU load path on one device: a second engine adopts the first
+    engine's packed blob (what the NCCL broadcast delivers) and agrees bitwise."""
+    sd = O.random_state_dict(4)
+    a = make_engine(ppgs_b200, sd, 'fp32')
+    b = ppgs_b200.Engine(0)
+    b.blob().copy_(a.blob())
+    torch.cuda.synchronize()
+    b.adopt_blob()
+    audio = O.synthetic_audio(2, 32000, 3).cuda()
+    assert torch.equal(a.from_audio(audio), b.from_audio(audio))

@@ -1,0 +1,132 @@
+"""Host-side logic that needs no GPU: the batch scheduler against the oracle's
+restatement of the reference sampler / collate, the WAV reader, the CLI flags,
+and the multi-process sharding (world_size 2 over gloo)."""
+import os
+import socket
+import subprocess
+import sys
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import ppg_oracle as O
+
+
+def write_wav(path, samples, rate=16000, seed=0, channels=1):
+    rng = np.random.default_rng(seed)
+    data = (rng.uniform(-0.5, 0.5, size=(samples, channels)) * 32767).astype(np.int16)
+    with wave.open(str(path), 'wb') as f:
+        f.setnchannels(channels)
+        f.setsampwidth(2)
+        f.setframerate(rate)
+        f.writeframes(data.tobytes())
+    return data
+
+
+@pytest.mark.parametrize('max_frames', [1000, 4000, 64000])
+def test_frame_budget_batches_equal_reference_sampler(max_frames):
+    from ppgs_b200 import data
+    rng = np.random.default_rng(3)
+    lengths = rng.integers(10, 1000, size=257).tolist()
+    mine = data.frame_budget_batches(lengths, max_frames)
+    assert mine == O.sampler_batches(lengths, max_frames)
+    assert sorted(i for b in mine for i in b) == list(range(257))
+    for batch in mine:
+        assert len(batch) == 1 or len(batch) * max(lengths[i] for i in batch) <= max_frames
+
+
+def test_collate_zero_pads_like_reference():
+    from ppgs_b200 import data
+    audios = [torch.randn(1, n) for n in (1600, 4801, 320)]
+    padded, lengths = data.collate(audios)
+    ref_padded, ref_lengths = O.collate(audios)
+    assert torch.equal(padded, ref_padded) and torch.equal(lengths, ref_lengths)
+
+
+def test_wav_reader_and_loader(tmp_path):
+    from ppgs_b200 import data, load
+    files, lengths = [], [16000, 4000, 32000, 8000, 8000]
+    for i, n in enumerate(lengths):
+        files.append(tmp_path / f'{i}.wav')
+        raw = write_wav(files[-1], n, seed=i)
+        audio = load.audio(files[-1])
+        assert audio.shape == (1, n) and audio.dtype == torch.float32
+        assert np.array_equal(audio[0].numpy(), raw[:, 0].astype(np.float32) / 32768.0)
+        assert load.wav_num_frames(files[-1]) == (n, 16000)
+    loader = data.loader(files, num_workers=2, max_frames=250)
+    seen = []
+    for audio, sample_lengths, names in loader:
+        assert audio.shape == (len(names), 1, int(sample_lengths.max()))
+        for row, n, name in zip(audio, sample_lengths, names):
+            assert torch.equal(row[0, :n], load.audio(name)[0])
+            assert not row[0, n:].any()
+        seen.extend(names)
+    assert sorted(seen) == sorted(files)
+    with pytest.warns(UserWarning, match='exceeds max_frames'):
+        assert len(data.Metadata(files, max_frames=100)) == 4
+    with pytest.raises(ValueError):
+        data.loader(files, features=['phonemes'])
+
+
+def test_shard_by_frames_balances():
+    from ppgs_b200 import parallel
+    lengths = [1000] * 7 + [250] * 9 + [40] * 30
+    parts = parallel.shard_by_frames(lengths, 4)
+    assert sorted(i for p in parts for i in p) == list(range(len(lengths)))
+    loads = [sum(lengths[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= 1000
+    assert parallel.shard(list(range(10)), rank=1, world=4) == [1, 5, 9]
+
+
+def test_cli_flags_match_reference():
+    from ppgs_b200.__main__ import parse_args
+    args = parse_args(['--audio_files', 'a.wav', 'b.wav', '--output_files', 'a.pt', 'b.pt',
+                       '--num-workers', '4', '--gpu', '1', '--max-frames', '64000',
+                       '--legacy-mode', '--checkpoint', 'x.pt'])
+    assert [str(p) for p in args.audio_files] == ['a.wav', 'b.wav']
+    assert args.num_workers == 4 and args.gpu == 1 and args.legacy_mode
+    assert args.representation == 'mel' and args.max_frames == 64000
+
+
+def test_unknown_representation_raises_value_error():
+    from ppgs_b200 import load, preprocess
+    with pytest.raises(ValueError):
+        preprocess.get('bottleneck')
+    with pytest.raises(ValueError):
+        load.model_kwargs('encodec')
+    assert load.model_kwargs('w2v2fb') == {'hidden_channels': 512, 'input_channels': 768}
+
+
+def test_engine_mel_basis_equals_oracle():
+    from ppgs_b200 import engine
+    assert np.array_equal(engine.mel_basis(), O.mel_basis())
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    """N>1 host path on CPU: two ranks over gloo build the same batch list, take
+    disjoint shards that cover every file, and receive rank 0's blob bytes."""
+    files = []
+    for i, n in enumerate([16000, 4000, 32000, 8000, 8000, 12000, 24000]):
+        files.append(str(tmp_path / f'{i}.wav'))
+        write_wav(files[-1], n, seed=i)
+    out = tmp_path / 'out'
+    out.mkdir()
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', str(free_port()),
+           os.path.join(ROOT, 'tests', '_dist_worker.py'), str(out)] + files
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS='1')
+    subprocess.run(cmd, check=True, timeout=240, env=env, cwd=ROOT)
+    shards = [open(out / f'rank{r}.txt').read().split() for r in range(2)]
+    assert sorted(shards[0] + shards[1]) == sorted(files)
+    assert not set(shards[0]) & set(shards[1])
+    blobs = [np.load(out / f'blob{r}.npy') for r in range(2)]
+    assert np.array_equal(blobs[0], blobs[1]) and blobs[0].sum() > 0
