@@ -1,0 +1,452 @@
+// Length-masked multi-head attention of the tensor-core path.
+//
+// Replaces F.scaled_dot_product_attention inside nn.MultiheadAttention as called
+// from ppgs/model/transformer.py:76-80 (key-padding mask from `lengths`, optional
+// square subsequent mask when IS_CAUSAL).
+#include <float.h>
+
+#include "attention_tc.cuh"
+#include "gemm_tc.cuh"
+#include "tc_common.cuh"
+
+namespace ppgs {
+
+using namespace tc;
+
+// ---------------------------------------------------------------------------
+// CUDA-core kernel over the split planes (fp32 arithmetic): block = (32 queries,
+// head, sequence), warp = 4 queries, lane = key inside a 32-key tile.
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+attention_planes_kernel(const __half* __restrict__ qkv, int64_t plane_stride, int H,
+                        const SeqInfo* __restrict__ seqs, int causal, float scale, int planes,
+                        __half* __restrict__ out, int64_t out_plane_stride) {
+    constexpr int QT = 32, KT = 32, DP = D + 1, PER = D / 32;
+    extern __shared__ float smem[];
+    float* qs = smem;
+    float* ks = qs + QT * D;
+    float* vs = ks + KT * DP;
+    const SeqInfo s = seqs[blockIdx.z];
+    const int q0 = blockIdx.x * QT;
+    if (q0 >= s.tensor_len) return;
+    const int head = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t ld = 3 * H;
+    const __half* base = qkv + (int64_t)s.row0 * ld;
+    auto load = [&](const __half* p) {
+        float v = __half2float(*p);
+        if (planes == 2) v += __half2float(p[plane_stride]);
+        return v;
+    };
+    for (int i = tid; i < QT * D; i += 256) {
+        int q = i / D, d = i - q * D;
+        qs[i] = load(base + (int64_t)(q0 + q) * ld + head * D + d);
+    }
+    float m[4], l[4], acc[4][PER];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        m[q] = -FLT_MAX;
+        l[q] = 0.f;
+#pragma unroll
+        for (int c = 0; c < PER; ++c) acc[q][c] = 0.f;
+    }
+    int kend = s.valid_len;
+    if (causal) kend = min(kend, q0 + QT);
+    for (int k0 = 0; k0 < kend; k0 += KT) {
+        __syncthreads();
+        for (int i = tid; i < KT * D; i += 256) {
+            int j = i / D, d = i - j * D;
+            const __half* r = base + (int64_t)(k0 + j) * ld + head * D + d;
+            ks[j * DP + d] = load(r + H);
+            vs[j * D + d] = load(r + 2 * H);
+        }
+        __syncthreads();
+        const int key = k0 + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int t = q0 + warp * 4 + q;
+            const float* qr = qs + (warp * 4 + q) * D;
+            float sc = 0.f;
+#pragma unroll 8
+            for (int d = 0; d < D; ++d) sc = fmaf(qr[d], ks[lane * DP + d], sc);
+            sc *= scale;
+            const bool ok = key < s.valid_len && (!causal || key <= t);
+            sc = ok ? sc : -FLT_MAX;
+            float tmax = sc;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+            const float mnew = fmaxf(m[q], tmax);
+            const float p = ok ? expf(sc - mnew) : 0.f;
+            const float corr = expf(m[q] - mnew);
+            float psum = p;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+            l[q] = l[q] * corr + psum;
+            m[q] = mnew;
+#pragma unroll
+            for (int c = 0; c < PER; ++c) acc[q][c] *= corr;
+            for (int j = 0; j < KT; ++j) {
+                const float pj = __shfl_sync(0xffffffffu, p, j);
+#pragma unroll
+                for (int c = 0; c < PER; ++c) acc[q][c] = fmaf(pj, vs[j * D + lane + 32 * c], acc[q][c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int t = q0 + warp * 4 + q;
+        const float inv = l[q] > 0.f ? 1.f / l[q] : 0.f;
+        __half* dst = out + (int64_t)(s.row0 + t) * H + head * D;
+#pragma unroll
+        for (int c = 0; c < PER; ++c) {
+            __half hi, lo;
+            split_f16(acc[q][c] * inv, hi, lo);
+            dst[lane + 32 * c] = hi;
+            dst[out_plane_stride + lane + 32 * c] = lo;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// tcgen05 kernel: one CTA per (128-query tile, head, sequence), keys <= 512.
+//
+//   warp 0      TMA producer: Q tile, K blocks (128 keys) through a 2-slot ring,
+//               then V chunks (64 keys) through a 4-slot ring that reuses the K ring
+//   warp 1      tcgen05.mma issuer: S_j = Q K_j^T into TMEM columns [128 j, 128 j + 128),
+//               then O += P_c V_c into columns [384, 512)
+//   warps 2-5   one query row per thread: row max over S (TMEM), p = exp2((s - max) c),
+//               split-fp16 P chunks written to the 128B-swizzled smem layout the MMA
+//               reads (2-slot ring that reuses the Q tile), final O / sum -> planes
+//
+// S for 4 key blocks fills all 512 TMEM columns; O reuses the columns of the last
+// block, so the chunks of that block are converted to P first and the first P.V MMA
+// waits for them.
+// ---------------------------------------------------------------------------
+constexpr int kAttnThreads = 192;
+constexpr int kTile16K = 16384;                // [128 rows][64 fp16]
+constexpr int kQBytes = 4 * kTile16K;          // [d chunk 2][plane 2]
+constexpr int kKSlotBytes = 4 * kTile16K;
+constexpr int kPSlotBytes = 2 * kTile16K;      // [plane 2][128 q][64 keys]
+constexpr int kVPlaneBytes = 8192;             // [64 keys][64 d]
+constexpr int kVSlotBytes = 4 * kVPlaneBytes;  // [d half 2][plane 2]
+constexpr size_t kAttnSmem = kQBytes + 2 * kKSlotBytes + 1024;
+constexpr int kOCol = 384;
+
+struct AttnParams {
+    const SeqInfo* seqs;
+    int H, causal, planes;
+    float scale_log2e;
+    __half* out;
+    int64_t out_plane_stride;
+    int* status;
+};
+
+__device__ __forceinline__ int chunk_order(int i, int nchunks) {
+    if (nchunks <= 6) return i;
+    const int pre = nchunks - 6;
+    return i < pre ? 6 + i : i - pre;
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_v,
+                    const AttnParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* q_smem = smem;              // later: P ring
+    unsigned char* k_ring = smem + kQBytes;    // later: V ring
+    __shared__ __align__(8) uint64_t q_full, s_full, o_full;
+    __shared__ __align__(8) uint64_t k_full[2], k_empty[2], p_full[2], p_empty[2];
+    __shared__ __align__(8) uint64_t v_full[4], v_empty[4];
+    __shared__ uint32_t tmem_slot;
+
+    const SeqInfo s = p.seqs[blockIdx.z];
+    const int q0 = blockIdx.x * 128, head = blockIdx.y;
+    if (q0 >= s.tensor_len) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int nkeys = s.valid_len;
+    if (p.causal) nkeys = min(nkeys, q0 + 128);
+    const int64_t out_row0 = (int64_t)(s.row0 + q0);
+    if (nkeys <= 0) {
+        // every key masked (chunk_lengths == 0 rows of transformer.py:59-60): zeros
+        for (int i = threadIdx.x; i < 128 * 128; i += kAttnThreads) {
+            const int r = i >> 7, d = i & 127;
+            __half* dst = p.out + (out_row0 + r) * p.H + head * 128 + d;
+            dst[0] = __float2half_rn(0.f);
+            dst[p.out_plane_stride] = __float2half_rn(0.f);
+        }
+        return;
+    }
+    const int nb = (nkeys + 127) >> 7, nchunks = (nkeys + 63) >> 6;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&q_full, 1);
+        mbar_init(&s_full, 1);
+        mbar_init(&o_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&p_empty[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(&tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            prefetch_tensormap(&map_qk);
+            prefetch_tensormap(&map_v);
+            const int col_q = head * 128, col_k = p.H + head * 128, col_v = 2 * p.H + head * 128;
+            bool ok = true;
+            mbar_arrive_expect_tx(&q_full, p.planes * 2 * kTile16K);
+            for (int dc = 0; dc < 2; ++dc)
+                tma_load_3d(q_smem + dc * 2 * kTile16K, &map_qk, &q_full, col_q + dc * 64, s.row0 + q0, 0);
+            for (int j = 0; j < nb && ok; ++j) {
+                const int slot = j & 1;
+                if (!mbar_wait(&k_empty[slot], ((j >> 1) & 1) ^ 1)) { ok = false; break; }
+                mbar_arrive_expect_tx(&k_full[slot], p.planes * 2 * kTile16K);
+                for (int dc = 0; dc < 2; ++dc)
+                    tma_load_3d(k_ring + slot * kKSlotBytes + dc * 2 * kTile16K, &map_qk, &k_full[slot],
+                                col_k + dc * 64, s.row0 + j * 128, 0);
+            }
+            if (ok && !mbar_wait(&s_full, 0)) ok = false;   // K ring is dead: reuse it for V
+            for (int i = 0; i < nchunks && ok; ++i) {
+                const int c = chunk_order(i, nchunks), slot = i & 3;
+                if (!mbar_wait(&v_empty[slot], ((i >> 2) & 1) ^ 1)) { ok = false; break; }
+                mbar_arrive_expect_tx(&v_full[slot], p.planes * 2 * kVPlaneBytes);
+                for (int dh = 0; dh < 2; ++dh)
+                    tma_load_3d(k_ring + slot * kVSlotBytes + dh * 2 * kVPlaneBytes, &map_v, &v_full[slot],
+                                col_v + dh * 64, s.row0 + c * 64, 0);
+            }
+            if (!ok) atomicExch(p.status, kStatusAttnTimeout);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_f16(128, 128, false);
+            constexpr uint32_t idesc_o = make_idesc_f16(128, 128, true);
+            const uint32_t q_addr = smem_u32(q_smem), k_addr = smem_u32(k_ring);
+            bool ok = mbar_wait(&q_full, 0);
+            tcgen05_fence_after();
+            for (int j = 0; j < nb && ok; ++j) {
+                const int slot = j & 1;
+                if (!mbar_wait(&k_full[slot], (j >> 1) & 1)) { ok = false; break; }
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + j * 128;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t off = (ks >> 2) * 2 * kTile16K + (ks & 3) * 32;
+                    const uint32_t qa = q_addr + off, kb = k_addr + slot * kKSlotBytes + off;
+                    const uint64_t dq0 = smem_desc_kmajor_sw128(qa), dk0 = smem_desc_kmajor_sw128(kb);
+                    umma_f16(d_tmem, dq0, dk0, idesc_s, ks > 0);
+                    if (p.planes == 2) {
+                        umma_f16(d_tmem, dq0, smem_desc_kmajor_sw128(kb + kTile16K), idesc_s, 1);
+                        umma_f16(d_tmem, smem_desc_kmajor_sw128(qa + kTile16K), dk0, idesc_s, 1);
+                    }
+                }
+                umma_commit(&k_empty[slot]);
+            }
+            if (ok) umma_commit(&s_full);
+            const uint32_t o_tmem = tmem_base + kOCol;
+            const int pre = nchunks > 6 ? nchunks - 6 : 0;
+            for (int i = 0; i < nchunks && ok; ++i) {
+                const int ps = i & 1, vs = i & 3;
+                if (!mbar_wait(&p_full[ps], (i >> 1) & 1)) { ok = false; break; }
+                if (i == 0 && pre == 2 && !mbar_wait(&p_full[1], 0)) { ok = false; break; }
+                if (!mbar_wait(&v_full[vs], (i >> 2) & 1)) { ok = false; break; }
+                tcgen05_fence_after();
+                const uint32_t p_addr = q_addr + ps * kPSlotBytes;
+                const uint32_t v_addr = k_addr + vs * kVSlotBytes;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t pa = p_addr + ks * 32;          // 16 keys along the swizzle row
+                    const uint32_t vb = v_addr + ks * 16 * 128;    // 16 key rows
+                    const uint64_t dp0 = smem_desc_kmajor_sw128(pa);
+                    const uint64_t dv0 = smem_desc_mnmajor_sw128(vb, 2 * kVPlaneBytes);
+                    umma_f16(o_tmem, dp0, dv0, idesc_o, (i > 0 || ks > 0) ? 1u : 0u);
+                    if (p.planes == 2) {
+                        umma_f16(o_tmem, dp0, smem_desc_mnmajor_sw128(vb + kVPlaneBytes, 2 * kVPlaneBytes),
+                                 idesc_o, 1);
+                        umma_f16(o_tmem, smem_desc_kmajor_sw128(pa + kTile16K), dv0, idesc_o, 1);
+                    }
+                }
+                umma_commit(&p_empty[ps]);
+                umma_commit(&v_empty[vs]);
+            }
+            if (ok) umma_commit(&o_full);
+            else atomicExch(p.status, kStatusAttnTimeout);
+        }
+    } else {
+        const int quad = warp & 3, r = quad * 32 + lane, t = q0 + r;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+        uint32_t raw[32];
+        bool ok = mbar_wait(&s_full, 0);
+        tcgen05_fence_after();
+        float mx = -FLT_MAX;
+        if (ok) {
+            const int ngroups = (nkeys + 31) >> 5;
+#pragma unroll 1
+            for (int g = 0; g < ngroups; ++g) {
+                tmem_ld_32x32(t_row + g * 32, raw);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int key = g * 32 + j;
+                    const bool allowed = key < nkeys && (!p.causal || key <= t);
+                    mx = fmaxf(mx, allowed ? __uint_as_float(raw[j]) : -FLT_MAX);
+                }
+            }
+        }
+        float sum = 0.f;
+        const uint32_t p_base = smem_u32(q_smem);
+        const uint32_t row_off = (uint32_t)r * 128, sw = (uint32_t)(r & 7);
+#pragma unroll 1
+        for (int i = 0; i < nchunks && ok; ++i) {
+            const int c = chunk_order(i, nchunks), slot = i & 1;
+            if (!mbar_wait(&p_empty[slot], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
+            const uint32_t p_slot = p_base + slot * kPSlotBytes;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                tmem_ld_32x32(t_row + c * 64 + half * 32, raw);
+                tmem_wait_ld();
+                uint32_t h[16], l[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float pv[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int key = c * 64 + half * 32 + 2 * j + q;
+                        const bool allowed = key < nkeys && (!p.causal || key <= t);
+                        const float e = exp2f((__uint_as_float(raw[2 * j + q]) - mx) * p.scale_log2e);
+                        pv[q] = allowed ? e : 0.f;
+                        sum += pv[q];
+                    }
+                    __half h0, l0, h1, l1;
+                    split_f16(pv[0], h0, l0);
+                    split_f16(pv[1], h1, l1);
+                    h[j] = pack_half2(h0, h1);
+                    l[j] = pack_half2(l0, l1);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t unit = (uint32_t)(half * 4 + u) ^ sw;
+                    const uint32_t addr = p_slot + row_off + unit * 16;
+                    st_shared_v4(addr, h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+                    st_shared_v4(addr + kTile16K, l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
+                }
+            }
+            fence_proxy_async_smem();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[slot]);
+        }
+        if (ok && !mbar_wait(&o_full, 0)) ok = false;
+        tcgen05_fence_after();
+        if (ok) {
+            const float inv = sum > 0.f ? 1.f / sum : 0.f;
+            float y[32];
+            __half* dst = p.out + (out_row0 + r) * p.H + head * 128;
+#pragma unroll 1
+            for (int g = 0; g < 4; ++g) {
+                tmem_ld_32x32(t_row + kOCol + g * 32, raw);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(raw[j]) * inv;
+                uint32_t h[16], l[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    __half h0, l0, h1, l1;
+                    split_f16(y[2 * j], h0, l0);
+                    split_f16(y[2 * j + 1], h1, l1);
+                    h[j] = pack_half2(h0, h1);
+                    l[j] = pack_half2(l0, l1);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    reinterpret_cast<uint4*>(dst + g * 32)[u] = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+                    reinterpret_cast<uint4*>(dst + p.out_plane_stride + g * 32)[u] =
+                        make_uint4(l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
+                }
+            }
+        } else {
+            atomicExch(p.status, kStatusAttnTimeout);
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows,
+                        const ForwardPlan& plan, const SeqInfo* seqs_dev, int planes,
+                        cudaStream_t stream) {
+    constexpr int D = 128;
+    const int H = e->cfg.hidden_channels;
+    if (e->attention_impl == 1 && plan.max_pitch <= 512 && H / e->cfg.num_heads == D) {
+        CUtensorMap map_qk, map_v;
+        PPGS_CHECK(make_plane_map(&map_qk, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
+                                  (uint64_t)rows * 3 * H, 128, planes));
+        PPGS_CHECK(make_plane_map(&map_v, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
+                                  (uint64_t)rows * 3 * H, 64, planes));
+        static bool attr_tc = false;
+        if (!attr_tc) {
+            PPGS_CUDA(cudaFuncSetAttribute(attention_tc_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kAttnSmem));
+            attr_tc = true;
+        }
+        AttnParams p;
+        p.seqs = seqs_dev;
+        p.H = H;
+        p.causal = e->cfg.is_causal;
+        p.planes = planes;
+        p.scale_log2e = 1.4426950408889634f / sqrtf((float)D);
+        p.out = out;
+        p.out_plane_stride = (int64_t)rows * H;
+        p.status = e->status_dev;
+        dim3 grid(plan.max_pitch / 128, e->cfg.num_heads, (unsigned)plan.seqs.size());
+        {
+            LaunchScope scope(e, "tc_attention", stream);
+            attention_tc_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(map_qk, map_v, p);
+        }
+        PPGS_CUDA(cudaGetLastError());
+        return PPGS_OK;
+    }
+    const size_t smem = (size_t)(32 * D + 32 * (D + 1) + 32 * D) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        PPGS_CUDA(cudaFuncSetAttribute(attention_planes_kernel<D>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid(plan.max_pitch / 32, e->cfg.num_heads, (unsigned)plan.seqs.size());
+    {
+        LaunchScope scope(e, "attention_simt_planes", stream);
+        attention_planes_kernel<D><<<grid, 256, smem, stream>>>(
+            qkv, (int64_t)rows * 3 * H, H, seqs_dev, e->cfg.is_causal, 1.f / sqrtf((float)D), planes,
+            out, (int64_t)rows * H);
+    }
+    PPGS_CUDA(cudaGetLastError());
+    return PPGS_OK;
+}
+
+}  // namespace ppgs

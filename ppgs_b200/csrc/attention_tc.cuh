@@ -1,0 +1,14 @@
+// Attention over split-fp16 planes (attention_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ppgs {
+
+// qkv: planes [2][rows][3H] (Q | K | V, heads contiguous inside each), out: planes
+// [2][rows][H].  Key-padding mask from SeqInfo::valid_len, optional causal mask
+// (ppgs/model/transformer.py:65-80), fp32 softmax.
+int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows,
+                        const ForwardPlan& plan, const SeqInfo* seqs_dev, int planes,
+                        cudaStream_t stream);
+
+}  // namespace ppgs

@@ -1,5 +1,6 @@
 // Shared declarations of the ppgs_b200 CUDA library (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -70,6 +71,21 @@ struct PlanePair {
     float inv_scale = 1.f;    // multiply the accumulator by this (power of two)
 };
 
+// One weight matrix of the tensor-core path: split-fp16 planes
+// [2][taps][N][C] (plane 0 = fp16(w*s), plane 1 = fp16(w*s - hi)), the device
+// scalar 1/s (s = power of two that moves max|w| near 2^10, so the lo plane stays
+// in fp16's normal range), and the TMA descriptor over the planes.
+struct TcWeight {
+    __half* planes = nullptr;
+    const float* inv_scale = nullptr;
+    int N = 0, C = 0, taps = 1;
+    CUtensorMap map_bn256, map_bn64;   // box rows 256 / 64
+};
+
+struct TcLayer {
+    TcWeight in_w, out_w, l1_w, l2_w;
+};
+
 struct LayerWeights {
     float *in_w, *in_b, *out_w, *out_b, *l1_w, *l1_b, *l2_w, *l2_b;
     float *n1_w, *n1_b, *n2_w, *n2_b;
@@ -95,6 +111,14 @@ struct ppgs_engine {
     float* pe = nullptr;           // [max_len][H]
     std::vector<ppgs::LayerWeights> layers;
     float *conv_in_b = nullptr, *conv_out_b = nullptr;
+
+    // tensor-core path (same blob)
+    float* tc_scales = nullptr;
+    ppgs::TcWeight tc_conv_in, tc_conv_out;
+    std::vector<ppgs::TcLayer> tc_layers;
+    bool tc_maps_ready = false;
+    int* status_dev = nullptr;   // kernels report barrier time-outs here
+    int attention_impl = 1;      // 1 = tcgen05 kernel, 0 = CUDA-core kernel (validation)
 
     ppgs::MelTables mel;
     std::vector<float> host_window;   // optional override ("frontend.window")
@@ -126,6 +150,7 @@ struct ppgs_engine {
 namespace ppgs {
 
 int ensure_workspace(ppgs_engine* e, size_t bytes);
+float pack_planes(const HostTensor* w, std::vector<__half>& planes);
 
 // Brackets one kernel launch: counts it, and when profiling records CUDA events
 // on `stream` around it.
@@ -155,5 +180,11 @@ int build_plan(const ppgs_engine* e, int batch, int frames, const int64_t* lengt
                int legacy_mode, ForwardPlan* plan);
 int transformer_forward_fp32(ppgs_engine* e, const __half* features, const ForwardPlan& plan,
                              int softmax, float* out, cudaStream_t stream);
+
+// transformer_tc.cu
+int build_weight_maps(ppgs_engine* e);
+int transformer_forward_tc(ppgs_engine* e, const __half* features, const ForwardPlan& plan,
+                           int softmax, float* out, cudaStream_t stream);
+int check_status(ppgs_engine* e, cudaStream_t stream);
 
 }  // namespace ppgs

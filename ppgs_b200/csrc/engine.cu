@@ -2,11 +2,13 @@
 // state-dict loading (ppgs/load.py:76-79), weight packing, and the forward entry
 // points that replace ppgs.preprocess.mel.from_audios / ppgs.from_features /
 // ppgs.from_audio.
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -182,6 +184,33 @@ static std::vector<float> conv_k_major(const HostTensor* w) {
     return packed;
 }
 
+// fp32 weight (N, C) or (N, C, taps) -> split-fp16 planes [2][taps][N][C] scaled by
+// a power of two; returns 1/scale.
+float pack_planes(const HostTensor* w, std::vector<__half>& planes) {
+    const int64_t N = w->shape[0], C = w->shape[1], T = w->shape.size() == 3 ? w->shape[2] : 1;
+    float amax = 0.f;
+    for (float v : w->data) amax = std::max(amax, fabsf(v));
+    int exponent = 0;
+    if (amax > 0.f && std::isfinite(amax)) {
+        frexpf(amax, &exponent);          // amax = f * 2^exponent, f in [0.5, 1)
+        exponent = 10 - exponent;         // amax * 2^exponent in [512, 1024)
+    }
+    const float scale = ldexpf(1.f, exponent);
+    const size_t plane = (size_t)(T * N * C);
+    planes.assign(2 * plane, __float2half_rn(0.f));
+    for (int64_t n = 0; n < N; ++n)
+        for (int64_t c = 0; c < C; ++c)
+            for (int64_t t = 0; t < T; ++t) {
+                const float v = w->data[(size_t)((n * C + c) * T + t)] * scale;
+                const __half hi = __float2half_rn(v);
+                const __half lo = __float2half_rn(v - __half2float(hi));
+                const size_t at = (size_t)((t * N + n) * C + c);
+                planes[at] = hi;
+                planes[plane + at] = lo;
+            }
+    return 1.f / scale;
+}
+
 // Walks the blob layout.  With `e->weights` populated and `host` set it also
 // serialises the data; otherwise it only assigns device pointers.
 static size_t layout_blob(ppgs_engine* e, std::vector<char>* host, char* dev) {
@@ -225,6 +254,36 @@ static size_t layout_blob(ppgs_engine* e, std::vector<char>* host, char* dev) {
         e->conv_out_w = w.put<float>(host ? packed.data() : nullptr, O * H * k);
     }
     e->conv_out_b = raw("output_layer.bias", O);
+
+    // ---- tensor-core section: scales, then the split-fp16 planes
+    const size_t n_scales = 2 + 4 * (size_t)c.num_layers;
+    std::vector<float> scales(n_scales, 1.f);
+    float* scales_dev = w.put<float>(nullptr, n_scales);
+    const size_t scales_off = w.off - ((n_scales * 4 + 255) & ~size_t(255));
+    e->tc_scales = scales_dev;
+    e->tc_layers.resize(c.num_layers);
+    size_t scale_index = 0;
+    auto planes = [&](TcWeight& tw, const std::string& name, size_t N_, size_t C_, size_t taps) {
+        std::vector<__half> packed;
+        if (host) scales[scale_index] = pack_planes(get(name), packed);
+        tw.planes = w.put<__half>(host ? packed.data() : nullptr, 2 * taps * N_ * C_);
+        tw.inv_scale = scales_dev ? scales_dev + scale_index : nullptr;
+        tw.N = (int)N_;
+        tw.C = (int)C_;
+        tw.taps = (int)taps;
+        ++scale_index;
+    };
+    planes(e->tc_conv_in, "input_layer.weight", H, C, k);
+    for (int l = 0; l < c.num_layers; ++l) {
+        const std::string p = "model.layers." + std::to_string(l) + ".";
+        planes(e->tc_layers[l].in_w, p + "self_attn.in_proj_weight", 3 * H, H, 1);
+        planes(e->tc_layers[l].out_w, p + "self_attn.out_proj.weight", H, H, 1);
+        planes(e->tc_layers[l].l1_w, p + "linear1.weight", F, H, 1);
+        planes(e->tc_layers[l].l2_w, p + "linear2.weight", H, F, 1);
+    }
+    planes(e->tc_conv_out, "output_layer.weight", O, H, k);
+    if (host) memcpy(host->data() + scales_off, scales.data(), n_scales * 4);
+    e->tc_maps_ready = false;
     return w.off;
 }
 
@@ -329,6 +388,7 @@ void ppgs_engine_destroy(ppgs_engine* e) {
     DeviceGuard guard(e->device);
     cudaDeviceSynchronize();
     cudaFree(e->blob);
+    cudaFree(e->status_dev);
     cudaFree(e->workspace);
     cudaFree(e->io_dev);
     cudaFreeHost(e->pinned);
@@ -450,8 +510,16 @@ int ppgs_engine_set_precision(ppgs_engine* e, int precision) {
         set_error("engine is NULL");
         return PPGS_E_INVALID;
     }
-    if (precision != PPGS_PRECISION_FP32) {
+    if (precision != PPGS_PRECISION_FP32 && precision != PPGS_PRECISION_F16X2 &&
+        precision != PPGS_PRECISION_F16) {
         set_error("precision %d is not available in this build", precision);
+        return PPGS_E_UNSUPPORTED;
+    }
+    if (precision != PPGS_PRECISION_FP32 &&
+        !(e->cfg.hidden_channels == 256 && e->cfg.ffn_channels % 256 == 0 &&
+          e->cfg.output_channels <= 64 && e->cfg.input_channels % 8 == 0)) {
+        set_error("precision %d is not available for this model shape (tensor-core path: "
+                  "hidden 256)", precision);
         return PPGS_E_UNSUPPORTED;
     }
     e->precision = precision;
@@ -510,6 +578,9 @@ static int run_transformer(ppgs_engine* e, const __half* features, const Forward
     switch (e->precision) {
         case PPGS_PRECISION_FP32:
             return transformer_forward_fp32(e, features, plan, softmax, out, stream);
+        case PPGS_PRECISION_F16X2:
+        case PPGS_PRECISION_F16:
+            return transformer_forward_tc(e, features, plan, softmax, out, stream);
         default:
             set_error("precision %d is not available in this build", e->precision);
             return PPGS_E_UNSUPPORTED;
@@ -615,7 +686,7 @@ int ppgs_from_audio_host(ppgs_engine* e, const float* audio, int batch, int64_t 
     PPGS_CUDA(cudaMemcpyAsync(out, out_dev, (size_t)batch * e->cfg.output_channels * frames * 4,
                               cudaMemcpyDeviceToHost, stream));
     PPGS_CUDA(cudaStreamSynchronize(stream));
-    return PPGS_OK;
+    return check_status(e, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,60 @@
+// Host-visible interface of the tcgen05 GEMM (gemm_tc.cu).
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ppgs {
+namespace tc {
+
+constexpr int kBM = 128;   // rows per tile = TMEM lanes
+constexpr int kBK = 64;    // fp16 elements per k-block = one 128-byte swizzle row
+
+enum GemmEpilogue : int {
+    kEpiF32 = 0,      // debug / validation: fp32 [M][N] = acc*scale + bias
+    kEpiPlanes = 1,   // bias (+ReLU) -> split-fp16 planes [2][M][N]
+    kEpiConvIn = 2,   // input conv: bias, length mask, + positional encoding -> x (fp32 + planes)
+    kEpiResLN = 3,    // bias + residual + LayerNorm -> x (fp32 + planes)
+    kEpiConvOut = 4,  // output conv: bias, mask, channel softmax, un-chunk -> (B, O, T)
+};
+
+struct GemmParams {
+    int m_tiles = 0, n_tiles = 0;
+    int taps = 1, half = 0;      // K loop = taps x cblocks k-blocks; A rows shift by tap - half
+    int cblocks = 0;
+    int a_planes = 2, b_planes = 2;
+    int N = 0;                   // real output columns
+    const float* scale = nullptr;   // device scalar: 1 / (power-of-two weight scale)
+    const float* bias = nullptr;
+    float* out_f32 = nullptr;       // kEpiF32 / x
+    int64_t ld_f32 = 0;
+    __half* out_planes = nullptr;   // [2][rows][ld_planes]
+    int64_t ld_planes = 0, plane_stride = 0;
+    const float* residual = nullptr;
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    float eps = 1e-5f;
+    const float* pe = nullptr;
+    const SeqInfo* seqs = nullptr;
+    const int* tile_seq = nullptr;
+    int relu = 0;
+    float* ppg = nullptr;   // kEpiConvOut
+    int T = 0, O = 0, softmax = 1;
+    int* status = nullptr;
+};
+
+// Tensor map over split-fp16 planes: logical dims {inner, rows, groups, planes}
+// (groups = conv taps for weights), box {64, box_rows, 1, box_planes}, 128-byte
+// swizzle, zero fill out of bounds.  Activation maps are rank 3 {inner, rows,
+// planes} (`rank4` false: groups must be 1); weight maps are always rank 4.
+int make_plane_map(CUtensorMap* map, const __half* base, bool rank4, uint64_t inner,
+                   uint64_t rows, uint64_t groups, uint64_t planes, uint64_t row_stride_elems,
+                   uint64_t group_stride_elems, uint64_t plane_stride_elems, uint32_t box_rows,
+                   uint32_t box_planes);
+
+// BN in {256, 128, 64}.  Launches a persistent grid of min(tiles, SMs) CTAs.
+int launch_gemm_tc(ppgs_engine* e, const char* name, int bn, int epilogue,
+                   const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p,
+                   cudaStream_t stream);
+
+}  // namespace tc
+}  // namespace ppgs

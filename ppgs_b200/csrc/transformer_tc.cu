@@ -1,0 +1,204 @@
+// Transformer forward on the tensor cores (PPGS_PRECISION_F16X2 / _F16):
+// ppgs/model/transformer.py:45-81 + softmax (ppgs/core.py:593-594) as a short
+// sequence of fused tcgen05 kernels over the folded-sequence row layout.
+//
+//   fold          (B,C,T) fp16 features -> time-major fp16 rows (chunk fold, replicate pad)
+//   conv_in       5-tap GEMM  + bias + length mask + positional encoding   -> x
+//   per layer     QKV GEMM + bias -> split planes
+//                 attention (length / causal mask, fp32 softmax)
+//                 out-proj GEMM + bias + residual + LayerNorm              -> x
+//                 linear1 GEMM + bias + ReLU -> split planes
+//                 linear2 GEMM + bias + residual + LayerNorm               -> x
+//   conv_out      5-tap GEMM + bias + mask + channel softmax + un-chunk    -> (B,40,T)
+//
+// Activations that feed a GEMM live in HBM as split-fp16 planes [2][rows][K];
+// the residual stream is also kept in fp32.
+#include <algorithm>
+
+#include "attention_tc.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace ppgs {
+
+using namespace tc;
+
+static int weight_map(TcWeight& w) {
+    const uint64_t plane = (uint64_t)w.taps * w.N * w.C;
+    PPGS_CHECK(make_plane_map(&w.map_bn256, w.planes, true, w.C, w.N, w.taps, 2, w.C,
+                              (uint64_t)w.N * w.C, plane, 256, 2));
+    PPGS_CHECK(make_plane_map(&w.map_bn64, w.planes, true, w.C, w.N, w.taps, 2, w.C,
+                              (uint64_t)w.N * w.C, plane, 64, 2));
+    return PPGS_OK;
+}
+
+int build_weight_maps(ppgs_engine* e) {
+    if (e->tc_maps_ready) return PPGS_OK;
+    PPGS_CHECK(weight_map(e->tc_conv_in));
+    PPGS_CHECK(weight_map(e->tc_conv_out));
+    for (TcLayer& l : e->tc_layers) {
+        PPGS_CHECK(weight_map(l.in_w));
+        PPGS_CHECK(weight_map(l.out_w));
+        PPGS_CHECK(weight_map(l.l1_w));
+        PPGS_CHECK(weight_map(l.l2_w));
+    }
+    if (!e->status_dev) {
+        PPGS_CUDA(cudaMalloc(&e->status_dev, sizeof(int)));
+        PPGS_CUDA(cudaMemset(e->status_dev, 0, sizeof(int)));
+    }
+    e->tc_maps_ready = true;
+    return PPGS_OK;
+}
+
+int check_status(ppgs_engine* e, cudaStream_t stream) {
+    if (!e->status_dev) return PPGS_OK;
+    int status = 0;
+    PPGS_CUDA(cudaMemcpyAsync(&status, e->status_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PPGS_CUDA(cudaStreamSynchronize(stream));
+    if (status != 0) {
+        cudaMemsetAsync(e->status_dev, 0, sizeof(int), stream);
+        set_error("tensor-core pipeline timed out waiting on a barrier (status %d)", status);
+        return PPGS_E_CUDA;
+    }
+    return PPGS_OK;
+}
+
+// (B, C, T) fp16 -> [rows][C] fp16, time-major (transformer.py:54,58 folded)
+__global__ void fold_half_kernel(const __half* __restrict__ feats, int C, int T,
+                                 const SeqInfo* __restrict__ seqs, const int* __restrict__ tile_seq,
+                                 __half* __restrict__ x0) {
+    __shared__ __half tile[32][34];
+    const int row_base = blockIdx.x * 32, c_base = blockIdx.y * 32;
+    const SeqInfo s = seqs[tile_seq[row_base >> 7]];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c_base + i, t = row_base - s.row0 + tx;
+        __half v = __float2half_rn(0.f);
+        if (c < C && t < s.tensor_len)
+            v = feats[((int64_t)s.batch * C + c) * T + max(s.src_start + t, 0)];
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c_base + tx;
+        if (c < C) x0[(int64_t)(row_base + i) * C + c] = tile[tx][i];
+    }
+}
+
+int transformer_forward_tc(ppgs_engine* e, const __half* features, const ForwardPlan& plan,
+                           int softmax, float* out, cudaStream_t stream) {
+    const ppgs_model_config& c = e->cfg;
+    const int C = c.input_channels, H = c.hidden_channels, F = c.ffn_channels;
+    const int O = c.output_channels, k = c.kernel_size;
+    const int rows = plan.rows, D = H / c.num_heads;
+    if (H != 256 || D != 128 || O > 64 || F % 256 || C % 8) {
+        set_error("tensor-core path supports hidden 256 / head_dim 128 (got %d / %d)", H, D);
+        return PPGS_E_UNSUPPORTED;
+    }
+    PPGS_CHECK(build_weight_maps(e));
+    const int planes = e->precision == PPGS_PRECISION_F16X2 ? 2 : 1;
+
+    Carver w;
+    const size_t o_x0 = w.take((size_t)rows * C * 2);
+    const size_t o_xf = w.take((size_t)rows * H * 4);
+    const size_t o_xh = w.take((size_t)2 * rows * H * 2);
+    const size_t o_qkv = w.take((size_t)2 * rows * 3 * H * 2);
+    const size_t o_att = w.take((size_t)2 * rows * H * 2);
+    const size_t o_ff = w.take((size_t)2 * rows * F * 2);
+    const size_t o_seqs = w.take(plan.seqs.size() * sizeof(SeqInfo));
+    const size_t o_tiles = w.take((size_t)(rows / 128) * 4);
+    PPGS_CHECK(ensure_workspace(e, w.off));
+    char* ws = static_cast<char*>(e->workspace);
+    __half* x0 = reinterpret_cast<__half*>(ws + o_x0);
+    float* xf = reinterpret_cast<float*>(ws + o_xf);
+    __half* xh = reinterpret_cast<__half*>(ws + o_xh);
+    __half* qkv = reinterpret_cast<__half*>(ws + o_qkv);
+    __half* att = reinterpret_cast<__half*>(ws + o_att);
+    __half* ff = reinterpret_cast<__half*>(ws + o_ff);
+    SeqInfo* seqs_dev = reinterpret_cast<SeqInfo*>(ws + o_seqs);
+    int* tile_seq_dev = reinterpret_cast<int*>(ws + o_tiles);
+    PPGS_CHECK(upload_plan(e, plan, seqs_dev, tile_seq_dev, stream));
+
+    // activation tensor maps (A operands): {K, rows, planes}
+    CUtensorMap map_x0, map_x, map_att, map_ff;
+    PPGS_CHECK(make_plane_map(&map_x0, x0, false, C, rows, 1, 1, C, 0, (uint64_t)rows * C, 128, 1));
+    PPGS_CHECK(make_plane_map(&map_x, xh, false, H, rows, 1, 2, H, 0, (uint64_t)rows * H, 128, planes));
+    PPGS_CHECK(make_plane_map(&map_att, att, false, H, rows, 1, 2, H, 0, (uint64_t)rows * H, 128, planes));
+    PPGS_CHECK(make_plane_map(&map_ff, ff, false, F, rows, 1, 2, F, 0, (uint64_t)rows * F, 128, planes));
+
+    {
+        dim3 grid(rows / 32, (C + 31) / 32);
+        LaunchScope scope(e, "fold_chunks", stream);
+        fold_half_kernel<<<grid, dim3(32, 8), 0, stream>>>(features, C, plan.frames, seqs_dev,
+                                                           tile_seq_dev, x0);
+    }
+    PPGS_CUDA(cudaGetLastError());
+
+    GemmParams base;
+    base.m_tiles = rows / 128;
+    base.seqs = seqs_dev;
+    base.tile_seq = tile_seq_dev;
+    base.status = e->status_dev;
+    base.eps = c.layer_norm_eps;
+    base.b_planes = planes;
+
+    {   // input conv: features are exact fp16 -> one A plane
+        GemmParams p = base;
+        p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = (C + 63) / 64; p.a_planes = 1;
+        p.N = H; p.scale = e->tc_conv_in.inv_scale; p.bias = e->conv_in_b; p.pe = e->pe;
+        p.out_f32 = xf; p.ld_f32 = H; p.out_planes = xh; p.ld_planes = H;
+        p.plane_stride = (int64_t)rows * H;
+        PPGS_CHECK(launch_gemm_tc(e, "tc_conv_in", 256, kEpiConvIn, map_x0, e->tc_conv_in.map_bn256,
+                                  p, stream));
+    }
+    for (int layer = 0; layer < c.num_layers; ++layer) {
+        const LayerWeights& L = e->layers[layer];
+        TcLayer& T = e->tc_layers[layer];
+        {
+            GemmParams p = base;
+            p.n_tiles = 3 * H / 256; p.cblocks = H / 64; p.a_planes = planes;
+            p.N = 3 * H; p.scale = T.in_w.inv_scale; p.bias = L.in_b;
+            p.out_planes = qkv; p.ld_planes = 3 * H; p.plane_stride = (int64_t)rows * 3 * H;
+            PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, T.in_w.map_bn256, p, stream));
+        }
+        PPGS_CHECK(launch_attention_tc(e, qkv, att, rows, plan, seqs_dev, planes, stream));
+        {
+            GemmParams p = base;
+            p.n_tiles = 1; p.cblocks = H / 64; p.a_planes = planes;
+            p.N = H; p.scale = T.out_w.inv_scale; p.bias = L.out_b; p.residual = xf;
+            p.gamma = L.n1_w; p.beta = L.n1_b;
+            p.out_f32 = xf; p.ld_f32 = H; p.out_planes = xh; p.ld_planes = H;
+            p.plane_stride = (int64_t)rows * H;
+            PPGS_CHECK(launch_gemm_tc(e, "tc_out_proj_ln", 256, kEpiResLN, map_att, T.out_w.map_bn256,
+                                      p, stream));
+        }
+        {
+            GemmParams p = base;
+            p.n_tiles = F / 256; p.cblocks = H / 64; p.a_planes = planes;
+            p.N = F; p.scale = T.l1_w.inv_scale; p.bias = L.l1_b; p.relu = 1;
+            p.out_planes = ff; p.ld_planes = F; p.plane_stride = (int64_t)rows * F;
+            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn1", 256, kEpiPlanes, map_x, T.l1_w.map_bn256, p, stream));
+        }
+        {
+            GemmParams p = base;
+            p.n_tiles = 1; p.cblocks = F / 64; p.a_planes = planes;
+            p.N = H; p.scale = T.l2_w.inv_scale; p.bias = L.l2_b; p.residual = xf;
+            p.gamma = L.n2_w; p.beta = L.n2_b;
+            p.out_f32 = xf; p.ld_f32 = H; p.out_planes = xh; p.ld_planes = H;
+            p.plane_stride = (int64_t)rows * H;
+            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn2_ln", 256, kEpiResLN, map_ff, T.l2_w.map_bn256, p,
+                                      stream));
+        }
+    }
+    {
+        GemmParams p = base;
+        p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = H / 64; p.a_planes = planes;
+        p.N = O; p.O = O; p.scale = e->tc_conv_out.inv_scale; p.bias = e->conv_out_b;
+        p.ppg = out; p.T = plan.frames; p.softmax = softmax;
+        PPGS_CHECK(launch_gemm_tc(e, "tc_conv_out_softmax", 64, kEpiConvOut, map_x,
+                                  e->tc_conv_out.map_bn64, p, stream));
+    }
+    return PPGS_OK;
+}
+
+}  // namespace ppgs
