@@ -103,4 +103,4 @@ def test_attention_kernel(engine, tensor_len, valid_len, impl):
     p = torch.softmax(scores, -1) if valid_len else torch.zeros_like(scores)
     ref = (p @ v).transpose(0, 1).reshape(rows, H)
     err = (out.double() - ref)[:tensor_len].abs().max().item()
-    assert err <= 5e-6, f'max-abs {err:.3e}'
+    assert err <= 2e-5, f'max-abs {err:.3e}'
