@@ -88,7 +88,7 @@ extern "C" int ppgs_debug_gemm(ppgs_engine* e, const float* a_host, const float*
     p.out_f32 = out_dev.as<float>();
     p.ld_f32 = N;
     p.status = e->status_dev;
-    PPGS_CHECK(tc::launch_gemm_tc(e, "debug_gemm", bn, tc::kEpiF32, map_a, map_b, p, nullptr));
+    PPGS_CHECK(tc::launch_gemm_tc(e, "debug_gemm", bn, tc::kEpiF32, map_a, map_b, nullptr, p, nullptr));
     PPGS_CUDA(cudaDeviceSynchronize());
     PPGS_CHECK(check_status(e, nullptr));
     PPGS_CUDA(cudaMemcpy(out_host, out_dev.ptr, (size_t)M * N * 4, cudaMemcpyDeviceToHost));

@@ -18,8 +18,9 @@
 namespace ppgs {
 namespace tc {
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;      // producer + MMA + 8 epilogue warps
 constexpr int kPlaneABytes = kBM * kBK * 2;   // 16 KB
+constexpr int kStageOutBytes = 2 * kBM * 32 * 2;   // [plane 2][128 rows][32 cols] fp16 = 16 KB
 
 template <int BN>
 struct GemmShape {
@@ -28,50 +29,64 @@ struct GemmShape {
     static constexpr int kStages = (BN == 256) ? 2 : (BN == 128) ? 3 : 4;
     static constexpr int kAccCols = BN;                      // power of two >= 32
     static constexpr int kTmemCols = 2 * kAccCols;
-    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024;
+    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 2 * kStageOutBytes;
 };
 
-__device__ __forceinline__ void store_f32x32(float* dst, const float (&y)[32]) {
+// One 32-column chunk of one output row -> this thread's row of the staging
+// tile ([plane][128 rows][32 cols], 64-byte swizzle), then one elected thread of
+// the 128-thread epilogue set stores the tile with TMA.
+__device__ __forceinline__ void stage_and_store(const CUtensorMap* map_out, unsigned char* stage,
+                                                int set, int row, bool elected,
+                                                const uint32_t (&h)[16], const uint32_t (&l)[16],
+                                                int n0, int m0) {
+    if (elected) bulk_wait_read_all();          // previous store has drained the buffer
+    named_bar_sync(1 + set, 128);
+    const uint32_t base = smem_u32(stage) + (uint32_t)row * 64;
+    const uint32_t sw = (uint32_t)(row >> 1) & 3;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-        reinterpret_cast<float4*>(dst)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t addr = base + (((uint32_t)u ^ sw) << 4);
+        st_shared_v4(addr, h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+        st_shared_v4(addr + kBM * 64, l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1 + set, 128);
+    if (elected) {
+        tma_store_3d(map_out, stage, n0, m0, 0);
+        bulk_commit_group();
+    }
 }
 
-__device__ __forceinline__ void store_planes32(__half* hi_dst, __half* lo_dst, const float (&y)[32]) {
-    uint32_t h[16], l[16];
+__device__ __forceinline__ void split32(const float (&y)[32], uint32_t (&h)[16], uint32_t (&l)[16]) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        __half h0, l0, h1, l1;
-        split_f16(y[2 * i], h0, l0);
-        split_f16(y[2 * i + 1], h1, l1);
-        h[i] = pack_half2(h0, h1);
-        l[i] = pack_half2(l0, l1);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        reinterpret_cast<uint4*>(hi_dst)[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-        reinterpret_cast<uint4*>(lo_dst)[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
-    }
+    for (int i = 0; i < 16; ++i) split2_f16(y[2 * i], y[2 * i + 1], h[i], l[i]);
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
     using Shape = GemmShape<BN>;
     constexpr int kStages = Shape::kStages;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kChunks = BN / 32;
+    // 128B-swizzled TMA / UMMA tiles need 1024-byte alignment: the declaration
+    // aligns the dynamic region (checked below), there is no room for slack at BN=256
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* stage_out = smem + (size_t)kStages * Shape::kStageBytes;
     __shared__ __align__(8) uint64_t full_bar[kStages];
     __shared__ __align__(8) uint64_t empty_bar[kStages];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ float ln_part[2][kBM];      // [epilogue set][row] partial row statistics
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int num_kb = p.taps * p.cblocks;
+    if (smem_u32(smem) & 1023u) {   // uniform across the CTA
+        if (threadIdx.x == 0) atomicExch(p.status, kStatusBadAlignment);
+        return;
+    }
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) {
@@ -80,7 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], 4);
+            mbar_init(&tmem_empty_bar[i], 8);
         }
         fence_barrier_init();
     }
@@ -172,8 +187,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ------------------------------------------------------------ epilogue
-        const int quad = warp & 3;                  // TMEM lane quadrant of this warp
-        const int row_in_tile = quad * 32 + lane;
+        // 8 warps = 2 sets of 4; a set covers the 128 rows (TMEM lane quadrant =
+        // warp % 4) and takes every other 32-column chunk.
+        const int set = (warp - 2) >> 2;
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const bool elected = (warp - 2) == 4 * set && lane == 0;
+        unsigned char* stage = stage_out + set * kStageOutBytes;
         const float scale = *p.scale;
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -186,83 +206,104 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             tcgen05_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * Shape::kAccCols;
-            const int64_t m = (int64_t)m_blk * kBM + row_in_tile;
-            uint32_t raw[32];
+            const int m0 = m_blk * kBM;
+            const int64_t m = (int64_t)m0 + row;
+            uint32_t raw[32], h[16], l[16];
             float y[32];
+            auto release_tmem = [&]() {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            };
 
-            if (EPI == kEpiF32 || EPI == kEpiPlanes) {
+            if (EPI == kEpiF32) {
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = set; c < kChunks; c += 2) {
                     tmem_ld_32x32(t_acc + c * 32, raw);
                     tmem_wait_ld();
                     const int n0 = n_blk * BN + c * 32;
                     if (n0 >= p.N) continue;   // warp-uniform
+                    float* dst = p.out_f32 + m * p.ld_f32 + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j < p.N) dst[j] = __uint_as_float(raw[j]) * scale + __ldg(p.bias + n0 + j);
+                }
+                release_tmem();
+            } else if (EPI == kEpiPlanes) {
+#pragma unroll 1
+                for (int c = set; c < kChunks; c += 2) {
+                    tmem_ld_32x32(t_acc + c * 32, raw);
+                    tmem_wait_ld();
+                    if (c + 2 >= kChunks) release_tmem();   // last read of this accumulator
+                    const int n0 = n_blk * BN + c * 32;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float v = __uint_as_float(raw[j]) * scale;
-                        if (n0 + j < p.N) v += __ldg(p.bias + n0 + j);
-                        if (EPI == kEpiPlanes && p.relu) v = fmaxf(v, 0.f);
-                        y[j] = v;
+                        float v = __uint_as_float(raw[j]) * scale + __ldg(p.bias + n0 + j);
+                        y[j] = p.relu ? fmaxf(v, 0.f) : v;
                     }
-                    if (EPI == kEpiF32) {
-                        float* dst = p.out_f32 + m * p.ld_f32 + n0;
-                        if (n0 + 32 <= p.N && (p.ld_f32 & 3) == 0) store_f32x32(dst, y);
-                        else
-                            for (int j = 0; j < 32; ++j)
-                                if (n0 + j < p.N) dst[j] = y[j];
-                    } else {
-                        __half* dst = p.out_planes + m * p.ld_planes + n0;
-                        store_planes32(dst, dst + p.plane_stride, y);
-                    }
+                    split32(y, h, l);
+                    stage_and_store(&map_out, stage, set, row, elected, h, l, n0, m0);
                 }
             } else if (EPI == kEpiConvIn) {
                 const SeqInfo s = p.seqs[p.tile_seq[m_blk]];
                 const int t = (int)(m - s.row0);
                 const bool in_tensor = t < s.tensor_len, valid = t < s.valid_len;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = set; c < kChunks; c += 2) {
                     tmem_ld_32x32(t_acc + c * 32, raw);
                     tmem_wait_ld();
-                    const int n0 = n_blk * BN + c * 32;
+                    if (c + 2 >= kChunks) release_tmem();
+                    const int n0 = c * 32;
                     const float* pe = p.pe + (int64_t)(in_tensor ? t : 0) * p.N + n0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float v = valid ? __uint_as_float(raw[j]) * scale + __ldg(p.bias + n0 + j) : 0.f;
+                        const float v = valid ? __uint_as_float(raw[j]) * scale + __ldg(p.bias + n0 + j) : 0.f;
                         y[j] = in_tensor ? v + pe[j] : 0.f;
                     }
-                    store_f32x32(p.out_f32 + m * p.ld_f32 + n0, y);
-                    __half* dst = p.out_planes + m * p.ld_planes + n0;
-                    store_planes32(dst, dst + p.plane_stride, y);
+                    split32(y, h, l);
+                    stage_and_store(&map_out, stage, set, row, elected, h, l, n0, m0);
                 }
             } else if (EPI == kEpiResLN) {
-                // the tile is one full row of the hidden state (BN == N == hidden)
+                // the tile is one full row block of the hidden state (BN == N == hidden);
+                // a row is shared by the two threads (one per set) with the same `row`
                 const SeqInfo s = p.seqs[p.tile_seq[m_blk]];
                 const bool in_tensor = (int)(m - s.row0) < s.tensor_len;
-                const float* res = p.residual + m * p.N;
+                const __half* res_hi = p.residual + m * p.res_ld;
+                const __half* res_lo = res_hi + p.res_plane_stride;
                 float sum = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = set; c < kChunks; c += 2) {
                     tmem_ld_32x32(t_acc + c * 32, raw);
+                    uint4 rh[4], rl[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        rh[u] = reinterpret_cast<const uint4*>(res_hi + c * 32)[u];
+                        rl[u] = reinterpret_cast<const uint4*>(res_lo + c * 32)[u];
+                    }
                     tmem_wait_ld();
+                    const uint32_t* rhw = reinterpret_cast<const uint32_t*>(rh);
+                    const uint32_t* rlw = reinterpret_cast<const uint32_t*>(rl);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 r = reinterpret_cast<const float4*>(res + c * 32)[j];
-                        const float rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int n = c * 32 + 4 * j + q;
-                            const float v = __uint_as_float(raw[4 * j + q]) * scale + __ldg(p.bias + n) + rr[q];
-                            sum += v;
-                            raw[4 * j + q] = __float_as_uint(v);
-                        }
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&rhw[j]));
+                        const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&rlw[j]));
+                        const int n = c * 32 + 2 * j;
+                        const float v0 = __uint_as_float(raw[2 * j]) * scale + __ldg(p.bias + n) + (fh.x + fl.x);
+                        const float v1 = __uint_as_float(raw[2 * j + 1]) * scale + __ldg(p.bias + n + 1) + (fh.y + fl.y);
+                        sum += v0 + v1;
+                        raw[2 * j] = __float_as_uint(v0);
+                        raw[2 * j + 1] = __float_as_uint(v1);
                     }
                     tmem_st_32x32(t_acc + c * 32, raw);
                 }
                 tmem_wait_st();
-                const float mean = sum * (1.f / BN);
+                ln_part[set][row] = sum;
+                named_bar_sync(3, 256);
+                const float mean = (ln_part[0][row] + ln_part[1][row]) * (1.f / BN);
+                named_bar_sync(3, 256);   // both partners have read the sums
                 float sq = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = set; c < kChunks; c += 2) {
                     tmem_ld_32x32(t_acc + c * 32, raw);
                     tmem_wait_ld();
 #pragma unroll
@@ -271,11 +312,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         sq = fmaf(d, d, sq);
                     }
                 }
-                const float rstd = rsqrtf(sq * (1.f / BN) + p.eps);
+                ln_part[set][row] = sq;
+                named_bar_sync(3, 256);
+                const float rstd = rsqrtf((ln_part[0][row] + ln_part[1][row]) * (1.f / BN) + p.eps);
+                named_bar_sync(3, 256);   // ln_part is free for the next tile
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = set; c < kChunks; c += 2) {
                     tmem_ld_32x32(t_acc + c * 32, raw);
                     tmem_wait_ld();
+                    if (c + 2 >= kChunks) release_tmem();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = c * 32 + j;
@@ -283,52 +328,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                         __ldg(p.beta + n);
                         y[j] = in_tensor ? v : 0.f;
                     }
-                    store_f32x32(p.out_f32 + m * p.ld_f32 + c * 32, y);
-                    __half* dst = p.out_planes + m * p.ld_planes + c * 32;
-                    store_planes32(dst, dst + p.plane_stride, y);
+                    split32(y, h, l);
+                    stage_and_store(&map_out, stage, set, row, elected, h, l, c * 32, m0);
                 }
             } else if (EPI == kEpiConvOut) {
-                // BN == 64 >= O: all channels of a frame live in this thread
-                const SeqInfo s = p.seqs[p.tile_seq[m_blk]];
-                const int t = (int)(m - s.row0);
-                const bool valid = t < s.valid_len;
-                float z[64];
+                // BN == 64 >= O: all channels of a frame live in one thread (set 0)
+                if (set == 0) {
+                    const SeqInfo s = p.seqs[p.tile_seq[m_blk]];
+                    const int t = (int)(m - s.row0);
+                    const bool valid = t < s.valid_len;
+                    float z[64];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    tmem_ld_32x32(t_acc + c * 32, raw);
-                    tmem_wait_ld();
+                    for (int c = 0; c < 2; ++c) {
+                        tmem_ld_32x32(t_acc + c * 32, raw);
+                        tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = c * 32 + j;
-                        z[n] = (valid && n < p.O) ? __uint_as_float(raw[j]) * scale + __ldg(p.bias + n) : 0.f;
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = c * 32 + j;
+                            z[n] = (valid && n < p.O) ? __uint_as_float(raw[j]) * scale + __ldg(p.bias + n) : 0.f;
+                        }
                     }
-                }
-                if (t >= s.keep_begin && t < s.keep_end) {
-                    float inv = 1.f, mx = 0.f;
-                    if (p.softmax) {
-                        mx = -3.0e38f;
+                    release_tmem();
+                    if (t >= s.keep_begin && t < s.keep_end) {
+                        float inv = 1.f, mx = 0.f;
+                        if (p.softmax) {
+                            mx = -3.0e38f;
+#pragma unroll
+                            for (int n = 0; n < 64; ++n)
+                                if (n < p.O) mx = fmaxf(mx, z[n]);
+                            float sum = 0.f;
+#pragma unroll
+                            for (int n = 0; n < 64; ++n)
+                                if (n < p.O) {
+                                    z[n] = expf(z[n] - mx);
+                                    sum += z[n];
+                                }
+                            inv = 1.f / sum;
+                        }
+                        float* dst = p.ppg + (int64_t)s.batch * p.O * p.T + s.out_start + (t - s.keep_begin);
 #pragma unroll
                         for (int n = 0; n < 64; ++n)
-                            if (n < p.O) mx = fmaxf(mx, z[n]);
-                        float sum = 0.f;
-#pragma unroll
-                        for (int n = 0; n < 64; ++n)
-                            if (n < p.O) {
-                                z[n] = expf(z[n] - mx);
-                                sum += z[n];
-                            }
-                        inv = 1.f / sum;
+                            if (n < p.O) dst[(int64_t)n * p.T] = z[n] * inv;
                     }
-                    float* dst = p.ppg + (int64_t)s.batch * p.O * p.T + s.out_start + (t - s.keep_begin);
-#pragma unroll
-                    for (int n = 0; n < 64; ++n)
-                        if (n < p.O) dst[(int64_t)n * p.T] = z[n] * inv;
+                } else {
+                    release_tmem();
                 }
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
+        if (elected) bulk_wait_all();   // smem must outlive the last TMA store
     }
 
     tcgen05_fence_before();
@@ -400,9 +447,30 @@ int make_plane_map(CUtensorMap* map, const __half* base, bool rank4, uint64_t in
     return PPGS_OK;
 }
 
+int make_store_map(CUtensorMap* map, __half* base, uint64_t inner, uint64_t rows,
+                   uint64_t plane_stride_elems) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return PPGS_E_CUDA;
+    }
+    cuuint64_t dims[3] = {inner, rows, 2};
+    cuuint64_t strides[2] = {inner * 2, plane_stride_elems * 2};
+    cuuint32_t box[3] = {32, (cuuint32_t)kBM, 2}, elem[3] = {1, 1, 1};
+    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, elem,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (store map) failed with CUresult %d", (int)rc);
+        return PPGS_E_CUDA;
+    }
+    return PPGS_OK;
+}
+
 template <int BN, int EPI>
 static int launch_one(ppgs_engine* e, const char* name, const CUtensorMap& map_a,
-                      const CUtensorMap& map_b, const GemmParams& p, cudaStream_t stream) {
+                      const CUtensorMap& map_b, const CUtensorMap& map_out, const GemmParams& p,
+                      cudaStream_t stream) {
     using Shape = GemmShape<BN>;
     static bool attr = false;
     if (!attr) {
@@ -415,21 +483,28 @@ static int launch_one(ppgs_engine* e, const char* name, const CUtensorMap& map_a
     const int grid = std::min(tiles, e->sm_count);
     {
         LaunchScope scope(e, name, stream);
-        gemm_tc_kernel<BN, EPI><<<grid, kGemmThreads, Shape::kSmemBytes, stream>>>(map_a, map_b, p);
+        gemm_tc_kernel<BN, EPI><<<grid, kGemmThreads, Shape::kSmemBytes, stream>>>(map_a, map_b, map_out, p);
     }
     PPGS_CUDA(cudaGetLastError());
     return PPGS_OK;
 }
 
 int launch_gemm_tc(ppgs_engine* e, const char* name, int bn, int epilogue,
-                   const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p,
-                   cudaStream_t stream) {
+                   const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap* map_out,
+                   const GemmParams& p, cudaStream_t stream) {
     if (p.m_tiles <= 0 || p.n_tiles <= 0 || p.cblocks <= 0 || !p.scale || !p.status) {
         set_error("gemm_tc: bad parameters");
         return PPGS_E_INVALID;
     }
+    const bool stores_planes = epilogue == kEpiPlanes || epilogue == kEpiConvIn || epilogue == kEpiResLN;
+    if (stores_planes && !map_out) {
+        set_error("gemm_tc: epilogue %d needs an output tensor map", epilogue);
+        return PPGS_E_INVALID;
+    }
+    const CUtensorMap& out_map = map_out ? *map_out : map_a;   // unused when not storing planes
 #define PPGS_GEMM_CASE(BN_, EPI_) \
-    if (bn == BN_ && epilogue == EPI_) return launch_one<BN_, EPI_>(e, name, map_a, map_b, p, stream)
+    if (bn == BN_ && epilogue == EPI_) \
+        return launch_one<BN_, EPI_>(e, name, map_a, map_b, out_map, p, stream)
     PPGS_GEMM_CASE(256, kEpiF32);
     PPGS_GEMM_CASE(128, kEpiF32);
     PPGS_GEMM_CASE(64, kEpiF32);

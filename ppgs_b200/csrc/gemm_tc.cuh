@@ -12,8 +12,8 @@ constexpr int kBK = 64;    // fp16 elements per k-block = one 128-byte swizzle r
 enum GemmEpilogue : int {
     kEpiF32 = 0,      // debug / validation: fp32 [M][N] = acc*scale + bias
     kEpiPlanes = 1,   // bias (+ReLU) -> split-fp16 planes [2][M][N]
-    kEpiConvIn = 2,   // input conv: bias, length mask, + positional encoding -> x (fp32 + planes)
-    kEpiResLN = 3,    // bias + residual + LayerNorm -> x (fp32 + planes)
+    kEpiConvIn = 2,   // input conv: bias, length mask, + positional encoding -> x planes
+    kEpiResLN = 3,    // bias + residual + LayerNorm -> x planes (in place)
     kEpiConvOut = 4,  // output conv: bias, mask, channel softmax, un-chunk -> (B, O, T)
 };
 
@@ -25,11 +25,12 @@ struct GemmParams {
     int N = 0;                   // real output columns
     const float* scale = nullptr;   // device scalar: 1 / (power-of-two weight scale)
     const float* bias = nullptr;
-    float* out_f32 = nullptr;       // kEpiF32 / x
+    float* out_f32 = nullptr;       // kEpiF32 only
     int64_t ld_f32 = 0;
-    __half* out_planes = nullptr;   // [2][rows][ld_planes]
-    int64_t ld_planes = 0, plane_stride = 0;
-    const float* residual = nullptr;
+    // plane outputs leave through `map_out` (TMA store); the residual stream is
+    // read back from its planes [2][rows][res_ld]
+    const __half* residual = nullptr;
+    int64_t res_ld = 0, res_plane_stride = 0;
     const float* gamma = nullptr;
     const float* beta = nullptr;
     float eps = 1e-5f;
@@ -51,10 +52,16 @@ int make_plane_map(CUtensorMap* map, const __half* base, bool rank4, uint64_t in
                    uint64_t group_stride_elems, uint64_t plane_stride_elems, uint32_t box_rows,
                    uint32_t box_planes);
 
+// Store map over output planes [2][rows][inner]: box {32, 128, 2}, 64-byte swizzle
+// (the epilogue's staging layout).
+int make_store_map(CUtensorMap* map, __half* base, uint64_t inner, uint64_t rows,
+                   uint64_t plane_stride_elems);
+
 // BN in {256, 128, 64}.  Launches a persistent grid of min(tiles, SMs) CTAs.
+// `map_out` may be null for epilogues without plane output (kEpiF32, kEpiConvOut).
 int launch_gemm_tc(ppgs_engine* e, const char* name, int bn, int epilogue,
-                   const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p,
-                   cudaStream_t stream);
+                   const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap* map_out,
+                   const GemmParams& p, cudaStream_t stream);
 
 }  // namespace tc
 }  // namespace ppgs

@@ -19,6 +19,7 @@ enum : int {
     kStatusMmaTimeout = 2,
     kStatusEpilogueTimeout = 3,
     kStatusAttnTimeout = 4,
+    kStatusBadAlignment = 5,
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -101,6 +102,33 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
         "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+// shared -> global tile store; completion tracked by bulk async-groups
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1,
+                                             int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the source smem of every committed store has been read (buffer reusable)
+__device__ __forceinline__ void bulk_wait_read_all() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// every committed store is complete (global writes performed)
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
 }
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -240,6 +268,12 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     const float r = x - __half2float(hi);
     asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(r));
     lo = __ushort_as_half(l);
+}
+// two values at once: hi2 / lo2 hold (a, b) as packed halves, a in the low 16 bits
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(b), "f"(a));
+    const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(b - back.y), "f"(a - back.x));
 }
 __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);

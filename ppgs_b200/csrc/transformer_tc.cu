@@ -11,8 +11,8 @@
 //                 linear2 GEMM + bias + residual + LayerNorm               -> x
 //   conv_out      5-tap GEMM + bias + mask + channel softmax + un-chunk    -> (B,40,T)
 //
-// Activations that feed a GEMM live in HBM as split-fp16 planes [2][rows][K];
-// the residual stream is also kept in fp32.
+// Every activation lives in HBM as split-fp16 planes [2][rows][K] (hi + lo carries
+// 22 significand bits), including the residual stream.
 #include <algorithm>
 
 #include "attention_tc.cuh"
@@ -100,7 +100,6 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
 
     Carver w;
     const size_t o_x0 = w.take((size_t)rows * C * 2);
-    const size_t o_xf = w.take((size_t)rows * H * 4);
     const size_t o_xh = w.take((size_t)2 * rows * H * 2);
     const size_t o_qkv = w.take((size_t)2 * rows * 3 * H * 2);
     const size_t o_att = w.take((size_t)2 * rows * H * 2);
@@ -110,7 +109,6 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     PPGS_CHECK(ensure_workspace(e, w.off));
     char* ws = static_cast<char*>(e->workspace);
     __half* x0 = reinterpret_cast<__half*>(ws + o_x0);
-    float* xf = reinterpret_cast<float*>(ws + o_xf);
     __half* xh = reinterpret_cast<__half*>(ws + o_xh);
     __half* qkv = reinterpret_cast<__half*>(ws + o_qkv);
     __half* att = reinterpret_cast<__half*>(ws + o_att);
@@ -125,6 +123,11 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     PPGS_CHECK(make_plane_map(&map_x, xh, false, H, rows, 1, 2, H, 0, (uint64_t)rows * H, 128, planes));
     PPGS_CHECK(make_plane_map(&map_att, att, false, H, rows, 1, 2, H, 0, (uint64_t)rows * H, 128, planes));
     PPGS_CHECK(make_plane_map(&map_ff, ff, false, F, rows, 1, 2, F, 0, (uint64_t)rows * F, 128, planes));
+    // output tensor maps (TMA stores of the epilogues)
+    CUtensorMap out_x, out_qkv, out_ff;
+    PPGS_CHECK(make_store_map(&out_x, xh, H, rows, (uint64_t)rows * H));
+    PPGS_CHECK(make_store_map(&out_qkv, qkv, 3 * H, rows, (uint64_t)rows * 3 * H));
+    PPGS_CHECK(make_store_map(&out_ff, ff, F, rows, (uint64_t)rows * F));
 
     {
         dim3 grid(rows / 32, (C + 31) / 32);
@@ -146,10 +149,8 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
         GemmParams p = base;
         p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = (C + 63) / 64; p.a_planes = 1;
         p.N = H; p.scale = e->tc_conv_in.inv_scale; p.bias = e->conv_in_b; p.pe = e->pe;
-        p.out_f32 = xf; p.ld_f32 = H; p.out_planes = xh; p.ld_planes = H;
-        p.plane_stride = (int64_t)rows * H;
         PPGS_CHECK(launch_gemm_tc(e, "tc_conv_in", 256, kEpiConvIn, map_x0, e->tc_conv_in.map_bn256,
-                                  p, stream));
+                                  &out_x, p, stream));
     }
     for (int layer = 0; layer < c.num_layers; ++layer) {
         const LayerWeights& L = e->layers[layer];
@@ -158,36 +159,34 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             GemmParams p = base;
             p.n_tiles = 3 * H / 256; p.cblocks = H / 64; p.a_planes = planes;
             p.N = 3 * H; p.scale = T.in_w.inv_scale; p.bias = L.in_b;
-            p.out_planes = qkv; p.ld_planes = 3 * H; p.plane_stride = (int64_t)rows * 3 * H;
-            PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, T.in_w.map_bn256, p, stream));
+            PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, T.in_w.map_bn256, &out_qkv,
+                                      p, stream));
         }
         PPGS_CHECK(launch_attention_tc(e, qkv, att, rows, plan, seqs_dev, planes, stream));
         {
             GemmParams p = base;
             p.n_tiles = 1; p.cblocks = H / 64; p.a_planes = planes;
-            p.N = H; p.scale = T.out_w.inv_scale; p.bias = L.out_b; p.residual = xf;
+            p.N = H; p.scale = T.out_w.inv_scale; p.bias = L.out_b;
+            p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
             p.gamma = L.n1_w; p.beta = L.n1_b;
-            p.out_f32 = xf; p.ld_f32 = H; p.out_planes = xh; p.ld_planes = H;
-            p.plane_stride = (int64_t)rows * H;
             PPGS_CHECK(launch_gemm_tc(e, "tc_out_proj_ln", 256, kEpiResLN, map_att, T.out_w.map_bn256,
-                                      p, stream));
+                                      &out_x, p, stream));
         }
         {
             GemmParams p = base;
             p.n_tiles = F / 256; p.cblocks = H / 64; p.a_planes = planes;
             p.N = F; p.scale = T.l1_w.inv_scale; p.bias = L.l1_b; p.relu = 1;
-            p.out_planes = ff; p.ld_planes = F; p.plane_stride = (int64_t)rows * F;
-            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn1", 256, kEpiPlanes, map_x, T.l1_w.map_bn256, p, stream));
+            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn1", 256, kEpiPlanes, map_x, T.l1_w.map_bn256, &out_ff,
+                                      p, stream));
         }
         {
             GemmParams p = base;
             p.n_tiles = 1; p.cblocks = F / 64; p.a_planes = planes;
-            p.N = H; p.scale = T.l2_w.inv_scale; p.bias = L.l2_b; p.residual = xf;
+            p.N = H; p.scale = T.l2_w.inv_scale; p.bias = L.l2_b;
+            p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
             p.gamma = L.n2_w; p.beta = L.n2_b;
-            p.out_f32 = xf; p.ld_f32 = H; p.out_planes = xh; p.ld_planes = H;
-            p.plane_stride = (int64_t)rows * H;
-            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn2_ln", 256, kEpiResLN, map_ff, T.l2_w.map_bn256, p,
-                                      stream));
+            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn2_ln", 256, kEpiResLN, map_ff, T.l2_w.map_bn256, &out_x,
+                                      p, stream));
         }
     }
     {
@@ -196,7 +195,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
         p.N = O; p.O = O; p.scale = e->tc_conv_out.inv_scale; p.bias = e->conv_out_b;
         p.ppg = out; p.T = plan.frames; p.softmax = softmax;
         PPGS_CHECK(launch_gemm_tc(e, "tc_conv_out_softmax", 64, kEpiConvOut, map_x,
-                                  e->tc_conv_out.map_bn64, p, stream));
+                                  e->tc_conv_out.map_bn64, nullptr, p, stream));
     }
     return PPGS_OK;
 }
