@@ -115,7 +115,7 @@ attention_planes_kernel(const __half* __restrict__ qkv, int64_t plane_stride, in
 //               then V chunks (64 keys) through a 4-slot ring that reuses the K ring
 //   warp 1      tcgen05.mma issuer: S_j = Q K_j^T into TMEM columns [128 j, 128 j + 128),
 //               then O += P_c V_c into columns [384, 512)
-//   warps 2-5   one query row per thread: row max over S (TMEM), p = exp2((s - max) c),
+//   warps 2-9   two threads per query row: row max over S (TMEM), p = exp2((s - max) c),
 //               split-fp16 P chunks written to the 128B-swizzled smem layout the MMA
 //               reads (2-slot ring that reuses the Q tile), final O / sum -> planes
 //
@@ -123,7 +123,7 @@ attention_planes_kernel(const __half* __restrict__ qkv, int64_t plane_stride, in
 // block, so the chunks of that block are converted to P first and the first P.V MMA
 // waits for them.
 // ---------------------------------------------------------------------------
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;   // producer + MMA + 8 softmax warps
 constexpr int kTile16K = 16384;                // [128 rows][64 fp16]
 constexpr int kQBytes = 4 * kTile16K;          // [d chunk 2][plane 2]
 constexpr int kKSlotBytes = 4 * kTile16K;
@@ -141,6 +141,13 @@ struct AttnParams {
     int64_t out_plane_stride;
     int* status;
 };
+
+// 2^x for x <= 0 (softmax exponents): one MUFU.EX2, flushes to zero on underflow
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ int chunk_order(int i, int nchunks) {
     if (nchunks <= 6) return i;
@@ -161,6 +168,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
     __shared__ __align__(8) uint64_t k_full[2], k_empty[2], p_full[2], p_empty[2];
     __shared__ __align__(8) uint64_t v_full[4], v_empty[4];
     __shared__ uint32_t tmem_slot;
+    __shared__ float row_part[2][128];   // per-row partial max / sum of the two halves
 
     const SeqInfo s = p.seqs[blockIdx.z];
     const int q0 = blockIdx.x * 128, head = blockIdx.y;
@@ -188,7 +196,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         for (int i = 0; i < 2; ++i) {
             mbar_init(&k_full[i], 1);
             mbar_init(&k_empty[i], 1);
-            mbar_init(&p_full[i], 4);
+            mbar_init(&p_full[i], 8);
             mbar_init(&p_empty[i], 1);
         }
         for (int i = 0; i < 4; ++i) {
@@ -287,6 +295,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
             else atomicExch(p.status, kStatusAttnTimeout);
         }
     } else {
+        // 8 softmax warps: a query row is shared by two threads (same TMEM lane
+        // quadrant, `half` = which 32 of every 64 keys / which 64 of the 128 output
+        // columns); row max and row sum are combined through shared memory.
+        const int half = (warp - 2) >> 2;
         const int quad = warp & 3, r = quad * 32 + lane, t = q0 + r;
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
         uint32_t raw[32];
@@ -296,17 +308,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         if (ok) {
             const int ngroups = (nkeys + 31) >> 5;
 #pragma unroll 1
-            for (int g = 0; g < ngroups; ++g) {
+            for (int g = half; g < ngroups; g += 2) {
                 tmem_ld_32x32(t_row + g * 32, raw);
                 tmem_wait_ld();
+                const bool full = g * 32 + 32 <= nkeys && (!p.causal || g * 32 + 31 <= q0);
+                if (full) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int key = g * 32 + j;
-                    const bool allowed = key < nkeys && (!p.causal || key <= t);
-                    mx = fmaxf(mx, allowed ? __uint_as_float(raw[j]) : -FLT_MAX);
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(raw[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int key = g * 32 + j;
+                        const bool allowed = key < nkeys && (!p.causal || key <= t);
+                        mx = fmaxf(mx, allowed ? __uint_as_float(raw[j]) : -FLT_MAX);
+                    }
                 }
             }
         }
+        row_part[half][r] = mx;
+        named_bar_sync(1, 256);
+        mx = fmaxf(row_part[0][r], row_part[1][r]);
+        named_bar_sync(1, 256);   // row_part is reused for the row sums
+        const float mc = mx * p.scale_log2e;
         float sum = 0.f;
         const uint32_t p_base = smem_u32(q_smem);
         const uint32_t row_off = (uint32_t)r * 128, sw = (uint32_t)(r & 7);
@@ -315,62 +338,63 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
             const int c = chunk_order(i, nchunks), slot = i & 1;
             if (!mbar_wait(&p_empty[slot], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
             const uint32_t p_slot = p_base + slot * kPSlotBytes;
+            const int key0 = c * 64 + half * 32;
+            tmem_ld_32x32(t_row + key0, raw);
+            tmem_wait_ld();
+            uint32_t h[16], l[16];
+            const bool full = key0 + 32 <= nkeys && (!p.causal || key0 + 31 <= q0);
+            if (full) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld_32x32(t_row + c * 64 + half * 32, raw);
-                tmem_wait_ld();
-                uint32_t h[16], l[16];
+                for (int j = 0; j < 16; ++j) {
+                    const float e0 = fast_exp2(fmaf(__uint_as_float(raw[2 * j]), p.scale_log2e, -mc));
+                    const float e1 = fast_exp2(fmaf(__uint_as_float(raw[2 * j + 1]), p.scale_log2e, -mc));
+                    sum += e0 + e1;
+                    split2_f16(e0, e1, h[j], l[j]);
+                }
+            } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     float pv[2];
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        const int key = c * 64 + half * 32 + 2 * j + q;
+                        const int key = key0 + 2 * j + q;
                         const bool allowed = key < nkeys && (!p.causal || key <= t);
-                        const float e = exp2f((__uint_as_float(raw[2 * j + q]) - mx) * p.scale_log2e);
+                        const float e = fast_exp2(fmaf(__uint_as_float(raw[2 * j + q]), p.scale_log2e, -mc));
                         pv[q] = allowed ? e : 0.f;
-                        sum += pv[q];
                     }
-                    __half h0, l0, h1, l1;
-                    split_f16(pv[0], h0, l0);
-                    split_f16(pv[1], h1, l1);
-                    h[j] = pack_half2(h0, h1);
-                    l[j] = pack_half2(l0, l1);
+                    sum += pv[0] + pv[1];
+                    split2_f16(pv[0], pv[1], h[j], l[j]);
                 }
+            }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t unit = (uint32_t)(half * 4 + u) ^ sw;
-                    const uint32_t addr = p_slot + row_off + unit * 16;
-                    st_shared_v4(addr, h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
-                    st_shared_v4(addr + kTile16K, l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
-                }
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t unit = (uint32_t)(half * 4 + u) ^ sw;
+                const uint32_t addr = p_slot + row_off + unit * 16;
+                st_shared_v4(addr, h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+                st_shared_v4(addr + kTile16K, l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
             }
             fence_proxy_async_smem();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[slot]);
         }
+        row_part[half][r] = sum;
+        named_bar_sync(1, 256);
+        sum = row_part[0][r] + row_part[1][r];
         if (ok && !mbar_wait(&o_full, 0)) ok = false;
         tcgen05_fence_after();
         if (ok) {
             const float inv = sum > 0.f ? 1.f / sum : 0.f;
-            float y[32];
-            __half* dst = p.out + (out_row0 + r) * p.H + head * 128;
+            __half* dst = p.out + (out_row0 + r) * p.H + head * 128 + half * 64;
 #pragma unroll 1
-            for (int g = 0; g < 4; ++g) {
-                tmem_ld_32x32(t_row + kOCol + g * 32, raw);
+            for (int g = 0; g < 2; ++g) {
+                tmem_ld_32x32(t_row + kOCol + half * 64 + g * 32, raw);
                 tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(raw[j]) * inv;
                 uint32_t h[16], l[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    __half h0, l0, h1, l1;
-                    split_f16(y[2 * j], h0, l0);
-                    split_f16(y[2 * j + 1], h1, l1);
-                    h[j] = pack_half2(h0, h1);
-                    l[j] = pack_half2(l0, l1);
-                }
+                for (int j = 0; j < 16; ++j)
+                    split2_f16(__uint_as_float(raw[2 * j]) * inv, __uint_as_float(raw[2 * j + 1]) * inv,
+                               h[j], l[j]);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     reinterpret_cast<uint4*>(dst + g * 32)[u] = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);

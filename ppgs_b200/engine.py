@@ -81,8 +81,9 @@ class Engine:
 
     def __del__(self):
         handle = getattr(self, '_handle', None)
-        if handle is not None and handle.value and _lib is not None:
-            _lib.lib.ppgs_engine_destroy(handle)
+        lib = getattr(_lib, 'lib', None) if _lib is not None else None   # None at interpreter exit
+        if handle is not None and handle.value and lib is not None:
+            lib.ppgs_engine_destroy(handle)
             self._handle = None
 
     # -- weights ----------------------------------------------------------
