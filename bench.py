@@ -213,7 +213,8 @@ def main():
     host = [O.synthetic_audio(BATCH, SAMPLES, 100 + rank * rotate + i).squeeze(1).pin_memory()
             for i in range(rotate)]
     dev = [h.to(device) for h in host]
-    out_host = torch.empty(BATCH, O_OUT, FRAMES, dtype=torch.float32).pin_memory()
+    out_host = [torch.empty(BATCH, O_OUT, FRAMES, dtype=torch.float32).pin_memory()
+                for _ in range(2)]
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -227,6 +228,7 @@ def main():
         start.record()
         for i in range(n):
             fn(i)
+        engine.wait()      # pipelined host requests: the last D2H has landed
         stop.record()
         barrier()
         ms = torch.tensor([start.elapsed_time(stop)], device=device)
@@ -235,11 +237,16 @@ def main():
         return ms.item()
 
     device_step = lambda i: engine.from_audio(dev[i % rotate])                      # noqa: E731
-    host_step = lambda i: engine.from_audio_host(host[i % rotate], out=out_host)    # noqa: E731
+    # reference-facing call with HOST buffers; requests are pipelined two deep (the
+    # H2D of step i+1 and the D2H of step i-1 overlap the kernels of step i), every
+    # step still copies its own input in and its own result out
+    host_step = lambda i: engine.from_audio_host(                                   # noqa: E731
+        host[i % rotate], out=out_host[i % 2], wait=False)
 
     for i in range(warmup):
         device_step(i)
         host_step(i)
+    engine.wait()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -331,7 +338,8 @@ def main():
         'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms / steps,
                 'h2d_bytes_per_step': BATCH * SAMPLES * 4 * world,
                 'd2h_bytes_per_step': BATCH * O_OUT * FRAMES * 4 * world,
-                'api': 'ppgs_from_audio_host (C ABI), pinned host buffers'},
+                'api': 'ppgs_from_audio_host_submit + ppgs_engine_wait (C ABI), pinned host '
+                       'buffers, 2 requests in flight'},
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': roofline,

@@ -141,6 +141,18 @@ int ppgs_from_audio_host(ppgs_engine* engine, const float* audio_host, int batch
                          int softmax, int legacy_mode, float* out_host,
                          void* stream);
 
+/* Pipelined form of `ppgs_from_audio_host` for serving / file loops (the batching
+ * loop of ppgs/core.py:325-365): enqueue the request and return.  Two requests can be
+ * in flight per engine — the H2D copy of request i+1 and the D2H copy of request
+ * i-1 run on the engine's copy streams while the kernels of request i run on
+ * `stream`.  A third submit blocks until the oldest request has landed.  `out_host`
+ * is valid after `ppgs_engine_wait`, which blocks until every submitted request
+ * has completed.  Host buffers must stay alive (and should be pinned) until then. */
+int ppgs_from_audio_host_submit(ppgs_engine* engine, const float* audio_host, int batch,
+                                int64_t samples, const int64_t* lengths_host, int softmax,
+                                int legacy_mode, float* out_host, void* stream);
+int ppgs_engine_wait(ppgs_engine* engine);
+
 /* Number of kernels this library launched since the engine was created
  * (bench.py's `gpu_launches`). */
 int64_t ppgs_engine_launch_count(const ppgs_engine* engine);

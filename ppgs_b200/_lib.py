@@ -53,6 +53,8 @@ SYMBOLS = {
     'ppgs_transformer_forward': (_i, [_vp, _vp, _i, _i, _c.POINTER(_i64), _i, _i, _vp, _vp]),
     'ppgs_from_audio': (_i, [_vp, _vp, _i, _i64, _i64, _c.POINTER(_i64), _i, _i, _vp, _vp]),
     'ppgs_from_audio_host': (_i, [_vp, _vp, _i, _i64, _c.POINTER(_i64), _i, _i, _vp, _vp]),
+    'ppgs_from_audio_host_submit': (_i, [_vp, _vp, _i, _i64, _c.POINTER(_i64), _i, _i, _vp, _vp]),
+    'ppgs_engine_wait': (_i, [_vp]),
     'ppgs_engine_launch_count': (_i64, [_vp]),
     'ppgs_engine_workspace_bytes': (_sz, [_vp]),
     'ppgs_engine_set_profiling': (_i, [_vp, _i]),

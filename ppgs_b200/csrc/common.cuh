@@ -79,7 +79,7 @@ struct TcWeight {
     __half* planes = nullptr;
     const float* inv_scale = nullptr;
     int N = 0, C = 0, taps = 1;
-    CUtensorMap map_bn256, map_bn64;   // box rows 256 / 64
+    CUtensorMap map_bn256, map_bn128, map_bn64;   // box rows 256 / 128 (CTA-pair halves) / 64
 };
 
 struct TcLayer {
@@ -119,6 +119,8 @@ struct ppgs_engine {
     bool tc_maps_ready = false;
     int* status_dev = nullptr;   // kernels report barrier time-outs here
     int attention_impl = 1;      // 1 = tcgen05 kernel, 0 = CUDA-core kernel (validation)
+    int gemm_pair = 1;           // 1 = CTA-pair (cta_group::2) GEMMs at BN = 256
+    unsigned long long* trace_dev = nullptr;   // [8 kernel kinds][8] cycle counters (PPGS_B200_TRACE=1)
 
     ppgs::MelTables mel;
     std::vector<float> host_window;   // optional override ("frontend.window")
@@ -129,9 +131,25 @@ struct ppgs_engine {
     // pinned staging for per-call tables
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
-    // device staging for the host-buffer entry point
+    // device staging for the device-buffer fused entry point (mel features)
     void* io_dev = nullptr;
     size_t io_dev_bytes = 0;
+    // host-buffer entry points: two request slots so that the H2D copy of request
+    // i+1 and the D2H copy of request i-1 overlap the kernels of request i
+    struct HostSlot {
+        void* dev = nullptr;
+        size_t bytes = 0;
+        cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+        bool busy = false;
+    };
+    HostSlot host_slots[2];
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    uint64_t submitted = 0;
+    // plan tables already resident on the device (skip the upload when a call
+    // repeats the previous call's shapes and lengths)
+    std::vector<ppgs::SeqInfo> cached_plan;
+    void* cached_plan_dev = nullptr;
+    cudaEvent_t plan_uploaded = nullptr;
 
     int64_t launches = 0;
 

@@ -43,9 +43,9 @@ int ensure_status(ppgs_engine* e) {
 
 extern "C" int ppgs_debug_gemm(ppgs_engine* e, const float* a_host, const float* w_host,
                                const float* bias_host, int M, int N, int C, int taps, int bn,
-                               int a_planes, int b_planes, float* out_host) {
+                               int pair, int a_planes, int b_planes, float* out_host) {
     if (!e || !a_host || !w_host || !bias_host || !out_host || M <= 0 || M % 128 || C % 8 ||
-        N <= 0 || taps <= 0 || (taps & 1) == 0) {
+        N <= 0 || taps <= 0 || (taps & 1) == 0 || (pair && (M % 256 || bn != 256))) {
         set_error("debug_gemm: bad argument");
         return PPGS_E_INVALID;
     }
@@ -73,7 +73,7 @@ extern "C" int ppgs_debug_gemm(ppgs_engine* e, const float* a_host, const float*
     PPGS_CHECK(tc::make_plane_map(&map_a, a_dev.as<__half>(), false, C, M, 1, 2, C, 0,
                                   (uint64_t)M * C, 128, a_planes));
     PPGS_CHECK(tc::make_plane_map(&map_b, w_dev.as<__half>(), true, C, N, taps, 2, C,
-                                  (uint64_t)N * C, (uint64_t)taps * N * C, bn, b_planes));
+                                  (uint64_t)N * C, (uint64_t)taps * N * C, pair ? bn / 2 : bn, b_planes));
     tc::GemmParams p;
     p.m_tiles = M / 128;
     p.n_tiles = (N + bn - 1) / bn;
@@ -82,6 +82,7 @@ extern "C" int ppgs_debug_gemm(ppgs_engine* e, const float* a_host, const float*
     p.cblocks = (C + 63) / 64;
     p.a_planes = a_planes;
     p.b_planes = b_planes;
+    p.pair = pair;
     p.N = N;
     p.scale = scale_dev.as<float>();
     p.bias = bias_dev.as<float>();
@@ -138,5 +139,21 @@ extern "C" int ppgs_debug_attention(ppgs_engine* e, const float* qkv_host, int r
     const size_t plane = (size_t)rows * H;
     for (size_t i = 0; i < plane; ++i)
         out_host[i] = __half2float(out_planes[i]) + __half2float(out_planes[plane + i]);
+    return PPGS_OK;
+}
+
+extern "C" int ppgs_debug_trace(ppgs_engine* e, unsigned long long* out64) {
+    if (!e || !out64) {
+        set_error("debug_trace: NULL argument");
+        return PPGS_E_INVALID;
+    }
+    if (!e->trace_dev) {
+        set_error("debug_trace: create the engine with PPGS_B200_TRACE=1");
+        return PPGS_E_STATE;
+    }
+    PPGS_CUDA(cudaSetDevice(e->device));
+    PPGS_CUDA(cudaDeviceSynchronize());
+    PPGS_CUDA(cudaMemcpy(out64, e->trace_dev, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    PPGS_CUDA(cudaMemset(e->trace_dev, 0, 64 * sizeof(unsigned long long)));
     return PPGS_OK;
 }

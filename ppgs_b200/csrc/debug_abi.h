@@ -10,17 +10,23 @@ extern "C" {
 
 /* out[m][n] = bias[n] + sum_{tap,c} A[m + tap - taps/2][c] * W[n][c][tap]
  * (rows outside [0, M) read as zero), through the tcgen05 GEMM with tile width
- * `bn` and `a_planes` / `b_planes` split-fp16 planes per operand.
+ * `bn` (`pair` = 1: the CTA-pair cta_group::2 kernel, needs M % 256 == 0 and bn = 256)
+ * and `a_planes` / `b_planes` split-fp16 planes per operand.
  * A: (M, C) fp32, M % 128 == 0, C % 8 == 0.  W: (N, C, taps) fp32 (torch Conv1d
  * layout; (N, C) when taps == 1). */
 int ppgs_debug_gemm(ppgs_engine* engine, const float* a_host, const float* w_host,
-                    const float* bias_host, int M, int N, int C, int taps, int bn, int a_planes,
-                    int b_planes, float* out_host);
+                    const float* bias_host, int M, int N, int C, int taps, int bn, int pair,
+                    int a_planes, int b_planes, float* out_host);
 
 /* One attention call on host data: qkv (rows, 3H) fp32 for one sequence of
  * `tensor_len` rows (rows % 128 == 0) with `valid_len` unmasked keys. */
 int ppgs_debug_attention(ppgs_engine* engine, const float* qkv_host, int rows, int tensor_len,
                          int valid_len, int planes, int use_tensor_cores, float* out_host);
+
+/* Copies out and clears the 64 cycle counters the GEMM kernels accumulate when the
+ * engine was created with PPGS_B200_TRACE=1 (8 kernel slots x 8 counters, see
+ * GemmParams::trace).  Synchronises the device. */
+int ppgs_debug_trace(ppgs_engine* engine, unsigned long long* out64);
 
 #ifdef __cplusplus
 }

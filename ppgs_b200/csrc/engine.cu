@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -31,6 +32,7 @@ int ensure_workspace(ppgs_engine* e, size_t bytes) {
         PPGS_CUDA(cudaFree(e->workspace));
         e->workspace = nullptr;
         e->workspace_bytes = 0;
+        e->cached_plan_dev = nullptr;
     }
     const size_t grown = bytes + bytes / 8;
     PPGS_CUDA(cudaMalloc(&e->workspace, grown));
@@ -98,9 +100,14 @@ int upload_plan(ppgs_engine* e, const ForwardPlan& plan, SeqInfo* seqs_dev, int*
                 cudaStream_t stream) {
     const size_t seq_bytes = plan.seqs.size() * sizeof(SeqInfo);
     const size_t tiles = plan.rows / 128;
-    // The staging buffer is reused by the next call: make sure the previous
-    // call's async copy has been consumed.
-    PPGS_CUDA(cudaStreamSynchronize(stream));
+    // same shapes and lengths as the previous call, same device location: the tables
+    // are already there (steady-state serving loops never touch the staging buffer)
+    if (e->cached_plan_dev == seqs_dev && e->cached_plan.size() == plan.seqs.size() &&
+        memcmp(e->cached_plan.data(), plan.seqs.data(), seq_bytes) == 0)
+        return PPGS_OK;
+    // the pinned staging buffer is reused: the previous upload must have been consumed
+    if (!e->plan_uploaded) PPGS_CUDA(cudaEventCreateWithFlags(&e->plan_uploaded, cudaEventDisableTiming));
+    else PPGS_CUDA(cudaEventSynchronize(e->plan_uploaded));
     PPGS_CHECK(ensure_pinned(e, seq_bytes + tiles * sizeof(int)));
     char* p = static_cast<char*>(e->pinned);
     memcpy(p, plan.seqs.data(), seq_bytes);
@@ -113,6 +120,9 @@ int upload_plan(ppgs_engine* e, const ForwardPlan& plan, SeqInfo* seqs_dev, int*
     PPGS_CUDA(cudaMemcpyAsync(seqs_dev, p, seq_bytes, cudaMemcpyHostToDevice, stream));
     PPGS_CUDA(cudaMemcpyAsync(tile_seq_dev, tile_seq, tiles * sizeof(int), cudaMemcpyHostToDevice,
                               stream));
+    PPGS_CUDA(cudaEventRecord(e->plan_uploaded, stream));
+    e->cached_plan = plan.seqs;
+    e->cached_plan_dev = seqs_dev;
     return PPGS_OK;
 }
 
@@ -379,6 +389,12 @@ int ppgs_engine_create(const ppgs_model_config* cfg, int device, ppgs_engine** o
     e->cfg = c;
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
+    if (const char* v = getenv("PPGS_B200_PAIR")) e->gemm_pair = atoi(v) != 0;      // validation switches
+    if (const char* v = getenv("PPGS_B200_ATTENTION")) e->attention_impl = atoi(v) != 0;
+    if (const char* v = getenv("PPGS_B200_TRACE")) {
+        if (atoi(v) != 0 && cudaMalloc(&e->trace_dev, 64 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(e->trace_dev, 0, 64 * sizeof(unsigned long long));
+    }
     *out = e;
     return PPGS_OK;
 }
@@ -389,8 +405,18 @@ void ppgs_engine_destroy(ppgs_engine* e) {
     cudaDeviceSynchronize();
     cudaFree(e->blob);
     cudaFree(e->status_dev);
+    cudaFree(e->trace_dev);
     cudaFree(e->workspace);
     cudaFree(e->io_dev);
+    for (auto& slot : e->host_slots) {
+        cudaFree(slot.dev);
+        if (slot.h2d_done) cudaEventDestroy(slot.h2d_done);
+        if (slot.compute_done) cudaEventDestroy(slot.compute_done);
+        if (slot.d2h_done) cudaEventDestroy(slot.d2h_done);
+    }
+    if (e->copy_in) cudaStreamDestroy(e->copy_in);
+    if (e->copy_out) cudaStreamDestroy(e->copy_out);
+    if (e->plan_uploaded) cudaEventDestroy(e->plan_uploaded);
     cudaFreeHost(e->pinned);
     cudaFree(e->mel.window);
     cudaFree(e->mel.tw512);
@@ -656,10 +682,61 @@ int ppgs_from_audio(ppgs_engine* e, const float* audio, int batch, int64_t sampl
                              static_cast<__half*>(e->io_dev), static_cast<cudaStream_t>(stream));
 }
 
-int ppgs_from_audio_host(ppgs_engine* e, const float* audio, int batch, int64_t samples,
-                         const int64_t* lengths, int softmax, int legacy_mode, float* out,
-                         void* stream_) {
-    PPGS_ENTER(e);
+// One request slot: H2D on the engine's copy-in stream, kernels on the caller's
+// stream, D2H on the copy-out stream, chained by events.
+static int submit_host(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                       const int64_t* lengths, int softmax, int legacy_mode, float* out,
+                       cudaStream_t stream, ppgs_engine::HostSlot** used) {
+    if (!e->copy_in) {
+        PPGS_CUDA(cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));
+        PPGS_CUDA(cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking));
+    }
+    ppgs_engine::HostSlot& slot = e->host_slots[e->submitted & 1];
+    if (!slot.h2d_done) {
+        PPGS_CUDA(cudaEventCreateWithFlags(&slot.h2d_done, cudaEventDisableTiming));
+        PPGS_CUDA(cudaEventCreateWithFlags(&slot.compute_done, cudaEventDisableTiming));
+        PPGS_CUDA(cudaEventCreateWithFlags(&slot.d2h_done, cudaEventDisableTiming));
+    }
+    if (slot.busy) {   // the request that used this slot two submissions ago
+        PPGS_CUDA(cudaEventSynchronize(slot.d2h_done));
+        slot.busy = false;
+    }
+    const int64_t frames = samples / kHopSamples;
+    const size_t audio_bytes = align256((size_t)batch * samples * 4);
+    const size_t mel_bytes = align256((size_t)batch * kMelChannels * frames * 2);
+    const size_t out_bytes = align256((size_t)batch * e->cfg.output_channels * frames * 4);
+    const size_t need = audio_bytes + mel_bytes + out_bytes;
+    if (need > slot.bytes) {
+        PPGS_CUDA(cudaDeviceSynchronize());
+        PPGS_CUDA(cudaFree(slot.dev));
+        slot.dev = nullptr;
+        slot.bytes = 0;
+        PPGS_CUDA(cudaMalloc(&slot.dev, need));
+        slot.bytes = need;
+    }
+    char* io = static_cast<char*>(slot.dev);
+    float* audio_dev = reinterpret_cast<float*>(io);
+    __half* mel_dev = reinterpret_cast<__half*>(io + audio_bytes);
+    float* out_dev = reinterpret_cast<float*>(io + audio_bytes + mel_bytes);
+    PPGS_CUDA(cudaMemcpyAsync(audio_dev, audio, (size_t)batch * samples * 4,
+                              cudaMemcpyHostToDevice, e->copy_in));
+    PPGS_CUDA(cudaEventRecord(slot.h2d_done, e->copy_in));
+    PPGS_CUDA(cudaStreamWaitEvent(stream, slot.h2d_done, 0));
+    PPGS_CHECK(from_audio_device(e, audio_dev, batch, samples, samples, lengths, softmax,
+                                 legacy_mode, out_dev, mel_dev, stream));
+    PPGS_CUDA(cudaEventRecord(slot.compute_done, stream));
+    PPGS_CUDA(cudaStreamWaitEvent(e->copy_out, slot.compute_done, 0));
+    PPGS_CUDA(cudaMemcpyAsync(out, out_dev, (size_t)batch * e->cfg.output_channels * frames * 4,
+                              cudaMemcpyDeviceToHost, e->copy_out));
+    PPGS_CUDA(cudaEventRecord(slot.d2h_done, e->copy_out));
+    slot.busy = true;
+    e->submitted += 1;
+    if (used) *used = &slot;
+    return PPGS_OK;
+}
+
+static int check_host_args(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                           float* out) {
     PPGS_CHECK(require_ready(e));
     if (!audio || !out || batch <= 0 || samples <= 0) {
         set_error("from_audio_host: bad argument");
@@ -669,24 +746,39 @@ int ppgs_from_audio_host(ppgs_engine* e, const float* audio, int batch, int64_t 
         set_error("from_audio_host: model does not take mel features");
         return PPGS_E_INVALID;
     }
+    return PPGS_OK;
+}
+
+int ppgs_from_audio_host(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                         const int64_t* lengths, int softmax, int legacy_mode, float* out,
+                         void* stream_) {
+    PPGS_ENTER(e);
+    PPGS_CHECK(check_host_args(e, audio, batch, samples, out));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const int64_t frames = samples / kHopSamples;
-    const size_t audio_bytes = align256((size_t)batch * samples * 4);
-    const size_t mel_bytes = align256((size_t)batch * kMelChannels * frames * 2);
-    const size_t out_bytes = align256((size_t)batch * e->cfg.output_channels * frames * 4);
-    PPGS_CHECK(ensure_io(e, audio_bytes + mel_bytes + out_bytes));
-    char* io = static_cast<char*>(e->io_dev);
-    float* audio_dev = reinterpret_cast<float*>(io);
-    __half* mel_dev = reinterpret_cast<__half*>(io + audio_bytes);
-    float* out_dev = reinterpret_cast<float*>(io + audio_bytes + mel_bytes);
-    PPGS_CUDA(cudaMemcpyAsync(audio_dev, audio, (size_t)batch * samples * 4,
-                              cudaMemcpyHostToDevice, stream));
-    PPGS_CHECK(from_audio_device(e, audio_dev, batch, samples, samples, lengths, softmax,
-                                 legacy_mode, out_dev, mel_dev, stream));
-    PPGS_CUDA(cudaMemcpyAsync(out, out_dev, (size_t)batch * e->cfg.output_channels * frames * 4,
-                              cudaMemcpyDeviceToHost, stream));
-    PPGS_CUDA(cudaStreamSynchronize(stream));
+    ppgs_engine::HostSlot* slot = nullptr;
+    PPGS_CHECK(submit_host(e, audio, batch, samples, lengths, softmax, legacy_mode, out, stream, &slot));
+    PPGS_CUDA(cudaEventSynchronize(slot->d2h_done));
+    slot->busy = false;
     return check_status(e, stream);
+}
+
+int ppgs_from_audio_host_submit(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                                const int64_t* lengths, int softmax, int legacy_mode, float* out,
+                                void* stream_) {
+    PPGS_ENTER(e);
+    PPGS_CHECK(check_host_args(e, audio, batch, samples, out));
+    return submit_host(e, audio, batch, samples, lengths, softmax, legacy_mode, out,
+                       static_cast<cudaStream_t>(stream_), nullptr);
+}
+
+int ppgs_engine_wait(ppgs_engine* e) {
+    PPGS_ENTER(e);
+    for (auto& slot : e->host_slots) {
+        if (!slot.busy) continue;
+        PPGS_CUDA(cudaEventSynchronize(slot.d2h_done));
+        slot.busy = false;
+    }
+    return check_status(e, nullptr);
 }
 
 }  // extern "C"

@@ -22,11 +22,15 @@ constexpr int kGemmThreads = 320;      // producer + MMA + 8 epilogue warps
 constexpr int kPlaneABytes = kBM * kBK * 2;   // 16 KB
 constexpr int kStageOutBytes = 2 * kBM * 32 * 2;   // [plane 2][128 rows][32 cols] fp16 = 16 KB
 
-template <int BN>
+// PAIR: two CTAs of a cluster form one cta_group::2 MMA (M = 256): each loads its
+// own 128 rows of A and HALF of the W tile, so a stage is 64 KB instead of 96 KB
+// per SM at BN = 256 and three stages fit.
+template <int BN, bool PAIR>
 struct GemmShape {
-    static constexpr int kPlaneBBytes = BN * kBK * 2;
+    static constexpr int kBRows = PAIR ? BN / 2 : BN;          // W rows held by this CTA
+    static constexpr int kPlaneBBytes = kBRows * kBK * 2;
     static constexpr int kStageBytes = 2 * kPlaneABytes + 2 * kPlaneBBytes;
-    static constexpr int kStages = (BN == 256) ? 2 : (BN == 128) ? 3 : 4;
+    static constexpr int kStages = PAIR ? 3 : (BN == 256) ? 2 : (BN == 128) ? 3 : 4;
     static constexpr int kAccCols = BN;                      // power of two >= 32
     static constexpr int kTmemCols = 2 * kAccCols;
     static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 2 * kStageOutBytes;
@@ -57,16 +61,29 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* map_out, unsi
     }
 }
 
+// 32 consecutive fp32 parameters (bias / gamma / beta / PE row), same address in
+// every lane: 8 broadcast 128-bit loads through the read-only path
+__device__ __forceinline__ void load_params32(const float* src, float (&out)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + j);
+        out[4 * j] = v.x;
+        out[4 * j + 1] = v.y;
+        out[4 * j + 2] = v.z;
+        out[4 * j + 3] = v.w;
+    }
+}
+
 __device__ __forceinline__ void split32(const float (&y)[32], uint32_t (&h)[16], uint32_t (&l)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) split2_f16(y[2 * i], y[2 * i + 1], h[i], l[i]);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
-    using Shape = GemmShape<BN>;
+    using Shape = GemmShape<BN, PAIR>;
     constexpr int kStages = Shape::kStages;
     constexpr int kChunks = BN / 32;
     // 128B-swizzled TMA / UMMA tiles need 1024-byte alignment: the declaration
@@ -81,7 +98,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __shared__ float ln_part[2][kBM];      // [epilogue set][row] partial row statistics
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    // work items: (m tile, n tile) per CTA, or (pair of m tiles, n tile) per CTA pair
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int total_tiles = (PAIR ? p.m_tiles / 2 : p.m_tiles) * p.n_tiles;
     const int num_kb = p.taps * p.cblocks;
     if (smem_u32(smem) & 1023u) {   // uniform across the CTA
         if (threadIdx.x == 0) atomicExch(p.status, kStatusBadAlignment);
@@ -95,13 +116,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], 8);
+            mbar_init(&tmem_empty_bar[i], PAIR ? 16 : 8);   // leader: epilogue warps of both CTAs
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<Shape::kTmemCols>(&tmem_slot);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_pair<Shape::kTmemCols>(&tmem_slot);
+        else tmem_alloc<Shape::kTmemCols>(&tmem_slot);
+    }
     tcgen05_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();   // peer barriers are initialised before any remote signal
+    else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
@@ -114,39 +139,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
-            for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-                const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
+            long long t_wait = 0;
+            const long long t_begin = clock64();
+            for (int tile = worker; tile < total_tiles && ok; tile += workers) {
+                const int m_unit = tile / p.n_tiles, n_blk = tile - m_unit * p.n_tiles;
+                const int m_blk = PAIR ? 2 * m_unit + (int)rank : m_unit;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-                    if (!mbar_wait(&empty_bar[stage], phase ^ 1)) {
+                    const long long t0 = clock64();
+                    const bool got = mbar_wait(&empty_bar[stage], phase ^ 1);
+                    t_wait += clock64() - t0;
+                    if (!got) {
                         atomicExch(p.status, kStatusProducerTimeout);
                         ok = false;
                         break;
                     }
                     unsigned char* sa = smem + (size_t)stage * Shape::kStageBytes;
                     unsigned char* sb = sa + 2 * kPlaneABytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-                    tma_load_3d(sa, &map_a, &full_bar[stage], cb * kBK, m_blk * kBM + tap - p.half, 0);
-                    tma_load_4d(sb, &map_b, &full_bar[stage], cb * kBK, n_blk * BN, tap, 0);
+                    if (PAIR) {
+                        // the leader's barrier collects the bytes of both CTAs
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
+                        const uint32_t leader_bar = map_to_cta(&full_bar[stage], 0);
+                        tma_load_3d_pair(sa, &map_a, leader_bar, cb * kBK, m_blk * kBM + tap - p.half, 0);
+                        tma_load_4d_pair(sb, &map_b, leader_bar, cb * kBK,
+                                         n_blk * BN + (int)rank * Shape::kBRows, tap, 0);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                        tma_load_3d(sa, &map_a, &full_bar[stage], cb * kBK, m_blk * kBM + tap - p.half, 0);
+                        tma_load_4d(sb, &map_b, &full_bar[stage], cb * kBK, n_blk * BN, tap, 0);
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
             }
+            if (p.trace) {
+                atomicAdd(p.trace + 5, (unsigned long long)t_wait);
+                atomicAdd(p.trace + 6, (unsigned long long)(clock64() - t_begin));
+                atomicAdd(p.trace + 7, 1ull);
+            }
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(kBM, BN);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * kBM : kBM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
             bool ok = true;
-            for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++iter) {
+            long long t_empty = 0, t_full = 0;
+            const long long t_begin = clock64();
+            for (int tile = worker; tile < total_tiles && ok; tile += workers, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
-                if (!mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1)) {
+                const long long t0 = clock64();
+                const bool got = mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                t_empty += clock64() - t0;
+                if (!got) {
                     atomicExch(p.status, kStatusMmaTimeout);
                     break;
                 }
@@ -154,7 +204,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t d_tmem = tmem_base + acc * Shape::kAccCols;
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    if (!mbar_wait(&full_bar[stage], phase)) {
+                    const long long t1 = clock64();
+                    const bool landed = mbar_wait(&full_bar[stage], phase);
+                    t_full += clock64() - t1;
+                    if (!landed) {
                         atomicExch(p.status, kStatusMmaTimeout);
                         ok = false;
                         break;
@@ -169,20 +222,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint32_t koff = k * 32;   // 16 fp16 along K inside the swizzle row
                         const uint64_t da0 = smem_desc_kmajor_sw128(a0 + koff);
                         const uint64_t db0 = smem_desc_kmajor_sw128(b0 + koff);
-                        umma_f16(d_tmem, da0, db0, idesc, accumulate);
+                        if (PAIR) {
+                            umma_f16_pair(d_tmem, da0, db0, idesc, accumulate);
+                            if (p.b_planes == 2)
+                                umma_f16_pair(d_tmem, da0, smem_desc_kmajor_sw128(b1 + koff), idesc, 1);
+                            if (p.a_planes == 2)
+                                umma_f16_pair(d_tmem, smem_desc_kmajor_sw128(a1 + koff), db0, idesc, 1);
+                        } else {
+                            umma_f16(d_tmem, da0, db0, idesc, accumulate);
+                            if (p.b_planes == 2)
+                                umma_f16(d_tmem, da0, smem_desc_kmajor_sw128(b1 + koff), idesc, 1);
+                            if (p.a_planes == 2)
+                                umma_f16(d_tmem, smem_desc_kmajor_sw128(a1 + koff), db0, idesc, 1);
+                        }
                         accumulate = 1;
-                        if (p.b_planes == 2)
-                            umma_f16(d_tmem, da0, smem_desc_kmajor_sw128(b1 + koff), idesc, 1);
-                        if (p.a_planes == 2)
-                            umma_f16(d_tmem, smem_desc_kmajor_sw128(a1 + koff), db0, idesc, 1);
                     }
-                    umma_commit(&empty_bar[stage]);   // frees the smem slot when the MMAs retire
+                    // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+                    if (PAIR) umma_commit_pair(&empty_bar[stage]);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                if (ok) umma_commit(&tmem_full_bar[acc]);
+                if (ok) {
+                    if (PAIR) umma_commit_pair(&tmem_full_bar[acc]);
+                    else umma_commit(&tmem_full_bar[acc]);
+                }
+            }
+            if (p.trace) {
+                atomicAdd(p.trace + 0, (unsigned long long)t_empty);
+                atomicAdd(p.trace + 1, (unsigned long long)t_full);
+                atomicAdd(p.trace + 2, (unsigned long long)(clock64() - t_begin));
             }
         }
     } else {
@@ -196,11 +267,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         unsigned char* stage = stage_out + set * kStageOutBytes;
         const float scale = *p.scale;
         int iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-            const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
+        long long t_wait = 0;
+        const long long t_begin = clock64();
+        for (int tile = worker; tile < total_tiles; tile += workers, ++iter) {
+            const int m_unit = tile / p.n_tiles, n_blk = tile - m_unit * p.n_tiles;
+            const int m_blk = PAIR ? 2 * m_unit + (int)rank : m_unit;
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
-            if (!mbar_wait(&tmem_full_bar[acc], acc_phase)) {
+            const long long t0 = clock64();
+            const bool ready = mbar_wait(&tmem_full_bar[acc], acc_phase);
+            t_wait += clock64() - t0;
+            if (!ready) {
                 atomicExch(p.status, kStatusEpilogueTimeout);
                 break;
             }
@@ -213,7 +290,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             auto release_tmem = [&]() {
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(map_to_cta(&tmem_empty_bar[acc], 0));
+                    else mbar_arrive(&tmem_empty_bar[acc]);
+                }
             };
 
             if (EPI == kEpiF32) {
@@ -236,9 +316,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tmem_wait_ld();
                     if (c + 2 >= kChunks) release_tmem();   // last read of this accumulator
                     const int n0 = n_blk * BN + c * 32;
+                    load_params32(p.bias + n0, y);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float v = __uint_as_float(raw[j]) * scale + __ldg(p.bias + n0 + j);
+                        const float v = fmaf(__uint_as_float(raw[j]), scale, y[j]);
                         y[j] = p.relu ? fmaxf(v, 0.f) : v;
                     }
                     split32(y, h, l);
@@ -254,10 +335,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tmem_wait_ld();
                     if (c + 2 >= kChunks) release_tmem();
                     const int n0 = c * 32;
-                    const float* pe = p.pe + (int64_t)(in_tensor ? t : 0) * p.N + n0;
+                    float pe[32];
+                    load_params32(p.bias + n0, y);
+                    load_params32(p.pe + (int64_t)(in_tensor ? t : 0) * p.N + n0, pe);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float v = valid ? __uint_as_float(raw[j]) * scale + __ldg(p.bias + n0 + j) : 0.f;
+                        const float v = valid ? fmaf(__uint_as_float(raw[j]), scale, y[j]) : 0.f;
                         y[j] = in_tensor ? v + pe[j] : 0.f;
                     }
                     split32(y, h, l);
@@ -271,25 +354,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const __half* res_hi = p.residual + m * p.res_ld;
                 const __half* res_lo = res_hi + p.res_plane_stride;
                 float sum = 0.f;
-#pragma unroll 1
-                for (int c = set; c < kChunks; c += 2) {
-                    tmem_ld_32x32(t_acc + c * 32, raw);
-                    uint4 rh[4], rl[4];
+                // residual rows come straight from HBM / L2 (row per thread): the loads of
+                // chunk c + 2 are in flight while chunk c is combined
+                uint4 rbuf[2][8];
+                auto load_res = [&](int c, uint4 (&dst)[8]) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        rh[u] = reinterpret_cast<const uint4*>(res_hi + c * 32)[u];
-                        rl[u] = reinterpret_cast<const uint4*>(res_lo + c * 32)[u];
+                        dst[u] = reinterpret_cast<const uint4*>(res_hi + c * 32)[u];
+                        dst[4 + u] = reinterpret_cast<const uint4*>(res_lo + c * 32)[u];
                     }
+                };
+                load_res(set, rbuf[0]);
+#pragma unroll
+                for (int i = 0; i < kChunks / 2; ++i) {
+                    const int c = set + 2 * i;
+                    if (i + 1 < kChunks / 2) load_res(c + 2, rbuf[(i + 1) & 1]);
+                    tmem_ld_32x32(t_acc + c * 32, raw);
+                    load_params32(p.bias + c * 32, y);
                     tmem_wait_ld();
-                    const uint32_t* rhw = reinterpret_cast<const uint32_t*>(rh);
-                    const uint32_t* rlw = reinterpret_cast<const uint32_t*>(rl);
+                    const uint32_t* rhw = reinterpret_cast<const uint32_t*>(&rbuf[i & 1][0]);
+                    const uint32_t* rlw = reinterpret_cast<const uint32_t*>(&rbuf[i & 1][4]);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&rhw[j]));
                         const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&rlw[j]));
-                        const int n = c * 32 + 2 * j;
-                        const float v0 = __uint_as_float(raw[2 * j]) * scale + __ldg(p.bias + n) + (fh.x + fl.x);
-                        const float v1 = __uint_as_float(raw[2 * j + 1]) * scale + __ldg(p.bias + n + 1) + (fh.y + fl.y);
+                        const float v0 = fmaf(__uint_as_float(raw[2 * j]), scale, y[2 * j]) + (fh.x + fl.x);
+                        const float v1 = fmaf(__uint_as_float(raw[2 * j + 1]), scale, y[2 * j + 1]) + (fh.y + fl.y);
                         sum += v0 + v1;
                         raw[2 * j] = __float_as_uint(v0);
                         raw[2 * j + 1] = __float_as_uint(v1);
@@ -321,11 +411,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tmem_ld_32x32(t_acc + c * 32, raw);
                     tmem_wait_ld();
                     if (c + 2 >= kChunks) release_tmem();
+                    float gamma[32];
+                    load_params32(p.gamma + c * 32, gamma);
+                    load_params32(p.beta + c * 32, y);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int n = c * 32 + j;
-                        const float v = (__uint_as_float(raw[j]) - mean) * rstd * __ldg(p.gamma + n) +
-                                        __ldg(p.beta + n);
+                        const float v = fmaf((__uint_as_float(raw[j]) - mean) * rstd, gamma[j], y[j]);
                         y[j] = in_tensor ? v : 0.f;
                     }
                     split32(y, h, l);
@@ -376,13 +467,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
         if (elected) bulk_wait_all();   // smem must outlive the last TMA store
+        if (p.trace && warp == 2 && lane == 0) {
+            atomicAdd(p.trace + 3, (unsigned long long)t_wait);
+            atomicAdd(p.trace + 4, (unsigned long long)(clock64() - t_begin));
+        }
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();   // the peer's smem / TMEM / barriers stay valid until both are done
+    else __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc<Shape::kTmemCols>(tmem_base);
+        if (PAIR) tmem_dealloc_pair<Shape::kTmemCols>(tmem_base);
+        else tmem_dealloc<Shape::kTmemCols>(tmem_base);
     }
 }
 
@@ -467,23 +564,42 @@ int make_store_map(CUtensorMap* map, __half* base, uint64_t inner, uint64_t rows
     return PPGS_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool PAIR>
 static int launch_one(ppgs_engine* e, const char* name, const CUtensorMap& map_a,
                       const CUtensorMap& map_b, const CUtensorMap& map_out, const GemmParams& p,
                       cudaStream_t stream) {
-    using Shape = GemmShape<BN>;
+    using Shape = GemmShape<BN, PAIR>;
     static bool attr = false;
     if (!attr) {
-        PPGS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>,
+        PPGS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, PAIR>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Shape::kSmemBytes));
         attr = true;
     }
-    const int tiles = p.m_tiles * p.n_tiles;
-    const int grid = std::min(tiles, e->sm_count);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attrs[1];
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Shape::kSmemBytes;
+    cfg.stream = stream;
+    if (PAIR) {
+        if (p.m_tiles % 2) {
+            set_error("gemm_tc: the CTA-pair kernel needs an even number of row tiles");
+            return PPGS_E_INVALID;
+        }
+        const int pair_tiles = (p.m_tiles / 2) * p.n_tiles;
+        cfg.gridDim = dim3(2 * std::min(pair_tiles, e->sm_count / 2));
+        attrs[0].id = cudaLaunchAttributeClusterDimension;
+        attrs[0].val.clusterDim.x = 2;
+        attrs[0].val.clusterDim.y = 1;
+        attrs[0].val.clusterDim.z = 1;
+        cfg.attrs = attrs;
+        cfg.numAttrs = 1;
+    } else {
+        cfg.gridDim = dim3(std::min(p.m_tiles * p.n_tiles, e->sm_count));
+    }
     {
         LaunchScope scope(e, name, stream);
-        gemm_tc_kernel<BN, EPI><<<grid, kGemmThreads, Shape::kSmemBytes, stream>>>(map_a, map_b, map_out, p);
+        PPGS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, PAIR>, map_a, map_b, map_out, p));
     }
     PPGS_CUDA(cudaGetLastError());
     return PPGS_OK;
@@ -502,18 +618,23 @@ int launch_gemm_tc(ppgs_engine* e, const char* name, int bn, int epilogue,
         return PPGS_E_INVALID;
     }
     const CUtensorMap& out_map = map_out ? *map_out : map_a;   // unused when not storing planes
-#define PPGS_GEMM_CASE(BN_, EPI_) \
-    if (bn == BN_ && epilogue == EPI_) \
-        return launch_one<BN_, EPI_>(e, name, map_a, map_b, out_map, p, stream)
-    PPGS_GEMM_CASE(256, kEpiF32);
-    PPGS_GEMM_CASE(128, kEpiF32);
-    PPGS_GEMM_CASE(64, kEpiF32);
-    PPGS_GEMM_CASE(256, kEpiPlanes);
-    PPGS_GEMM_CASE(256, kEpiConvIn);
-    PPGS_GEMM_CASE(256, kEpiResLN);
-    PPGS_GEMM_CASE(64, kEpiConvOut);
+    const bool pair = p.pair != 0;
+#define PPGS_GEMM_CASE(BN_, EPI_, PAIR_) \
+    if (bn == BN_ && epilogue == EPI_ && pair == PAIR_) \
+        return launch_one<BN_, EPI_, PAIR_>(e, name, map_a, map_b, out_map, p, stream)
+    PPGS_GEMM_CASE(256, kEpiF32, false);
+    PPGS_GEMM_CASE(256, kEpiF32, true);
+    PPGS_GEMM_CASE(128, kEpiF32, false);
+    PPGS_GEMM_CASE(64, kEpiF32, false);
+    PPGS_GEMM_CASE(256, kEpiPlanes, false);
+    PPGS_GEMM_CASE(256, kEpiPlanes, true);
+    PPGS_GEMM_CASE(256, kEpiConvIn, false);
+    PPGS_GEMM_CASE(256, kEpiConvIn, true);
+    PPGS_GEMM_CASE(256, kEpiResLN, false);
+    PPGS_GEMM_CASE(256, kEpiResLN, true);
+    PPGS_GEMM_CASE(64, kEpiConvOut, false);
 #undef PPGS_GEMM_CASE
-    set_error("gemm_tc: no kernel for BN=%d epilogue=%d", bn, epilogue);
+    set_error("gemm_tc: no kernel for BN=%d epilogue=%d pair=%d", bn, epilogue, (int)pair);
     return PPGS_E_UNSUPPORTED;
 }
 

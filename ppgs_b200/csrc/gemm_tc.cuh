@@ -22,6 +22,7 @@ struct GemmParams {
     int taps = 1, half = 0;      // K loop = taps x cblocks k-blocks; A rows shift by tap - half
     int cblocks = 0;
     int a_planes = 2, b_planes = 2;
+    int pair = 0;                // 1: CTA-pair kernel (cta_group::2); W map must have box rows BN/2
     int N = 0;                   // real output columns
     const float* scale = nullptr;   // device scalar: 1 / (power-of-two weight scale)
     const float* bias = nullptr;
@@ -41,6 +42,10 @@ struct GemmParams {
     float* ppg = nullptr;   // kEpiConvOut
     int T = 0, O = 0, softmax = 1;
     int* status = nullptr;
+    // optional cycle accounting (validation builds of the pipeline, see debug_abi.h):
+    // [0] MMA wait tmem_empty [1] MMA wait full [2] MMA total [3] epilogue wait tmem_full
+    // [4] epilogue total [5] producer wait empty [6] producer total [7] CTAs
+    unsigned long long* trace = nullptr;
 };
 
 // Tensor map over split-fp16 planes: logical dims {inner, rows, groups, planes}
@@ -52,12 +57,12 @@ int make_plane_map(CUtensorMap* map, const __half* base, bool rank4, uint64_t in
                    uint64_t group_stride_elems, uint64_t plane_stride_elems, uint32_t box_rows,
                    uint32_t box_planes);
 
+// BN in {256, 128, 64}.  Launches a persistent grid of min(tiles, SMs) CTAs.
 // Store map over output planes [2][rows][inner]: box {32, 128, 2}, 64-byte swizzle
 // (the epilogue's staging layout).
 int make_store_map(CUtensorMap* map, __half* base, uint64_t inner, uint64_t rows,
                    uint64_t plane_stride_elems);
 
-// BN in {256, 128, 64}.  Launches a persistent grid of min(tiles, SMs) CTAs.
 // `map_out` may be null for epilogues without plane output (kEpiF32, kEpiConvOut).
 int launch_gemm_tc(ppgs_engine* e, const char* name, int bn, int epilogue,
                    const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap* map_out,

@@ -103,6 +103,47 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// CTA-pair (cta_group::2) variants: both CTAs of the pair load into their own
+// shared memory, the transaction bytes are credited to the LEADER CTA's mbarrier
+// (`leader_bar` = shared::cluster address of the barrier in CTA rank 0).
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map,
+                                                 uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1),
+        "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map,
+                                                 uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+        : "memory");
+}
+// shared::cluster address of `ptr`'s counterpart in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* ptr, uint32_t rank) {
+    uint32_t out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_u32(ptr)), "r"(rank));
+    return out;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // shared -> global tile store; completion tracked by bulk async-groups
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1,
                                              int c2) {
@@ -149,6 +190,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
                  : "memory");
 }
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_in_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(slot_in_smem)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
+                 : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -166,6 +220,27 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// CTA pair: M = 256 rows (128 per CTA), A / B halves read from both CTAs' smem at
+// the same offsets, issued by the leader CTA only
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at the same offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+        "[%0], %1;" ::"r"(smem_u32(bar)),
+        "h"((uint16_t)3)
         : "memory");
 }
 // all previously issued tcgen05.mma of this thread arrive on `bar` when complete

@@ -82,6 +82,10 @@ int build_plan(const ppgs_engine* e, int batch, int frames, const int64_t* lengt
             }
         }
     }
+    if (row % 256) {
+        // the CTA-pair GEMMs work on pairs of 128-row tiles: pad with one empty sequence
+        add(0, 0, 0, 0, 0, 0, 0);
+    }
     plan->rows = row;
     return PPGS_OK;
 }

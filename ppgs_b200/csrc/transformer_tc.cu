@@ -27,6 +27,8 @@ static int weight_map(TcWeight& w) {
     const uint64_t plane = (uint64_t)w.taps * w.N * w.C;
     PPGS_CHECK(make_plane_map(&w.map_bn256, w.planes, true, w.C, w.N, w.taps, 2, w.C,
                               (uint64_t)w.N * w.C, plane, 256, 2));
+    PPGS_CHECK(make_plane_map(&w.map_bn128, w.planes, true, w.C, w.N, w.taps, 2, w.C,
+                              (uint64_t)w.N * w.C, plane, 128, 2));
     PPGS_CHECK(make_plane_map(&w.map_bn64, w.planes, true, w.C, w.N, w.taps, 2, w.C,
                               (uint64_t)w.N * w.C, plane, 64, 2));
     return PPGS_OK;
@@ -144,12 +146,18 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     base.status = e->status_dev;
     base.eps = c.layer_norm_eps;
     base.b_planes = planes;
+    const int pair = (e->gemm_pair && rows % 256 == 0) ? 1 : 0;
+    base.pair = pair;
+    auto wmap = [&](TcWeight& w) -> const CUtensorMap& { return pair ? w.map_bn128 : w.map_bn256; };
+    // cycle accounting slots: 0 conv_in, 1 qkv, 2 out_proj, 3 ffn1, 4 ffn2, 5 conv_out
+    auto trace = [&](int slot) { return e->trace_dev ? e->trace_dev + 8 * slot : nullptr; };
 
     {   // input conv: features are exact fp16 -> one A plane
         GemmParams p = base;
         p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = (C + 63) / 64; p.a_planes = 1;
         p.N = H; p.scale = e->tc_conv_in.inv_scale; p.bias = e->conv_in_b; p.pe = e->pe;
-        PPGS_CHECK(launch_gemm_tc(e, "tc_conv_in", 256, kEpiConvIn, map_x0, e->tc_conv_in.map_bn256,
+        p.trace = trace(0);
+        PPGS_CHECK(launch_gemm_tc(e, "tc_conv_in", 256, kEpiConvIn, map_x0, wmap(e->tc_conv_in),
                                   &out_x, p, stream));
     }
     for (int layer = 0; layer < c.num_layers; ++layer) {
@@ -158,34 +166,34 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
         {
             GemmParams p = base;
             p.n_tiles = 3 * H / 256; p.cblocks = H / 64; p.a_planes = planes;
-            p.N = 3 * H; p.scale = T.in_w.inv_scale; p.bias = L.in_b;
-            PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, T.in_w.map_bn256, &out_qkv,
+            p.N = 3 * H; p.scale = T.in_w.inv_scale; p.bias = L.in_b; p.trace = trace(1);
+            PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, wmap(T.in_w), &out_qkv,
                                       p, stream));
         }
         PPGS_CHECK(launch_attention_tc(e, qkv, att, rows, plan, seqs_dev, planes, stream));
         {
             GemmParams p = base;
             p.n_tiles = 1; p.cblocks = H / 64; p.a_planes = planes;
-            p.N = H; p.scale = T.out_w.inv_scale; p.bias = L.out_b;
+            p.N = H; p.scale = T.out_w.inv_scale; p.bias = L.out_b; p.trace = trace(2);
             p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
             p.gamma = L.n1_w; p.beta = L.n1_b;
-            PPGS_CHECK(launch_gemm_tc(e, "tc_out_proj_ln", 256, kEpiResLN, map_att, T.out_w.map_bn256,
+            PPGS_CHECK(launch_gemm_tc(e, "tc_out_proj_ln", 256, kEpiResLN, map_att, wmap(T.out_w),
                                       &out_x, p, stream));
         }
         {
             GemmParams p = base;
             p.n_tiles = F / 256; p.cblocks = H / 64; p.a_planes = planes;
-            p.N = F; p.scale = T.l1_w.inv_scale; p.bias = L.l1_b; p.relu = 1;
-            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn1", 256, kEpiPlanes, map_x, T.l1_w.map_bn256, &out_ff,
+            p.N = F; p.scale = T.l1_w.inv_scale; p.bias = L.l1_b; p.relu = 1; p.trace = trace(3);
+            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn1", 256, kEpiPlanes, map_x, wmap(T.l1_w), &out_ff,
                                       p, stream));
         }
         {
             GemmParams p = base;
             p.n_tiles = 1; p.cblocks = F / 64; p.a_planes = planes;
-            p.N = H; p.scale = T.l2_w.inv_scale; p.bias = L.l2_b;
+            p.N = H; p.scale = T.l2_w.inv_scale; p.bias = L.l2_b; p.trace = trace(4);
             p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
             p.gamma = L.n2_w; p.beta = L.n2_b;
-            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn2_ln", 256, kEpiResLN, map_ff, T.l2_w.map_bn256, &out_x,
+            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn2_ln", 256, kEpiResLN, map_ff, wmap(T.l2_w), &out_x,
                                       p, stream));
         }
     }
@@ -193,7 +201,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
         GemmParams p = base;
         p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = H / 64; p.a_planes = planes;
         p.N = O; p.O = O; p.scale = e->tc_conv_out.inv_scale; p.bias = e->conv_out_b;
-        p.ppg = out; p.T = plan.frames; p.softmax = softmax;
+        p.ppg = out; p.T = plan.frames; p.softmax = softmax; p.pair = 0;
         PPGS_CHECK(launch_gemm_tc(e, "tc_conv_out_softmax", 64, kEpiConvOut, map_x,
                                   e->tc_conv_out.map_bn64, nullptr, p, stream));
     }

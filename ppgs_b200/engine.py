@@ -190,9 +190,11 @@ class Engine:
             ctypes.c_void_p(out.data_ptr()), _stream_ptr(self.device)))
         return out
 
-    def from_audio_host(self, audio, out=None, lengths=None, softmax=True, legacy_mode=False):
-        """Host buffers in, host buffers out (H2D + compute + D2H, synchronous).
-        audio: CPU fp32 (B,1,samples) (pinned for full PCIe speed)."""
+    def from_audio_host(self, audio, out=None, lengths=None, softmax=True, legacy_mode=False,
+                        wait=True):
+        """Host buffers in, host buffers out (H2D + compute + D2H).  audio: CPU fp32
+        (B,1,samples), pinned for full PCIe speed.  `wait=False` only enqueues the
+        request (two may be in flight); call `wait()` before reading `out`."""
         if audio.dim() == 3:
             audio = audio.squeeze(1)
         if audio.device.type != 'cpu' or audio.dtype != torch.float32 or not audio.is_contiguous():
@@ -203,11 +205,19 @@ class Engine:
             out = torch.empty(batch, self.cfg.output_channels, frames, dtype=torch.float32,
                               pin_memory=True)
         lengths_host = None if lengths is None else _host_lengths(lengths, batch)
-        _lib.check(_lib.lib.ppgs_from_audio_host(
+        call = _lib.lib.ppgs_from_audio_host if wait else _lib.lib.ppgs_from_audio_host_submit
+        _lib.check(call(
             self._handle, ctypes.c_void_p(audio.data_ptr()), batch, samples, lengths_host,
             int(bool(softmax)), int(bool(legacy_mode)), ctypes.c_void_p(out.data_ptr()),
             _stream_ptr(self.device)))
+        if not wait:   # the library reads / writes these buffers until wait()
+            self._in_flight = (getattr(self, '_in_flight', None) or [])[-1:] + [(audio, out)]
         return out
+
+    def wait(self):
+        """Block until every request enqueued with `wait=False` has landed."""
+        _lib.check(_lib.lib.ppgs_engine_wait(self._handle))
+        self._in_flight = None
 
     def _on_device(self, tensor, dtype):
         if tensor.device != self.device or tensor.dtype != dtype:

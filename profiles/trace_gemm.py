@@ -1,0 +1,35 @@
+"""Cycle accounting of the GEMM pipeline roles (PPGS_B200_TRACE=1): who waits for whom."""
+import ctypes
+import os
+import sys
+
+os.environ['PPGS_B200_TRACE'] = '1'
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import ppgs_b200  # noqa: E402
+from ppgs_b200 import _lib  # noqa: E402
+from oracle import ppg_oracle as O  # noqa: E402
+
+engine = ppgs_b200.Engine(0).load_state_dict(O.random_state_dict(0, peaky=True))
+engine.precision = 'f16x2'
+audio = O.synthetic_audio(64, 160000, 0).cuda()
+engine.from_audio(audio)
+buf = (ctypes.c_ulonglong * 64)()
+_lib.lib.ppgs_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+_lib.check(_lib.lib.ppgs_debug_trace(engine._handle, buf))
+forwards = 3
+for _ in range(forwards):
+    engine.from_audio(audio)
+_lib.check(_lib.lib.ppgs_debug_trace(engine._handle, buf))
+names = ['conv_in', 'qkv', 'out_proj', 'ffn1', 'ffn2']
+launches = [1, 5, 5, 5, 5]
+print('per launch, averaged over CTAs, in kcycles: mma[wait_tmem_empty wait_full total] '
+      'epi[wait_tmem_full total] prod[wait_empty total]')
+for k, name in enumerate(names):
+    c = [buf[8 * k + i] for i in range(8)]
+    ctas = max(c[7], 1)
+    mma_ctas = ctas / 2 if engine else ctas   # pair mode: one MMA issuer per pair
+    f = lambda x, n: x / n / 1e3   # noqa: E731
+    print(f'{name:9s} mma[{f(c[0], mma_ctas):8.1f} {f(c[1], mma_ctas):8.1f} {f(c[2], mma_ctas):8.1f}] '
+          f'epi[{f(c[3], ctas):8.1f} {f(c[4], ctas):8.1f}] prod[{f(c[5], ctas):8.1f} {f(c[6], ctas):8.1f}] '
+          f'ctas/launch {ctas / forwards / launches[k]:.0f}')

@@ -24,20 +24,20 @@ def debug_lib():
     lib = _lib.lib
     vp, i = ctypes.c_void_p, ctypes.c_int
     lib.ppgs_debug_gemm.restype = i
-    lib.ppgs_debug_gemm.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    lib.ppgs_debug_gemm.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]
     lib.ppgs_debug_attention.restype = i
     lib.ppgs_debug_attention.argtypes = [vp, vp, i, i, i, i, i, vp]
     return _lib
 
 
-def run_gemm(engine, a, w, bias, taps, bn, a_planes, b_planes):
+def run_gemm(engine, a, w, bias, taps, bn, a_planes, b_planes, pair=0):
     lib = debug_lib()
     M, C = a.shape
     N = w.shape[0]
     out = torch.empty(M, N)
     a, w, bias = a.contiguous(), w.contiguous(), bias.contiguous()
     lib.check(lib.lib.ppgs_debug_gemm(
-        engine._handle, a.data_ptr(), w.data_ptr(), bias.data_ptr(), M, N, C, taps, bn,
+        engine._handle, a.data_ptr(), w.data_ptr(), bias.data_ptr(), M, N, C, taps, bn, pair,
         a_planes, b_planes, out.data_ptr()))
     return out
 
@@ -53,7 +53,13 @@ def reference_gemm(a, w, bias, taps):
 
 
 GEMM_CASES = [
-    # M, N, C, taps, bn
+    # M, N, C, taps, bn[, pair]
+    (256, 256, 64, 1, 256, 1),
+    (256, 768, 256, 1, 256, 1),
+    (512, 2048, 256, 1, 256, 1),
+    (256, 256, 2048, 1, 256, 1),
+    (256, 256, 80, 5, 256, 1),
+    (256 * 160, 256, 128, 1, 256, 1),  # CTA pairs: more pair-tiles than clusters
     (128, 256, 64, 1, 256),
     (128, 256, 256, 1, 256),
     (384, 768, 256, 1, 256),
@@ -66,16 +72,18 @@ GEMM_CASES = [
 ]
 
 
-@pytest.mark.parametrize('M,N,C,taps,bn', GEMM_CASES)
+@pytest.mark.parametrize('case', GEMM_CASES, ids=lambda c: 'x'.join(map(str, c)))
 @pytest.mark.parametrize('planes', [(2, 2), (1, 2), (1, 1)])
-def test_tcgen05_gemm(engine, M, N, C, taps, bn, planes):
+def test_tcgen05_gemm(engine, case, planes):
+    M, N, C, taps, bn = case[:5]
+    pair = case[5] if len(case) > 5 else 0
     g = torch.Generator().manual_seed(M + N + C + taps)
     a = torch.randn(M, C, generator=g)
     if planes[0] == 1:
         a = a.half().float()          # exact fp16 A (the input conv's case)
     w = torch.randn(N, C, taps, generator=g) / (C * taps) ** 0.5
     bias = torch.randn(N, generator=g)
-    out = run_gemm(engine, a, w, bias, taps, bn, *planes)
+    out = run_gemm(engine, a, w, bias, taps, bn, *planes, pair=pair)
     ref = reference_gemm(a, w, bias, taps)
     err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
     # split-fp16 passes keep ~22 bits per operand; the fp32 TMEM accumulation adds

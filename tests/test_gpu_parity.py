@@ -121,6 +121,11 @@ def test_from_audio_end_to_end_vs_oracle(ppgs_b200, frames, lengths, precision):
     pinned = audio.pin_memory()
     host = engine.from_audio_host(pinned, lengths=sample_lengths).numpy()
     assert np.array_equal(host, out)
+    # pipelined submit / wait: three requests through the two slots
+    outs = [engine.from_audio_host(pinned, lengths=sample_lengths, wait=False) for _ in range(3)]
+    engine.wait()
+    for other in outs:
+        assert np.array_equal(other.numpy(), out)
 
 
 @pytest.mark.parametrize('precision', PRECISIONS)
