@@ -158,7 +158,7 @@ __device__ __forceinline__ int chunk_order(int i, int nchunks) {
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_v,
-                    const AttnParams p) {
+                    const __grid_constant__ CUtensorMap map_out, const AttnParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -384,27 +384,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         if (ok && !mbar_wait(&o_full, 0)) ok = false;
         tcgen05_fence_after();
         if (ok) {
+            // O / sum -> split planes, staged as four [128 rows][64 cols] 128B-swizzled tiles
+            // (column half x plane) in the dead P ring, then stored with TMA: full 128-byte
+            // rows instead of 16-byte pieces per thread
             const float inv = sum > 0.f ? 1.f / sum : 0.f;
-            __half* dst = p.out + (out_row0 + r) * p.H + head * 128 + half * 64;
-#pragma unroll 1
+            uint32_t h[32], l[32];
+#pragma unroll
             for (int g = 0; g < 2; ++g) {
                 tmem_ld_32x32(t_row + kOCol + half * 64 + g * 32, raw);
                 tmem_wait_ld();
-                uint32_t h[16], l[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     split2_f16(__uint_as_float(raw[2 * j]) * inv, __uint_as_float(raw[2 * j + 1]) * inv,
-                               h[j], l[j]);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    reinterpret_cast<uint4*>(dst + g * 32)[u] = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
-                    reinterpret_cast<uint4*>(dst + p.out_plane_stride + g * 32)[u] =
-                        make_uint4(l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
-                }
+                               h[g * 16 + j], l[g * 16 + j]);
             }
-        } else {
-            atomicExch(p.status, kStatusAttnTimeout);
+            const uint32_t tile_hi = p_base + (uint32_t)(half * 2) * kTile16K;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t addr = tile_hi + row_off + (((uint32_t)u ^ sw) << 4);
+                st_shared_v4(addr, h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+                st_shared_v4(addr + kTile16K, l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
+            }
+            fence_proxy_async_smem();
         }
+        named_bar_sync(1, 256);
+        if (ok && warp == 2 && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                tma_store_3d(&map_out, q_smem + i * kTile16K, head * 128 + (i >> 1) * 64,
+                             (int)out_row0, i & 1);
+            bulk_commit_group();
+            bulk_wait_all();
+        }
+        if (!ok) atomicExch(p.status, kStatusAttnTimeout);
     }
 
     tcgen05_fence_before();
@@ -421,7 +433,8 @@ int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows
     constexpr int D = 128;
     const int H = e->cfg.hidden_channels;
     if (e->attention_impl == 1 && plan.max_pitch <= 512 && H / e->cfg.num_heads == D) {
-        CUtensorMap map_qk, map_v;
+        CUtensorMap map_qk, map_v, map_out;
+        PPGS_CHECK(make_store_map(&map_out, out, H, rows, (uint64_t)rows * H));
         PPGS_CHECK(make_plane_map(&map_qk, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
                                   (uint64_t)rows * 3 * H, 128, planes));
         PPGS_CHECK(make_plane_map(&map_v, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
@@ -445,7 +458,7 @@ int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows
         dim3 grid(plan.max_pitch / 128, e->cfg.num_heads, (unsigned)plan.seqs.size());
         {
             LaunchScope scope(e, "tc_attention", stream);
-            attention_tc_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(map_qk, map_v, p);
+            attention_tc_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(map_qk, map_v, map_out, p);
         }
         PPGS_CUDA(cudaGetLastError());
         return PPGS_OK;

@@ -79,7 +79,7 @@ struct TcWeight {
     __half* planes = nullptr;
     const float* inv_scale = nullptr;
     int N = 0, C = 0, taps = 1;
-    CUtensorMap map_bn256, map_bn128, map_bn64;   // box rows 256 / 128 (CTA-pair halves) / 64
+    CUtensorMap map_bn256, map_bn128, map_bn64, map_bn32;   // box rows 256 / 128 (CTA-pair halves) / 64 / 32
 };
 
 struct TcLayer {
@@ -120,6 +120,8 @@ struct ppgs_engine {
     int* status_dev = nullptr;   // kernels report barrier time-outs here
     int attention_impl = 1;      // 1 = tcgen05 kernel, 0 = CUDA-core kernel (validation)
     int gemm_pair = 1;           // 1 = CTA-pair (cta_group::2) GEMMs at BN = 256
+    int fused_ffn = 0;           // 1 = one fused kernel for linear1 + ReLU + linear2 + LN (PPGS_B200_FUSED_FFN;
+                                 // parity-green but shared-memory-bound and slower than the two GEMMs)
     unsigned long long* trace_dev = nullptr;   // [8 kernel kinds][8] cycle counters (PPGS_B200_TRACE=1)
 
     ppgs::MelTables mel;

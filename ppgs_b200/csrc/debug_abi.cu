@@ -153,7 +153,7 @@ extern "C" int ppgs_debug_trace(ppgs_engine* e, unsigned long long* out64) {
     }
     PPGS_CUDA(cudaSetDevice(e->device));
     PPGS_CUDA(cudaDeviceSynchronize());
-    PPGS_CUDA(cudaMemcpy(out64, e->trace_dev, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    PPGS_CUDA(cudaMemset(e->trace_dev, 0, 64 * sizeof(unsigned long long)));
+    PPGS_CUDA(cudaMemcpy(out64, e->trace_dev, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    PPGS_CUDA(cudaMemset(e->trace_dev, 0, 128 * sizeof(unsigned long long)));
     return PPGS_OK;
 }

@@ -23,10 +23,10 @@ int ppgs_debug_gemm(ppgs_engine* engine, const float* a_host, const float* w_hos
 int ppgs_debug_attention(ppgs_engine* engine, const float* qkv_host, int rows, int tensor_len,
                          int valid_len, int planes, int use_tensor_cores, float* out_host);
 
-/* Copies out and clears the 64 cycle counters the GEMM kernels accumulate when the
+/* Copies out and clears the 128 cycle counters the GEMM kernels accumulate when the
  * engine was created with PPGS_B200_TRACE=1 (8 kernel slots x 8 counters, see
  * GemmParams::trace).  Synchronises the device. */
-int ppgs_debug_trace(ppgs_engine* engine, unsigned long long* out64);
+int ppgs_debug_trace(ppgs_engine* engine, unsigned long long* out128);
 
 #ifdef __cplusplus
 }

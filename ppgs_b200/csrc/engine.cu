@@ -391,9 +391,10 @@ int ppgs_engine_create(const ppgs_model_config* cfg, int device, ppgs_engine** o
     e->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("PPGS_B200_PAIR")) e->gemm_pair = atoi(v) != 0;      // validation switches
     if (const char* v = getenv("PPGS_B200_ATTENTION")) e->attention_impl = atoi(v) != 0;
+    if (const char* v = getenv("PPGS_B200_FUSED_FFN")) e->fused_ffn = atoi(v) != 0;
     if (const char* v = getenv("PPGS_B200_TRACE")) {
-        if (atoi(v) != 0 && cudaMalloc(&e->trace_dev, 64 * sizeof(unsigned long long)) == cudaSuccess)
-            cudaMemset(e->trace_dev, 0, 64 * sizeof(unsigned long long));
+        if (atoi(v) != 0 && cudaMalloc(&e->trace_dev, 128 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(e->trace_dev, 0, 128 * sizeof(unsigned long long));
     }
     *out = e;
     return PPGS_OK;

@@ -20,7 +20,7 @@ namespace tc {
 
 constexpr int kGemmThreads = 320;      // producer + MMA + 8 epilogue warps
 constexpr int kPlaneABytes = kBM * kBK * 2;   // 16 KB
-constexpr int kStageOutBytes = 2 * kBM * 32 * 2;   // [plane 2][128 rows][32 cols] fp16 = 16 KB
+constexpr int kStageOutBytes = kBM * 64 * 2;   // [128 rows][64 cols] fp16 = 16 KB, one plane
 
 // PAIR: two CTAs of a cluster form one cta_group::2 MMA (M = 256): each loads its
 // own 128 rows of A and HALF of the W tile, so a stage is 64 KB instead of 96 KB
@@ -36,27 +36,27 @@ struct GemmShape {
     static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 2 * kStageOutBytes;
 };
 
-// One 32-column chunk of one output row -> this thread's row of the staging
-// tile ([plane][128 rows][32 cols], 64-byte swizzle), then one elected thread of
-// the 128-thread epilogue set stores the tile with TMA.
-__device__ __forceinline__ void stage_and_store(const CUtensorMap* map_out, unsigned char* stage,
-                                                int set, int row, bool elected,
-                                                const uint32_t (&h)[16], const uint32_t (&l)[16],
-                                                int n0, int m0) {
-    if (elected) bulk_wait_read_all();          // previous store has drained the buffer
+// One plane (hi or lo) of one 64-column group of one output row -> this thread's
+// 128-byte row of the staging tile ([128 rows][64 cols] fp16, 128-byte swizzle), then
+// one elected thread of the 128-thread epilogue set stores the tile with TMA.  Rows
+// of 128 contiguous bytes keep the number of L2 write requests per byte at its
+// minimum (64-byte rows cost twice the requests and made the stores the bottleneck).
+__device__ __forceinline__ void stage_store_plane(const CUtensorMap* map_out, unsigned char* stage,
+                                                  int set, int row, bool elected,
+                                                  const uint32_t (&w)[32], int n0, int m0, int plane,
+                                                  int debug_flags) {
+    if (debug_flags & 1) return;
+    if (elected && !(debug_flags & 8)) bulk_wait_read_all();   // previous store has drained the buffer
     named_bar_sync(1 + set, 128);
-    const uint32_t base = smem_u32(stage) + (uint32_t)row * 64;
-    const uint32_t sw = (uint32_t)(row >> 1) & 3;
+    const uint32_t base = smem_u32(stage) + (uint32_t)row * 128;
+    const uint32_t sw = (uint32_t)row & 7;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const uint32_t addr = base + (((uint32_t)u ^ sw) << 4);
-        st_shared_v4(addr, h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
-        st_shared_v4(addr + kBM * 64, l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
-    }
+    for (int u = 0; u < 8; ++u)
+        st_shared_v4(base + (((uint32_t)u ^ sw) << 4), w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
     fence_proxy_async_smem();
     named_bar_sync(1 + set, 128);
-    if (elected) {
-        tma_store_3d(map_out, stage, n0, m0, 0);
+    if (elected && !(debug_flags & 4)) {
+        tma_store_3d(map_out, stage, n0, m0, plane);
         bulk_commit_group();
     }
 }
@@ -74,9 +74,11 @@ __device__ __forceinline__ void load_params32(const float* src, float (&out)[32]
     }
 }
 
-__device__ __forceinline__ void split32(const float (&y)[32], uint32_t (&h)[16], uint32_t (&l)[16]) {
+// 32 values -> 16 packed (hi, lo) words at h[at .. at + 16), l[at .. at + 16)
+__device__ __forceinline__ void split32(const float (&y)[32], uint32_t (&h)[32], uint32_t (&l)[32],
+                                        int at) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) split2_f16(y[2 * i], y[2 * i + 1], h[i], l[i]);
+    for (int i = 0; i < 16; ++i) split2_f16(y[2 * i], y[2 * i + 1], h[at + i], l[at + i]);
 }
 
 template <int BN, int EPI, bool PAIR>
@@ -285,13 +287,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * Shape::kAccCols;
             const int m0 = m_blk * kBM;
             const int64_t m = (int64_t)m0 + row;
-            uint32_t raw[32], h[16], l[16];
+            uint32_t raw[32], h[32], l[32];
             float y[32];
             auto release_tmem = [&]() {
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (PAIR) mbar_arrive_cluster(map_to_cta(&tmem_empty_bar[acc], 0));
+                    if (PAIR) mbar_arrive_cluster_relaxed(map_to_cta(&tmem_empty_bar[acc], 0));
                     else mbar_arrive(&tmem_empty_bar[acc]);
                 }
             };
@@ -310,47 +312,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 release_tmem();
             } else if (EPI == kEpiPlanes) {
+                // set s owns columns [128 s, 128 s + 128) of the tile: two 64-column groups,
+                // each leaves as one hi-plane and one lo-plane TMA store
 #pragma unroll 1
-                for (int c = set; c < kChunks; c += 2) {
-                    tmem_ld_32x32(t_acc + c * 32, raw);
-                    tmem_wait_ld();
-                    if (c + 2 >= kChunks) release_tmem();   // last read of this accumulator
-                    const int n0 = n_blk * BN + c * 32;
-                    load_params32(p.bias + n0, y);
+                for (int g = 0; g < kChunks / 4; ++g) {
+                    const int col = set * (BN / 2) + g * 64;
+                    const int n0 = n_blk * BN + col;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float v = fmaf(__uint_as_float(raw[j]), scale, y[j]);
-                        y[j] = p.relu ? fmaxf(v, 0.f) : v;
+                    for (int half = 0; half < 2; ++half) {
+                        tmem_ld_32x32(t_acc + col + half * 32, raw);
+                        if (p.debug_flags & 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) y[j] = 0.f;
+                        } else {
+                            load_params32(p.bias + n0 + half * 32, y);
+                        }
+                        tmem_wait_ld();
+                        if (g + 1 == kChunks / 4 && half == 1) release_tmem();   // last read
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = fmaf(__uint_as_float(raw[j]), scale, y[j]);
+                            y[j] = p.relu ? fmaxf(v, 0.f) : v;
+                        }
+                        split32(y, h, l, half * 16);
                     }
-                    split32(y, h, l);
-                    stage_and_store(&map_out, stage, set, row, elected, h, l, n0, m0);
+                    stage_store_plane(&map_out, stage, set, row, elected, h, n0, m0, 0, p.debug_flags);
+                    stage_store_plane(&map_out, stage, set, row, elected, l, n0, m0, 1, p.debug_flags);
                 }
             } else if (EPI == kEpiConvIn) {
                 const SeqInfo s = p.seqs[p.tile_seq[m_blk]];
                 const int t = (int)(m - s.row0);
                 const bool in_tensor = t < s.tensor_len, valid = t < s.valid_len;
 #pragma unroll 1
-                for (int c = set; c < kChunks; c += 2) {
-                    tmem_ld_32x32(t_acc + c * 32, raw);
-                    tmem_wait_ld();
-                    if (c + 2 >= kChunks) release_tmem();
-                    const int n0 = c * 32;
-                    float pe[32];
-                    load_params32(p.bias + n0, y);
-                    load_params32(p.pe + (int64_t)(in_tensor ? t : 0) * p.N + n0, pe);
+                for (int g = 0; g < kChunks / 4; ++g) {
+                    const int n0 = set * (BN / 2) + g * 64;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float v = valid ? fmaf(__uint_as_float(raw[j]), scale, y[j]) : 0.f;
-                        y[j] = in_tensor ? v + pe[j] : 0.f;
+                    for (int half = 0; half < 2; ++half) {
+                        float pe[32];
+                        tmem_ld_32x32(t_acc + n0 + half * 32, raw);
+                        load_params32(p.bias + n0 + half * 32, y);
+                        load_params32(p.pe + (int64_t)(in_tensor ? t : 0) * p.N + n0 + half * 32, pe);
+                        tmem_wait_ld();
+                        if (g + 1 == kChunks / 4 && half == 1) release_tmem();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = valid ? fmaf(__uint_as_float(raw[j]), scale, y[j]) : 0.f;
+                            y[j] = in_tensor ? v + pe[j] : 0.f;
+                        }
+                        split32(y, h, l, half * 16);
                     }
-                    split32(y, h, l);
-                    stage_and_store(&map_out, stage, set, row, elected, h, l, n0, m0);
+                    stage_store_plane(&map_out, stage, set, row, elected, h, n0, m0, 0, p.debug_flags);
+                    stage_store_plane(&map_out, stage, set, row, elected, l, n0, m0, 1, p.debug_flags);
                 }
             } else if (EPI == kEpiResLN) {
                 // the tile is one full row block of the hidden state (BN == N == hidden);
                 // a row is shared by the two threads (one per set) with the same `row`
                 const SeqInfo s = p.seqs[p.tile_seq[m_blk]];
                 const bool in_tensor = (int)(m - s.row0) < s.tensor_len;
+                const long long ln_t0 = clock64();
                 const __half* res_hi = p.residual + m * p.res_ld;
                 const __half* res_lo = res_hi + p.res_plane_stride;
                 float sum = 0.f;
@@ -364,11 +383,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         dst[4 + u] = reinterpret_cast<const uint4*>(res_lo + c * 32)[u];
                     }
                 };
-                load_res(set, rbuf[0]);
+                const int c_first = set * (kChunks / 2);   // set s owns chunks [4 s, 4 s + 4)
+                load_res(c_first, rbuf[0]);
 #pragma unroll
                 for (int i = 0; i < kChunks / 2; ++i) {
-                    const int c = set + 2 * i;
-                    if (i + 1 < kChunks / 2) load_res(c + 2, rbuf[(i + 1) & 1]);
+                    const int c = c_first + i;
+                    if (i + 1 < kChunks / 2) load_res(c + 1, rbuf[(i + 1) & 1]);
                     tmem_ld_32x32(t_acc + c * 32, raw);
                     load_params32(p.bias + c * 32, y);
                     tmem_wait_ld();
@@ -387,13 +407,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tmem_st_32x32(t_acc + c * 32, raw);
                 }
                 tmem_wait_st();
+                const long long ln_t1 = clock64();
                 ln_part[set][row] = sum;
                 named_bar_sync(3, 256);
                 const float mean = (ln_part[0][row] + ln_part[1][row]) * (1.f / BN);
                 named_bar_sync(3, 256);   // both partners have read the sums
+                const long long ln_t2 = clock64();
                 float sq = 0.f;
 #pragma unroll 1
-                for (int c = set; c < kChunks; c += 2) {
+                for (int c = c_first; c < c_first + kChunks / 2; ++c) {
                     tmem_ld_32x32(t_acc + c * 32, raw);
                     tmem_wait_ld();
 #pragma unroll
@@ -402,25 +424,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         sq = fmaf(d, d, sq);
                     }
                 }
+                const long long ln_t3 = clock64();
                 ln_part[set][row] = sq;
                 named_bar_sync(3, 256);
                 const float rstd = rsqrtf((ln_part[0][row] + ln_part[1][row]) * (1.f / BN) + p.eps);
                 named_bar_sync(3, 256);   // ln_part is free for the next tile
+                const long long ln_t4 = clock64();
 #pragma unroll 1
-                for (int c = set; c < kChunks; c += 2) {
-                    tmem_ld_32x32(t_acc + c * 32, raw);
-                    tmem_wait_ld();
-                    if (c + 2 >= kChunks) release_tmem();
-                    float gamma[32];
-                    load_params32(p.gamma + c * 32, gamma);
-                    load_params32(p.beta + c * 32, y);
+                for (int g = 0; g < kChunks / 4; ++g) {
+                    const int n0 = (c_first + 2 * g) * 32;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float v = fmaf((__uint_as_float(raw[j]) - mean) * rstd, gamma[j], y[j]);
-                        y[j] = in_tensor ? v : 0.f;
+                    for (int half = 0; half < 2; ++half) {
+                        float gamma[32];
+                        tmem_ld_32x32(t_acc + n0 + half * 32, raw);
+                        load_params32(p.gamma + n0 + half * 32, gamma);
+                        load_params32(p.beta + n0 + half * 32, y);
+                        tmem_wait_ld();
+                        if (g + 1 == kChunks / 4 && half == 1) release_tmem();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = fmaf((__uint_as_float(raw[j]) - mean) * rstd, gamma[j], y[j]);
+                            y[j] = in_tensor ? v : 0.f;
+                        }
+                        split32(y, h, l, half * 16);
                     }
-                    split32(y, h, l);
-                    stage_and_store(&map_out, stage, set, row, elected, h, l, c * 32, m0);
+                    stage_store_plane(&map_out, stage, set, row, elected, h, n0, m0, 0, p.debug_flags);
+                    stage_store_plane(&map_out, stage, set, row, elected, l, n0, m0, 1, p.debug_flags);
+                }
+                if (p.trace_ln && warp == 2 && lane == 0) {
+                    atomicAdd(p.trace_ln + 0, (unsigned long long)(ln_t1 - ln_t0));
+                    atomicAdd(p.trace_ln + 1, (unsigned long long)(ln_t2 - ln_t1));
+                    atomicAdd(p.trace_ln + 2, (unsigned long long)(ln_t3 - ln_t2));
+                    atomicAdd(p.trace_ln + 3, (unsigned long long)(ln_t4 - ln_t3));
+                    atomicAdd(p.trace_ln + 4, (unsigned long long)(clock64() - ln_t4));
+                    atomicAdd(p.trace_ln + 5, 1ull);
                 }
             } else if (EPI == kEpiConvOut) {
                 // BN == 64 >= O: all channels of a frame live in one thread (set 0)
@@ -553,9 +590,9 @@ int make_store_map(CUtensorMap* map, __half* base, uint64_t inner, uint64_t rows
     }
     cuuint64_t dims[3] = {inner, rows, 2};
     cuuint64_t strides[2] = {inner * 2, plane_stride_elems * 2};
-    cuuint32_t box[3] = {32, (cuuint32_t)kBM, 2}, elem[3] = {1, 1, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)kBM, 1}, elem[3] = {1, 1, 1};
     CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, elem,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled (store map) failed with CUresult %d", (int)rc);

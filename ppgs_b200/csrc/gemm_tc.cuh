@@ -46,6 +46,8 @@ struct GemmParams {
     // [0] MMA wait tmem_empty [1] MMA wait full [2] MMA total [3] epilogue wait tmem_full
     // [4] epilogue total [5] producer wait empty [6] producer total [7] CTAs
     unsigned long long* trace = nullptr;
+    unsigned long long* trace_ln = nullptr;   // kEpiResLN phases: pass1, exchange, pass2, exchange, pass3
+    int debug_flags = 0;   // timing experiments only: 1 = skip plane stores, 2 = skip parameter loads
 };
 
 // Tensor map over split-fp16 planes: logical dims {inner, rows, groups, planes}
@@ -58,8 +60,8 @@ int make_plane_map(CUtensorMap* map, const __half* base, bool rank4, uint64_t in
                    uint32_t box_planes);
 
 // BN in {256, 128, 64}.  Launches a persistent grid of min(tiles, SMs) CTAs.
-// Store map over output planes [2][rows][inner]: box {32, 128, 2}, 64-byte swizzle
-// (the epilogue's staging layout).
+// Store map over output planes [2][rows][inner]: box {64, 128, 1 plane}, 128-byte
+// swizzle (the epilogue's staging layout).
 int make_store_map(CUtensorMap* map, __half* base, uint64_t inner, uint64_t rows,
                    uint64_t plane_stride_elems);
 
@@ -67,6 +69,30 @@ int make_store_map(CUtensorMap* map, __half* base, uint64_t inner, uint64_t rows
 int launch_gemm_tc(ppgs_engine* e, const char* name, int bn, int epilogue,
                    const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap* map_out,
                    const GemmParams& p, cudaStream_t stream);
+
+// Fused linear1 + ReLU + linear2 + residual + LayerNorm (ffn_tc.cu), CTA pairs.
+struct FfnParams {
+    int m_tiles, num_chunks, planes;
+    const float* scale1;
+    const float* scale2;
+    const float* bias1;
+    const float* bias2;
+    const float* gamma;
+    const float* beta;
+    float eps;
+    const SeqInfo* seqs;
+    const int* tile_seq;
+    int* status;
+    // cycle accounting (PPGS_B200_TRACE=1): MMA waits [0] x_full [1] hacc_empty [2] w1_full
+    // [3] h1_full [4] w2_full [5] y_empty [6] total; epilogue [8] hacc_full [9] h1_empty
+    // [10] y_full [11] LayerNorm [12] total [13] CTAs
+    unsigned long long* trace;
+};
+// map_x: activation planes {256, rows, 2}, box {64, 128, planes}; map_w1: linear1 planes,
+// box rows 32; map_w2: linear2 planes, box rows 128; map_out: store map of the x planes.
+int launch_ffn_fused(ppgs_engine* e, const CUtensorMap& map_x, const CUtensorMap& map_w1,
+                     const CUtensorMap& map_w2, const CUtensorMap& map_out, const FfnParams& p,
+                     cudaStream_t stream);
 
 }  // namespace tc
 }  // namespace ppgs

@@ -13,6 +13,8 @@
 //
 // Every activation lives in HBM as split-fp16 planes [2][rows][K] (hi + lo carries
 // 22 significand bits), including the residual stream.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "attention_tc.cuh"
@@ -29,6 +31,8 @@ static int weight_map(TcWeight& w) {
                               (uint64_t)w.N * w.C, plane, 256, 2));
     PPGS_CHECK(make_plane_map(&w.map_bn128, w.planes, true, w.C, w.N, w.taps, 2, w.C,
                               (uint64_t)w.N * w.C, plane, 128, 2));
+    PPGS_CHECK(make_plane_map(&w.map_bn32, w.planes, true, w.C, w.N, w.taps, 2, w.C,
+                              (uint64_t)w.N * w.C, plane, 32, 2));
     PPGS_CHECK(make_plane_map(&w.map_bn64, w.planes, true, w.C, w.N, w.taps, 2, w.C,
                               (uint64_t)w.N * w.C, plane, 64, 2));
     return PPGS_OK;
@@ -148,6 +152,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     base.b_planes = planes;
     const int pair = (e->gemm_pair && rows % 256 == 0) ? 1 : 0;
     base.pair = pair;
+    if (const char* v = getenv("PPGS_B200_DEBUG_FLAGS")) base.debug_flags = atoi(v);   // timing experiments
     auto wmap = [&](TcWeight& w) -> const CUtensorMap& { return pair ? w.map_bn128 : w.map_bn256; };
     // cycle accounting slots: 0 conv_in, 1 qkv, 2 out_proj, 3 ffn1, 4 ffn2, 5 conv_out
     auto trace = [&](int slot) { return e->trace_dev ? e->trace_dev + 8 * slot : nullptr; };
@@ -174,27 +179,38 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
         {
             GemmParams p = base;
             p.n_tiles = 1; p.cblocks = H / 64; p.a_planes = planes;
-            p.N = H; p.scale = T.out_w.inv_scale; p.bias = L.out_b; p.trace = trace(2);
+            p.N = H; p.scale = T.out_w.inv_scale; p.bias = L.out_b; p.trace = trace(2); p.trace_ln = trace(6);
             p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
             p.gamma = L.n1_w; p.beta = L.n1_b;
             PPGS_CHECK(launch_gemm_tc(e, "tc_out_proj_ln", 256, kEpiResLN, map_att, wmap(T.out_w),
                                       &out_x, p, stream));
         }
-        {
-            GemmParams p = base;
-            p.n_tiles = F / 256; p.cblocks = H / 64; p.a_planes = planes;
-            p.N = F; p.scale = T.l1_w.inv_scale; p.bias = L.l1_b; p.relu = 1; p.trace = trace(3);
-            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn1", 256, kEpiPlanes, map_x, wmap(T.l1_w), &out_ff,
-                                      p, stream));
-        }
-        {
-            GemmParams p = base;
-            p.n_tiles = 1; p.cblocks = F / 64; p.a_planes = planes;
-            p.N = H; p.scale = T.l2_w.inv_scale; p.bias = L.l2_b; p.trace = trace(4);
-            p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
-            p.gamma = L.n2_w; p.beta = L.n2_b;
-            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn2_ln", 256, kEpiResLN, map_ff, wmap(T.l2_w), &out_x,
-                                      p, stream));
+        if (pair && e->fused_ffn && F % 64 == 0) {
+            FfnParams f;
+            f.m_tiles = rows / 128; f.num_chunks = F / 64; f.planes = planes;
+            f.scale1 = T.l1_w.inv_scale; f.scale2 = T.l2_w.inv_scale;
+            f.bias1 = L.l1_b; f.bias2 = L.l2_b; f.gamma = L.n2_w; f.beta = L.n2_b;
+            f.eps = c.layer_norm_eps; f.seqs = seqs_dev; f.tile_seq = tile_seq_dev;
+            f.status = e->status_dev;
+            f.trace = e->trace_dev ? e->trace_dev + 64 : nullptr;   // counters 64..79
+            PPGS_CHECK(launch_ffn_fused(e, map_x, T.l1_w.map_bn32, T.l2_w.map_bn128, out_x, f, stream));
+        } else {
+            {
+                GemmParams p = base;
+                p.n_tiles = F / 256; p.cblocks = H / 64; p.a_planes = planes;
+                p.N = F; p.scale = T.l1_w.inv_scale; p.bias = L.l1_b; p.relu = 1; p.trace = trace(3);
+                PPGS_CHECK(launch_gemm_tc(e, "tc_ffn1", 256, kEpiPlanes, map_x, wmap(T.l1_w), &out_ff,
+                                          p, stream));
+            }
+            {
+                GemmParams p = base;
+                p.n_tiles = 1; p.cblocks = F / 64; p.a_planes = planes;
+                p.N = H; p.scale = T.l2_w.inv_scale; p.bias = L.l2_b; p.trace = trace(4); p.trace_ln = trace(7);
+                p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
+                p.gamma = L.n2_w; p.beta = L.n2_b;
+                PPGS_CHECK(launch_gemm_tc(e, "tc_ffn2_ln", 256, kEpiResLN, map_ff, wmap(T.l2_w), &out_x,
+                                          p, stream));
+            }
         }
     }
     {

@@ -14,7 +14,7 @@ engine = ppgs_b200.Engine(0).load_state_dict(O.random_state_dict(0, peaky=True))
 engine.precision = 'f16x2'
 audio = O.synthetic_audio(64, 160000, 0).cuda()
 engine.from_audio(audio)
-buf = (ctypes.c_ulonglong * 64)()
+buf = (ctypes.c_ulonglong * 128)()
 _lib.lib.ppgs_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 _lib.check(_lib.lib.ppgs_debug_trace(engine._handle, buf))
 forwards = 3
@@ -33,3 +33,18 @@ for k, name in enumerate(names):
     print(f'{name:9s} mma[{f(c[0], mma_ctas):8.1f} {f(c[1], mma_ctas):8.1f} {f(c[2], mma_ctas):8.1f}] '
           f'epi[{f(c[3], ctas):8.1f} {f(c[4], ctas):8.1f}] prod[{f(c[5], ctas):8.1f} {f(c[6], ctas):8.1f}] '
           f'ctas/launch {ctas / forwards / launches[k]:.0f}')
+
+print('LayerNorm epilogue phases, cycles per tile (warp 2 lane 0): pass1 exch1 pass2 exch2 pass3')
+for slot, name in ((6, 'out_proj'), (7, 'ffn2')):
+    c = [buf[8 * slot + i] for i in range(8)]
+    n = max(c[5], 1)
+    print(f'{name:9s} ' + ' '.join(f'{c[i] / n:8.0f}' for i in range(5)) + f'   tiles {n}')
+
+c = [buf[64 + i] for i in range(16)]
+if c[13]:
+    n_cta, n_mma = c[13], c[13] / 2
+    print('fused FFN per launch per CTA (kcycles): MMA waits x_full hacc_empty w1_full h1_full w2_full '
+          'y_empty | total')
+    print('   ' + ' '.join(f'{c[i] / n_mma / 1e3:8.1f}' for i in range(7)))
+    print('epilogue waits hacc_full h1_empty y_full | LayerNorm | total')
+    print('   ' + ' '.join(f'{c[8 + i] / n_cta / 1e3:8.1f}' for i in range(5)))
