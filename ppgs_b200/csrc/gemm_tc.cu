@@ -266,6 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         const bool elected = (warp - 2) == 4 * set && lane == 0;
+        const int tid_in_set = (int)threadIdx.x - 64 - 128 * set;
         unsigned char* stage = stage_out + set * kStageOutBytes;
         const float scale = *p.scale;
         int iter = 0;
@@ -370,30 +371,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const SeqInfo s = p.seqs[p.tile_seq[m_blk]];
                 const bool in_tensor = (int)(m - s.row0) < s.tensor_len;
                 const long long ln_t0 = clock64();
-                const __half* res_hi = p.residual + m * p.res_ld;
-                const __half* res_lo = res_hi + p.res_plane_stride;
                 float sum = 0.f;
-                // residual rows come straight from HBM / L2 (row per thread): the loads of
-                // chunk c + 2 are in flight while chunk c is combined
-                uint4 rbuf[2][8];
-                auto load_res = [&](int c, uint4 (&dst)[8]) {
+                // The residual tile comes from HBM / L2.  Row-per-thread loads would touch 32
+                // different lines per instruction (16 bytes each); instead the 128 threads of
+                // the set load each 32-column chunk cooperatively (8 rows x 64 contiguous
+                // bytes per warp instruction), pass it through the set's staging tile
+                // ([hi|lo][128 rows][64 B], XOR-swizzled) and read their own row back.  The
+                // loads of chunk i + 1 are in flight while chunk i is combined.
+                const int c_first = set * (kChunks / 2);   // set s owns chunks [4 s, 4 s + 4)
+                const uint32_t stage_addr = smem_u32(stage);
+                uint4 pre[8];
+                auto coop_load = [&](int c) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        dst[u] = reinterpret_cast<const uint4*>(res_hi + c * 32)[u];
-                        dst[4 + u] = reinterpret_cast<const uint4*>(res_lo + c * 32)[u];
+                    for (int it8 = 0; it8 < 8; ++it8) {
+                        const int idx = it8 * 128 + tid_in_set;
+                        const int u = idx & 3, r = (idx >> 2) & 127, plane = idx >> 9;
+                        pre[it8] = *reinterpret_cast<const uint4*>(
+                            p.residual + plane * p.res_plane_stride + (int64_t)(m0 + r) * p.res_ld + c * 32 + u * 8);
                     }
                 };
-                const int c_first = set * (kChunks / 2);   // set s owns chunks [4 s, 4 s + 4)
-                load_res(c_first, rbuf[0]);
+                coop_load(c_first);
 #pragma unroll
                 for (int i = 0; i < kChunks / 2; ++i) {
                     const int c = c_first + i;
-                    if (i + 1 < kChunks / 2) load_res(c + 1, rbuf[(i + 1) & 1]);
+                    if (i == 0 && elected) bulk_wait_read_all();   // previous tile's stores drained
+                    named_bar_sync(1 + set, 128);                   // staging tile is free
+#pragma unroll
+                    for (int it8 = 0; it8 < 8; ++it8) {
+                        const int idx = it8 * 128 + tid_in_set;
+                        const int u = idx & 3, r = (idx >> 2) & 127, plane = idx >> 9;
+                        st_shared_v4(stage_addr + (uint32_t)plane * 8192 + (uint32_t)r * 64 +
+                                         (((uint32_t)u ^ ((uint32_t)(r >> 1) & 3)) << 4),
+                                     pre[it8].x, pre[it8].y, pre[it8].z, pre[it8].w);
+                    }
+                    named_bar_sync(1 + set, 128);
+                    if (i + 1 < kChunks / 2) coop_load(c + 1);
                     tmem_ld_32x32(t_acc + c * 32, raw);
                     load_params32(p.bias + c * 32, y);
+                    uint4 rh[4], rl[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t addr = stage_addr + (uint32_t)row * 64 +
+                                              (((uint32_t)u ^ ((uint32_t)(row >> 1) & 3)) << 4);
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(rh[u].x), "=r"(rh[u].y), "=r"(rh[u].z), "=r"(rh[u].w)
+                                     : "r"(addr));
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(rl[u].x), "=r"(rl[u].y), "=r"(rl[u].z), "=r"(rl[u].w)
+                                     : "r"(addr + 8192));
+                    }
                     tmem_wait_ld();
-                    const uint32_t* rhw = reinterpret_cast<const uint32_t*>(&rbuf[i & 1][0]);
-                    const uint32_t* rlw = reinterpret_cast<const uint32_t*>(&rbuf[i & 1][4]);
+                    const uint32_t* rhw = reinterpret_cast<const uint32_t*>(rh);
+                    const uint32_t* rlw = reinterpret_cast<const uint32_t*>(rl);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&rhw[j]));
