@@ -75,7 +75,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '20'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -274,6 +274,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
 
     peaks = load_peaks()
@@ -348,6 +349,7 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -140,6 +140,9 @@ struct AttnParams {
     __half* out;
     int64_t out_plane_stride;
     int* status;
+    // cycle accounting (PPGS_B200_TRACE=1): MMA [0] wait q [1] wait k [2] wait p [3] wait v [4] total;
+    // softmax warp 2: [8] wait s [9] row max [10] wait p_empty [11] chunk work [12] wait o [13] total [14] CTAs
+    unsigned long long* trace;
 };
 
 // 2^x for x <= 0 (softmax exponents): one MUFU.EX2, flushes to zero on underflow
@@ -244,11 +247,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
             constexpr uint32_t idesc_s = make_idesc_f16(128, 128, false);
             constexpr uint32_t idesc_o = make_idesc_f16(128, 128, true);
             const uint32_t q_addr = smem_u32(q_smem), k_addr = smem_u32(k_ring);
-            bool ok = mbar_wait(&q_full, 0);
+            long long tw[4] = {0, 0, 0, 0};
+            const long long t_begin = clock64();
+            auto timed = [&](uint64_t* bar, uint32_t parity, int slot_id) {
+                const long long t0 = clock64();
+                const bool got = mbar_wait(bar, parity);
+                tw[slot_id] += clock64() - t0;
+                return got;
+            };
+            bool ok = timed(&q_full, 0, 0);
             tcgen05_fence_after();
             for (int j = 0; j < nb && ok; ++j) {
                 const int slot = j & 1;
-                if (!mbar_wait(&k_full[slot], (j >> 1) & 1)) { ok = false; break; }
+                if (!timed(&k_full[slot], (j >> 1) & 1, 1)) { ok = false; break; }
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + j * 128;
 #pragma unroll
@@ -269,9 +280,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
             const int pre = nchunks > 6 ? nchunks - 6 : 0;
             for (int i = 0; i < nchunks && ok; ++i) {
                 const int ps = i & 1, vs = i & 3;
-                if (!mbar_wait(&p_full[ps], (i >> 1) & 1)) { ok = false; break; }
-                if (i == 0 && pre == 2 && !mbar_wait(&p_full[1], 0)) { ok = false; break; }
-                if (!mbar_wait(&v_full[vs], (i >> 2) & 1)) { ok = false; break; }
+                if (!timed(&p_full[ps], (i >> 1) & 1, 2)) { ok = false; break; }
+                if (i == 0 && pre == 2 && !timed(&p_full[1], 0, 2)) { ok = false; break; }
+                if (!timed(&v_full[vs], (i >> 2) & 1, 3)) { ok = false; break; }
                 tcgen05_fence_after();
                 const uint32_t p_addr = q_addr + ps * kPSlotBytes;
                 const uint32_t v_addr = k_addr + vs * kVSlotBytes;
@@ -293,6 +304,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
             }
             if (ok) umma_commit(&o_full);
             else atomicExch(p.status, kStatusAttnTimeout);
+            if (p.trace) {
+                for (int i = 0; i < 4; ++i) atomicAdd(p.trace + i, (unsigned long long)tw[i]);
+                atomicAdd(p.trace + 4, (unsigned long long)(clock64() - t_begin));
+            }
         }
     } else {
         // 8 softmax warps: a query row is shared by two threads (same TMEM lane
@@ -302,7 +317,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         const int quad = warp & 3, r = quad * 32 + lane, t = q0 + r;
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
         uint32_t raw[32];
+        const long long ts0 = clock64();
         bool ok = mbar_wait(&s_full, 0);
+        const long long ts1 = clock64();
+        long long t_pempty = 0;
         tcgen05_fence_after();
         float mx = -FLT_MAX;
         if (ok) {
@@ -329,6 +347,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         named_bar_sync(1, 256);
         mx = fmaxf(row_part[0][r], row_part[1][r]);
         named_bar_sync(1, 256);   // row_part is reused for the row sums
+        const long long ts2 = clock64();
         const float mc = mx * p.scale_log2e;
         float sum = 0.f;
         const uint32_t p_base = smem_u32(q_smem);
@@ -336,7 +355,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
 #pragma unroll 1
         for (int i = 0; i < nchunks && ok; ++i) {
             const int c = chunk_order(i, nchunks), slot = i & 1;
-            if (!mbar_wait(&p_empty[slot], ((i >> 1) & 1) ^ 1)) { ok = false; break; }
+            {
+                const long long t0 = clock64();
+                const bool got = mbar_wait(&p_empty[slot], ((i >> 1) & 1) ^ 1);
+                t_pempty += clock64() - t0;
+                if (!got) { ok = false; break; }
+            }
             const uint32_t p_slot = p_base + slot * kPSlotBytes;
             const int key0 = c * 64 + half * 32;
             tmem_ld_32x32(t_row + key0, raw);
@@ -381,7 +405,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         row_part[half][r] = sum;
         named_bar_sync(1, 256);
         sum = row_part[0][r] + row_part[1][r];
+        const long long ts3 = clock64();
         if (ok && !mbar_wait(&o_full, 0)) ok = false;
+        const long long ts4 = clock64();
         tcgen05_fence_after();
         if (ok) {
             // O / sum -> split planes, staged as four [128 rows][64 cols] 128B-swizzled tiles
@@ -417,6 +443,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
             bulk_wait_all();
         }
         if (!ok) atomicExch(p.status, kStatusAttnTimeout);
+        if (p.trace && warp == 2 && lane == 0) {
+            atomicAdd(p.trace + 8, (unsigned long long)(ts1 - ts0));
+            atomicAdd(p.trace + 9, (unsigned long long)(ts2 - ts1));
+            atomicAdd(p.trace + 10, (unsigned long long)t_pempty);
+            atomicAdd(p.trace + 11, (unsigned long long)(ts3 - ts2 - t_pempty));
+            atomicAdd(p.trace + 12, (unsigned long long)(ts4 - ts3));
+            atomicAdd(p.trace + 13, (unsigned long long)(clock64() - ts0));
+            atomicAdd(p.trace + 14, 1ull);
+        }
     }
 
     tcgen05_fence_before();
@@ -455,6 +490,7 @@ int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows
         p.out = out;
         p.out_plane_stride = (int64_t)rows * H;
         p.status = e->status_dev;
+        p.trace = e->trace_dev ? e->trace_dev + 80 : nullptr;
         dim3 grid(plan.max_pitch / 128, e->cfg.num_heads, (unsigned)plan.seqs.size());
         {
             LaunchScope scope(e, "tc_attention", stream);

@@ -277,6 +277,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int m_blk = PAIR ? 2 * m_unit + (int)rank : m_unit;
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
+            // ResLN: the residual loads of the first two column chunks are in flight while
+            // this warp waits for the accumulator
+            uint4 pre[2][8];
+            auto coop_load = [&](int c, uint4 (&dst)[8]) {
+#pragma unroll
+                for (int it8 = 0; it8 < 8; ++it8) {
+                    const int idx = it8 * 128 + tid_in_set;
+                    const int u = idx & 3, r = (idx >> 2) & 127, plane = idx >> 9;
+                    dst[it8] = ld_global_stream(p.residual + plane * p.res_plane_stride +
+                                                (int64_t)(m_blk * kBM + r) * p.res_ld + c * 32 + u * 8);
+                }
+            };
+            if (EPI == kEpiResLN) {
+                coop_load(set * (kChunks / 2), pre[0]);
+                coop_load(set * (kChunks / 2) + 1, pre[1]);
+            }
             const long long t0 = clock64();
             const bool ready = mbar_wait(&tmem_full_bar[acc], acc_phase);
             t_wait += clock64() - t0;
@@ -377,20 +393,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 // the set load each 32-column chunk cooperatively (8 rows x 64 contiguous
                 // bytes per warp instruction), pass it through the set's staging tile
                 // ([hi|lo][128 rows][64 B], XOR-swizzled) and read their own row back.  The
-                // loads of chunk i + 1 are in flight while chunk i is combined.
+                // loads run two chunks ahead (the first two are issued before the accumulator wait).
                 const int c_first = set * (kChunks / 2);   // set s owns chunks [4 s, 4 s + 4)
                 const uint32_t stage_addr = smem_u32(stage);
-                uint4 pre[8];
-                auto coop_load = [&](int c) {
-#pragma unroll
-                    for (int it8 = 0; it8 < 8; ++it8) {
-                        const int idx = it8 * 128 + tid_in_set;
-                        const int u = idx & 3, r = (idx >> 2) & 127, plane = idx >> 9;
-                        pre[it8] = *reinterpret_cast<const uint4*>(
-                            p.residual + plane * p.res_plane_stride + (int64_t)(m0 + r) * p.res_ld + c * 32 + u * 8);
-                    }
-                };
-                coop_load(c_first);
 #pragma unroll
                 for (int i = 0; i < kChunks / 2; ++i) {
                     const int c = c_first + i;
@@ -402,10 +407,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const int u = idx & 3, r = (idx >> 2) & 127, plane = idx >> 9;
                         st_shared_v4(stage_addr + (uint32_t)plane * 8192 + (uint32_t)r * 64 +
                                          (((uint32_t)u ^ ((uint32_t)(r >> 1) & 3)) << 4),
-                                     pre[it8].x, pre[it8].y, pre[it8].z, pre[it8].w);
+                                     pre[i & 1][it8].x, pre[i & 1][it8].y, pre[i & 1][it8].z, pre[i & 1][it8].w);
                     }
                     named_bar_sync(1 + set, 128);
-                    if (i + 1 < kChunks / 2) coop_load(c + 1);
+                    if (i + 2 < kChunks / 2) coop_load(c + 2, pre[i & 1]);
                     tmem_ld_32x32(t_acc + c * 32, raw);
                     load_params32(p.bias + c * 32, y);
                     uint4 rh[4], rl[4];

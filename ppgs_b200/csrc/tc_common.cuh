@@ -176,6 +176,15 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
                  : "memory");
 }
+// streaming 16-byte global load that does not allocate in L1 (keeps the small L1 that
+// is left beside a 224 KB shared-memory carve-out for the epilogue parameters)
+__device__ __forceinline__ uint4 ld_global_stream(const void* ptr) {
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(ptr));
+    return v;
+}
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -48,3 +48,11 @@ if c[13]:
     print('   ' + ' '.join(f'{c[i] / n_mma / 1e3:8.1f}' for i in range(7)))
     print('epilogue waits hacc_full h1_empty y_full | LayerNorm | total')
     print('   ' + ' '.join(f'{c[8 + i] / n_cta / 1e3:8.1f}' for i in range(5)))
+
+c = [buf[80 + i] for i in range(16)]
+if c[14]:
+    n = c[14]
+    print(f'attention per CTA (cycles, {n} CTAs): MMA waits q k p v | total')
+    print('   ' + ' '.join(f'{c[i] / n:8.0f}' for i in range(5)))
+    print('softmax warp: wait S | row max | wait p_empty | chunk work | wait O | total')
+    print('   ' + ' '.join(f'{c[8 + i] / n:8.0f}' for i in range(6)))

@@ -142,6 +142,23 @@ def test_legacy_mode_and_logits(ppgs_b200, precision):
     assert np.abs(chunked - out).max() > 1e-3      # chunking is semantics
 
 
+@pytest.mark.parametrize('switch', ['PPGS_B200_FUSED_FFN=1', 'PPGS_B200_PAIR=0', 'PPGS_B200_ATTENTION=0'])
+def test_alternative_kernel_paths(ppgs_b200, monkeypatch, switch):
+    """The optional kernels stay parity-checked: the fused FFN kernel, the single-CTA
+    (cta_group::1) GEMMs and the CUDA-core attention kernel (read at engine creation)."""
+    name, value = switch.split('=')
+    monkeypatch.setenv(name, value)
+    sd = O.random_state_dict(6, peaky=True)
+    engine = make_engine(ppgs_b200, sd, 'f16x2')
+    for frames, lengths in ((400, [400, 250, 31]), (1000, [1000, 640])):
+        audio = O.synthetic_audio(len(lengths), frames * 160, seed=frames + 1)
+        sample_lengths = torch.tensor(lengths) * 160
+        ref = O.from_audio(sd, audio, lengths=sample_lengths).numpy()
+        out = engine.from_audio(audio.cuda(), lengths=sample_lengths).cpu().numpy()
+        for row, n in enumerate(lengths):
+            assert np.abs(out[row, :, :n] - ref[row, :, :n]).max() <= PPG_TOL
+
+
 def test_error_conventions(ppgs_b200):
     engine = make_engine(ppgs_b200, O.random_state_dict(0), 'fp32')
     feats = torch.zeros(2, 80, 100, dtype=torch.float16, device='cuda')
