@@ -61,6 +61,18 @@ def load_peaks():
             'source': 'fallback'}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at this
+    workload, from the committed `ncu --set full` capture (profiles/ncu_traffic.json);
+    None when the kernel has no capture."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if not os.path.exists(path):
+        return None
+    entry = json.load(open(path)).get('kernels', {}).get(kernel)
+    return None if entry is None else {'bytes_per_launch': entry['dram_bytes'],
+                                       'source': entry['source']}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
 
@@ -271,6 +283,21 @@ def main():
         ref = O.from_audio(O.random_state_dict(0, peaky=True), host[last][:2].unsqueeze(1))
         parity = (got - ref).abs().max().item()
 
+    # context only (never the headline): the same kernels with ONE fp16 MMA pass, i.e. the
+    # reference's own CUDA-autocast numerics class, which misses the 1e-4 parity bar
+    single_pass = None
+    if precision == 'f16x2' and rank == 0 and world == 1:
+        engine.precision = 'f16'
+        for i in range(3):
+            device_step(i)
+        ms = timed(device_step, steps) / steps
+        got = engine.from_audio(dev[0][:2].contiguous()).cpu()
+        ref = O.from_audio(O.random_state_dict(0, peaky=True), host[0][:2].unsqueeze(1))
+        single_pass = {'ms_per_step': ms, 'frames_per_sec': BATCH * FRAMES / (ms / 1e3),
+                       'max_abs_vs_oracle': (got - ref).abs().max().item(),
+                       'note': 'PPGS_PRECISION_F16, not parity-valid; for context'}
+        engine.precision = precision
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -293,7 +320,7 @@ def main():
         'out_proj': 2 * H * H * computed, 'conv_in': 2 * KSIZE * C_IN * H * computed,
         'conv_out': 2 * KSIZE * H * O_OUT * computed, 'attention': BATCH * ATTN_PER_UTT / LAYERS}
     roofline = {'kernel': name, 'share_of_step': kernel_ms / total_kernel_ms,
-                'ms_per_launch': per_launch_ms, 'traffic': None}
+                'ms_per_launch': per_launch_ms, 'traffic': ncu_traffic(name)}
     key = next((k for k in sorted(flops_by_kernel, key=len, reverse=True) if k in name), None)
     if key is not None:
         achieved = flops_by_kernel[key] / (per_launch_ms * 1e-3) / 1e12
@@ -345,6 +372,7 @@ def main():
         'clocks': clocks,
         'roofline': roofline,
         'cpu_baseline': cpu,
+        'single_pass_f16_context': single_pass,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

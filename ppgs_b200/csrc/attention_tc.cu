@@ -352,26 +352,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         float sum = 0.f;
         const uint32_t p_base = smem_u32(q_smem);
         const uint32_t row_off = (uint32_t)r * 128, sw = (uint32_t)(r & 7);
-#pragma unroll 1
-        for (int i = 0; i < nchunks && ok; ++i) {
+        // one chunk: `cur` holds this thread's 32 scores (its tcgen05.ld was issued one
+        // chunk earlier); the next chunk's load is issued before the math so TMEM latency
+        // hides behind it, and the P slot is only waited for right before it is written
+        auto chunk = [&](int i, uint32_t (&cur)[32], uint32_t (&nxt)[32]) -> bool {
             const int c = chunk_order(i, nchunks), slot = i & 1;
-            {
-                const long long t0 = clock64();
-                const bool got = mbar_wait(&p_empty[slot], ((i >> 1) & 1) ^ 1);
-                t_pempty += clock64() - t0;
-                if (!got) { ok = false; break; }
-            }
-            const uint32_t p_slot = p_base + slot * kPSlotBytes;
             const int key0 = c * 64 + half * 32;
-            tmem_ld_32x32(t_row + key0, raw);
             tmem_wait_ld();
+            if (i + 1 < nchunks)
+                tmem_ld_32x32(t_row + chunk_order(i + 1, nchunks) * 64 + half * 32, nxt);
             uint32_t h[16], l[16];
             const bool full = key0 + 32 <= nkeys && (!p.causal || key0 + 31 <= q0);
             if (full) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float e0 = fast_exp2(fmaf(__uint_as_float(raw[2 * j]), p.scale_log2e, -mc));
-                    const float e1 = fast_exp2(fmaf(__uint_as_float(raw[2 * j + 1]), p.scale_log2e, -mc));
+                    const float e0 = fast_exp2(fmaf(__uint_as_float(cur[2 * j]), p.scale_log2e, -mc));
+                    const float e1 = fast_exp2(fmaf(__uint_as_float(cur[2 * j + 1]), p.scale_log2e, -mc));
                     sum += e0 + e1;
                     split2_f16(e0, e1, h[j], l[j]);
                 }
@@ -383,13 +379,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
                     for (int q = 0; q < 2; ++q) {
                         const int key = key0 + 2 * j + q;
                         const bool allowed = key < nkeys && (!p.causal || key <= t);
-                        const float e = fast_exp2(fmaf(__uint_as_float(raw[2 * j + q]), p.scale_log2e, -mc));
+                        const float e = fast_exp2(fmaf(__uint_as_float(cur[2 * j + q]), p.scale_log2e, -mc));
                         pv[q] = allowed ? e : 0.f;
                     }
                     sum += pv[0] + pv[1];
                     split2_f16(pv[0], pv[1], h[j], l[j]);
                 }
             }
+            {
+                const long long t0 = clock64();
+                const bool got = mbar_wait(&p_empty[slot], ((i >> 1) & 1) ^ 1);
+                t_pempty += clock64() - t0;
+                if (!got) return false;
+            }
+            const uint32_t p_slot = p_base + slot * kPSlotBytes;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t unit = (uint32_t)(half * 4 + u) ^ sw;
@@ -401,7 +404,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[slot]);
+            return true;
+        };
+        uint32_t raw_b[32];
+        if (ok) tmem_ld_32x32(t_row + chunk_order(0, nchunks) * 64 + half * 32, raw);
+#pragma unroll 1
+        for (int i = 0; i < nchunks && ok; i += 2) {
+            ok = chunk(i, raw, raw_b);
+            if (ok && i + 1 < nchunks) ok = chunk(i + 1, raw_b, raw);
         }
+        tmem_wait_ld();
         row_part[half][r] = sum;
         named_bar_sync(1, 256);
         sum = row_part[0][r] + row_part[1][r];
