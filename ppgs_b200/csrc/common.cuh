@@ -79,7 +79,11 @@ struct TcWeight {
     __half* planes = nullptr;
     const float* inv_scale = nullptr;
     int N = 0, C = 0, taps = 1;
-    CUtensorMap map_bn256, map_bn128, map_bn64, map_bn32;   // box rows 256 / 128 (CTA-pair halves) / 64 / 32
+    // TMA descriptors by W-tile rows (256 / 128 = CTA-pair halves / 64 / 32 = fused-FFN
+    // halves); index [0] loads the hi plane only (PPGS_PRECISION_F16), [1] both planes
+    struct Maps {
+        CUtensorMap bn256, bn128, bn64, bn32;
+    } maps[2];
 };
 
 struct TcLayer {

@@ -27,14 +27,14 @@ using namespace tc;
 
 static int weight_map(TcWeight& w) {
     const uint64_t plane = (uint64_t)w.taps * w.N * w.C;
-    PPGS_CHECK(make_plane_map(&w.map_bn256, w.planes, true, w.C, w.N, w.taps, 2, w.C,
-                              (uint64_t)w.N * w.C, plane, 256, 2));
-    PPGS_CHECK(make_plane_map(&w.map_bn128, w.planes, true, w.C, w.N, w.taps, 2, w.C,
-                              (uint64_t)w.N * w.C, plane, 128, 2));
-    PPGS_CHECK(make_plane_map(&w.map_bn32, w.planes, true, w.C, w.N, w.taps, 2, w.C,
-                              (uint64_t)w.N * w.C, plane, 32, 2));
-    PPGS_CHECK(make_plane_map(&w.map_bn64, w.planes, true, w.C, w.N, w.taps, 2, w.C,
-                              (uint64_t)w.N * w.C, plane, 64, 2));
+    for (int planes = 1; planes <= 2; ++planes) {
+        TcWeight::Maps& m = w.maps[planes - 1];
+        const struct { CUtensorMap* map; uint32_t rows; } boxes[4] = {
+            {&m.bn256, 256}, {&m.bn128, 128}, {&m.bn64, 64}, {&m.bn32, 32}};
+        for (const auto& box : boxes)
+            PPGS_CHECK(make_plane_map(box.map, w.planes, true, w.C, w.N, w.taps, 2, w.C,
+                                      (uint64_t)w.N * w.C, plane, box.rows, planes));
+    }
     return PPGS_OK;
 }
 
@@ -153,7 +153,9 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     const int pair = (e->gemm_pair && rows % 256 == 0) ? 1 : 0;
     base.pair = pair;
     if (const char* v = getenv("PPGS_B200_DEBUG_FLAGS")) base.debug_flags = atoi(v);   // timing experiments
-    auto wmap = [&](TcWeight& w) -> const CUtensorMap& { return pair ? w.map_bn128 : w.map_bn256; };
+    auto wmap = [&](TcWeight& w) -> const CUtensorMap& {
+        return pair ? w.maps[planes - 1].bn128 : w.maps[planes - 1].bn256;
+    };
     // cycle accounting slots: 0 conv_in, 1 qkv, 2 out_proj, 3 ffn1, 4 ffn2, 5 conv_out
     auto trace = [&](int slot) { return e->trace_dev ? e->trace_dev + 8 * slot : nullptr; };
 
@@ -193,7 +195,8 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             f.eps = c.layer_norm_eps; f.seqs = seqs_dev; f.tile_seq = tile_seq_dev;
             f.status = e->status_dev;
             f.trace = e->trace_dev ? e->trace_dev + 64 : nullptr;   // counters 64..79
-            PPGS_CHECK(launch_ffn_fused(e, map_x, T.l1_w.map_bn32, T.l2_w.map_bn128, out_x, f, stream));
+            PPGS_CHECK(launch_ffn_fused(e, map_x, T.l1_w.maps[planes - 1].bn32, T.l2_w.maps[planes - 1].bn128, out_x, f,
+                                        stream));
         } else {
             {
                 GemmParams p = base;
@@ -219,7 +222,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
         p.N = O; p.O = O; p.scale = e->tc_conv_out.inv_scale; p.bias = e->conv_out_b;
         p.ppg = out; p.T = plan.frames; p.softmax = softmax; p.pair = 0;
         PPGS_CHECK(launch_gemm_tc(e, "tc_conv_out_softmax", 64, kEpiConvOut, map_x,
-                                  e->tc_conv_out.map_bn64, nullptr, p, stream));
+                                  e->tc_conv_out.maps[planes - 1].bn64, nullptr, p, stream));
     }
     return PPGS_OK;
 }

@@ -214,6 +214,11 @@ class Engine:
             self._in_flight = (getattr(self, '_in_flight', None) or [])[-1:] + [(audio, out)]
         return out
 
+    def check(self):
+        """Synchronise and raise if a kernel reported a pipeline time-out (the device
+        entry points are asynchronous and cannot report it themselves)."""
+        _lib.check(_lib.lib.ppgs_engine_wait(self._handle))
+
     def wait(self):
         """Block until every request enqueued with `wait=False` has landed."""
         _lib.check(_lib.lib.ppgs_engine_wait(self._handle))

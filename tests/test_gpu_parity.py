@@ -99,6 +99,7 @@ def test_transformer_vs_reference_golden(ppgs_b200, name, precision):
     assert err <= PPG_TOL, f'{name} {precision}: max-abs {err:.3e}'
     logits = engine.transformer(feats.cuda(), lengths, softmax=False).cpu().numpy()
     assert np.abs(logits - g['logits']).max() <= 2e-3
+    engine.check()      # no kernel reported a pipeline time-out
 
 
 @pytest.mark.parametrize('precision', PRECISIONS)
@@ -152,7 +153,10 @@ def test_single_pass_f16_mode_is_the_autocast_numerics_class(ppgs_b200):
     err = {}
     for precision in ('f16', 'f16x2'):
         engine = make_engine(ppgs_b200, sd, precision)
-        err[precision] = np.abs(engine.from_audio(audio.cuda()).cpu().numpy() - ref).max()
+        out = torch.full((2, 40, 400), float('nan'), device='cuda')   # never a recycled result
+        out.copy_(engine.from_audio(audio.cuda()))
+        engine.check()
+        err[precision] = np.abs(out.cpu().numpy() - ref).max()
     assert err['f16x2'] <= PPG_TOL < err['f16'] <= 2e-2
 
 
@@ -171,6 +175,7 @@ def test_alternative_kernel_paths(ppgs_b200, monkeypatch, switch):
         out = engine.from_audio(audio.cuda(), lengths=sample_lengths).cpu().numpy()
         for row, n in enumerate(lengths):
             assert np.abs(out[row, :, :n] - ref[row, :, :n]).max() <= PPG_TOL
+    engine.check()
 
 
 def test_error_conventions(ppgs_b200):
@@ -255,6 +260,7 @@ def test_config2_full_size_properties(ppgs_b200, precision):
     assert (sub - out[5:7]).abs().max() <= 1e-6
     ref = O.from_audio(sd, audio[5:7])
     assert (out[5:7].cpu() - ref).abs().max() <= PPG_TOL
+    engine.check()
     # launch accounting used by bench.py
     before = engine.launches
     engine.from_audio(audio.cuda())
