@@ -90,6 +90,8 @@ int ppgs_engine_set_weight(ppgs_engine* engine, const char* name,
  * conv weights, split-fp16 planes, power-of-two scales). */
 int ppgs_engine_finalize(ppgs_engine* engine);
 
+/* Default (chosen at finalize): PPGS_PRECISION_F16X2 when the model shape has tensor-core
+ * kernels (hidden 256, head_dim 128 — the mel model), else PPGS_PRECISION_FP32. */
 int ppgs_engine_set_precision(ppgs_engine* engine, int precision);
 int ppgs_engine_get_precision(const ppgs_engine* engine);
 
@@ -111,6 +113,22 @@ int ppgs_engine_adopt_blob(ppgs_engine* engine);
 int ppgs_mel_forward(ppgs_engine* engine, const float* audio_dev, int batch,
                      int64_t samples, int64_t audio_stride, void* mel_dev,
                      void* stream);
+
+/* ppgs.preprocess.w2v2fb.from_audios (ppgs/preprocess/w2v2fb/core.py:32-75): the
+ * Hugging Face Wav2Vec2Model('facebook/wav2vec2-base') forward on the audio padded by 40
+ * zeros each side, with the padding mask derived from `lengths_host` (samples; NULL = all
+ * full length), `last_hidden_state` nearest-upsampled to samples/160 frames, fp16.
+ * The wav2vec2 weights are uploaded with ppgs_engine_set_weight under their Hugging Face
+ * state-dict keys prefixed by "w2v2." (e.g. "w2v2.encoder.layers.0.attention.q_proj.weight"),
+ * then packed by ppgs_w2v2_finalize (strict: every key, exact shapes; folds the weight
+ * norm of the positional convolution).
+ *   audio_dev    : (batch, samples) fp32, row stride `audio_stride`
+ *   features_dev : (batch, 768, samples/160) fp16, contiguous
+ * This round the front-end computes in fp32 on the CUDA cores. */
+int ppgs_w2v2_finalize(ppgs_engine* engine);
+int ppgs_w2v2fb_forward(ppgs_engine* engine, const float* audio_dev, int batch, int64_t samples,
+                        int64_t audio_stride, const int64_t* lengths_host, void* features_dev,
+                        void* stream);
 
 /* ppgs.from_features -> ppgs.infer -> Transformer.forward (ppgs/core.py:72-128,
  * 551-596; ppgs/model/transformer.py:45-81), including the 500/400/50 chunking

@@ -50,6 +50,8 @@ SYMBOLS = {
     'ppgs_engine_blob_dev': (_vp, [_vp]),
     'ppgs_engine_adopt_blob': (_i, [_vp]),
     'ppgs_mel_forward': (_i, [_vp, _vp, _i, _i64, _i64, _vp, _vp]),
+    'ppgs_w2v2_finalize': (_i, [_vp]),
+    'ppgs_w2v2fb_forward': (_i, [_vp, _vp, _i, _i64, _i64, _c.POINTER(_i64), _vp, _vp]),
     'ppgs_transformer_forward': (_i, [_vp, _vp, _i, _i, _c.POINTER(_i64), _i, _i, _vp, _vp]),
     'ppgs_from_audio': (_i, [_vp, _vp, _i, _i64, _i64, _c.POINTER(_i64), _i, _i, _vp, _vp]),
     'ppgs_from_audio_host': (_i, [_vp, _vp, _i, _i64, _c.POINTER(_i64), _i, _i, _vp, _vp]),

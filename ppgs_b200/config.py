@@ -46,3 +46,8 @@ MODEL_KWARGS = {
 # Hugging Face checkpoint names (ppgs/load.py:59-67)
 HF_REPO = 'CameronChurchwell/ppgs'
 HF_CHECKPOINTS = {'mel': 'mel-800k.pt', 'w2v2fb': 'w2v2fb-425k.pt'}
+
+# w2v2fb front-end (ppgs/preprocess/w2v2fb/core.py:17-24): Hugging Face model id the
+# reference downloads; a local directory / state-dict file can be given instead
+W2V2FB_CONFIG = 'facebook/wav2vec2-base'
+W2V2FB_CHECKPOINT = None

@@ -97,10 +97,15 @@ struct LayerWeights {
 
 }  // namespace ppgs
 
+namespace ppgs {
+struct W2v2Weights;
+}
+
 struct ppgs_engine {
     ppgs_model_config cfg;
     int device = 0;
     int precision = PPGS_PRECISION_FP32;
+    bool precision_chosen = false;   // false: finalize picks the tensor-core parity mode when the shape allows
     bool finalized = false;
     int sm_count = 148;
 
@@ -127,6 +132,10 @@ struct ppgs_engine {
     int fused_ffn = 0;           // 1 = one fused kernel for linear1 + ReLU + linear2 + LN (PPGS_B200_FUSED_FFN;
                                  // parity-green but shared-memory-bound and slower than the two GEMMs)
     unsigned long long* trace_dev = nullptr;   // [8 kernel kinds][8] cycle counters (PPGS_B200_TRACE=1)
+
+    // wav2vec2-base front-end of the `w2v2fb` representation (optional)
+    std::map<std::string, ppgs::HostTensor> w2v2_host;
+    ppgs::W2v2Weights* w2v2 = nullptr;
 
     ppgs::MelTables mel;
     std::vector<float> host_window;   // optional override ("frontend.window")
@@ -204,6 +213,13 @@ int build_plan(const ppgs_engine* e, int batch, int frames, const int64_t* lengt
                int legacy_mode, ForwardPlan* plan);
 int transformer_forward_fp32(ppgs_engine* e, const __half* features, const ForwardPlan& plan,
                              int softmax, float* out, cudaStream_t stream);
+
+// w2v2_fp32.cu
+int w2v2_accepts_key(const std::string& key, const std::vector<int64_t>& shape);   // 1 = ignore
+int w2v2_finalize(ppgs_engine* e);
+void w2v2_free(ppgs_engine* e);
+int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t samples, int64_t stride,
+                   const int64_t* lengths, __half* out, cudaStream_t stream);
 
 // transformer_tc.cu
 int build_weight_maps(ppgs_engine* e);

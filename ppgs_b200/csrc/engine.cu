@@ -407,6 +407,7 @@ void ppgs_engine_destroy(ppgs_engine* e) {
     cudaFree(e->blob);
     cudaFree(e->status_dev);
     cudaFree(e->trace_dev);
+    w2v2_free(e);
     cudaFree(e->workspace);
     cudaFree(e->io_dev);
     for (auto& slot : e->host_slots) {
@@ -439,6 +440,18 @@ int ppgs_engine_set_weight(ppgs_engine* e, const char* name, const float* data,
     size_t numel = 1;
     for (int64_t d : shp) numel *= (size_t)d;
     const std::string key(name);
+    if (key.rfind("w2v2.", 0) == 0) {
+        const std::string inner = key.substr(5);
+        const int rc = w2v2_accepts_key(inner, shp);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            HostTensor t;
+            t.data.assign(data, data + numel);
+            t.shape = shp;
+            e->w2v2_host[inner] = std::move(t);
+        }
+        return PPGS_OK;
+    }
     if (key == "frontend.window") {
         if (numel != 1024) {
             set_error("frontend.window must have 1024 elements");
@@ -475,6 +488,16 @@ int ppgs_engine_set_weight(ppgs_engine* e, const char* name, const float* data,
     return PPGS_E_INVALID;
 }
 
+static bool tensor_core_shape(const ppgs_model_config& c) {
+    return c.hidden_channels == 256 && c.hidden_channels / c.num_heads == 128 &&
+           c.ffn_channels % 256 == 0 && c.output_channels <= 64 && c.input_channels % 8 == 0;
+}
+
+static void pick_default_precision(ppgs_engine* e) {
+    if (!e->precision_chosen)
+        e->precision = tensor_core_shape(e->cfg) ? PPGS_PRECISION_F16X2 : PPGS_PRECISION_FP32;
+}
+
 int ppgs_engine_finalize(ppgs_engine* e) {
     PPGS_ENTER(e);
     for (const KeySpec& spec : expected_keys(e->cfg)) {
@@ -501,6 +524,7 @@ int ppgs_engine_finalize(ppgs_engine* e) {
         else i = e->weights.erase(i);
     }
     e->finalized = true;
+    pick_default_precision(e);
     return PPGS_OK;
 }
 
@@ -529,7 +553,24 @@ int ppgs_engine_adopt_blob(ppgs_engine* e) {
     if (it != e->weights.end()) basis = it->second.data.data();
     PPGS_CHECK(build_mel_tables(e, basis));
     e->finalized = true;
+    pick_default_precision(e);
     return PPGS_OK;
+}
+
+int ppgs_w2v2_finalize(ppgs_engine* e) {
+    PPGS_ENTER(e);
+    return w2v2_finalize(e);
+}
+
+int ppgs_w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                        int64_t stride, const int64_t* lengths, void* features, void* stream) {
+    PPGS_ENTER(e);
+    if (!audio || !features || batch <= 0 || samples <= 0 || stride < samples) {
+        set_error("w2v2fb_forward: bad argument");
+        return PPGS_E_INVALID;
+    }
+    return w2v2fb_forward(e, audio, batch, samples, stride, lengths, static_cast<__half*>(features),
+                          static_cast<cudaStream_t>(stream));
 }
 
 int ppgs_engine_set_precision(ppgs_engine* e, int precision) {
@@ -542,14 +583,13 @@ int ppgs_engine_set_precision(ppgs_engine* e, int precision) {
         set_error("precision %d is not available in this build", precision);
         return PPGS_E_UNSUPPORTED;
     }
-    if (precision != PPGS_PRECISION_FP32 &&
-        !(e->cfg.hidden_channels == 256 && e->cfg.ffn_channels % 256 == 0 &&
-          e->cfg.output_channels <= 64 && e->cfg.input_channels % 8 == 0)) {
+    if (precision != PPGS_PRECISION_FP32 && !tensor_core_shape(e->cfg)) {
         set_error("precision %d is not available for this model shape (tensor-core path: "
                   "hidden 256)", precision);
         return PPGS_E_UNSUPPORTED;
     }
     e->precision = precision;
+    e->precision_chosen = true;
     return PPGS_OK;
 }
 

@@ -120,22 +120,6 @@ __global__ void fold_kernel(const __half* __restrict__ feats, int C, int T,
 // ---------------------------------------------------------------------------
 // SGEMM: out[M,N] = A[M,K] (row stride lda, rows may overlap: conv-as-GEMM) * B[N,K]^T
 // ---------------------------------------------------------------------------
-enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RES = 2, EPI_IN = 3 };
-
-struct SgemmArgs {
-    const float* A;
-    int64_t lda;
-    const float* B;   // [N][K]
-    const float* bias;
-    float* out;
-    int64_t ldo;
-    int M, N, K;
-    const float* res;      // EPI_BIAS_RES: [M][N]
-    const float* pe;       // EPI_IN: [max_len][N]
-    const SeqInfo* seqs;   // EPI_IN
-    const int* tile_seq;
-};
-
 template <int EPI>
 __global__ void __launch_bounds__(256) sgemm_kernel(SgemmArgs a) {
     constexpr int BM = 128, BN = 64, BK = 16;
@@ -198,6 +182,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(SgemmArgs a) {
             if (n >= a.N) continue;
             float v = acc[i][j] + a.bias[n];
             if (EPI == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+            if (EPI == EPI_BIAS_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
             if (EPI == EPI_BIAS_RES) v += a.res[(int64_t)m * a.N + n];
             if (EPI == EPI_IN) {
                 const int t = m - s.row0;
@@ -219,6 +204,21 @@ static int launch_sgemm(ppgs_engine* e, const char* name, const SgemmArgs& a,
     }
     PPGS_CUDA(cudaGetLastError());
     return PPGS_OK;
+}
+
+int launch_sgemm_any(ppgs_engine* e, const char* name, int epi, const SgemmArgs& a,
+                     cudaStream_t stream) {
+    if (a.M % 128 || a.K % 16 || a.lda % 4) {
+        set_error("sgemm %s: M %% 128, K %% 16 and lda %% 4 must be 0 (M=%d K=%d)", name, a.M, a.K);
+        return PPGS_E_INVALID;
+    }
+    switch (epi) {
+        case EPI_BIAS: return launch_sgemm<EPI_BIAS>(e, name, a, stream);
+        case EPI_BIAS_RELU: return launch_sgemm<EPI_BIAS_RELU>(e, name, a, stream);
+        case EPI_BIAS_RES: return launch_sgemm<EPI_BIAS_RES>(e, name, a, stream);
+        case EPI_BIAS_GELU: return launch_sgemm<EPI_BIAS_GELU>(e, name, a, stream);
+        default: set_error("sgemm: unknown epilogue %d", epi); return PPGS_E_INVALID;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -435,6 +435,27 @@ static int launch_attention(ppgs_engine* e, const float* qkv, const ForwardPlan&
     }
     PPGS_CUDA(cudaGetLastError());
     return PPGS_OK;
+}
+
+int launch_attention_fp32_any(ppgs_engine* e, int head_dim, const float* qkv, int H, int heads,
+                              int max_pitch, int nseq, const SeqInfo* seqs, int causal,
+                              float* out, cudaStream_t stream) {
+    auto run = [&](auto kernel, int D) -> int {
+        const size_t smem = (size_t)(32 * D + 32 * (D + 1) + 32 * D) * sizeof(float);
+        PPGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(max_pitch / 32, heads, (unsigned)nseq);
+        {
+            LaunchScope scope(e, "attention_fp32", stream);
+            kernel<<<grid, 256, smem, stream>>>(qkv, H, seqs, causal, 1.f / sqrtf((float)D), out);
+        }
+        PPGS_CUDA(cudaGetLastError());
+        return PPGS_OK;
+    };
+    if (head_dim == 64) return run(attention_fp32_kernel<64>, 64);
+    if (head_dim == 128) return run(attention_fp32_kernel<128>, 128);
+    if (head_dim == 256) return run(attention_fp32_kernel<256>, 256);
+    set_error("attention_fp32: head_dim %d not built", head_dim);
+    return PPGS_E_UNSUPPORTED;
 }
 
 int transformer_forward_fp32(ppgs_engine* e, const __half* features, const ForwardPlan& plan,

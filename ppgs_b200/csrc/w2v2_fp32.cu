@@ -1,0 +1,522 @@
+// `w2v2fb` representation: wav2vec2-base latents, nearest-upsampled to the PPG frame
+// rate — replaces ppgs.preprocess.w2v2fb.from_audios (ppgs/preprocess/w2v2fb/core.py:32-75)
+// and the Hugging Face `Wav2Vec2Model` forward it calls (transformers, un-vendored:
+// modeling_wav2vec2.py feature encoder :254-324,:382-419, projection :422-436, positional
+// conv :326-380, encoder layers :576-610, encoder :658-728, mask reduction :1005-1044).
+//
+// This round the front-end runs in the CUDA-core fp32 arithmetic (PPGS_PRECISION_FP32
+// class): every contraction goes through the SGEMM kernel of transformer_fp32.cu.  All
+// activations are time-major [rows][C]; utterance b owns rows [b*P_l, b*P_l + T_l) of
+// layer l with pitches P_{l-1} = 2 P_l, so a stride-2 convolution is a GEMM whose A rows
+// start every 2*C floats and overlap (lda = stride*C, K = kernel*C).
+#include <math.h>
+
+#include <algorithm>
+#include <string>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace ppgs {
+
+namespace {
+
+constexpr int kConvDim = 512, kHidden = 768, kHeads = 12, kLayers = 12, kFfn = 3072;
+constexpr int kPosKernel = 128, kPosGroups = 16, kPosPer = kHidden / kPosGroups;   // 48
+constexpr int kNumConv = 7;
+const int kConvKernel[kNumConv] = {10, 3, 3, 3, 3, 2, 2};
+const int kConvStride[kNumConv] = {5, 2, 2, 2, 2, 2, 2};
+constexpr int kW2v2Pad = 40;   // w2v2fb/core.py:54
+
+// ---- layer 0: Conv1d(1, 512, k=10, s=5), no bias.  Block = 32 frames x 512 channels.
+__global__ void __launch_bounds__(256)
+conv0_kernel(const float* __restrict__ audio, int64_t stride, int samples, int T0, int64_t P0,
+             const float* __restrict__ w /* [512][10] */, float* __restrict__ out /* [B*P0][512] */) {
+    __shared__ float xs[32 * 5 + 5];
+    __shared__ float ws[kConvDim * 10];
+    const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x;
+    for (int i = tid; i < kConvDim * 10; i += 256) ws[i] = w[i];
+    for (int i = tid; i < 32 * 5 + 5; i += 256) {
+        const int64_t pos = (int64_t)t0 * 5 + i - kW2v2Pad;   // index into the un-padded audio
+        xs[i] = (pos >= 0 && pos < samples) ? audio[(int64_t)b * stride + pos] : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < 32 * kConvDim; i += 256) {
+        const int tt = i / kConvDim, c = i - tt * kConvDim;
+        if (t0 + tt >= T0) continue;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) acc = fmaf(ws[c * 10 + j], xs[tt * 5 + j], acc);
+        out[((int64_t)b * P0 + t0 + tt) * kConvDim + c] = acc;
+    }
+}
+
+// ---- GroupNorm(512 groups of 1 channel) statistics over time: double sums per (b, c)
+__global__ void __launch_bounds__(512)
+groupnorm_stats_kernel(const float* __restrict__ x, int T0, int64_t P0, double* __restrict__ sums /* [B][512][2] */) {
+    const int b = blockIdx.y, c = threadIdx.x;
+    const int t_begin = blockIdx.x * 256, t_end = min(t_begin + 256, T0);
+    float s = 0.f, q = 0.f;
+    for (int t = t_begin; t < t_end; ++t) {
+        const float v = x[((int64_t)b * P0 + t) * kConvDim + c];
+        s += v;
+        q = fmaf(v, v, q);
+    }
+    atomicAdd(&sums[((int64_t)b * kConvDim + c) * 2], (double)s);
+    atomicAdd(&sums[((int64_t)b * kConvDim + c) * 2 + 1], (double)q);
+}
+
+__device__ __forceinline__ float gelu_exact(float v) {
+    return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+}
+
+__global__ void __launch_bounds__(512)
+groupnorm_gelu_kernel(float* __restrict__ x, int T0, int64_t P0, const double* __restrict__ sums,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    const int b = blockIdx.y, c = threadIdx.x;
+    const double mean = sums[((int64_t)b * kConvDim + c) * 2] / T0;
+    const double var = sums[((int64_t)b * kConvDim + c) * 2 + 1] / T0 - mean * mean;
+    const float m = (float)mean, r = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma[c], be = beta[c];
+    const int t_begin = blockIdx.x * 64, t_end = min(t_begin + 64, T0);
+    for (int t = t_begin; t < t_end; ++t) {
+        float* p = x + ((int64_t)b * P0 + t) * kConvDim + c;
+        *p = gelu_exact((*p - m) * r * g + be);
+    }
+}
+
+// ---- out = LayerNorm(a [+ b]) per row; rows with t >= limit[b] (optional) -> 0
+template <int H>
+__global__ void __launch_bounds__(256)
+add_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b2,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     int rows, float* __restrict__ out) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    constexpr int PER = H / 32;
+    float v[PER];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int64_t at = (int64_t)row * H + lane + 32 * i;
+        v[i] = a[at] + (b2 ? b2[at] : 0.f);
+        sum += v[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / H;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const float d = v[i] - mean;
+        sq = fmaf(d, d, sq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / H + eps);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        out[(int64_t)row * H + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    }
+}
+
+// ---- zero the rows that are padding tokens or beyond the sequence (modeling :681-684)
+__global__ void mask_rows_kernel(float* __restrict__ h, int64_t P, const int* __restrict__ out_len,
+                                 int C) {
+    const int64_t row = blockIdx.x;
+    const int b = (int)(row / P), t = (int)(row - (int64_t)b * P);
+    if (t < out_len[b]) return;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) h[row * C + c] = 0.f;
+}
+
+// ---- h [M][768] -> group-major copy Xg [16][64 + M + 64][48] (64 zero guard rows each side)
+__global__ void group_major_kernel(const float* __restrict__ h, int64_t M, float* __restrict__ xg) {
+    const int64_t row = blockIdx.x;
+    for (int c = threadIdx.x; c < kHidden; c += blockDim.x) {
+        const int g = c / kPosPer, i = c - g * kPosPer;
+        xg[((int64_t)g * (M + 128) + 64 + row) * kPosPer + i] = h[row * kHidden + c];
+    }
+}
+
+// ---- (B*P rows, 768) hidden -> (B, 768, frames) fp16, nearest neighbour in time
+__global__ void upsample_kernel(const float* __restrict__ h, int64_t P, int T6, int frames,
+                                float scale, __half* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, f0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // (32, 8)
+    for (int i = ty; i < 32; i += 8) {
+        const int f = f0 + i;
+        float v = 0.f;
+        if (f < frames) {
+            const int src = min((int)floorf((float)f * scale), T6 - 1);
+            v = h[((int64_t)b * P + src) * kHidden + c0 + tx];
+        }
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int f = f0 + tx, c = c0 + i;
+        if (f < frames) out[((int64_t)b * kHidden + c) * frames + f] = __float2half_rn(tile[tx][i]);
+    }
+}
+
+std::vector<float> k_major(const HostTensor& w) {   // (O, I, K) -> [O][tap*I + i]
+    const int64_t O = w.shape[0], I = w.shape[1], K = w.shape[2];
+    std::vector<float> out((size_t)(O * I * K));
+    for (int64_t o = 0; o < O; ++o)
+        for (int64_t i = 0; i < I; ++i)
+            for (int64_t t = 0; t < K; ++t)
+                out[(size_t)((o * K + t) * I + i)] = w.data[(size_t)((o * I + i) * K + t)];
+    return out;
+}
+
+}  // namespace
+
+struct W2v2Layer {
+    float *qkv_w, *qkv_b, *out_w, *out_b, *ln1_w, *ln1_b, *ff1_w, *ff1_b, *ff2_w, *ff2_b, *ln2_w, *ln2_b;
+};
+
+struct W2v2Weights {
+    void* blob = nullptr;
+    float* conv_w[kNumConv];
+    float *gn_w, *gn_b, *fp_ln_w, *fp_ln_b, *fp_w, *fp_b, *pos_w, *pos_b, *enc_ln_w, *enc_ln_b, *zero_bias;
+    W2v2Layer layers[kLayers];
+};
+
+static std::vector<std::pair<std::string, std::vector<int64_t>>> w2v2_expected_keys() {
+    std::vector<std::pair<std::string, std::vector<int64_t>>> keys;
+    int c_in = 1;
+    for (int i = 0; i < kNumConv; ++i) {
+        keys.push_back({"feature_extractor.conv_layers." + std::to_string(i) + ".conv.weight",
+                        {kConvDim, c_in, kConvKernel[i]}});
+        c_in = kConvDim;
+    }
+    keys.push_back({"feature_extractor.conv_layers.0.layer_norm.weight", {kConvDim}});
+    keys.push_back({"feature_extractor.conv_layers.0.layer_norm.bias", {kConvDim}});
+    keys.push_back({"feature_projection.layer_norm.weight", {kConvDim}});
+    keys.push_back({"feature_projection.layer_norm.bias", {kConvDim}});
+    keys.push_back({"feature_projection.projection.weight", {kHidden, kConvDim}});
+    keys.push_back({"feature_projection.projection.bias", {kHidden}});
+    keys.push_back({"encoder.pos_conv_embed.conv.bias", {kHidden}});
+    keys.push_back({"encoder.pos_conv_embed.conv.parametrizations.weight.original0", {1, 1, kPosKernel}});
+    keys.push_back({"encoder.pos_conv_embed.conv.parametrizations.weight.original1",
+                    {kHidden, kPosPer, kPosKernel}});
+    keys.push_back({"encoder.layer_norm.weight", {kHidden}});
+    keys.push_back({"encoder.layer_norm.bias", {kHidden}});
+    for (int l = 0; l < kLayers; ++l) {
+        const std::string p = "encoder.layers." + std::to_string(l) + ".";
+        for (const char* name : {"q_proj", "k_proj", "v_proj", "out_proj"}) {
+            keys.push_back({p + "attention." + name + ".weight", {kHidden, kHidden}});
+            keys.push_back({p + "attention." + name + ".bias", {kHidden}});
+        }
+        keys.push_back({p + "layer_norm.weight", {kHidden}});
+        keys.push_back({p + "layer_norm.bias", {kHidden}});
+        keys.push_back({p + "feed_forward.intermediate_dense.weight", {kFfn, kHidden}});
+        keys.push_back({p + "feed_forward.intermediate_dense.bias", {kFfn}});
+        keys.push_back({p + "feed_forward.output_dense.weight", {kHidden, kFfn}});
+        keys.push_back({p + "feed_forward.output_dense.bias", {kHidden}});
+        keys.push_back({p + "final_layer_norm.weight", {kHidden}});
+        keys.push_back({p + "final_layer_norm.bias", {kHidden}});
+    }
+    return keys;
+}
+
+int w2v2_accepts_key(const std::string& key, const std::vector<int64_t>& shape) {
+    for (const auto& spec : w2v2_expected_keys()) {
+        if (spec.first != key) continue;
+        if (spec.second != shape) {
+            set_error("size mismatch for w2v2.%s", key.c_str());
+            return PPGS_E_INVALID;
+        }
+        return PPGS_OK;
+    }
+    if (key == "masked_spec_embed") return 1;   // present in HF checkpoints, unused in eval
+    set_error("unexpected key in state_dict: w2v2.%s", key.c_str());
+    return PPGS_E_INVALID;
+}
+
+void w2v2_free(ppgs_engine* e) {
+    if (!e->w2v2) return;
+    cudaFree(e->w2v2->blob);
+    delete e->w2v2;
+    e->w2v2 = nullptr;
+}
+
+int w2v2_finalize(ppgs_engine* e) {
+    for (const auto& spec : w2v2_expected_keys())
+        if (!e->w2v2_host.count(spec.first)) {
+            set_error("missing key in state_dict: w2v2.%s", spec.first.c_str());
+            return PPGS_E_STATE;
+        }
+    std::vector<float> host;
+    std::vector<std::pair<float**, size_t>> slots;
+    auto put = [&](float** dst, const std::vector<float>& data) {
+        slots.push_back({dst, host.size()});
+        host.insert(host.end(), data.begin(), data.end());
+        host.resize((host.size() + 63) & ~size_t(63), 0.f);   // 256-byte aligned
+    };
+    auto raw = [&](float** dst, const std::string& key) { put(dst, e->w2v2_host.at(key).data); };
+    w2v2_free(e);
+    W2v2Weights* w = new W2v2Weights();
+    e->w2v2 = w;
+    for (int i = 0; i < kNumConv; ++i) {
+        const HostTensor& t = e->w2v2_host.at("feature_extractor.conv_layers." + std::to_string(i) + ".conv.weight");
+        if (i == 0) put(&w->conv_w[0], t.data);        // [512][1][10] is already [512][10]
+        else put(&w->conv_w[i], k_major(t));
+    }
+    raw(&w->gn_w, "feature_extractor.conv_layers.0.layer_norm.weight");
+    raw(&w->gn_b, "feature_extractor.conv_layers.0.layer_norm.bias");
+    raw(&w->fp_ln_w, "feature_projection.layer_norm.weight");
+    raw(&w->fp_ln_b, "feature_projection.layer_norm.bias");
+    raw(&w->fp_w, "feature_projection.projection.weight");
+    raw(&w->fp_b, "feature_projection.projection.bias");
+    {   // fold the weight norm (dim=2): w = v * g / ||v||, norm over (out, in) per tap; then
+        // per group [48 out][tap*48 + in]
+        const HostTensor& g = e->w2v2_host.at("encoder.pos_conv_embed.conv.parametrizations.weight.original0");
+        const HostTensor& v = e->w2v2_host.at("encoder.pos_conv_embed.conv.parametrizations.weight.original1");
+        std::vector<double> norm(kPosKernel, 0.0);
+        for (int o = 0; o < kHidden; ++o)
+            for (int i = 0; i < kPosPer; ++i)
+                for (int t = 0; t < kPosKernel; ++t) {
+                    const double x = v.data[(size_t)((o * kPosPer + i) * kPosKernel + t)];
+                    norm[t] += x * x;
+                }
+        std::vector<float> packed((size_t)kHidden * kPosPer * kPosKernel);
+        for (int o = 0; o < kHidden; ++o)
+            for (int i = 0; i < kPosPer; ++i)
+                for (int t = 0; t < kPosKernel; ++t) {
+                    const float scale = g.data[t] / (float)sqrt(norm[t]);
+                    packed[(size_t)o * kPosPer * kPosKernel + (size_t)t * kPosPer + i] =
+                        v.data[(size_t)((o * kPosPer + i) * kPosKernel + t)] * scale;
+                }
+        put(&w->pos_w, packed);
+    }
+    raw(&w->pos_b, "encoder.pos_conv_embed.conv.bias");
+    raw(&w->enc_ln_w, "encoder.layer_norm.weight");
+    raw(&w->enc_ln_b, "encoder.layer_norm.bias");
+    put(&w->zero_bias, std::vector<float>(kFfn, 0.f));
+    for (int l = 0; l < kLayers; ++l) {
+        const std::string p = "encoder.layers." + std::to_string(l) + ".";
+        W2v2Layer& L = w->layers[l];
+        std::vector<float> qkv_w, qkv_b;
+        for (const char* name : {"q_proj", "k_proj", "v_proj"}) {
+            const HostTensor& tw = e->w2v2_host.at(p + "attention." + name + ".weight");
+            const HostTensor& tb = e->w2v2_host.at(p + "attention." + name + ".bias");
+            qkv_w.insert(qkv_w.end(), tw.data.begin(), tw.data.end());
+            qkv_b.insert(qkv_b.end(), tb.data.begin(), tb.data.end());
+        }
+        put(&L.qkv_w, qkv_w);
+        put(&L.qkv_b, qkv_b);
+        raw(&L.out_w, p + "attention.out_proj.weight");
+        raw(&L.out_b, p + "attention.out_proj.bias");
+        raw(&L.ln1_w, p + "layer_norm.weight");
+        raw(&L.ln1_b, p + "layer_norm.bias");
+        raw(&L.ff1_w, p + "feed_forward.intermediate_dense.weight");
+        raw(&L.ff1_b, p + "feed_forward.intermediate_dense.bias");
+        raw(&L.ff2_w, p + "feed_forward.output_dense.weight");
+        raw(&L.ff2_b, p + "feed_forward.output_dense.bias");
+        raw(&L.ln2_w, p + "final_layer_norm.weight");
+        raw(&L.ln2_b, p + "final_layer_norm.bias");
+    }
+    PPGS_CUDA(cudaMalloc(&w->blob, host.size() * sizeof(float)));
+    PPGS_CUDA(cudaMemcpy(w->blob, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    for (auto& slot : slots) *slot.first = static_cast<float*>(w->blob) + slot.second;
+    e->w2v2_host.clear();
+    return PPGS_OK;
+}
+
+int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t samples, int64_t stride,
+                   const int64_t* lengths, __half* out, cudaStream_t stream) {
+    if (!e->w2v2) {
+        set_error("w2v2fb: no wav2vec2 weights loaded (ppgs_engine_set_weight(\"w2v2.*\") + "
+                  "ppgs_w2v2_finalize)");
+        return PPGS_E_STATE;
+    }
+    const W2v2Weights& w = *e->w2v2;
+    const int frames = (int)(samples / kHopSamples);
+    int T[kNumConv];
+    int64_t t = samples + 2 * kW2v2Pad;
+    for (int l = 0; l < kNumConv; ++l) {
+        t = (t - kConvKernel[l]) / kConvStride[l] + 1;
+        if (t <= 0) {
+            set_error("w2v2fb: audio too short (%lld samples)", (long long)samples);
+            return PPGS_E_INVALID;
+        }
+        T[l] = (int)t;
+    }
+    const int T6 = T[6];
+    // pitches: P6 >= T6 + 128 (zero tail = right halo of the k=128 positional conv and the
+    // left halo of the next utterance), P_{l-1} = 2 P_l
+    int64_t P[kNumConv];
+    P[6] = ((int64_t)T6 + 128 + 127) / 128 * 128;
+    for (int l = 5; l >= 0; --l) P[l] = 2 * P[l + 1];
+    const int64_t M = (int64_t)batch * P[6];
+    if ((int64_t)batch * P[0] > INT32_MAX || M > INT32_MAX) {
+        set_error("w2v2fb: batch too large");
+        return PPGS_E_TOO_LARGE;
+    }
+    std::vector<int> out_len(batch);
+    std::vector<SeqInfo> seqs(batch);
+    for (int b = 0; b < batch; ++b) {
+        int64_t len = (lengths ? lengths[b] : samples) + 2 * kW2v2Pad;
+        for (int l = 0; l < kNumConv; ++l) len = (len - kConvKernel[l]) / kConvStride[l] + 1;
+        out_len[b] = (int)std::max<int64_t>(std::min<int64_t>(len, T6), 0);
+        SeqInfo s{};
+        s.row0 = (int)(b * P[6]);
+        s.tensor_len = T6;
+        s.valid_len = out_len[b];
+        s.batch = b;
+        seqs[b] = s;
+    }
+
+    // workspace: ping-pong conv activations + encoder buffers (fp32)
+    Carver c;
+    const size_t slack = 16 * (size_t)kConvDim * 4;
+    const size_t o_act0 = c.take((size_t)batch * P[0] * kConvDim * 4 + slack);
+    const size_t o_act1 = c.take((size_t)batch * P[1] * kConvDim * 4 + slack);
+    const size_t o_sums = c.take((size_t)batch * kConvDim * 2 * sizeof(double));
+    const size_t o_h = c.take((size_t)M * kHidden * 4);
+    const size_t o_y = c.take((size_t)M * kHidden * 4);
+    const size_t o_qkv = c.take((size_t)M * 3 * kHidden * 4);
+    const size_t o_ff = c.take((size_t)M * kFfn * 4);
+    const size_t o_xg = c.take((size_t)kPosGroups * (M + 128) * kPosPer * 4 + slack);
+    const size_t o_seqs = c.take(batch * sizeof(SeqInfo));
+    const size_t o_len = c.take(batch * sizeof(int));
+    PPGS_CHECK(ensure_workspace(e, c.off));
+    e->cached_plan_dev = nullptr;   // the PPG transformer's plan tables are overwritten
+    char* ws = static_cast<char*>(e->workspace);
+    float* act[2] = {reinterpret_cast<float*>(ws + o_act0), reinterpret_cast<float*>(ws + o_act1)};
+    double* sums = reinterpret_cast<double*>(ws + o_sums);
+    float* h = reinterpret_cast<float*>(ws + o_h);
+    float* y = reinterpret_cast<float*>(ws + o_y);
+    float* qkv = reinterpret_cast<float*>(ws + o_qkv);
+    float* ff = reinterpret_cast<float*>(ws + o_ff);
+    float* xg = reinterpret_cast<float*>(ws + o_xg);
+    SeqInfo* seqs_dev = reinterpret_cast<SeqInfo*>(ws + o_seqs);
+    int* len_dev = reinterpret_cast<int*>(ws + o_len);
+    // small tables: synchronous pageable copies are fine here (two tiny transfers per call)
+    PPGS_CUDA(cudaMemcpyAsync(seqs_dev, seqs.data(), batch * sizeof(SeqInfo), cudaMemcpyHostToDevice, stream));
+    PPGS_CUDA(cudaMemcpyAsync(len_dev, out_len.data(), batch * sizeof(int), cudaMemcpyHostToDevice, stream));
+    PPGS_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
+
+    // ---- feature encoder
+    PPGS_CUDA(cudaMemsetAsync(act[0], 0, (size_t)batch * P[0] * kConvDim * 4 + slack, stream));
+    PPGS_CUDA(cudaMemsetAsync(sums, 0, (size_t)batch * kConvDim * 2 * sizeof(double), stream));
+    {
+        LaunchScope scope(e, "w2v2_conv0", stream);
+        conv0_kernel<<<dim3((T[0] + 31) / 32, batch), 256, 0, stream>>>(audio, stride, (int)samples, T[0],
+                                                                          P[0], w.conv_w[0], act[0]);
+    }
+    {
+        LaunchScope scope(e, "w2v2_groupnorm_stats", stream);
+        groupnorm_stats_kernel<<<dim3((T[0] + 255) / 256, batch), 512, 0, stream>>>(act[0], T[0], P[0], sums);
+    }
+    {
+        LaunchScope scope(e, "w2v2_groupnorm_gelu", stream);
+        groupnorm_gelu_kernel<<<dim3((T[0] + 63) / 64, batch), 512, 0, stream>>>(
+            act[0], T[0], P[0], sums, w.gn_w, w.gn_b, 1e-5f);
+    }
+    PPGS_CUDA(cudaGetLastError());
+    int cur = 0;
+    for (int l = 1; l < kNumConv; ++l) {
+        SgemmArgs a{};
+        a.A = act[cur];
+        a.lda = (int64_t)kConvStride[l] * kConvDim;
+        a.B = w.conv_w[l];
+        a.bias = w.zero_bias;
+        a.out = act[cur ^ 1];
+        a.ldo = kConvDim;
+        a.M = (int)(batch * P[l]);
+        a.N = kConvDim;
+        a.K = kConvKernel[l] * kConvDim;
+        PPGS_CHECK(launch_sgemm_any(e, "w2v2_conv_gemm", EPI_BIAS_GELU, a, stream));
+        cur ^= 1;
+    }
+    float* feats = act[cur];            // [M][512], rows t >= T6 hold finite junk
+    float* normed = act[cur ^ 1];       // reuse the other conv buffer
+
+    // ---- feature projection + padding mask
+    {
+        LaunchScope scope(e, "w2v2_layernorm", stream);
+        add_layernorm_kernel<kConvDim><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
+            feats, nullptr, w.fp_ln_w, w.fp_ln_b, 1e-5f, (int)M, normed);
+    }
+    {
+        SgemmArgs a{};
+        a.A = normed; a.lda = kConvDim; a.B = w.fp_w; a.bias = w.fp_b; a.out = h; a.ldo = kHidden;
+        a.M = (int)M; a.N = kHidden; a.K = kConvDim;
+        PPGS_CHECK(launch_sgemm_any(e, "w2v2_projection", EPI_BIAS, a, stream));
+    }
+    {
+        LaunchScope scope(e, "w2v2_mask", stream);
+        mask_rows_kernel<<<(unsigned)M, 256, 0, stream>>>(h, P[6], len_dev, kHidden);
+    }
+
+    // ---- positional convolution (grouped, k=128) + LayerNorm
+    PPGS_CUDA(cudaMemsetAsync(xg, 0, (size_t)kPosGroups * (M + 128) * kPosPer * 4 + slack, stream));
+    {
+        LaunchScope scope(e, "w2v2_group_major", stream);
+        group_major_kernel<<<(unsigned)M, 256, 0, stream>>>(h, M, xg);
+    }
+    for (int g = 0; g < kPosGroups; ++g) {
+        SgemmArgs a{};
+        a.A = xg + (int64_t)g * (M + 128) * kPosPer;      // output row m <- rows m .. m+127 of the guarded copy
+        a.lda = kPosPer;
+        a.B = w.pos_w + (int64_t)g * kPosPer * kPosPer * kPosKernel;
+        a.bias = w.pos_b + g * kPosPer;
+        a.out = y + g * kPosPer;
+        a.ldo = kHidden;
+        a.M = (int)M; a.N = kPosPer; a.K = kPosKernel * kPosPer;
+        PPGS_CHECK(launch_sgemm_any(e, "w2v2_pos_conv_gemm", EPI_BIAS_GELU, a, stream));
+    }
+    {
+        LaunchScope scope(e, "w2v2_layernorm", stream);
+        add_layernorm_kernel<kHidden><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
+            h, y, w.enc_ln_w, w.enc_ln_b, 1e-5f, (int)M, h);
+    }
+    PPGS_CUDA(cudaGetLastError());
+
+    // ---- 12 post-LN encoder layers
+    for (int l = 0; l < kLayers; ++l) {
+        const W2v2Layer& L = w.layers[l];
+        SgemmArgs a{};
+        a.M = (int)M;
+        a.A = h; a.lda = kHidden; a.B = L.qkv_w; a.bias = L.qkv_b; a.out = qkv; a.ldo = 3 * kHidden;
+        a.N = 3 * kHidden; a.K = kHidden;
+        PPGS_CHECK(launch_sgemm_any(e, "w2v2_qkv", EPI_BIAS, a, stream));
+        PPGS_CHECK(launch_attention_fp32_any(e, kHidden / kHeads, qkv, kHidden, kHeads, (int)P[6], batch,
+                                             seqs_dev, 0, y, stream));
+        a.A = y; a.B = L.out_w; a.bias = L.out_b; a.out = qkv; a.ldo = kHidden; a.N = kHidden; a.res = h;
+        PPGS_CHECK(launch_sgemm_any(e, "w2v2_out_proj", EPI_BIAS_RES, a, stream));
+        {
+            LaunchScope scope(e, "w2v2_layernorm", stream);
+            add_layernorm_kernel<kHidden><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
+                qkv, nullptr, L.ln1_w, L.ln1_b, 1e-5f, (int)M, h);
+        }
+        a.A = h; a.B = L.ff1_w; a.bias = L.ff1_b; a.out = ff; a.ldo = kFfn; a.N = kFfn; a.K = kHidden;
+        a.res = nullptr;
+        PPGS_CHECK(launch_sgemm_any(e, "w2v2_ffn1", EPI_BIAS_GELU, a, stream));
+        a.A = ff; a.lda = kFfn; a.B = L.ff2_w; a.bias = L.ff2_b; a.out = qkv; a.ldo = kHidden;
+        a.N = kHidden; a.K = kFfn; a.res = h;
+        PPGS_CHECK(launch_sgemm_any(e, "w2v2_ffn2", EPI_BIAS_RES, a, stream));
+        {
+            LaunchScope scope(e, "w2v2_layernorm", stream);
+            add_layernorm_kernel<kHidden><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
+                qkv, nullptr, L.ln2_w, L.ln2_b, 1e-5f, (int)M, h);
+        }
+        PPGS_CUDA(cudaGetLastError());
+    }
+
+    // ---- nearest upsample to the PPG frame rate, fp16 (w2v2fb/core.py:70-75)
+    {
+        LaunchScope scope(e, "w2v2_upsample", stream);
+        const float scale = (float)T6 / (float)frames;
+        upsample_kernel<<<dim3((frames + 31) / 32, kHidden / 32, batch), dim3(32, 8), 0, stream>>>(
+            h, P[6], T6, frames, scale, out);
+    }
+    PPGS_CUDA(cudaGetLastError());
+    return PPGS_OK;
+}
+
+}  // namespace ppgs

@@ -102,6 +102,16 @@ class Engine:
         _lib.check(_lib.lib.ppgs_engine_finalize(self._handle))
         return self
 
+    def load_w2v2_state_dict(self, state_dict):
+        """Strict load of a Hugging Face `Wav2Vec2Model` ('facebook/wav2vec2-base'
+        architecture) state dict: the front-end of the w2v2fb representation
+        (ppgs/preprocess/w2v2fb/core.py:44-47)."""
+        for name, tensor in state_dict.items():
+            self._set('w2v2.' + name, tensor)
+        _lib.check(_lib.lib.ppgs_w2v2_finalize(self._handle))
+        self.has_w2v2 = True
+        return self
+
     def blob(self):
         """The packed weight blob as a uint8 CUDA tensor view (for the one-off
         torch.distributed broadcast from rank 0)."""
@@ -158,6 +168,21 @@ class Engine:
         stride = audio.stride(0) if batch > 1 else samples
         _lib.check(_lib.lib.ppgs_mel_forward(
             self._handle, ctypes.c_void_p(audio.data_ptr()), batch, samples, stride,
+            ctypes.c_void_p(out.data_ptr()), _stream_ptr(self.device)))
+        return out
+
+    def w2v2fb(self, audio, lengths=None):
+        """audio (B,1,samples) fp32 (zero padded), lengths in samples -> wav2vec2-base
+        latents upsampled to the frame rate, (B,768,samples//160) fp16."""
+        if audio.dim() == 3:
+            audio = audio.squeeze(1)
+        audio = self._on_device(audio, torch.float32).contiguous()
+        batch, samples = audio.shape
+        out = torch.empty(batch, 768, samples // config.HOPSIZE, dtype=torch.float16,
+                          device=self.device)
+        lengths_host = None if lengths is None else _host_lengths(lengths, batch)
+        _lib.check(_lib.lib.ppgs_w2v2fb_forward(
+            self._handle, ctypes.c_void_p(audio.data_ptr()), batch, samples, samples, lengths_host,
             ctypes.c_void_p(out.data_ptr()), _stream_ptr(self.device)))
         return out
 

@@ -5,8 +5,9 @@ import torch
 
 from .. import config
 from . import mel
+from . import w2v2fb
 
-REGISTRY = {'mel': mel}
+REGISTRY = {'mel': mel, 'w2v2fb': w2v2fb}
 
 
 def get(representation):

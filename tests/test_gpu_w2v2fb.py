@@ -1,0 +1,74 @@
+"""w2v2fb representation on the GPU (BASELINE config 3 shape family):
+the CUDA wav2vec2-base front-end against golden outputs of the real Hugging Face module
+and against the oracle, then the d=512 PPG Transformer on those features."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import ppg_oracle as O
+from oracle import w2v2_oracle as W
+from oracle.make_golden_w2v2 import case_inputs
+from test_w2v2_oracle import CASES, close_fp16
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ppgs_b200():
+    import ppgs_b200
+    return ppgs_b200
+
+
+def frontend(ppgs_b200, seed):
+    engine = ppgs_b200.Engine(0).load_state_dict(O.random_state_dict(0))
+    return engine.load_w2v2_state_dict(W.random_state_dict(seed))
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_features_vs_hf_golden(ppgs_b200, name):
+    g = golden(name)
+    audio, lengths = case_inputs(int(g['samples']), g['lengths'].tolist(), int(g['audio_seed']))
+    engine = frontend(ppgs_b200, int(g['weight_seed']))
+    feats = engine.w2v2fb(audio.cuda(), lengths).cpu().numpy()
+    engine.check()
+    assert feats.shape == g['features'].shape and feats.dtype == np.float16
+    assert close_fp16(feats, g['features']).all()
+    assert (feats != g['features']).mean() <= 5e-2
+
+
+def test_features_ragged_batch_vs_oracle(ppgs_b200):
+    sd = W.random_state_dict(2)
+    audio, lengths = case_inputs(24000, [24000, 12345, 800, 24000], 7)
+    ref = W.from_audios(sd, audio, lengths).numpy()
+    engine = frontend(ppgs_b200, 2)
+    feats = engine.w2v2fb(audio.cuda(), lengths).cpu().numpy()
+    engine.check()
+    assert close_fp16(feats, ref).all()
+    with pytest.raises(RuntimeError, match='no wav2vec2 weights'):
+        ppgs_b200.Engine(0).load_state_dict(O.random_state_dict(0)).w2v2fb(audio.cuda(), lengths)
+    bad = dict(W.random_state_dict(2))
+    bad.pop('encoder.layer_norm.bias')
+    with pytest.raises(RuntimeError, match='missing key'):
+        ppgs_b200.Engine(0).load_state_dict(O.random_state_dict(0)).load_w2v2_state_dict(bad)
+
+
+def test_w2v2fb_ppg_end_to_end(ppgs_b200, tmp_path):
+    """representation='w2v2fb' through the public API: wav2vec2 front-end + the hidden-512 /
+    input-768 PPG Transformer (ppgs/load.py:40-42, ppgs/config/w2v2fb.py:7-10)."""
+    ppg_sd = O.random_state_dict(4, input_channels=768, hidden_channels=512)
+    ckpt = tmp_path / 'w2v2fb.pt'
+    torch.save({'model': ppg_sd}, ckpt)
+    w_sd = W.random_state_dict(3)
+    ppgs_b200.preprocess.w2v2fb.engine(0, weights=w_sd)
+    audio = O.synthetic_audio(2, 16000 * 3, 5)
+    feats = ppgs_b200.preprocess.from_audio(audio, 'w2v2fb', 16000, gpu=0)
+    assert feats.shape == (2, 768, 300) and feats.dtype == torch.float16
+    out = ppgs_b200.from_audio(audio, 16000, representation='w2v2fb', checkpoint=ckpt, gpu=0)
+    assert out.shape == (2, 40, 300)
+    # T2: identical features into engine and oracle
+    lengths = torch.tensor([300, 300])
+    ref = O.from_features(ppg_sd, feats.cpu(), lengths).numpy()
+    assert np.abs(out.cpu().numpy() - ref).max() <= 1e-4
+    # T1: features vs oracle
+    assert close_fp16(feats.cpu().numpy(), W.from_audios(w_sd, audio, torch.tensor([48000, 48000])).numpy()).all()
