@@ -6,6 +6,7 @@ include/ppgs_b200.h.  Importing the package loads libppgs_b200.so and raises if 
 has not been built — there is no CPU / PyTorch fallback."""
 from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
 from .config import *  # noqa: F401,F403
+from .config import configure  # noqa: F401
 from .phonemes import PHONEMES, PHONEME_TO_INDEX_MAPPING, SILENCE  # noqa: F401
 from . import config, data, load, preprocess, parallel  # noqa: F401
 from .engine import Engine  # noqa: F401

@@ -23,13 +23,14 @@ def parse_args(argv=None):
     parser.add_argument('--legacy-mode', action='store_true',
                         help='Use legacy (unchunked) inference')
     parser.add_argument('--config', type=Path, nargs='*',
-                        help='accepted for compatibility with yapecs; ignored')
+                        help='yapecs-style configuration files (UPPER_CASE overrides)')
     return parser.parse_args(argv)
 
 
 def main(argv=None):
     args = vars(parse_args(argv))
-    args.pop('config', None)
+    for file in args.pop('config', None) or []:
+        ppgs_b200.configure(file)
     ppgs_b200.from_files_to_files(**args)
 
 

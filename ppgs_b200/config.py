@@ -51,3 +51,23 @@ HF_CHECKPOINTS = {'mel': 'mel-800k.pt', 'w2v2fb': 'w2v2fb-425k.pt'}
 # reference downloads; a local directory / state-dict file can be given instead
 W2V2FB_CONFIG = 'facebook/wav2vec2-base'
 W2V2FB_CHECKPOINT = None
+
+
+def configure(source):
+    """Apply a yapecs-style configuration (the reference reads `--config file.py` at import,
+    ppgs/__init__.py:7-15): every UPPER_CASE name of a python file (or dict) overrides the
+    attribute of the same name, e.g. IS_CAUSAL = True from config/causal_transformer.py.
+    Call before engines are created."""
+    import runpy
+    import sys
+    values = dict(source) if isinstance(source, dict) else runpy.run_path(str(source))
+    package = sys.modules.get('ppgs_b200')
+    module = sys.modules[__name__]
+    applied = {}
+    for name, value in values.items():
+        if name.isupper() and not name.startswith('_'):
+            setattr(module, name, value)
+            if package is not None:
+                setattr(package, name, value)
+            applied[name] = value
+    return applied

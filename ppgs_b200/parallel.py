@@ -20,14 +20,18 @@ def init(backend=None):
         return 0, 1
     if not dist.is_initialized():
         if backend is None:
-            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+            backend = os.environ.get('PPGS_B200_DIST_BACKEND') or (
+                'nccl' if torch.cuda.is_available() else 'gloo')
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group(backend)
     return dist.get_rank(), dist.get_world_size()
 
 
 def local_device():
-    return int(os.environ.get('LOCAL_RANK', '0'))
+    """CUDA ordinal of this rank: LOCAL_RANK, folded onto the visible devices (several ranks
+    may share one GPU in tests)."""
+    count = max(torch.cuda.device_count(), 1)
+    return int(os.environ.get('LOCAL_RANK', '0')) % count
 
 
 def broadcast_engine(state_dict=None, representation=None, gpu=None, src=0, **kwargs):

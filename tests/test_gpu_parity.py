@@ -278,3 +278,67 @@ def test_weight_blob_roundtrip(ppgs_b200):
     b.adopt_blob()
     audio = O.synthetic_audio(2, 32000, 3).cuda()
     assert torch.equal(a.from_audio(audio), b.from_audio(audio))
+
+
+def test_config4_causal_windows(ppgs_b200):
+    """BASELINE config 4: config/causal_transformer.py (IS_CAUSAL=True), 256 windows of 160
+    frames.  The reference has no streaming state: 256 independent windows with
+    a square subsequent mask + key padding."""
+    sd = O.random_state_dict(2, peaky=True)
+    engine = make_engine(ppgs_b200, sd, 'f16x2', is_causal=True)
+    audio = O.synthetic_audio(256, 160 * 160, 11)
+    out = engine.from_audio(audio.cuda())
+    engine.check()
+    assert out.shape == (256, 40, 160) and torch.isfinite(out).all()
+    assert (out.sum(1) - 1).abs().max() <= 1e-5
+    rows = [0, 97, 255]
+    ref = O.from_audio(sd, audio[rows], is_causal=True)
+    assert (out[rows].cpu() - ref).abs().max() <= PPG_TOL
+    # causality: perturbing the last second of a window leaves the early posteriors alone,
+    # up to the 2 + 2 frames of look-ahead of the k=5 convolutions and the STFT window
+    changed = audio.clone()
+    changed[:, :, -16000:] = 0
+    early = engine.from_audio(changed.cuda())[:, :, :50]
+    assert (early - out[:, :, :50]).abs().max() <= 1e-6
+    non_causal = make_engine(ppgs_b200, sd, 'f16x2')
+    a = non_causal.from_audio(audio[:4].cuda())[:, :, :50]
+    b = non_causal.from_audio(changed[:4].cuda())[:, :, :50]
+    assert (a - b).abs().max() > 1e-4
+
+
+def test_config5_sharded_files_two_ranks(ppgs_b200, tmp_path):
+    """BASELINE config 5 in miniature: `from_files_to_files` sharded over two ranks under
+    torchrun (both on cuda:0 here, gloo for the one weight-blob broadcast): every file is
+    written once and equals the single-process batched result."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from test_host_logic import free_port, write_wav
+    sd = O.random_state_dict(3)
+    ckpt = tmp_path / 'ckpt.pt'
+    torch.save({'model': sd}, ckpt)
+    lengths = [16000, 40000, 90000, 8000, 16161, 32000, 64000]
+    files = []
+    for i, n in enumerate(lengths):
+        files.append(str(tmp_path / f'{i}.wav'))
+        write_wav(files[-1], n, seed=20 + i)
+    single = [str(tmp_path / f'{i}-single.pt') for i in range(len(files))]
+    ppgs_b200.from_files_to_files(files, single, checkpoint=ckpt, num_workers=2, gpu=0, max_frames=900)
+    sharded = [str(tmp_path / f'{i}-sharded.pt') for i in range(len(files))]
+    worker = tmp_path / 'worker.py'
+    worker.write_text(
+        'import sys, json\n'
+        'from ppgs_b200 import parallel\n'
+        'args = json.loads(sys.argv[1])\n'
+        'parallel.from_files_to_files(args["files"], args["out"], checkpoint=args["ckpt"],\n'
+        '                             num_workers=2, max_frames=900)\n')
+    import json
+    payload = json.dumps({'files': files, 'out': sharded, 'ckpt': str(ckpt)})
+    env = dict(os.environ, PYTHONPATH=ROOT, PPGS_B200_DIST_BACKEND='gloo', LOCAL_RANK_GPU='0')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', str(free_port()), str(worker), payload]
+    subprocess.run(cmd, check=True, timeout=300, env=env, cwd=ROOT)
+    for a, b, n in zip(single, sharded, lengths):
+        x, y = torch.load(a), torch.load(b)
+        assert x.shape == (40, n // 160)
+        assert torch.equal(x, y)

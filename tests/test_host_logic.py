@@ -130,3 +130,17 @@ def test_two_rank_gloo_sharding(tmp_path):
     assert not set(shards[0]) & set(shards[1])
     blobs = [np.load(out / f'blob{r}.npy') for r in range(2)]
     assert np.array_equal(blobs[0], blobs[1]) and blobs[0].sum() > 0
+
+
+def test_configure_applies_yapecs_style_overrides(tmp_path):
+    import ppgs_b200
+    file = tmp_path / 'causal_transformer.py'
+    file.write_text("MODULE = 'ppgs'\nCONFIG = 'causal_transformer'\nIS_CAUSAL = True\nlower = 1\n")
+    try:
+        applied = ppgs_b200.configure(file)
+        assert applied == {'MODULE': 'ppgs', 'CONFIG': 'causal_transformer', 'IS_CAUSAL': True}
+        assert ppgs_b200.IS_CAUSAL is True and ppgs_b200.config.IS_CAUSAL is True
+        assert ppgs_b200.load.cache_key.__defaults__ is not None
+    finally:
+        ppgs_b200.configure({'IS_CAUSAL': False})
+    assert ppgs_b200.config.IS_CAUSAL is False
