@@ -124,7 +124,8 @@ int ppgs_mel_forward(ppgs_engine* engine, const float* audio_dev, int batch,
  * norm of the positional convolution).
  *   audio_dev    : (batch, samples) fp32, row stride `audio_stride`
  *   features_dev : (batch, 768, samples/160) fp16, contiguous
- * This round the front-end computes in fp32 on the CUDA cores. */
+ * Encoder projections / FFN run as split-fp16 tcgen05 GEMMs, everything else of the
+ * front-end in fp32 on the CUDA cores (PPGS_B200_W2V2_TC=0: all fp32). */
 int ppgs_w2v2_finalize(ppgs_engine* engine);
 int ppgs_w2v2fb_forward(ppgs_engine* engine, const float* audio_dev, int batch, int64_t samples,
                         int64_t audio_stride, const int64_t* lengths_host, void* features_dev,

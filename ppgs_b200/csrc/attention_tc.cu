@@ -474,6 +474,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
     }
 }
 
+int launch_attention_planes(ppgs_engine* e, int head_dim, const __half* qkv, __half* out, int rows,
+                            int H, int heads, int max_pitch, int nseq, const SeqInfo* seqs_dev,
+                            int causal, int planes, cudaStream_t stream) {
+    auto run = [&](auto kernel, int D) -> int {
+        const size_t smem = (size_t)(32 * D + 32 * (D + 1) + 32 * D) * sizeof(float);
+        PPGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(max_pitch / 32, heads, (unsigned)nseq);
+        {
+            LaunchScope scope(e, "attention_simt_planes", stream);
+            kernel<<<grid, 256, smem, stream>>>(qkv, (int64_t)rows * 3 * H, H, seqs_dev, causal,
+                                                1.f / sqrtf((float)D), planes, out, (int64_t)rows * H);
+        }
+        PPGS_CUDA(cudaGetLastError());
+        return PPGS_OK;
+    };
+    if (head_dim == 64) return run(attention_planes_kernel<64>, 64);
+    if (head_dim == 128) return run(attention_planes_kernel<128>, 128);
+    set_error("attention_planes: head_dim %d not built", head_dim);
+    return PPGS_E_UNSUPPORTED;
+}
+
 int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows,
                         const ForwardPlan& plan, const SeqInfo* seqs_dev, int planes,
                         cudaStream_t stream) {

@@ -222,6 +222,8 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
                    const int64_t* lengths, __half* out, cudaStream_t stream);
 
 // transformer_tc.cu
+int build_weight_map(TcWeight& w);        // TMA descriptors of one packed weight
+int ensure_status_word(ppgs_engine* e);
 int build_weight_maps(ppgs_engine* e);
 int transformer_forward_tc(ppgs_engine* e, const __half* features, const ForwardPlan& plan,
                            int softmax, float* out, cudaStream_t stream);

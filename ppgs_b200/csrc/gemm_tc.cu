@@ -349,7 +349,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float v = fmaf(__uint_as_float(raw[j]), scale, y[j]);
-                            y[j] = p.relu ? fmaxf(v, 0.f) : v;
+                            y[j] = p.relu == 1 ? fmaxf(v, 0.f)
+                                 : p.relu == 2 ? 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)) : v;
                         }
                         split32(y, h, l, half * 16);
                     }

@@ -38,7 +38,7 @@ struct GemmParams {
     const float* pe = nullptr;
     const SeqInfo* seqs = nullptr;
     const int* tile_seq = nullptr;
-    int relu = 0;
+    int relu = 0;                // kEpiPlanes activation: 0 none, 1 ReLU, 2 exact GELU
     float* ppg = nullptr;   // kEpiConvOut
     int T = 0, O = 0, softmax = 1;
     int* status = nullptr;

@@ -25,7 +25,7 @@ namespace ppgs {
 
 using namespace tc;
 
-static int weight_map(TcWeight& w) {
+int build_weight_map(TcWeight& w) {
     const uint64_t plane = (uint64_t)w.taps * w.N * w.C;
     for (int planes = 1; planes <= 2; ++planes) {
         TcWeight::Maps& m = w.maps[planes - 1];
@@ -40,19 +40,24 @@ static int weight_map(TcWeight& w) {
 
 int build_weight_maps(ppgs_engine* e) {
     if (e->tc_maps_ready) return PPGS_OK;
-    PPGS_CHECK(weight_map(e->tc_conv_in));
-    PPGS_CHECK(weight_map(e->tc_conv_out));
+    PPGS_CHECK(build_weight_map(e->tc_conv_in));
+    PPGS_CHECK(build_weight_map(e->tc_conv_out));
     for (TcLayer& l : e->tc_layers) {
-        PPGS_CHECK(weight_map(l.in_w));
-        PPGS_CHECK(weight_map(l.out_w));
-        PPGS_CHECK(weight_map(l.l1_w));
-        PPGS_CHECK(weight_map(l.l2_w));
+        PPGS_CHECK(build_weight_map(l.in_w));
+        PPGS_CHECK(build_weight_map(l.out_w));
+        PPGS_CHECK(build_weight_map(l.l1_w));
+        PPGS_CHECK(build_weight_map(l.l2_w));
     }
+    PPGS_CHECK(ensure_status_word(e));
+    e->tc_maps_ready = true;
+    return PPGS_OK;
+}
+
+int ensure_status_word(ppgs_engine* e) {
     if (!e->status_dev) {
         PPGS_CUDA(cudaMalloc(&e->status_dev, sizeof(int)));
         PPGS_CUDA(cudaMemset(e->status_dev, 0, sizeof(int)));
     }
-    e->tc_maps_ready = true;
     return PPGS_OK;
 }
 

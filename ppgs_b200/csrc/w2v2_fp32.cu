@@ -4,17 +4,21 @@
 // modeling_wav2vec2.py feature encoder :254-324,:382-419, projection :422-436, positional
 // conv :326-380, encoder layers :576-610, encoder :658-728, mask reduction :1005-1044).
 //
-// This round the front-end runs in the CUDA-core fp32 arithmetic (PPGS_PRECISION_FP32
-// class): every contraction goes through the SGEMM kernel of transformer_fp32.cu.  All
+// The convolutional feature encoder, the positional convolution and the attention run in
+// the CUDA-core fp32 arithmetic (SGEMM / attention kernels of transformer_fp32.cu); the
+// encoder projections and FFN go through the split-fp16 tcgen05 GEMM (gemm_tc.cu).  All
 // activations are time-major [rows][C]; utterance b owns rows [b*P_l, b*P_l + T_l) of
 // layer l with pitches P_{l-1} = 2 P_l, so a stride-2 convolution is a GEMM whose A rows
 // start every 2*C floats and overlap (lda = stride*C, K = kernel*C).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
 
+#include "attention_tc.cuh"
 #include "common.cuh"
+#include "gemm_tc.cuh"
 #include "kernels.cuh"
 
 namespace ppgs {
@@ -161,6 +165,67 @@ __global__ void upsample_kernel(const float* __restrict__ h, int64_t P, int T6, 
     }
 }
 
+// ---- fp32 rows -> split-fp16 planes [2][M][C]
+__global__ void to_planes_kernel(const float* __restrict__ x, int64_t count, __half* __restrict__ planes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    __half hi, lo;
+    tc::split_f16(x[i], hi, lo);
+    planes[i] = hi;
+    planes[count + i] = lo;
+}
+
+// ---- x <- LayerNorm(x + y) over split planes (one warp per row), optional fp32 copy
+template <int H>
+__global__ void __launch_bounds__(256)
+add_layernorm_planes_kernel(__half* __restrict__ x, const __half* __restrict__ y, int64_t plane_stride,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                            int rows, float* __restrict__ out_f32) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    constexpr int PER = H / 64;   // half2 per lane
+    float v[2 * PER];
+    float sum = 0.f;
+    const int64_t base = (int64_t)row * H;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int64_t at = base + 2 * (lane + 32 * i);
+        const float2 xh = __half22float2(*reinterpret_cast<const __half2*>(x + at));
+        const float2 xl = __half22float2(*reinterpret_cast<const __half2*>(x + plane_stride + at));
+        const float2 yh = __half22float2(*reinterpret_cast<const __half2*>(y + at));
+        const float2 yl = __half22float2(*reinterpret_cast<const __half2*>(y + plane_stride + at));
+        v[2 * i] = (xh.x + xl.x) + (yh.x + yl.x);
+        v[2 * i + 1] = (xh.y + xl.y) + (yh.y + yl.y);
+        sum += v[2 * i] + v[2 * i + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / H;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 * PER; ++i) {
+        const float d = v[i] - mean;
+        sq = fmaf(d, d, sq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / H + eps);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = 2 * (lane + 32 * i);
+        const float a = (v[2 * i] - mean) * rstd * gamma[c] + beta[c];
+        const float b = (v[2 * i + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1];
+        uint32_t hi2, lo2;
+        tc::split2_f16(a, b, hi2, lo2);
+        *reinterpret_cast<uint32_t*>(x + base + c) = hi2;
+        *reinterpret_cast<uint32_t*>(x + plane_stride + base + c) = lo2;
+        if (out_f32) {
+            out_f32[base + c] = a;
+            out_f32[base + c + 1] = b;
+        }
+    }
+}
+
 std::vector<float> k_major(const HostTensor& w) {   // (O, I, K) -> [O][tap*I + i]
     const int64_t O = w.shape[0], I = w.shape[1], K = w.shape[2];
     std::vector<float> out((size_t)(O * I * K));
@@ -177,8 +242,16 @@ struct W2v2Layer {
     float *qkv_w, *qkv_b, *out_w, *out_b, *ln1_w, *ln1_b, *ff1_w, *ff1_b, *ff2_w, *ff2_b, *ln2_w, *ln2_b;
 };
 
+struct W2v2TcLayer {
+    TcWeight qkv, out, ff1, ff2;
+};
+
 struct W2v2Weights {
     void* blob = nullptr;
+    // split-fp16 planes of the encoder projections for the tcgen05 GEMMs
+    void* tc_blob = nullptr;
+    float* tc_scales = nullptr;
+    W2v2TcLayer tc[kLayers];
     float* conv_w[kNumConv];
     float *gn_w, *gn_b, *fp_ln_w, *fp_ln_b, *fp_w, *fp_b, *pos_w, *pos_b, *enc_ln_w, *enc_ln_b, *zero_bias;
     W2v2Layer layers[kLayers];
@@ -239,6 +312,8 @@ int w2v2_accepts_key(const std::string& key, const std::vector<int64_t>& shape) 
 void w2v2_free(ppgs_engine* e) {
     if (!e->w2v2) return;
     cudaFree(e->w2v2->blob);
+    cudaFree(e->w2v2->tc_blob);
+    cudaFree(e->w2v2->tc_scales);
     delete e->w2v2;
     e->w2v2 = nullptr;
 }
@@ -322,6 +397,50 @@ int w2v2_finalize(ppgs_engine* e) {
     PPGS_CUDA(cudaMalloc(&w->blob, host.size() * sizeof(float)));
     PPGS_CUDA(cudaMemcpy(w->blob, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
     for (auto& slot : slots) *slot.first = static_cast<float*>(w->blob) + slot.second;
+
+    // tensor-core copies of the encoder projections: [2][N][K] planes + 1/scale each
+    {
+        std::vector<__half> planes_all;
+        std::vector<float> scales;
+        struct Slot { TcWeight* w; size_t offset; int N, K; };
+        std::vector<Slot> tc_slots;
+        auto pack = [&](TcWeight* dst, const HostTensor& t) {
+            std::vector<__half> planes;
+            scales.push_back(pack_planes(&t, planes));
+            tc_slots.push_back({dst, planes_all.size(), (int)t.shape[0], (int)t.shape[1]});
+            planes_all.insert(planes_all.end(), planes.begin(), planes.end());
+            planes_all.resize((planes_all.size() + 127) & ~size_t(127), __float2half_rn(0.f));
+        };
+        for (int l = 0; l < kLayers; ++l) {
+            const std::string p = "encoder.layers." + std::to_string(l) + ".";
+            HostTensor qkv;
+            qkv.shape = {3 * kHidden, kHidden};
+            for (const char* name : {"q_proj", "k_proj", "v_proj"}) {
+                const HostTensor& tw = e->w2v2_host.at(p + "attention." + name + ".weight");
+                qkv.data.insert(qkv.data.end(), tw.data.begin(), tw.data.end());
+            }
+            pack(&w->tc[l].qkv, qkv);
+            pack(&w->tc[l].out, e->w2v2_host.at(p + "attention.out_proj.weight"));
+            pack(&w->tc[l].ff1, e->w2v2_host.at(p + "feed_forward.intermediate_dense.weight"));
+            pack(&w->tc[l].ff2, e->w2v2_host.at(p + "feed_forward.output_dense.weight"));
+        }
+        PPGS_CUDA(cudaMalloc(&w->tc_blob, planes_all.size() * sizeof(__half)));
+        PPGS_CUDA(cudaMemcpy(w->tc_blob, planes_all.data(), planes_all.size() * sizeof(__half),
+                             cudaMemcpyHostToDevice));
+        PPGS_CUDA(cudaMalloc(&w->tc_scales, scales.size() * sizeof(float)));
+        PPGS_CUDA(cudaMemcpy(w->tc_scales, scales.data(), scales.size() * sizeof(float),
+                             cudaMemcpyHostToDevice));
+        for (size_t i = 0; i < tc_slots.size(); ++i) {
+            TcWeight& tw = *tc_slots[i].w;
+            tw.planes = static_cast<__half*>(w->tc_blob) + tc_slots[i].offset;
+            tw.inv_scale = w->tc_scales + i;
+            tw.N = tc_slots[i].N;
+            tw.C = tc_slots[i].K;
+            tw.taps = 1;
+            PPGS_CHECK(build_weight_map(tw));
+        }
+        PPGS_CHECK(ensure_status_word(e));
+    }
     e->w2v2_host.clear();
     return PPGS_OK;
 }
@@ -349,7 +468,7 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
     // pitches: P6 >= T6 + 128 (zero tail = right halo of the k=128 positional conv and the
     // left halo of the next utterance), P_{l-1} = 2 P_l
     int64_t P[kNumConv];
-    P[6] = ((int64_t)T6 + 128 + 127) / 128 * 128;
+    P[6] = ((int64_t)T6 + 128 + 255) / 256 * 256;   // multiple of 256: CTA-pair GEMM tiles
     for (int l = 5; l >= 0; --l) P[l] = 2 * P[l + 1];
     const int64_t M = (int64_t)batch * P[6];
     if ((int64_t)batch * P[0] > INT32_MAX || M > INT32_MAX) {
@@ -477,7 +596,75 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
     }
     PPGS_CUDA(cudaGetLastError());
 
-    // ---- 12 post-LN encoder layers
+    // ---- 12 post-LN encoder layers.  Default: projections / FFN on the tensor cores
+    // (split-fp16 3-pass CTA-pair GEMMs), attention and LayerNorm over the split planes on
+    // the CUDA cores; PPGS_B200_W2V2_TC=0 keeps the all-fp32 CUDA-core layers below.
+    static const bool use_tc = [] { const char* v = getenv("PPGS_B200_W2V2_TC"); return !v || atoi(v) != 0; }();
+    if (use_tc) {
+        using namespace tc;
+        Carver pc;
+        const size_t o_xh = pc.take((size_t)2 * M * kHidden * 2);
+        const size_t o_yh = pc.take((size_t)2 * M * kHidden * 2);
+        const size_t o_ah = pc.take((size_t)2 * M * kHidden * 2);
+        const size_t o_qh = pc.take((size_t)2 * M * 3 * kHidden * 2);
+        const size_t o_fh = pc.take((size_t)2 * M * kFfn * 2);
+        // the conv activation buffers are dead by now: carve the planes out of them
+        if (pc.off > o_h) {
+            set_error("w2v2fb: internal workspace layout error");
+            return PPGS_E_STATE;
+        }
+        __half* xh = reinterpret_cast<__half*>(ws + o_xh);
+        __half* yh = reinterpret_cast<__half*>(ws + o_yh);
+        __half* ah = reinterpret_cast<__half*>(ws + o_ah);
+        __half* qh = reinterpret_cast<__half*>(ws + o_qh);
+        __half* fh = reinterpret_cast<__half*>(ws + o_fh);
+        CUtensorMap a_x, a_att, a_ff, s_qkv, s_y, s_ff;
+        PPGS_CHECK(make_plane_map(&a_x, xh, false, kHidden, M, 1, 2, kHidden, 0, (uint64_t)M * kHidden, 128, 2));
+        PPGS_CHECK(make_plane_map(&a_att, ah, false, kHidden, M, 1, 2, kHidden, 0, (uint64_t)M * kHidden, 128, 2));
+        PPGS_CHECK(make_plane_map(&a_ff, fh, false, kFfn, M, 1, 2, kFfn, 0, (uint64_t)M * kFfn, 128, 2));
+        PPGS_CHECK(make_store_map(&s_qkv, qh, 3 * kHidden, M, (uint64_t)M * 3 * kHidden));
+        PPGS_CHECK(make_store_map(&s_y, yh, kHidden, M, (uint64_t)M * kHidden));
+        PPGS_CHECK(make_store_map(&s_ff, fh, kFfn, M, (uint64_t)M * kFfn));
+        {
+            const int64_t count = M * kHidden;
+            LaunchScope scope(e, "w2v2_to_planes", stream);
+            to_planes_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(h, count, xh);
+        }
+        auto gemm = [&](const char* name, const CUtensorMap& a, TcWeight& wt, const CUtensorMap& out_map,
+                        const float* bias, int act) -> int {
+            GemmParams p;
+            p.m_tiles = (int)(M / 128);
+            p.n_tiles = wt.N / 256;
+            p.cblocks = wt.C / 64;
+            p.a_planes = 2;
+            p.b_planes = 2;
+            p.pair = 1;
+            p.N = wt.N;
+            p.scale = wt.inv_scale;
+            p.bias = bias;
+            p.relu = act;
+            p.status = e->status_dev;
+            return launch_gemm_tc(e, name, 256, kEpiPlanes, a, wt.maps[1].bn128, &out_map, p, stream);
+        };
+        auto add_ln = [&](const float* g, const float* b2, float* f32) {
+            LaunchScope scope(e, "w2v2_add_layernorm_planes", stream);
+            add_layernorm_planes_kernel<kHidden><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
+                xh, yh, M * kHidden, g, b2, 1e-5f, (int)M, f32);
+        };
+        for (int l = 0; l < kLayers; ++l) {
+            const W2v2Layer& L = w.layers[l];
+            W2v2TcLayer& T = e->w2v2->tc[l];
+            PPGS_CHECK(gemm("w2v2_tc_qkv", a_x, T.qkv, s_qkv, L.qkv_b, 0));
+            PPGS_CHECK(launch_attention_planes(e, kHidden / kHeads, qh, ah, (int)M, kHidden, kHeads,
+                                               (int)P[6], batch, seqs_dev, 0, 2, stream));
+            PPGS_CHECK(gemm("w2v2_tc_out_proj", a_att, T.out, s_y, L.out_b, 0));
+            add_ln(L.ln1_w, L.ln1_b, nullptr);
+            PPGS_CHECK(gemm("w2v2_tc_ffn1", a_x, T.ff1, s_ff, L.ff1_b, 2));
+            PPGS_CHECK(gemm("w2v2_tc_ffn2", a_ff, T.ff2, s_y, L.ff2_b, 0));
+            add_ln(L.ln2_w, L.ln2_b, l == kLayers - 1 ? h : nullptr);
+            PPGS_CUDA(cudaGetLastError());
+        }
+    } else
     for (int l = 0; l < kLayers; ++l) {
         const W2v2Layer& L = w.layers[l];
         SgemmArgs a{};
