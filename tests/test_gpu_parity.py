@@ -105,7 +105,8 @@ def test_transformer_vs_reference_golden(ppgs_b200, name, precision):
 @pytest.mark.parametrize('precision', PRECISIONS)
 @pytest.mark.parametrize('frames,lengths', [
     (160, [160]), (400, [400, 399, 3]), (500, [500]), (501, [501, 500]),
-    (900, [900, 450, 451, 50, 49]), (1000, [1000] * 3), (1234, [1234, 2])])
+    (900, [900, 450, 451, 50, 49]), (1000, [1000] * 3), (1234, [1234, 2]),
+    (3, [3]), (5, [5, 4, 1]), (4801, [4801])])
 def test_from_audio_end_to_end_vs_oracle(ppgs_b200, frames, lengths, precision):
     """T3: audio in, posteriors out, batched-vs-batched, equal and ragged lengths
     around the 500/400/50 chunk boundaries."""
