@@ -162,12 +162,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         // the leader's barrier collects the bytes of both CTAs
                         if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
                         const uint32_t leader_bar = map_to_cta(&full_bar[stage], 0);
-                        tma_load_3d_pair(sa, &map_a, leader_bar, cb * kBK, m_blk * kBM + tap - p.half, 0);
+                        tma_load_3d_pair(sa, &map_a, leader_bar, cb * kBK, m_blk * kBM * p.row_mul + tap - p.half, 0);
                         tma_load_4d_pair(sb, &map_b, leader_bar, cb * kBK,
                                          n_blk * BN + (int)rank * Shape::kBRows, tap, 0);
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-                        tma_load_3d(sa, &map_a, &full_bar[stage], cb * kBK, m_blk * kBM + tap - p.half, 0);
+                        tma_load_3d(sa, &map_a, &full_bar[stage], cb * kBK, m_blk * kBM * p.row_mul + tap - p.half, 0);
                         tma_load_4d(sb, &map_b, &full_bar[stage], cb * kBK, n_blk * BN, tap, 0);
                     }
                     if (++stage == kStages) {
@@ -579,7 +579,7 @@ static EncodeTiledFn encode_tiled() {
 int make_plane_map(CUtensorMap* map, const __half* base, bool rank4, uint64_t inner,
                    uint64_t rows, uint64_t groups, uint64_t planes, uint64_t row_stride_elems,
                    uint64_t group_stride_elems, uint64_t plane_stride_elems, uint32_t box_rows,
-                   uint32_t box_planes) {
+                   uint32_t box_planes, uint32_t row_step) {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -596,7 +596,12 @@ int make_plane_map(CUtensorMap* map, const __half* base, bool rank4, uint64_t in
         rank = 3;
         dims[0] = inner; dims[1] = rows; dims[2] = planes;
         strides[0] = row_stride_elems * 2; strides[1] = plane_stride_elems * 2;
-        box[0] = kBK; box[1] = box_rows; box[2] = box_planes;
+        box[0] = kBK; box[1] = box_rows * row_step; box[2] = box_planes;
+        elem[1] = row_step;   // box_rows rows, every row_step-th one
+        if (box[1] > 256) {
+            set_error("make_plane_map: box of %u rows with step %u exceeds the TMA limit", box_rows, row_step);
+            return PPGS_E_INVALID;
+        }
     } else {
         rank = 4;
         dims[0] = inner; dims[1] = rows; dims[2] = groups; dims[3] = planes;

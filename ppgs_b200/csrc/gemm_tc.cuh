@@ -20,6 +20,7 @@ enum GemmEpilogue : int {
 struct GemmParams {
     int m_tiles = 0, n_tiles = 0;
     int taps = 1, half = 0;      // K loop = taps x cblocks k-blocks; A rows shift by tap - half
+    int row_mul = 1;             // A row of output row m = m * row_mul + tap - half (strided conv)
     int cblocks = 0;
     int a_planes = 2, b_planes = 2;
     int pair = 0;                // 1: CTA-pair kernel (cta_group::2); W map must have box rows BN/2
@@ -57,7 +58,9 @@ struct GemmParams {
 int make_plane_map(CUtensorMap* map, const __half* base, bool rank4, uint64_t inner,
                    uint64_t rows, uint64_t groups, uint64_t planes, uint64_t row_stride_elems,
                    uint64_t group_stride_elems, uint64_t plane_stride_elems, uint32_t box_rows,
-                   uint32_t box_planes);
+                   uint32_t box_planes, uint32_t row_step = 1);
+// `row_step` > 1: the box takes every row_step-th row (TMA element stride) — the A operand
+// of a strided convolution over time-major activations (rank-3 maps only).
 
 // BN in {256, 128, 64}.  Launches a persistent grid of min(tiles, SMs) CTAs.
 // Store map over output planes [2][rows][inner]: box {64, 128, 1 plane}, 128-byte

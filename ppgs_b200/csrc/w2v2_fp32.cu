@@ -89,21 +89,100 @@ groupnorm_gelu_kernel(float* __restrict__ x, int T0, int64_t P0, const double* _
     }
 }
 
+// same, but the activation leaves as split-fp16 planes [2][B*P0][512] (tensor-core convs)
+__global__ void __launch_bounds__(512)
+groupnorm_gelu_planes_kernel(const float* __restrict__ x, int T0, int64_t P0, int64_t plane_stride,
+                             const double* __restrict__ sums, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float eps, __half* __restrict__ planes) {
+    const int b = blockIdx.y, c = threadIdx.x;
+    const double mean = sums[((int64_t)b * kConvDim + c) * 2] / T0;
+    const double var = sums[((int64_t)b * kConvDim + c) * 2 + 1] / T0 - mean * mean;
+    const float m = (float)mean, r = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma[c], be = beta[c];
+    const int t_begin = blockIdx.x * 64, t_end = (int)min((int64_t)t_begin + 64, P0);
+    for (int t = t_begin; t < t_end; ++t) {   // rows [T0, P0) -> 0: finite inputs for the junk rows
+        const int64_t at = ((int64_t)b * P0 + t) * kConvDim + c;
+        __half hi = __float2half_rn(0.f), lo = hi;
+        if (t < T0) tc::split_f16(gelu_exact((x[at] - m) * r * g + be), hi, lo);
+        planes[at] = hi;
+        planes[plane_stride + at] = lo;
+    }
+}
+
+// ---- feature-projection LayerNorm(512): conv rows (pitch Q, split planes or fp32) -> fp32
+// rows at the encoder pitch P; rows t >= T of a sequence and the dummy tail rows -> 0
+template <bool PLANES>
+__global__ void __launch_bounds__(256)
+feature_layernorm_kernel(const void* __restrict__ src, int64_t plane_stride, int64_t Q, int64_t P,
+                         int T, int batch, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, int rows, float* __restrict__ out) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    constexpr int H = kConvDim, PER = H / 32;
+    const int b = (int)(row / P), t = (int)(row - (int64_t)b * P);
+    float* dst = out + (int64_t)row * H;
+    if (b >= batch || t >= T) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) dst[lane + 32 * i] = 0.f;
+        return;
+    }
+    const int64_t base = ((int64_t)b * Q + t) * H;
+    float v[PER];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int64_t at = base + lane + 32 * i;
+        if (PLANES) {
+            const __half* x = static_cast<const __half*>(src);
+            v[i] = __half2float(x[at]) + __half2float(x[plane_stride + at]);
+        } else {
+            v[i] = static_cast<const float*>(src)[at];
+        }
+        sum += v[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / H;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const float d = v[i] - mean;
+        sq = fmaf(d, d, sq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / H + eps);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        dst[c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    }
+}
+
 // ---- out = LayerNorm(a [+ b]) per row; rows with t >= limit[b] (optional) -> 0
 template <int H>
 __global__ void __launch_bounds__(256)
 add_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b2,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                     int rows, float* __restrict__ out) {
+                     int rows, float* __restrict__ out, int64_t pitch_a = 0, int64_t pitch_b = 0,
+                     int batch = 0) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     constexpr int PER = H / 32;
     float v[PER];
     float sum = 0.f;
+    // b2 rows of sequence s start at s * pitch_b instead of s * pitch_a (positional conv output)
+    int64_t row_b = row;
+    bool has_b = b2 != nullptr;
+    if (pitch_b) {
+        const int64_t s = row / pitch_a;
+        row_b = s * pitch_b + (row - s * pitch_a);
+        has_b = has_b && s < batch;
+    }
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         const int64_t at = (int64_t)row * H + lane + 32 * i;
-        v[i] = a[at] + (b2 ? b2[at] : 0.f);
+        v[i] = a[at] + (has_b ? b2[row_b * H + lane + 32 * i] : 0.f);
         sum += v[i];
     }
 #pragma unroll
@@ -127,19 +206,22 @@ add_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b2,
 
 // ---- zero the rows that are padding tokens or beyond the sequence (modeling :681-684)
 __global__ void mask_rows_kernel(float* __restrict__ h, int64_t P, const int* __restrict__ out_len,
-                                 int C) {
+                                 int C, int batch) {
     const int64_t row = blockIdx.x;
     const int b = (int)(row / P), t = (int)(row - (int64_t)b * P);
-    if (t < out_len[b]) return;
+    if (b < batch && t < out_len[b]) return;
     for (int c = threadIdx.x; c < C; c += blockDim.x) h[row * C + c] = 0.f;
 }
 
-// ---- h [M][768] -> group-major copy Xg [16][64 + M + 64][48] (64 zero guard rows each side)
-__global__ void group_major_kernel(const float* __restrict__ h, int64_t M, float* __restrict__ xg) {
+// ---- h (pitch P) -> group-major copy Xg [16][64 + Mg + 64][48] at pitch Pg = P + 128: the
+// zero rows between utterances are the halo of the k=128 positional convolution
+__global__ void group_major_kernel(const float* __restrict__ h, int64_t P, int64_t Pg, int64_t Mg,
+                                   float* __restrict__ xg) {
     const int64_t row = blockIdx.x;
+    const int64_t b = row / P, dst = 64 + b * Pg + (row - b * P);
     for (int c = threadIdx.x; c < kHidden; c += blockDim.x) {
         const int g = c / kPosPer, i = c - g * kPosPer;
-        xg[((int64_t)g * (M + 128) + 64 + row) * kPosPer + i] = h[row * kHidden + c];
+        xg[((int64_t)g * (Mg + 128) + dst) * kPosPer + i] = h[row * kHidden + c];
     }
 }
 
@@ -252,6 +334,7 @@ struct W2v2Weights {
     void* tc_blob = nullptr;
     float* tc_scales = nullptr;
     W2v2TcLayer tc[kLayers];
+    TcWeight tc_conv[kNumConv];   // [1..6]: conv layers as tap GEMMs
     float* conv_w[kNumConv];
     float *gn_w, *gn_b, *fp_ln_w, *fp_ln_b, *fp_w, *fp_b, *pos_w, *pos_b, *enc_ln_w, *enc_ln_b, *zero_bias;
     W2v2Layer layers[kLayers];
@@ -402,15 +485,19 @@ int w2v2_finalize(ppgs_engine* e) {
     {
         std::vector<__half> planes_all;
         std::vector<float> scales;
-        struct Slot { TcWeight* w; size_t offset; int N, K; };
+        struct Slot { TcWeight* w; size_t offset; int N, K, taps; };
         std::vector<Slot> tc_slots;
         auto pack = [&](TcWeight* dst, const HostTensor& t) {
             std::vector<__half> planes;
             scales.push_back(pack_planes(&t, planes));
-            tc_slots.push_back({dst, planes_all.size(), (int)t.shape[0], (int)t.shape[1]});
+            tc_slots.push_back({dst, planes_all.size(), (int)t.shape[0], (int)t.shape[1],
+                                t.shape.size() == 3 ? (int)t.shape[2] : 1});
             planes_all.insert(planes_all.end(), planes.begin(), planes.end());
             planes_all.resize((planes_all.size() + 127) & ~size_t(127), __float2half_rn(0.f));
         };
+        for (int i = 1; i < kNumConv; ++i)
+            pack(&w->tc_conv[i],
+                 e->w2v2_host.at("feature_extractor.conv_layers." + std::to_string(i) + ".conv.weight"));
         for (int l = 0; l < kLayers; ++l) {
             const std::string p = "encoder.layers." + std::to_string(l) + ".";
             HostTensor qkv;
@@ -436,7 +523,7 @@ int w2v2_finalize(ppgs_engine* e) {
             tw.inv_scale = w->tc_scales + i;
             tw.N = tc_slots[i].N;
             tw.C = tc_slots[i].K;
-            tw.taps = 1;
+            tw.taps = tc_slots[i].taps;
             PPGS_CHECK(build_weight_map(tw));
         }
         PPGS_CHECK(ensure_status_word(e));
@@ -465,13 +552,17 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
         T[l] = (int)t;
     }
     const int T6 = T[6];
-    // pitches: P6 >= T6 + 128 (zero tail = right halo of the k=128 positional conv and the
-    // left halo of the next utterance), P_{l-1} = 2 P_l
-    int64_t P[kNumConv];
-    P[6] = ((int64_t)T6 + 128 + 255) / 256 * 256;   // multiple of 256: CTA-pair GEMM tiles
-    for (int l = 5; l >= 0; --l) P[l] = 2 * P[l + 1];
-    const int64_t M = (int64_t)batch * P[6];
-    if ((int64_t)batch * P[0] > INT32_MAX || M > INT32_MAX) {
+    // Pitches.  Conv layers: Q_{l-1} = 2 Q_l with Q_l >= T_l, so a stride-2 convolution is a
+    // GEMM over overlapping A rows.  Encoder: P >= T6, multiple of 128; the positional
+    // convolution works at Pg = P + 128 (zero halo rows between utterances).  M = encoder
+    // rows, padded to a multiple of 256 (CTA-pair tiles) with dummy rows.
+    int64_t Q[kNumConv];
+    Q[6] = 1;
+    for (int l = 0; l < kNumConv; ++l) Q[6] = std::max<int64_t>(Q[6], ((int64_t)T[l] + (1 << (6 - l)) - 1) >> (6 - l));
+    for (int l = 5; l >= 0; --l) Q[l] = 2 * Q[l + 1];
+    const int64_t P = ((int64_t)T6 + 127) / 128 * 128, Pg = P + 128;
+    const int64_t M = ((int64_t)batch * P + 255) / 256 * 256, Mg = (int64_t)batch * Pg;
+    if ((int64_t)batch * Q[0] + 1024 > INT32_MAX || Mg > INT32_MAX) {
         set_error("w2v2fb: batch too large");
         return PPGS_E_TOO_LARGE;
     }
@@ -482,24 +573,30 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
         for (int l = 0; l < kNumConv; ++l) len = (len - kConvKernel[l]) / kConvStride[l] + 1;
         out_len[b] = (int)std::max<int64_t>(std::min<int64_t>(len, T6), 0);
         SeqInfo s{};
-        s.row0 = (int)(b * P[6]);
+        s.row0 = (int)(b * P);
         s.tensor_len = T6;
         s.valid_len = out_len[b];
         s.batch = b;
         seqs[b] = s;
     }
+    static const bool use_tc = [] { const char* v = getenv("PPGS_B200_W2V2_TC"); return !v || atoi(v) != 0; }();
 
-    // workspace: ping-pong conv activations + encoder buffers (fp32)
+    // workspace: two conv activation buffers (fp32 rows, or split-fp16 planes: same bytes
+    // per element) + encoder buffers (fp32).  512 slack rows: GEMM tiles round M up.
     Carver c;
-    const size_t slack = 16 * (size_t)kConvDim * 4;
-    const size_t o_act0 = c.take((size_t)batch * P[0] * kConvDim * 4 + slack);
-    const size_t o_act1 = c.take((size_t)batch * P[1] * kConvDim * 4 + slack);
+    // (the encoder's split planes are carved out of the same two buffers once the convs are done)
+    const size_t plane_bytes = (size_t)M * (3 * kHidden + 3 * kHidden + kFfn) * 4 + 5 * 1024;
+    const size_t act_bytes = std::max({((size_t)batch * Q[0] + 512) * kConvDim * 4,
+                                       (size_t)M * kConvDim * 4, (plane_bytes + 1) / 2});
+    const size_t o_act0 = c.take(act_bytes);
+    const size_t o_act1 = c.take(act_bytes);
     const size_t o_sums = c.take((size_t)batch * kConvDim * 2 * sizeof(double));
     const size_t o_h = c.take((size_t)M * kHidden * 4);
-    const size_t o_y = c.take((size_t)M * kHidden * 4);
+    const size_t o_y = c.take((size_t)std::max(M, Mg) * kHidden * 4);
     const size_t o_qkv = c.take((size_t)M * 3 * kHidden * 4);
     const size_t o_ff = c.take((size_t)M * kFfn * 4);
-    const size_t o_xg = c.take((size_t)kPosGroups * (M + 128) * kPosPer * 4 + slack);
+    const size_t xg_bytes = (size_t)kPosGroups * (Mg + 128) * kPosPer * 4 + 16 * kConvDim * 4;
+    const size_t o_xg = c.take(xg_bytes);
     const size_t o_seqs = c.take(batch * sizeof(SeqInfo));
     const size_t o_len = c.take(batch * sizeof(int));
     PPGS_CHECK(ensure_workspace(e, c.off));
@@ -519,48 +616,94 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
     PPGS_CUDA(cudaMemcpyAsync(len_dev, out_len.data(), batch * sizeof(int), cudaMemcpyHostToDevice, stream));
     PPGS_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope
 
-    // ---- feature encoder
-    PPGS_CUDA(cudaMemsetAsync(act[0], 0, (size_t)batch * P[0] * kConvDim * 4 + slack, stream));
+    // ---- feature encoder: conv0 + GroupNorm + GELU on the CUDA cores, then six stride-2
+    // convolutions as GEMMs (tensor cores: taps = k-blocks, A boxes take every 2nd row)
+    PPGS_CUDA(cudaMemsetAsync(act[0], 0, act_bytes, stream));
     PPGS_CUDA(cudaMemsetAsync(sums, 0, (size_t)batch * kConvDim * 2 * sizeof(double), stream));
     {
         LaunchScope scope(e, "w2v2_conv0", stream);
         conv0_kernel<<<dim3((T[0] + 31) / 32, batch), 256, 0, stream>>>(audio, stride, (int)samples, T[0],
-                                                                          P[0], w.conv_w[0], act[0]);
+                                                                          Q[0], w.conv_w[0], act[0]);
     }
     {
         LaunchScope scope(e, "w2v2_groupnorm_stats", stream);
-        groupnorm_stats_kernel<<<dim3((T[0] + 255) / 256, batch), 512, 0, stream>>>(act[0], T[0], P[0], sums);
+        groupnorm_stats_kernel<<<dim3((T[0] + 255) / 256, batch), 512, 0, stream>>>(act[0], T[0], Q[0], sums);
     }
-    {
-        LaunchScope scope(e, "w2v2_groupnorm_gelu", stream);
-        groupnorm_gelu_kernel<<<dim3((T[0] + 63) / 64, batch), 512, 0, stream>>>(
-            act[0], T[0], P[0], sums, w.gn_w, w.gn_b, 1e-5f);
+    float* normed;   // LayerNorm(512) of the conv features, encoder pitch
+    if (use_tc) {
+        using namespace tc;
+        // planes of layer l: [2][B*Q_l (+ slack)][512] fp16, alternating between the buffers
+        __half* bufs[2] = {reinterpret_cast<__half*>(act[0]), reinterpret_cast<__half*>(act[1])};
+        const int64_t rows0 = (int64_t)batch * Q[0];
+        {
+            LaunchScope scope(e, "w2v2_groupnorm_gelu", stream);
+            groupnorm_gelu_planes_kernel<<<dim3((unsigned)((Q[0] + 63) / 64), batch), 512, 0, stream>>>(
+                act[0], T[0], Q[0], rows0 * kConvDim, sums, w.gn_w, w.gn_b, 1e-5f, bufs[1]);
+        }
+        PPGS_CUDA(cudaGetLastError());
+        int cur = 1;
+        for (int l = 1; l < kNumConv; ++l) {
+            const int64_t rows_in = (int64_t)batch * Q[l - 1], rows_out = (int64_t)batch * Q[l];
+            TcWeight& wt = e->w2v2->tc_conv[l];
+            CUtensorMap map_a, map_out;
+            PPGS_CHECK(make_plane_map(&map_a, bufs[cur], false, kConvDim, rows_in, 1, 2, kConvDim, 0,
+                                      (uint64_t)rows_in * kConvDim, 128, 2, 2));
+            PPGS_CHECK(make_store_map(&map_out, bufs[cur ^ 1], kConvDim, rows_out,
+                                      (uint64_t)rows_out * kConvDim));
+            GemmParams p;
+            p.m_tiles = (int)((rows_out + 255) / 256) * 2;
+            p.n_tiles = kConvDim / 256;
+            p.cblocks = kConvDim / 64;
+            p.taps = kConvKernel[l];
+            p.half = 0;
+            p.row_mul = 2;
+            p.a_planes = 2;
+            p.b_planes = 2;
+            p.pair = 1;
+            p.N = kConvDim;
+            p.scale = wt.inv_scale;
+            p.bias = w.zero_bias;
+            p.relu = 2;   // GELU
+            p.status = e->status_dev;
+            PPGS_CHECK(launch_gemm_tc(e, "w2v2_tc_conv", 256, kEpiPlanes, map_a, wt.maps[1].bn128, &map_out,
+                                      p, stream));
+            cur ^= 1;
+        }
+        normed = reinterpret_cast<float*>(bufs[cur ^ 1]);
+        LaunchScope scope(e, "w2v2_layernorm", stream);
+        feature_layernorm_kernel<true><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
+            bufs[cur], (int64_t)batch * Q[6] * kConvDim, Q[6], P, T6, batch, w.fp_ln_w, w.fp_ln_b, 1e-5f,
+            (int)M, normed);
+    } else {
+        {
+            LaunchScope scope(e, "w2v2_groupnorm_gelu", stream);
+            groupnorm_gelu_kernel<<<dim3((T[0] + 63) / 64, batch), 512, 0, stream>>>(
+                act[0], T[0], Q[0], sums, w.gn_w, w.gn_b, 1e-5f);
+        }
+        PPGS_CUDA(cudaGetLastError());
+        int cur = 0;
+        for (int l = 1; l < kNumConv; ++l) {
+            SgemmArgs a{};
+            a.A = act[cur];
+            a.lda = (int64_t)kConvStride[l] * kConvDim;
+            a.B = w.conv_w[l];
+            a.bias = w.zero_bias;
+            a.out = act[cur ^ 1];
+            a.ldo = kConvDim;
+            a.M = (int)(((int64_t)batch * Q[l] + 127) / 128 * 128);   // tail rows land in the slack
+            a.N = kConvDim;
+            a.K = kConvKernel[l] * kConvDim;
+            PPGS_CHECK(launch_sgemm_any(e, "w2v2_conv_gemm", EPI_BIAS_GELU, a, stream));
+            cur ^= 1;
+        }
+        normed = act[cur ^ 1];
+        LaunchScope scope(e, "w2v2_layernorm", stream);
+        feature_layernorm_kernel<false><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
+            act[cur], 0, Q[6], P, T6, batch, w.fp_ln_w, w.fp_ln_b, 1e-5f, (int)M, normed);
     }
     PPGS_CUDA(cudaGetLastError());
-    int cur = 0;
-    for (int l = 1; l < kNumConv; ++l) {
-        SgemmArgs a{};
-        a.A = act[cur];
-        a.lda = (int64_t)kConvStride[l] * kConvDim;
-        a.B = w.conv_w[l];
-        a.bias = w.zero_bias;
-        a.out = act[cur ^ 1];
-        a.ldo = kConvDim;
-        a.M = (int)(batch * P[l]);
-        a.N = kConvDim;
-        a.K = kConvKernel[l] * kConvDim;
-        PPGS_CHECK(launch_sgemm_any(e, "w2v2_conv_gemm", EPI_BIAS_GELU, a, stream));
-        cur ^= 1;
-    }
-    float* feats = act[cur];            // [M][512], rows t >= T6 hold finite junk
-    float* normed = act[cur ^ 1];       // reuse the other conv buffer
 
     // ---- feature projection + padding mask
-    {
-        LaunchScope scope(e, "w2v2_layernorm", stream);
-        add_layernorm_kernel<kConvDim><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
-            feats, nullptr, w.fp_ln_w, w.fp_ln_b, 1e-5f, (int)M, normed);
-    }
     {
         SgemmArgs a{};
         a.A = normed; a.lda = kConvDim; a.B = w.fp_w; a.bias = w.fp_b; a.out = h; a.ldo = kHidden;
@@ -569,37 +712,36 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
     }
     {
         LaunchScope scope(e, "w2v2_mask", stream);
-        mask_rows_kernel<<<(unsigned)M, 256, 0, stream>>>(h, P[6], len_dev, kHidden);
+        mask_rows_kernel<<<(unsigned)M, 256, 0, stream>>>(h, P, len_dev, kHidden, batch);
     }
 
     // ---- positional convolution (grouped, k=128) + LayerNorm
-    PPGS_CUDA(cudaMemsetAsync(xg, 0, (size_t)kPosGroups * (M + 128) * kPosPer * 4 + slack, stream));
+    PPGS_CUDA(cudaMemsetAsync(xg, 0, xg_bytes, stream));
     {
         LaunchScope scope(e, "w2v2_group_major", stream);
-        group_major_kernel<<<(unsigned)M, 256, 0, stream>>>(h, M, xg);
+        group_major_kernel<<<(unsigned)((int64_t)batch * P), 256, 0, stream>>>(h, P, Pg, Mg, xg);
     }
     for (int g = 0; g < kPosGroups; ++g) {
         SgemmArgs a{};
-        a.A = xg + (int64_t)g * (M + 128) * kPosPer;      // output row m <- rows m .. m+127 of the guarded copy
+        a.A = xg + (int64_t)g * (Mg + 128) * kPosPer;     // output row m <- rows m .. m+127 of the guarded copy
         a.lda = kPosPer;
         a.B = w.pos_w + (int64_t)g * kPosPer * kPosPer * kPosKernel;
         a.bias = w.pos_b + g * kPosPer;
         a.out = y + g * kPosPer;
         a.ldo = kHidden;
-        a.M = (int)M; a.N = kPosPer; a.K = kPosKernel * kPosPer;
+        a.M = (int)Mg; a.N = kPosPer; a.K = kPosKernel * kPosPer;
         PPGS_CHECK(launch_sgemm_any(e, "w2v2_pos_conv_gemm", EPI_BIAS_GELU, a, stream));
     }
     {
         LaunchScope scope(e, "w2v2_layernorm", stream);
         add_layernorm_kernel<kHidden><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
-            h, y, w.enc_ln_w, w.enc_ln_b, 1e-5f, (int)M, h);
+            h, y, w.enc_ln_w, w.enc_ln_b, 1e-5f, (int)M, h, P, Pg, batch);
     }
     PPGS_CUDA(cudaGetLastError());
 
     // ---- 12 post-LN encoder layers.  Default: projections / FFN on the tensor cores
     // (split-fp16 3-pass CTA-pair GEMMs), attention and LayerNorm over the split planes on
     // the CUDA cores; PPGS_B200_W2V2_TC=0 keeps the all-fp32 CUDA-core layers below.
-    static const bool use_tc = [] { const char* v = getenv("PPGS_B200_W2V2_TC"); return !v || atoi(v) != 0; }();
     if (use_tc) {
         using namespace tc;
         Carver pc;
@@ -625,6 +767,7 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
         PPGS_CHECK(make_store_map(&s_qkv, qh, 3 * kHidden, M, (uint64_t)M * 3 * kHidden));
         PPGS_CHECK(make_store_map(&s_y, yh, kHidden, M, (uint64_t)M * kHidden));
         PPGS_CHECK(make_store_map(&s_ff, fh, kFfn, M, (uint64_t)M * kFfn));
+        PPGS_CUDA(cudaMemsetAsync(ah, 0, (size_t)2 * M * kHidden * 2, stream));   // rows no sequence owns
         {
             const int64_t count = M * kHidden;
             LaunchScope scope(e, "w2v2_to_planes", stream);
@@ -656,7 +799,7 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
             W2v2TcLayer& T = e->w2v2->tc[l];
             PPGS_CHECK(gemm("w2v2_tc_qkv", a_x, T.qkv, s_qkv, L.qkv_b, 0));
             PPGS_CHECK(launch_attention_planes(e, kHidden / kHeads, qh, ah, (int)M, kHidden, kHeads,
-                                               (int)P[6], batch, seqs_dev, 0, 2, stream));
+                                               (int)P, batch, seqs_dev, 0, 2, stream));
             PPGS_CHECK(gemm("w2v2_tc_out_proj", a_att, T.out, s_y, L.out_b, 0));
             add_ln(L.ln1_w, L.ln1_b, nullptr);
             PPGS_CHECK(gemm("w2v2_tc_ffn1", a_x, T.ff1, s_ff, L.ff1_b, 2));
@@ -672,7 +815,7 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
         a.A = h; a.lda = kHidden; a.B = L.qkv_w; a.bias = L.qkv_b; a.out = qkv; a.ldo = 3 * kHidden;
         a.N = 3 * kHidden; a.K = kHidden;
         PPGS_CHECK(launch_sgemm_any(e, "w2v2_qkv", EPI_BIAS, a, stream));
-        PPGS_CHECK(launch_attention_fp32_any(e, kHidden / kHeads, qkv, kHidden, kHeads, (int)P[6], batch,
+        PPGS_CHECK(launch_attention_fp32_any(e, kHidden / kHeads, qkv, kHidden, kHeads, (int)P, batch,
                                              seqs_dev, 0, y, stream));
         a.A = y; a.B = L.out_w; a.bias = L.out_b; a.out = qkv; a.ldo = kHidden; a.N = kHidden; a.res = h;
         PPGS_CHECK(launch_sgemm_any(e, "w2v2_out_proj", EPI_BIAS_RES, a, stream));
@@ -700,7 +843,7 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
         LaunchScope scope(e, "w2v2_upsample", stream);
         const float scale = (float)T6 / (float)frames;
         upsample_kernel<<<dim3((frames + 31) / 32, kHidden / 32, batch), dim3(32, 8), 0, stream>>>(
-            h, P[6], T6, frames, scale, out);
+            h, P, T6, frames, scale, out);
     }
     PPGS_CUDA(cudaGetLastError());
     return PPGS_OK;
