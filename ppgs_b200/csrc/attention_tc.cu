@@ -109,29 +109,48 @@ attention_planes_kernel(const __half* __restrict__ qkv, int64_t plane_stride, in
 
 
 // ---------------------------------------------------------------------------
-// tcgen05 kernel: one CTA per (128-query tile, head, sequence), keys <= 512.
+// tcgen05 kernel: one CTA per (128-query tile, head, sequence), keys <= 512,
+// head_dim D in {64, 128, 256}.
 //
-//   warp 0      TMA producer: Q tile, K blocks (128 keys) through a 2-slot ring,
-//               then V chunks (64 keys) through a 4-slot ring that reuses the K ring
-//   warp 1      tcgen05.mma issuer: S_j = Q K_j^T into TMEM columns [128 j, 128 j + 128),
-//               then O += P_c V_c into columns [384, 512)
+//   warp 0      TMA producer: Q tile, K blocks (KB keys) through a ring, then V chunks
+//               (64 keys) through a ring that reuses the K ring
+//   warp 1      tcgen05.mma issuer: S_j = Q K_j^T into TMEM columns [KB j, KB j + KB),
+//               then O += P_c V_c into the last D columns
 //   warps 2-9   two threads per query row: row max over S (TMEM), p = exp2((s - max) c),
 //               split-fp16 P chunks written to the 128B-swizzled smem layout the MMA
-//               reads (2-slot ring that reuses the Q tile), final O / sum -> planes
+//               reads (ring that reuses the Q tile), final O / sum -> planes
 //
-// S for 4 key blocks fills all 512 TMEM columns; O reuses the columns of the last
-// block, so the chunks of that block are converted to P first and the first P.V MMA
-// waits for them.
+// S for 512 keys fills all 512 TMEM columns; O reuses the last D of them, so the 64-key
+// chunks that live there are converted to P first (chunk_order) and the first P.V MMA
+// waits for all of them — the P ring has at least that many slots.
+//
+// Shared memory: region A = Q tile [D/64 d chunks][2 planes][128 x 64], later the P ring
+// and the output staging tiles; region B = K ring, later the V ring.  D = 256 only fits
+// one K / V slot beside its 128 KB Q tile (loads and MMAs alternate there).
 // ---------------------------------------------------------------------------
 constexpr int kAttnThreads = 320;   // producer + MMA + 8 softmax warps
 constexpr int kTile16K = 16384;                // [128 rows][64 fp16]
-constexpr int kQBytes = 4 * kTile16K;          // [d chunk 2][plane 2]
-constexpr int kKSlotBytes = 4 * kTile16K;
 constexpr int kPSlotBytes = 2 * kTile16K;      // [plane 2][128 q][64 keys]
 constexpr int kVPlaneBytes = 8192;             // [64 keys][64 d]
-constexpr int kVSlotBytes = 4 * kVPlaneBytes;  // [d half 2][plane 2]
-constexpr size_t kAttnSmem = kQBytes + 2 * kKSlotBytes + 1024;
-constexpr int kOCol = 384;
+
+template <int D>
+struct AttnShape {
+    static constexpr int kDC = D / 64;                          // 64-wide d chunks
+    static constexpr int kKB = D == 256 ? 64 : 128;             // keys per K block
+    static constexpr int kKTile = kKB * 128;                    // [KB keys][64 fp16]
+    static constexpr int kQBytes = kDC * 2 * kTile16K;
+    static constexpr int kNP = D == 256 ? 4 : 2;                // P ring slots
+    static constexpr int kABytes = kQBytes > kNP * kPSlotBytes ? kQBytes : kNP * kPSlotBytes;
+    static constexpr int kKSlotBytes = kDC * 2 * kKTile;
+    static constexpr int kNK = D == 256 ? 1 : 2;
+    static constexpr int kVSlotBytes = kDC * 2 * kVPlaneBytes;
+    static constexpr int kNV = kNK * kKSlotBytes / kVSlotBytes;
+    static constexpr int kOCol = 512 - D;
+    static constexpr int kSafeChunks = kOCol / 64;              // chunks whose S columns O never touches
+    static constexpr size_t kSmem = kABytes + kNK * kKSlotBytes + 1024;
+    static_assert(8 - kSafeChunks <= kNP, "P ring must hold every chunk that overlaps O");
+    static_assert(kNV >= 1 && kNV <= 4 && kNK <= 2 && kNP <= 4, "ring sizes");
+};
 
 struct AttnParams {
     const SeqInfo* seqs;
@@ -152,23 +171,28 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+template <int SAFE>
 __device__ __forceinline__ int chunk_order(int i, int nchunks) {
-    if (nchunks <= 6) return i;
-    const int pre = nchunks - 6;
-    return i < pre ? 6 + i : i - pre;
+    if (nchunks <= SAFE) return i;
+    const int pre = nchunks - SAFE;
+    return i < pre ? SAFE + i : i - pre;
 }
 
 
+template <int D>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_v,
                     const __grid_constant__ CUtensorMap map_out, const AttnParams p) {
+    using Shape = AttnShape<D>;
+    constexpr int DC = Shape::kDC, KB = Shape::kKB, NP = Shape::kNP, NK = Shape::kNK, NV = Shape::kNV;
+    constexpr int SAFE = Shape::kSafeChunks;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* q_smem = smem;              // later: P ring
-    unsigned char* k_ring = smem + kQBytes;    // later: V ring
+    unsigned char* q_smem = smem;                      // later: P ring, output staging
+    unsigned char* k_ring = smem + Shape::kABytes;     // later: V ring
     __shared__ __align__(8) uint64_t q_full, s_full, o_full;
-    __shared__ __align__(8) uint64_t k_full[2], k_empty[2], p_full[2], p_empty[2];
+    __shared__ __align__(8) uint64_t k_full[2], k_empty[2], p_full[4], p_empty[4];
     __shared__ __align__(8) uint64_t v_full[4], v_empty[4];
     __shared__ uint32_t tmem_slot;
     __shared__ float row_part[2][128];   // per-row partial max / sum of the two halves
@@ -182,15 +206,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
     const int64_t out_row0 = (int64_t)(s.row0 + q0);
     if (nkeys <= 0) {
         // every key masked (chunk_lengths == 0 rows of transformer.py:59-60): zeros
-        for (int i = threadIdx.x; i < 128 * 128; i += kAttnThreads) {
-            const int r = i >> 7, d = i & 127;
-            __half* dst = p.out + (out_row0 + r) * p.H + head * 128 + d;
+        for (int i = threadIdx.x; i < 128 * D; i += kAttnThreads) {
+            const int r = i / D, d = i - r * D;
+            __half* dst = p.out + (out_row0 + r) * p.H + head * D + d;
             dst[0] = __float2half_rn(0.f);
             dst[p.out_plane_stride] = __float2half_rn(0.f);
         }
         return;
     }
-    const int nb = (nkeys + 127) >> 7, nchunks = (nkeys + 63) >> 6;
+    const int nb = (nkeys + KB - 1) / KB, nchunks = (nkeys + 63) >> 6;
 
     if (threadIdx.x == 0) {
         mbar_init(&q_full, 1);
@@ -199,10 +223,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         for (int i = 0; i < 2; ++i) {
             mbar_init(&k_full[i], 1);
             mbar_init(&k_empty[i], 1);
-            mbar_init(&p_full[i], 8);
-            mbar_init(&p_empty[i], 1);
         }
         for (int i = 0; i < 4; ++i) {
+            mbar_init(&p_full[i], 8);
+            mbar_init(&p_empty[i], 1);
             mbar_init(&v_full[i], 1);
             mbar_init(&v_empty[i], 1);
         }
@@ -218,34 +242,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         if (lane == 0) {
             prefetch_tensormap(&map_qk);
             prefetch_tensormap(&map_v);
-            const int col_q = head * 128, col_k = p.H + head * 128, col_v = 2 * p.H + head * 128;
+            const int col_q = head * D, col_k = p.H + head * D, col_v = 2 * p.H + head * D;
+            const CUtensorMap* map_k = KB == 128 ? &map_qk : &map_v;   // box of KB rows
             bool ok = true;
-            mbar_arrive_expect_tx(&q_full, p.planes * 2 * kTile16K);
-            for (int dc = 0; dc < 2; ++dc)
+            mbar_arrive_expect_tx(&q_full, p.planes * DC * kTile16K);
+            for (int dc = 0; dc < DC; ++dc)
                 tma_load_3d(q_smem + dc * 2 * kTile16K, &map_qk, &q_full, col_q + dc * 64, s.row0 + q0, 0);
             for (int j = 0; j < nb && ok; ++j) {
-                const int slot = j & 1;
-                if (!mbar_wait(&k_empty[slot], ((j >> 1) & 1) ^ 1)) { ok = false; break; }
-                mbar_arrive_expect_tx(&k_full[slot], p.planes * 2 * kTile16K);
-                for (int dc = 0; dc < 2; ++dc)
-                    tma_load_3d(k_ring + slot * kKSlotBytes + dc * 2 * kTile16K, &map_qk, &k_full[slot],
-                                col_k + dc * 64, s.row0 + j * 128, 0);
+                const int slot = j % NK;
+                if (!mbar_wait(&k_empty[slot], ((j / NK) & 1) ^ 1)) { ok = false; break; }
+                mbar_arrive_expect_tx(&k_full[slot], p.planes * DC * Shape::kKTile);
+                for (int dc = 0; dc < DC; ++dc)
+                    tma_load_3d(k_ring + slot * Shape::kKSlotBytes + dc * 2 * Shape::kKTile, map_k,
+                                &k_full[slot], col_k + dc * 64, s.row0 + j * KB, 0);
             }
             if (ok && !mbar_wait(&s_full, 0)) ok = false;   // K ring is dead: reuse it for V
             for (int i = 0; i < nchunks && ok; ++i) {
-                const int c = chunk_order(i, nchunks), slot = i & 3;
-                if (!mbar_wait(&v_empty[slot], ((i >> 2) & 1) ^ 1)) { ok = false; break; }
-                mbar_arrive_expect_tx(&v_full[slot], p.planes * 2 * kVPlaneBytes);
-                for (int dh = 0; dh < 2; ++dh)
-                    tma_load_3d(k_ring + slot * kVSlotBytes + dh * 2 * kVPlaneBytes, &map_v, &v_full[slot],
-                                col_v + dh * 64, s.row0 + c * 64, 0);
+                const int c = chunk_order<SAFE>(i, nchunks), slot = i % NV;
+                if (!mbar_wait(&v_empty[slot], ((i / NV) & 1) ^ 1)) { ok = false; break; }
+                mbar_arrive_expect_tx(&v_full[slot], p.planes * DC * kVPlaneBytes);
+                for (int dh = 0; dh < DC; ++dh)
+                    tma_load_3d(k_ring + slot * Shape::kVSlotBytes + dh * 2 * kVPlaneBytes, &map_v,
+                                &v_full[slot], col_v + dh * 64, s.row0 + c * 64, 0);
             }
             if (!ok) atomicExch(p.status, kStatusAttnTimeout);
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_f16(128, 128, false);
-            constexpr uint32_t idesc_o = make_idesc_f16(128, 128, true);
+            constexpr uint32_t idesc_s = make_idesc_f16(128, KB, false);
+            constexpr uint32_t idesc_o = make_idesc_f16(128, D, true);
             const uint32_t q_addr = smem_u32(q_smem), k_addr = smem_u32(k_ring);
             long long tw[4] = {0, 0, 0, 0};
             const long long t_begin = clock64();
@@ -258,34 +283,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
             bool ok = timed(&q_full, 0, 0);
             tcgen05_fence_after();
             for (int j = 0; j < nb && ok; ++j) {
-                const int slot = j & 1;
-                if (!timed(&k_full[slot], (j >> 1) & 1, 1)) { ok = false; break; }
+                const int slot = j % NK;
+                if (!timed(&k_full[slot], (j / NK) & 1, 1)) { ok = false; break; }
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + j * 128;
+                const uint32_t d_tmem = tmem_base + j * KB;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t off = (ks >> 2) * 2 * kTile16K + (ks & 3) * 32;
-                    const uint32_t qa = q_addr + off, kb = k_addr + slot * kKSlotBytes + off;
+                for (int ks = 0; ks < D / 16; ++ks) {
+                    const uint32_t qa = q_addr + (ks >> 2) * 2 * kTile16K + (ks & 3) * 32;
+                    const uint32_t kb = k_addr + slot * Shape::kKSlotBytes + (ks >> 2) * 2 * Shape::kKTile +
+                                        (ks & 3) * 32;
                     const uint64_t dq0 = smem_desc_kmajor_sw128(qa), dk0 = smem_desc_kmajor_sw128(kb);
                     umma_f16(d_tmem, dq0, dk0, idesc_s, ks > 0);
                     if (p.planes == 2) {
-                        umma_f16(d_tmem, dq0, smem_desc_kmajor_sw128(kb + kTile16K), idesc_s, 1);
+                        umma_f16(d_tmem, dq0, smem_desc_kmajor_sw128(kb + Shape::kKTile), idesc_s, 1);
                         umma_f16(d_tmem, smem_desc_kmajor_sw128(qa + kTile16K), dk0, idesc_s, 1);
                     }
                 }
                 umma_commit(&k_empty[slot]);
             }
             if (ok) umma_commit(&s_full);
-            const uint32_t o_tmem = tmem_base + kOCol;
-            const int pre = nchunks > 6 ? nchunks - 6 : 0;
+            const uint32_t o_tmem = tmem_base + Shape::kOCol;
+            const int pre = nchunks > SAFE ? nchunks - SAFE : 0;
             for (int i = 0; i < nchunks && ok; ++i) {
-                const int ps = i & 1, vs = i & 3;
-                if (!timed(&p_full[ps], (i >> 1) & 1, 2)) { ok = false; break; }
-                if (i == 0 && pre == 2 && !timed(&p_full[1], 0, 2)) { ok = false; break; }
-                if (!timed(&v_full[vs], (i >> 2) & 1, 3)) { ok = false; break; }
+                const int ps = i % NP, vs = i % NV;
+                if (!timed(&p_full[ps], (i / NP) & 1, 2)) { ok = false; break; }
+                if (i == 0)   // every chunk whose scores live in O's columns has been converted
+                    for (int k = 1; k < pre && ok; ++k) ok = timed(&p_full[k], 0, 2);
+                if (!ok) break;
+                if (!timed(&v_full[vs], (i / NV) & 1, 3)) { ok = false; break; }
                 tcgen05_fence_after();
                 const uint32_t p_addr = q_addr + ps * kPSlotBytes;
-                const uint32_t v_addr = k_addr + vs * kVSlotBytes;
+                const uint32_t v_addr = k_addr + vs * Shape::kVSlotBytes;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint32_t pa = p_addr + ks * 32;          // 16 keys along the swizzle row
@@ -311,7 +339,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         }
     } else {
         // 8 softmax warps: a query row is shared by two threads (same TMEM lane
-        // quadrant, `half` = which 32 of every 64 keys / which 64 of the 128 output
+        // quadrant, `half` = which 32 of every 64 keys / which D/2 of the D output
         // columns); row max and row sum are combined through shared memory.
         const int half = (warp - 2) >> 2;
         const int quad = warp & 3, r = quad * 32 + lane, t = q0 + r;
@@ -356,11 +384,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         // chunk earlier); the next chunk's load is issued before the math so TMEM latency
         // hides behind it, and the P slot is only waited for right before it is written
         auto chunk = [&](int i, uint32_t (&cur)[32], uint32_t (&nxt)[32]) -> bool {
-            const int c = chunk_order(i, nchunks), slot = i & 1;
+            const int c = chunk_order<SAFE>(i, nchunks), slot = i % NP;
             const int key0 = c * 64 + half * 32;
             tmem_wait_ld();
             if (i + 1 < nchunks)
-                tmem_ld_32x32(t_row + chunk_order(i + 1, nchunks) * 64 + half * 32, nxt);
+                tmem_ld_32x32(t_row + chunk_order<SAFE>(i + 1, nchunks) * 64 + half * 32, nxt);
             uint32_t h[16], l[16];
             const bool full = key0 + 32 <= nkeys && (!p.causal || key0 + 31 <= q0);
             if (full) {
@@ -388,7 +416,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
             }
             {
                 const long long t0 = clock64();
-                const bool got = mbar_wait(&p_empty[slot], ((i >> 1) & 1) ^ 1);
+                const bool got = mbar_wait(&p_empty[slot], ((i / NP) & 1) ^ 1);
                 t_pempty += clock64() - t0;
                 if (!got) return false;
             }
@@ -407,7 +435,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
             return true;
         };
         uint32_t raw_b[32];
-        if (ok) tmem_ld_32x32(t_row + chunk_order(0, nchunks) * 64 + half * 32, raw);
+        if (ok) tmem_ld_32x32(t_row + chunk_order<SAFE>(0, nchunks) * 64 + half * 32, raw);
 #pragma unroll 1
         for (int i = 0; i < nchunks && ok; i += 2) {
             ok = chunk(i, raw, raw_b);
@@ -422,34 +450,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         const long long ts4 = clock64();
         tcgen05_fence_after();
         if (ok) {
-            // O / sum -> split planes, staged as four [128 rows][64 cols] 128B-swizzled tiles
-            // (column half x plane) in the dead P ring, then stored with TMA: full 128-byte
-            // rows instead of 16-byte pieces per thread
+            // O / sum -> split planes, staged as [128 rows][64 cols] 128B-swizzled tiles
+            // (64-column block x plane) in the dead P ring, then stored with TMA: full
+            // 128-byte rows instead of 16-byte pieces per thread
             const float inv = sum > 0.f ? 1.f / sum : 0.f;
-            uint32_t h[32], l[32];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                tmem_ld_32x32(t_row + kOCol + half * 64 + g * 32, raw);
+            for (int g = 0; g < D / 64; ++g) {
+                const int col = half * (D / 2) + g * 32;   // this thread's 32 output columns
+                tmem_ld_32x32(t_row + Shape::kOCol + col, raw);
                 tmem_wait_ld();
+                uint32_t h[16], l[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     split2_f16(__uint_as_float(raw[2 * j]) * inv, __uint_as_float(raw[2 * j + 1]) * inv,
-                               h[g * 16 + j], l[g * 16 + j]);
-            }
-            const uint32_t tile_hi = p_base + (uint32_t)(half * 2) * kTile16K;
+                               h[j], l[j]);
+                const uint32_t tile_hi = p_base + (uint32_t)((col >> 6) * 2) * kTile16K;
+                const uint32_t unit0 = (uint32_t)(col & 63) >> 3;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t addr = tile_hi + row_off + (((uint32_t)u ^ sw) << 4);
-                st_shared_v4(addr, h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
-                st_shared_v4(addr + kTile16K, l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t addr = tile_hi + row_off + (((unit0 + u) ^ sw) << 4);
+                    st_shared_v4(addr, h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+                    st_shared_v4(addr + kTile16K, l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
+                }
             }
             fence_proxy_async_smem();
         }
         named_bar_sync(1, 256);
         if (ok && warp == 2 && lane == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                tma_store_3d(&map_out, q_smem + i * kTile16K, head * 128 + (i >> 1) * 64,
+            for (int i = 0; i < 2 * DC; ++i)
+                tma_store_3d(&map_out, q_smem + i * kTile16K, head * D + (i >> 1) * 64,
                              (int)out_row0, i & 1);
             bulk_commit_group();
             bulk_wait_all();
@@ -491,63 +521,68 @@ int launch_attention_planes(ppgs_engine* e, int head_dim, const __half* qkv, __h
     };
     if (head_dim == 64) return run(attention_planes_kernel<64>, 64);
     if (head_dim == 128) return run(attention_planes_kernel<128>, 128);
+    if (head_dim == 256) return run(attention_planes_kernel<256>, 256);
     set_error("attention_planes: head_dim %d not built", head_dim);
     return PPGS_E_UNSUPPORTED;
+}
+
+template <int D>
+static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows, int H, int heads,
+                            int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
+                            cudaStream_t stream) {
+    using Shape = AttnShape<D>;
+    CUtensorMap map_qk, map_v, map_out;
+    PPGS_CHECK(make_store_map(&map_out, out, H, rows, (uint64_t)rows * H));
+    PPGS_CHECK(make_plane_map(&map_qk, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
+                              (uint64_t)rows * 3 * H, 128, planes));
+    PPGS_CHECK(make_plane_map(&map_v, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
+                              (uint64_t)rows * 3 * H, 64, planes));
+    static bool attr_tc = false;
+    if (!attr_tc) {
+        PPGS_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Shape::kSmem));
+        attr_tc = true;
+    }
+    AttnParams p;
+    p.seqs = seqs_dev;
+    p.H = H;
+    p.causal = causal;
+    p.planes = planes;
+    p.scale_log2e = 1.4426950408889634f / sqrtf((float)D);
+    p.out = out;
+    p.out_plane_stride = (int64_t)rows * H;
+    p.status = e->status_dev;
+    p.trace = e->trace_dev ? e->trace_dev + 80 : nullptr;
+    dim3 grid(max_pitch / 128, heads, (unsigned)nseq);
+    {
+        LaunchScope scope(e, "tc_attention", stream);
+        attention_tc_kernel<D><<<grid, kAttnThreads, Shape::kSmem, stream>>>(map_qk, map_v, map_out, p);
+    }
+    PPGS_CUDA(cudaGetLastError());
+    return PPGS_OK;
+}
+
+int launch_attention_any(ppgs_engine* e, const __half* qkv, __half* out, int rows, int H, int heads,
+                         int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
+                         cudaStream_t stream) {
+    const int D = H / heads;
+    if (e->attention_impl == 1 && max_pitch <= 512 && max_pitch % 128 == 0 && e->status_dev) {
+        if (D == 64)
+            return run_attention_tc<64>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream);
+        if (D == 128)
+            return run_attention_tc<128>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream);
+        if (D == 256)
+            return run_attention_tc<256>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream);
+    }
+    return launch_attention_planes(e, D, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes,
+                                   stream);
 }
 
 int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows,
                         const ForwardPlan& plan, const SeqInfo* seqs_dev, int planes,
                         cudaStream_t stream) {
-    constexpr int D = 128;
-    const int H = e->cfg.hidden_channels;
-    if (e->attention_impl == 1 && plan.max_pitch <= 512 && H / e->cfg.num_heads == D) {
-        CUtensorMap map_qk, map_v, map_out;
-        PPGS_CHECK(make_store_map(&map_out, out, H, rows, (uint64_t)rows * H));
-        PPGS_CHECK(make_plane_map(&map_qk, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
-                                  (uint64_t)rows * 3 * H, 128, planes));
-        PPGS_CHECK(make_plane_map(&map_v, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
-                                  (uint64_t)rows * 3 * H, 64, planes));
-        static bool attr_tc = false;
-        if (!attr_tc) {
-            PPGS_CUDA(cudaFuncSetAttribute(attention_tc_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)kAttnSmem));
-            attr_tc = true;
-        }
-        AttnParams p;
-        p.seqs = seqs_dev;
-        p.H = H;
-        p.causal = e->cfg.is_causal;
-        p.planes = planes;
-        p.scale_log2e = 1.4426950408889634f / sqrtf((float)D);
-        p.out = out;
-        p.out_plane_stride = (int64_t)rows * H;
-        p.status = e->status_dev;
-        p.trace = e->trace_dev ? e->trace_dev + 80 : nullptr;
-        dim3 grid(plan.max_pitch / 128, e->cfg.num_heads, (unsigned)plan.seqs.size());
-        {
-            LaunchScope scope(e, "tc_attention", stream);
-            attention_tc_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(map_qk, map_v, map_out, p);
-        }
-        PPGS_CUDA(cudaGetLastError());
-        return PPGS_OK;
-    }
-    const size_t smem = (size_t)(32 * D + 32 * (D + 1) + 32 * D) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        PPGS_CUDA(cudaFuncSetAttribute(attention_planes_kernel<D>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
-    dim3 grid(plan.max_pitch / 32, e->cfg.num_heads, (unsigned)plan.seqs.size());
-    {
-        LaunchScope scope(e, "attention_simt_planes", stream);
-        attention_planes_kernel<D><<<grid, 256, smem, stream>>>(
-            qkv, (int64_t)rows * 3 * H, H, seqs_dev, e->cfg.is_causal, 1.f / sqrtf((float)D), planes,
-            out, (int64_t)rows * H);
-    }
-    PPGS_CUDA(cudaGetLastError());
-    return PPGS_OK;
+    return launch_attention_any(e, qkv, out, rows, e->cfg.hidden_channels, e->cfg.num_heads, plan.max_pitch,
+                                (int)plan.seqs.size(), seqs_dev, e->cfg.is_causal, planes, stream);
 }
 
 }  // namespace ppgs

@@ -11,7 +11,13 @@ int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows
                         const ForwardPlan& plan, const SeqInfo* seqs_dev, int planes,
                         cudaStream_t stream);
 
-// CUDA-core attention over split planes for any (hidden, heads, head_dim in {64, 128}):
+// Same for any (hidden, heads): tcgen05 kernel when head_dim is 64 / 128 / 256 and the
+// pitch is <= 512 rows, CUDA-core kernel otherwise.
+int launch_attention_any(ppgs_engine* e, const __half* qkv, __half* out, int rows, int H, int heads,
+                         int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
+                         cudaStream_t stream);
+
+// CUDA-core attention over split planes for any (hidden, heads, head_dim in {64, 128, 256}):
 // used by the wav2vec2 encoder (12 heads x 64).
 int launch_attention_planes(ppgs_engine* e, int head_dim, const __half* qkv, __half* out, int rows,
                             int H, int heads, int max_pitch, int nseq, const SeqInfo* seqs_dev,

@@ -224,6 +224,7 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
 // transformer_tc.cu
 int build_weight_map(TcWeight& w);        // TMA descriptors of one packed weight
 int ensure_status_word(ppgs_engine* e);
+bool tensor_core_shape(const ppgs_model_config& c);   // model shapes the tcgen05 path covers
 int build_weight_maps(ppgs_engine* e);
 int transformer_forward_tc(ppgs_engine* e, const __half* features, const ForwardPlan& plan,
                            int softmax, float* out, cudaStream_t stream);

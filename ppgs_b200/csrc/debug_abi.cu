@@ -97,29 +97,22 @@ extern "C" int ppgs_debug_gemm(ppgs_engine* e, const float* a_host, const float*
 }
 
 extern "C" int ppgs_debug_attention(ppgs_engine* e, const float* qkv_host, int rows, int tensor_len,
-                                    int valid_len, int planes, int use_tensor_cores,
-                                    float* out_host) {
-    if (!e || !qkv_host || !out_host || rows <= 0 || rows % 128 || tensor_len > rows - 2 ||
-        valid_len > tensor_len) {
+                                    int valid_len, int H, int heads, int causal, int planes,
+                                    int use_tensor_cores, float* out_host) {
+    if (!e || !qkv_host || !out_host || rows <= 0 || rows % 128 || tensor_len > rows ||
+        valid_len > tensor_len || heads <= 0 || H % heads) {
         set_error("debug_attention: bad argument");
         return PPGS_E_INVALID;
     }
     PPGS_CUDA(cudaSetDevice(e->device));
     PPGS_CHECK(ensure_status(e));
-    const int H = e->cfg.hidden_channels;
     std::vector<__half> qkv_planes;
     split_planes(qkv_host, (size_t)rows * 3 * H, qkv_planes);
-    ForwardPlan plan;
     SeqInfo s{};
     s.row0 = 0;
     s.tensor_len = tensor_len;
     s.valid_len = valid_len;
     s.keep_end = tensor_len;
-    plan.seqs.push_back(s);
-    plan.rows = rows;
-    plan.max_pitch = rows;
-    plan.batch = 1;
-    plan.frames = tensor_len;
     DeviceBuffer qkv_dev, out_dev, seq_dev;
     PPGS_CHECK(qkv_dev.alloc(qkv_planes.size() * 2));
     PPGS_CHECK(out_dev.alloc((size_t)2 * rows * H * 2));
@@ -128,8 +121,8 @@ extern "C" int ppgs_debug_attention(ppgs_engine* e, const float* qkv_host, int r
     PPGS_CUDA(cudaMemcpy(seq_dev.ptr, &s, sizeof(SeqInfo), cudaMemcpyHostToDevice));
     const int saved = e->attention_impl;
     e->attention_impl = use_tensor_cores ? 1 : 0;
-    const int rc = launch_attention_tc(e, qkv_dev.as<__half>(), out_dev.as<__half>(), rows, plan,
-                                       seq_dev.as<SeqInfo>(), planes, nullptr);
+    const int rc = launch_attention_any(e, qkv_dev.as<__half>(), out_dev.as<__half>(), rows, H, heads, rows, 1,
+                                        seq_dev.as<SeqInfo>(), causal, planes, nullptr);
     e->attention_impl = saved;
     PPGS_CHECK(rc);
     PPGS_CUDA(cudaDeviceSynchronize());

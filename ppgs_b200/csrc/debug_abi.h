@@ -19,9 +19,11 @@ int ppgs_debug_gemm(ppgs_engine* engine, const float* a_host, const float* w_hos
                     int a_planes, int b_planes, float* out_host);
 
 /* One attention call on host data: qkv (rows, 3H) fp32 for one sequence of
- * `tensor_len` rows (rows % 128 == 0) with `valid_len` unmasked keys. */
+ * `tensor_len` rows (rows % 128 == 0) with `valid_len` unmasked keys, `heads` heads of
+ * H / heads channels (64, 128 or 256 on the tensor cores). */
 int ppgs_debug_attention(ppgs_engine* engine, const float* qkv_host, int rows, int tensor_len,
-                         int valid_len, int planes, int use_tensor_cores, float* out_host);
+                         int valid_len, int H, int heads, int causal, int planes,
+                         int use_tensor_cores, float* out_host);
 
 /* Copies out and clears the 128 cycle counters the GEMM kernels accumulate when the
  * engine was created with PPGS_B200_TRACE=1 (8 kernel slots x 8 counters, see

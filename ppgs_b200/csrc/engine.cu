@@ -305,6 +305,13 @@ static int alloc_blob(ppgs_engine* e) {
     return PPGS_OK;
 }
 
+bool tensor_core_shape(const ppgs_model_config& c) {
+    const int H = c.hidden_channels, D = c.num_heads > 0 ? H / c.num_heads : 0;
+    return (H == 256 || H == 512 || H == 768 || H == 1024) && D * c.num_heads == H &&
+           (D == 64 || D == 128 || D == 256) && c.ffn_channels % 256 == 0 && c.output_channels <= 64 &&
+           c.input_channels % 8 == 0;
+}
+
 }  // namespace ppgs
 
 using namespace ppgs;
@@ -488,10 +495,6 @@ int ppgs_engine_set_weight(ppgs_engine* e, const char* name, const float* data,
     return PPGS_E_INVALID;
 }
 
-static bool tensor_core_shape(const ppgs_model_config& c) {
-    return c.hidden_channels == 256 && c.hidden_channels / c.num_heads == 128 &&
-           c.ffn_channels % 256 == 0 && c.output_channels <= 64 && c.input_channels % 8 == 0;
-}
 
 static void pick_default_precision(ppgs_engine* e) {
     if (!e->precision_chosen)
@@ -585,7 +588,7 @@ int ppgs_engine_set_precision(ppgs_engine* e, int precision) {
     }
     if (precision != PPGS_PRECISION_FP32 && !tensor_core_shape(e->cfg)) {
         set_error("precision %d is not available for this model shape (tensor-core path: "
-                  "hidden 256)", precision);
+                  "hidden 256 / 512 / 768 / 1024, head_dim 64 / 128 / 256)", precision);
         return PPGS_E_UNSUPPORTED;
     }
     e->precision = precision;

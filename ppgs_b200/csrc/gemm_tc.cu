@@ -363,11 +363,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const bool in_tensor = t < s.tensor_len, valid = t < s.valid_len;
 #pragma unroll 1
                 for (int g = 0; g < kChunks / 4; ++g) {
-                    const int n0 = set * (BN / 2) + g * 64;
+                    const int col = set * (BN / 2) + g * 64;
+                    const int n0 = n_blk * BN + col;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         float pe[32];
-                        tmem_ld_32x32(t_acc + n0 + half * 32, raw);
+                        tmem_ld_32x32(t_acc + col + half * 32, raw);
                         load_params32(p.bias + n0 + half * 32, y);
                         load_params32(p.pe + (int64_t)(in_tensor ? t : 0) * p.N + n0 + half * 32, pe);
                         tmem_wait_ld();

@@ -74,6 +74,64 @@ int check_status(ppgs_engine* e, cudaStream_t stream) {
     return PPGS_OK;
 }
 
+// x <- LayerNorm(x + y) over split planes, one warp per row; rows outside the sequence
+// tensor -> 0 (they are the zero halo of the output convolution).  Hidden sizes > 256,
+// where the GEMM epilogue cannot see a whole row.
+template <int H>
+__global__ void __launch_bounds__(256)
+residual_layernorm_planes_kernel(__half* __restrict__ x, const __half* __restrict__ y, int64_t plane_stride,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 const SeqInfo* __restrict__ seqs, const int* __restrict__ tile_seq, int rows) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    constexpr int PER = H / 64;   // half2 per lane
+    const SeqInfo s = seqs[tile_seq[row >> 7]];
+    const int64_t base = (int64_t)row * H;
+    if (row - s.row0 >= s.tensor_len) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int64_t at = base + 2 * (lane + 32 * i);
+            *reinterpret_cast<uint32_t*>(x + at) = 0u;
+            *reinterpret_cast<uint32_t*>(x + plane_stride + at) = 0u;
+        }
+        return;
+    }
+    float v[2 * PER];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int64_t at = base + 2 * (lane + 32 * i);
+        const float2 xh = __half22float2(*reinterpret_cast<const __half2*>(x + at));
+        const float2 xl = __half22float2(*reinterpret_cast<const __half2*>(x + plane_stride + at));
+        const float2 yh = __half22float2(*reinterpret_cast<const __half2*>(y + at));
+        const float2 yl = __half22float2(*reinterpret_cast<const __half2*>(y + plane_stride + at));
+        v[2 * i] = (xh.x + xl.x) + (yh.x + yl.x);
+        v[2 * i + 1] = (xh.y + xl.y) + (yh.y + yl.y);
+        sum += v[2 * i] + v[2 * i + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / H;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 * PER; ++i) {
+        const float d = v[i] - mean;
+        sq = fmaf(d, d, sq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / H + eps);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = 2 * (lane + 32 * i);
+        uint32_t hi2, lo2;
+        tc::split2_f16((v[2 * i] - mean) * rstd * gamma[c] + beta[c],
+                       (v[2 * i + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1], hi2, lo2);
+        *reinterpret_cast<uint32_t*>(x + base + c) = hi2;
+        *reinterpret_cast<uint32_t*>(x + plane_stride + base + c) = lo2;
+    }
+}
+
 // (B, C, T) fp16 -> [rows][C] fp16, time-major (transformer.py:54,58 folded)
 __global__ void fold_half_kernel(const __half* __restrict__ feats, int C, int T,
                                  const SeqInfo* __restrict__ seqs, const int* __restrict__ tile_seq,
@@ -102,10 +160,14 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     const int C = c.input_channels, H = c.hidden_channels, F = c.ffn_channels;
     const int O = c.output_channels, k = c.kernel_size;
     const int rows = plan.rows, D = H / c.num_heads;
-    if (H != 256 || D != 128 || O > 64 || F % 256 || C % 8) {
-        set_error("tensor-core path supports hidden 256 / head_dim 128 (got %d / %d)", H, D);
+    if (!tensor_core_shape(c)) {
+        set_error("tensor-core path supports hidden %% 256 == 0 with head_dim 64 / 128 / 256 (got %d / %d)",
+                  H, D);
         return PPGS_E_UNSUPPORTED;
     }
+    // hidden 256: one GEMM tile spans a full row and the residual + LayerNorm live in the
+    // epilogue; wider models store the projection and normalise in a separate pass
+    const bool fused_ln = H == 256;
     PPGS_CHECK(build_weight_maps(e));
     const int planes = e->precision == PPGS_PRECISION_F16X2 ? 2 : 1;
 
@@ -115,6 +177,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     const size_t o_qkv = w.take((size_t)2 * rows * 3 * H * 2);
     const size_t o_att = w.take((size_t)2 * rows * H * 2);
     const size_t o_ff = w.take((size_t)2 * rows * F * 2);
+    const size_t o_y = w.take(fused_ln ? 0 : (size_t)2 * rows * H * 2);
     const size_t o_seqs = w.take(plan.seqs.size() * sizeof(SeqInfo));
     const size_t o_tiles = w.take((size_t)(rows / 128) * 4);
     PPGS_CHECK(ensure_workspace(e, w.off));
@@ -124,6 +187,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     __half* qkv = reinterpret_cast<__half*>(ws + o_qkv);
     __half* att = reinterpret_cast<__half*>(ws + o_att);
     __half* ff = reinterpret_cast<__half*>(ws + o_ff);
+    __half* yh = reinterpret_cast<__half*>(ws + o_y);
     SeqInfo* seqs_dev = reinterpret_cast<SeqInfo*>(ws + o_seqs);
     int* tile_seq_dev = reinterpret_cast<int*>(ws + o_tiles);
     PPGS_CHECK(upload_plan(e, plan, seqs_dev, tile_seq_dev, stream));
@@ -135,8 +199,9 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     PPGS_CHECK(make_plane_map(&map_att, att, false, H, rows, 1, 2, H, 0, (uint64_t)rows * H, 128, planes));
     PPGS_CHECK(make_plane_map(&map_ff, ff, false, F, rows, 1, 2, F, 0, (uint64_t)rows * F, 128, planes));
     // output tensor maps (TMA stores of the epilogues)
-    CUtensorMap out_x, out_qkv, out_ff;
+    CUtensorMap out_x, out_qkv, out_ff, out_y;
     PPGS_CHECK(make_store_map(&out_x, xh, H, rows, (uint64_t)rows * H));
+    if (!fused_ln) PPGS_CHECK(make_store_map(&out_y, yh, H, rows, (uint64_t)rows * H));
     PPGS_CHECK(make_store_map(&out_qkv, qkv, 3 * H, rows, (uint64_t)rows * 3 * H));
     PPGS_CHECK(make_store_map(&out_ff, ff, F, rows, (uint64_t)rows * F));
 
@@ -166,7 +231,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
 
     {   // input conv: features are exact fp16 -> one A plane
         GemmParams p = base;
-        p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = (C + 63) / 64; p.a_planes = 1;
+        p.n_tiles = H / 256; p.taps = k; p.half = k / 2; p.cblocks = (C + 63) / 64; p.a_planes = 1;
         p.N = H; p.scale = e->tc_conv_in.inv_scale; p.bias = e->conv_in_b; p.pe = e->pe;
         p.trace = trace(0);
         PPGS_CHECK(launch_gemm_tc(e, "tc_conv_in", 256, kEpiConvIn, map_x0, wmap(e->tc_conv_in),
@@ -183,16 +248,37 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
                                       p, stream));
         }
         PPGS_CHECK(launch_attention_tc(e, qkv, att, rows, plan, seqs_dev, planes, stream));
-        {
+        // x <- LayerNorm(x + projection): epilogue of the GEMM (hidden 256) or its own pass
+        auto project_ln = [&](const char* name, const CUtensorMap& map_a, TcWeight& wt, int cblocks,
+                              const float* bias, const float* gamma, const float* beta, int slot,
+                              int slot_ln) -> int {
             GemmParams p = base;
-            p.n_tiles = 1; p.cblocks = H / 64; p.a_planes = planes;
-            p.N = H; p.scale = T.out_w.inv_scale; p.bias = L.out_b; p.trace = trace(2); p.trace_ln = trace(6);
-            p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
-            p.gamma = L.n1_w; p.beta = L.n1_b;
-            PPGS_CHECK(launch_gemm_tc(e, "tc_out_proj_ln", 256, kEpiResLN, map_att, wmap(T.out_w),
-                                      &out_x, p, stream));
-        }
-        if (pair && e->fused_ffn && F % 64 == 0) {
+            p.cblocks = cblocks; p.a_planes = planes;
+            p.N = H; p.scale = wt.inv_scale; p.bias = bias; p.trace = trace(slot);
+            if (fused_ln) {
+                p.n_tiles = 1; p.trace_ln = trace(slot_ln);
+                p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
+                p.gamma = gamma; p.beta = beta;
+                return launch_gemm_tc(e, name, 256, kEpiResLN, map_a, wmap(wt), &out_x, p, stream);
+            }
+            p.n_tiles = H / 256;
+            PPGS_CHECK(launch_gemm_tc(e, name, 256, kEpiPlanes, map_a, wmap(wt), &out_y, p, stream));
+            LaunchScope scope(e, "residual_layernorm_planes", stream);
+            if (H == 512)
+                residual_layernorm_planes_kernel<512><<<(rows + 7) / 8, 256, 0, stream>>>(
+                    xh, yh, (int64_t)rows * H, gamma, beta, c.layer_norm_eps, seqs_dev, tile_seq_dev, rows);
+            else if (H == 768)
+                residual_layernorm_planes_kernel<768><<<(rows + 7) / 8, 256, 0, stream>>>(
+                    xh, yh, (int64_t)rows * H, gamma, beta, c.layer_norm_eps, seqs_dev, tile_seq_dev, rows);
+            else
+                residual_layernorm_planes_kernel<1024><<<(rows + 7) / 8, 256, 0, stream>>>(
+                    xh, yh, (int64_t)rows * H, gamma, beta, c.layer_norm_eps, seqs_dev, tile_seq_dev, rows);
+            PPGS_CUDA(cudaGetLastError());
+            return PPGS_OK;
+        };
+        PPGS_CHECK(project_ln(fused_ln ? "tc_out_proj_ln" : "tc_out_proj", map_att, T.out_w, H / 64, L.out_b,
+                              L.n1_w, L.n1_b, 2, 6));
+        if (pair && e->fused_ffn && fused_ln && F % 64 == 0) {
             FfnParams f;
             f.m_tiles = rows / 128; f.num_chunks = F / 64; f.planes = planes;
             f.scale1 = T.l1_w.inv_scale; f.scale2 = T.l2_w.inv_scale;
@@ -210,15 +296,8 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
                 PPGS_CHECK(launch_gemm_tc(e, "tc_ffn1", 256, kEpiPlanes, map_x, wmap(T.l1_w), &out_ff,
                                           p, stream));
             }
-            {
-                GemmParams p = base;
-                p.n_tiles = 1; p.cblocks = F / 64; p.a_planes = planes;
-                p.N = H; p.scale = T.l2_w.inv_scale; p.bias = L.l2_b; p.trace = trace(4); p.trace_ln = trace(7);
-                p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
-                p.gamma = L.n2_w; p.beta = L.n2_b;
-                PPGS_CHECK(launch_gemm_tc(e, "tc_ffn2_ln", 256, kEpiResLN, map_ff, wmap(T.l2_w), &out_x,
-                                          p, stream));
-            }
+            PPGS_CHECK(project_ln(fused_ln ? "tc_ffn2_ln" : "tc_ffn2", map_ff, T.l2_w, F / 64, L.l2_b, L.n2_w,
+                                  L.n2_b, 4, 7));
         }
     }
     {

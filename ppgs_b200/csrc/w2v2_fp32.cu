@@ -162,9 +162,9 @@ feature_layernorm_kernel(const void* __restrict__ src, int64_t plane_stride, int
 // ---- out = LayerNorm(a [+ b]) per row; rows with t >= limit[b] (optional) -> 0
 template <int H>
 __global__ void __launch_bounds__(256)
-add_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b2,
+add_layernorm_kernel(const float* a /* may alias out */, const float* __restrict__ b2,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                     int rows, float* __restrict__ out, int64_t pitch_a = 0, int64_t pitch_b = 0,
+                     int rows, float* out, int64_t pitch_a = 0, int64_t pitch_b = 0,
                      int batch = 0) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -798,8 +798,8 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
             const W2v2Layer& L = w.layers[l];
             W2v2TcLayer& T = e->w2v2->tc[l];
             PPGS_CHECK(gemm("w2v2_tc_qkv", a_x, T.qkv, s_qkv, L.qkv_b, 0));
-            PPGS_CHECK(launch_attention_planes(e, kHidden / kHeads, qh, ah, (int)M, kHidden, kHeads,
-                                               (int)P, batch, seqs_dev, 0, 2, stream));
+            PPGS_CHECK(launch_attention_any(e, qh, ah, (int)M, kHidden, kHeads, (int)P, batch, seqs_dev, 0,
+                                            2, stream));
             PPGS_CHECK(gemm("w2v2_tc_out_proj", a_att, T.out, s_y, L.out_b, 0));
             add_ln(L.ln1_w, L.ln1_b, nullptr);
             PPGS_CHECK(gemm("w2v2_tc_ffn1", a_x, T.ff1, s_ff, L.ff1_b, 2));

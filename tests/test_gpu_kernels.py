@@ -26,7 +26,7 @@ def debug_lib():
     lib.ppgs_debug_gemm.restype = i
     lib.ppgs_debug_gemm.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]
     lib.ppgs_debug_attention.restype = i
-    lib.ppgs_debug_attention.argtypes = [vp, vp, i, i, i, i, i, vp]
+    lib.ppgs_debug_attention.argtypes = [vp, vp, i, i, i, i, i, i, i, i, vp]
     return _lib
 
 
@@ -94,20 +94,25 @@ def test_tcgen05_gemm(engine, case, planes):
 
 @pytest.mark.parametrize('tensor_len,valid_len', [(126, 126), (500, 500), (500, 317), (250, 1), (300, 0)])
 @pytest.mark.parametrize('impl', [0, 1])
-def test_attention_kernel(engine, tensor_len, valid_len, impl):
+@pytest.mark.parametrize('H,heads,causal', [(256, 2, 0), (128, 2, 0), (512, 2, 0), (768, 12, 0), (256, 2, 1),
+                                            (512, 2, 1)])
+def test_attention_kernel(engine, tensor_len, valid_len, impl, H, heads, causal):
+    """head_dim 128 (mel PPG model), 64 (wav2vec2 encoder) and 256 (w2v2fb PPG model)."""
     lib = debug_lib()
-    H, heads = 256, 2
     rows = (tensor_len + 2 + 127) // 128 * 128
     g = torch.Generator().manual_seed(tensor_len + valid_len)
     qkv = torch.randn(rows, 3 * H, generator=g)
     qkv[:, :H] *= 2.0
     out = torch.empty(rows, H)
     rc = lib.lib.ppgs_debug_attention(
-        engine._handle, qkv.data_ptr(), rows, tensor_len, valid_len, 2, impl, out.data_ptr())
+        engine._handle, qkv.data_ptr(), rows, tensor_len, valid_len, H, heads, causal, 2, impl,
+        out.data_ptr())
     lib.check(rc)
     q, k, v = [t.double().reshape(rows, heads, H // heads).transpose(0, 1) for t in qkv.split(H, 1)]
     scores = q @ k.transpose(1, 2) / (H // heads) ** 0.5
     scores[:, :, valid_len:] = float('-inf')
+    if causal:
+        scores = scores.masked_fill(torch.ones(rows, rows).triu(1).bool(), float('-inf'))
     p = torch.softmax(scores, -1) if valid_len else torch.zeros_like(scores)
     ref = (p @ v).transpose(0, 1).reshape(rows, H)
     err = (out.double() - ref)[:tensor_len].abs().max().item()

@@ -94,3 +94,22 @@ def test_fp32_encoder_switch(ppgs_b200, monkeypatch):
     audio, lengths = case_inputs(16000, [16000, 7777], 12)
     feats = frontend(ppgs_b200, 6).w2v2fb(audio.cuda(), lengths).cpu().numpy()
     assert close_fp16(feats, W.from_audios(sd, audio, lengths).numpy()).all()
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'f16x2'])
+@pytest.mark.parametrize('frames,lengths', [(300, [300, 211]), (1000, [1000, 640, 77])])
+def test_hidden512_ppg_model_vs_oracle(ppgs_b200, precision, frames, lengths):
+    """T2 for the w2v2fb PPG model (input 768, hidden 512, 2 heads of 256): the tensor-core
+    path (GEMMs with a separate residual-LayerNorm pass, head_dim-256 attention) and the
+    fp32 CUDA-core path on identical fp16 features, chunked and ragged."""
+    sd = O.random_state_dict(4, input_channels=768, hidden_channels=512, peaky=True)
+    engine = ppgs_b200.Engine(0, input_channels=768, hidden_channels=512).load_state_dict(sd)
+    assert engine.precision == 'f16x2'          # default for shapes the tcgen05 path covers
+    engine.precision = precision
+    g = torch.Generator().manual_seed(frames)
+    feats = torch.randn(len(lengths), 768, frames, generator=g).half()
+    lengths = torch.tensor(lengths)
+    out = engine.transformer(feats.cuda(), lengths).cpu().numpy()
+    engine.check()
+    ref = O.from_features(sd, feats, lengths).numpy()
+    assert np.abs(out - ref).max() <= 1e-4
