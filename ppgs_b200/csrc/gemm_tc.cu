@@ -146,6 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int tile = worker; tile < total_tiles && ok; tile += workers) {
                 const int m_unit = tile / p.n_tiles, n_blk = tile - m_unit * p.n_tiles;
                 const int m_blk = PAIR ? 2 * m_unit + (int)rank : m_unit;
+                const int a_row0 = m_blk * kBM * p.row_mul - p.half + n_blk * p.a_group_rows;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                     const long long t0 = clock64();
@@ -162,12 +163,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         // the leader's barrier collects the bytes of both CTAs
                         if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
                         const uint32_t leader_bar = map_to_cta(&full_bar[stage], 0);
-                        tma_load_3d_pair(sa, &map_a, leader_bar, cb * kBK, m_blk * kBM * p.row_mul + tap - p.half, 0);
+                        tma_load_3d_pair(sa, &map_a, leader_bar, cb * kBK, a_row0 + tap, 0);
                         tma_load_4d_pair(sb, &map_b, leader_bar, cb * kBK,
                                          n_blk * BN + (int)rank * Shape::kBRows, tap, 0);
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-                        tma_load_3d(sa, &map_a, &full_bar[stage], cb * kBK, m_blk * kBM * p.row_mul + tap - p.half, 0);
+                        tma_load_3d(sa, &map_a, &full_bar[stage], cb * kBK, a_row0 + tap, 0);
                         tma_load_4d(sb, &map_b, &full_bar[stage], cb * kBK, n_blk * BN, tap, 0);
                     }
                     if (++stage == kStages) {
@@ -320,12 +321,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int c = set; c < kChunks; c += 2) {
                     tmem_ld_32x32(t_acc + c * 32, raw);
                     tmem_wait_ld();
-                    const int n0 = n_blk * BN + c * 32;
-                    if (n0 >= p.N) continue;   // warp-uniform
+                    const int n0 = (p.group_cols ? n_blk * p.group_cols : n_blk * BN) + c * 32;
+                    const int n_end = p.group_cols ? min(p.N, (n_blk + 1) * p.group_cols) : p.N;
+                    if (n0 >= n_end) continue;   // warp-uniform
                     float* dst = p.out_f32 + m * p.ld_f32 + n0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (n0 + j < p.N) dst[j] = __uint_as_float(raw[j]) * scale + __ldg(p.bias + n0 + j);
+                        if (n0 + j < n_end) {
+                            const float v = __uint_as_float(raw[j]) * scale + __ldg(p.bias + n0 + j);
+                            dst[j] = p.relu == 1 ? fmaxf(v, 0.f)
+                                   : p.relu == 2 ? 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)) : v;
+                        }
                 }
                 release_tmem();
             } else if (EPI == kEpiPlanes) {

@@ -10,7 +10,7 @@ constexpr int kBM = 128;   // rows per tile = TMEM lanes
 constexpr int kBK = 64;    // fp16 elements per k-block = one 128-byte swizzle row
 
 enum GemmEpilogue : int {
-    kEpiF32 = 0,      // debug / validation: fp32 [M][N] = acc*scale + bias
+    kEpiF32 = 0,      // fp32 [M][N] = act(acc*scale + bias): validation, grouped positional conv
     kEpiPlanes = 1,   // bias (+ReLU) -> split-fp16 planes [2][M][N]
     kEpiConvIn = 2,   // input conv: bias, length mask, + positional encoding -> x planes
     kEpiResLN = 3,    // bias + residual + LayerNorm -> x planes (in place)
@@ -22,6 +22,9 @@ struct GemmParams {
     int taps = 1, half = 0;      // K loop = taps x cblocks k-blocks; A rows shift by tap - half
     int row_mul = 1;             // A row of output row m = m * row_mul + tap - half (strided conv)
     int cblocks = 0;
+    // grouped GEMM (block-diagonal weights): n tile g reads A rows shifted by g * a_group_rows
+    // and owns output columns [g * group_cols, (g + 1) * group_cols) (kEpiF32 only)
+    int a_group_rows = 0, group_cols = 0;
     int a_planes = 2, b_planes = 2;
     int pair = 0;                // 1: CTA-pair kernel (cta_group::2); W map must have box rows BN/2
     int N = 0;                   // real output columns

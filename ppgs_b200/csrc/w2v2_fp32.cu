@@ -225,6 +225,22 @@ __global__ void group_major_kernel(const float* __restrict__ h, int64_t P, int64
     }
 }
 
+// same copy as split-fp16 planes [2][16 * (Mg + 128)][48] (tensor-core positional conv)
+__global__ void group_major_planes_kernel(const float* __restrict__ h, int64_t P, int64_t Pg, int64_t Mg,
+                                          __half* __restrict__ xg) {
+    const int64_t row = blockIdx.x;
+    const int64_t b = row / P, dst = 64 + b * Pg + (row - b * P);
+    const int64_t plane_stride = (int64_t)kPosGroups * (Mg + 128) * kPosPer;
+    for (int c = threadIdx.x; c < kHidden; c += blockDim.x) {
+        const int g = c / kPosPer, i = c - g * kPosPer;
+        __half hi, lo;
+        tc::split_f16(h[row * kHidden + c], hi, lo);
+        const int64_t at = ((int64_t)g * (Mg + 128) + dst) * kPosPer + i;
+        xg[at] = hi;
+        xg[plane_stride + at] = lo;
+    }
+}
+
 // ---- (B*P rows, 768) hidden -> (B, 768, frames) fp16, nearest neighbour in time
 __global__ void upsample_kernel(const float* __restrict__ h, int64_t P, int T6, int frames,
                                 float scale, __half* __restrict__ out) {
@@ -335,6 +351,7 @@ struct W2v2Weights {
     float* tc_scales = nullptr;
     W2v2TcLayer tc[kLayers];
     TcWeight tc_conv[kNumConv];   // [1..6]: conv layers as tap GEMMs
+    TcWeight tc_pos;              // positional conv: [16 groups x 64 rows (48 + zero pad)][128 taps x 48]
     float* conv_w[kNumConv];
     float *gn_w, *gn_b, *fp_ln_w, *fp_ln_b, *fp_w, *fp_b, *pos_w, *pos_b, *enc_ln_w, *enc_ln_b, *zero_bias;
     W2v2Layer layers[kLayers];
@@ -429,6 +446,7 @@ int w2v2_finalize(ppgs_engine* e) {
     raw(&w->fp_ln_b, "feature_projection.layer_norm.bias");
     raw(&w->fp_w, "feature_projection.projection.weight");
     raw(&w->fp_b, "feature_projection.projection.bias");
+    HostTensor pos_tc;   // folded positional-conv weight, one 64-row block per group
     {   // fold the weight norm (dim=2): w = v * g / ||v||, norm over (out, in) per tap; then
         // per group [48 out][tap*48 + in]
         const HostTensor& g = e->w2v2_host.at("encoder.pos_conv_embed.conv.parametrizations.weight.original0");
@@ -449,6 +467,13 @@ int w2v2_finalize(ppgs_engine* e) {
                         v.data[(size_t)((o * kPosPer + i) * kPosKernel + t)] * scale;
                 }
         put(&w->pos_w, packed);
+        pos_tc.shape = {kPosGroups * 64, (int64_t)kPosPer * kPosKernel};
+        pos_tc.data.assign((size_t)kPosGroups * 64 * kPosPer * kPosKernel, 0.f);
+        for (int g = 0; g < kPosGroups; ++g)
+            for (int o = 0; o < kPosPer; ++o)
+                std::copy_n(packed.begin() + (size_t)(g * kPosPer + o) * kPosPer * kPosKernel,
+                            (size_t)kPosPer * kPosKernel,
+                            pos_tc.data.begin() + (size_t)(g * 64 + o) * kPosPer * kPosKernel);
     }
     raw(&w->pos_b, "encoder.pos_conv_embed.conv.bias");
     raw(&w->enc_ln_w, "encoder.layer_norm.weight");
@@ -498,6 +523,7 @@ int w2v2_finalize(ppgs_engine* e) {
         for (int i = 1; i < kNumConv; ++i)
             pack(&w->tc_conv[i],
                  e->w2v2_host.at("feature_extractor.conv_layers." + std::to_string(i) + ".conv.weight"));
+        pack(&w->tc_pos, pos_tc);
         for (int l = 0; l < kLayers; ++l) {
             const std::string p = "encoder.layers." + std::to_string(l) + ".";
             HostTensor qkv;
@@ -715,22 +741,55 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
         mask_rows_kernel<<<(unsigned)M, 256, 0, stream>>>(h, P, len_dev, kHidden, batch);
     }
 
-    // ---- positional convolution (grouped, k=128) + LayerNorm
+    // ---- positional convolution (grouped, k=128) + LayerNorm.  Group g of output row m is a
+    // dot product over 128 x 48 contiguous values of the guarded group-major copy starting at
+    // row m: a GEMM whose A rows overlap (row stride 48 elements, K = 6144).
     PPGS_CUDA(cudaMemsetAsync(xg, 0, xg_bytes, stream));
-    {
-        LaunchScope scope(e, "w2v2_group_major", stream);
-        group_major_kernel<<<(unsigned)((int64_t)batch * P), 256, 0, stream>>>(h, P, Pg, Mg, xg);
-    }
-    for (int g = 0; g < kPosGroups; ++g) {
-        SgemmArgs a{};
-        a.A = xg + (int64_t)g * (Mg + 128) * kPosPer;     // output row m <- rows m .. m+127 of the guarded copy
-        a.lda = kPosPer;
-        a.B = w.pos_w + (int64_t)g * kPosPer * kPosPer * kPosKernel;
-        a.bias = w.pos_b + g * kPosPer;
-        a.out = y + g * kPosPer;
-        a.ldo = kHidden;
-        a.M = (int)Mg; a.N = kPosPer; a.K = kPosKernel * kPosPer;
-        PPGS_CHECK(launch_sgemm_any(e, "w2v2_pos_conv_gemm", EPI_BIAS_GELU, a, stream));
+    if (use_tc) {
+        using namespace tc;
+        __half* xgh = reinterpret_cast<__half*>(xg);
+        {
+            LaunchScope scope(e, "w2v2_group_major", stream);
+            group_major_planes_kernel<<<(unsigned)((int64_t)batch * P), 256, 0, stream>>>(h, P, Pg, Mg, xgh);
+        }
+        const uint64_t group_rows = (uint64_t)(Mg + 128);
+        CUtensorMap map_a;
+        PPGS_CHECK(make_plane_map(&map_a, xgh, false, (uint64_t)kPosKernel * kPosPer,
+                                  kPosGroups * group_rows - 128, 1, 2, kPosPer, 0,
+                                  kPosGroups * group_rows * kPosPer, 128, 2));
+        TcWeight& wt = e->w2v2->tc_pos;
+        GemmParams p;
+        p.m_tiles = (int)(Mg / 128);
+        p.n_tiles = kPosGroups;
+        p.cblocks = kPosKernel * kPosPer / 64;
+        p.a_group_rows = (int)group_rows;
+        p.group_cols = kPosPer;
+        p.a_planes = 2;
+        p.b_planes = 2;
+        p.N = kHidden;
+        p.scale = wt.inv_scale;
+        p.bias = w.pos_b;
+        p.relu = 2;   // GELU
+        p.out_f32 = y;
+        p.ld_f32 = kHidden;
+        p.status = e->status_dev;
+        PPGS_CHECK(launch_gemm_tc(e, "w2v2_tc_pos_conv", 64, kEpiF32, map_a, wt.maps[1].bn64, nullptr, p, stream));
+    } else {
+        {
+            LaunchScope scope(e, "w2v2_group_major", stream);
+            group_major_kernel<<<(unsigned)((int64_t)batch * P), 256, 0, stream>>>(h, P, Pg, Mg, xg);
+        }
+        for (int g = 0; g < kPosGroups; ++g) {
+            SgemmArgs a{};
+            a.A = xg + (int64_t)g * (Mg + 128) * kPosPer;     // output row m <- rows m .. m+127 of the guarded copy
+            a.lda = kPosPer;
+            a.B = w.pos_w + (int64_t)g * kPosPer * kPosPer * kPosKernel;
+            a.bias = w.pos_b + g * kPosPer;
+            a.out = y + g * kPosPer;
+            a.ldo = kHidden;
+            a.M = (int)Mg; a.N = kPosPer; a.K = kPosKernel * kPosPer;
+            PPGS_CHECK(launch_sgemm_any(e, "w2v2_pos_conv_gemm", EPI_BIAS_GELU, a, stream));
+        }
     }
     {
         LaunchScope scope(e, "w2v2_layernorm", stream);
