@@ -352,11 +352,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                         tmem_wait_ld();
                         if (g + 1 == kChunks / 4 && half == 1) release_tmem();   // last read
+                        // the activation is launch-uniform: keep erff out of the ReLU / linear loop
+                        if (p.relu == 2) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float v = fmaf(__uint_as_float(raw[j]), scale, y[j]);
-                            y[j] = p.relu == 1 ? fmaxf(v, 0.f)
-                                 : p.relu == 2 ? 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)) : v;
+                            for (int j = 0; j < 32; ++j) {
+                                const float v = fmaf(__uint_as_float(raw[j]), scale, y[j]);
+                                y[j] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+                            }
+                        } else {
+                            const float floor = p.relu == 1 ? 0.f : -INFINITY;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                y[j] = fmaxf(fmaf(__uint_as_float(raw[j]), scale, y[j]), floor);
                         }
                         split32(y, h, l, half * 16);
                     }

@@ -268,15 +268,18 @@ def test_config2_full_size_properties(ppgs_b200, precision):
     assert engine.launches > before
 
 
-def test_weight_blob_roundtrip(ppgs_b200):
+@pytest.mark.parametrize('precision', ['fp32', 'f16x2'])
+def test_weight_blob_roundtrip(ppgs_b200, precision):
     """The multi-GPU load path on one device: a second engine adopts the first
-    engine's packed blob (what the NCCL broadcast delivers) and agrees bitwise."""
+    engine's packed blob (what the NCCL broadcast delivers) and agrees bitwise at the
+    same arithmetic mode."""
     sd = O.random_state_dict(4)
-    a = make_engine(ppgs_b200, sd, 'fp32')
+    a = make_engine(ppgs_b200, sd, precision)
     b = ppgs_b200.Engine(0)
     b.blob().copy_(a.blob())
     torch.cuda.synchronize()
     b.adopt_blob()
+    b.precision = precision
     audio = O.synthetic_audio(2, 32000, 3).cuda()
     assert torch.equal(a.from_audio(audio), b.from_audio(audio))
 
