@@ -188,6 +188,64 @@ int ppgs_engine_kernel_stat(ppgs_engine* engine, int index, char* name, size_t n
 /* Device bytes currently held by the engine's grow-only workspace. */
 size_t ppgs_engine_workspace_bytes(const ppgs_engine* engine);
 
+/* ---- audio ingest / posteriorgram egress of the file API -------------------------------- */
+
+/* torchaudio.info as used by ppgs/data/dataset.py:187 (list-of-files metadata): header
+ * probe of a RIFF/WAVE file (PCM 8/16/24/32 bit, IEEE float 32/64, WAVE_FORMAT_EXTENSIBLE).
+ * Any out pointer may be NULL.  PPGS_E_UNSUPPORTED: not a WAVE file / compressed codec. */
+int ppgs_wav_info(const char* path, int64_t* frames, int* sample_rate, int* channels,
+                  int* bits, int* is_float);
+
+/* torchaudio.load as used by ppgs/load.py:17-30, for WAVE files: channel 0 (what
+ * ppgs/data/collate.py:27 keeps) as fp32 normalised to [-1, 1) (int16 / 32768 ...). */
+int ppgs_wav_read_f32(const char* path, float* dst_host, int64_t capacity, int64_t* frames,
+                      int* sample_rate);
+
+/* The /32768 normalisation of torchaudio.load on the device: `count` int16 samples ->
+ * fp32 (both buffers 16-byte aligned), so that file batches cross PCIe as 2-byte PCM. */
+int ppgs_pcm16_to_f32(ppgs_engine* engine, const void* pcm_dev, int64_t count,
+                      float* out_dev, void* stream);
+
+/* ppgs.resample (ppgs/core.py:599-608) = torchaudio.transforms.Resample(orig, target)
+ * with its defaults (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99) on the
+ * device.  Output length per row = ppgs_resample_length = ceil(target * samples / orig).
+ *   audio_dev : (batch, samples) fp32, row stride `audio_stride`
+ *   out_dev   : (batch, out_len) fp32, row stride `out_stride` */
+int64_t ppgs_resample_length(int64_t samples, int orig_rate, int target_rate);
+int ppgs_resample(ppgs_engine* engine, const float* audio_dev, int batch, int64_t samples,
+                  int64_t audio_stride, int orig_rate, int target_rate, float* out_dev,
+                  int64_t out_stride, void* stream);
+/* The filter table of that resampler (host; for inspection / tests): `taps` receives
+ * [ntaps][phases] fp32 when not NULL; phases = target/gcd, ntaps = 2*width + orig/gcd. */
+int ppgs_resample_taps(int orig_rate, int target_rate, float* taps, int64_t capacity,
+                       int* ntaps, int* phases, int* width);
+
+/* torch.save(tensor) of ppgs.preprocess.save_masked (ppgs/preprocess/core.py:219-221)
+ * without Python: writes a torch.load-compatible archive holding the contiguous fp32
+ * tensor (rows, cols) read from `data` with row stride `row_stride` (the crop of a padded
+ * batch row is a strided read). */
+int ppgs_pt_write_f32(const char* path, const float* data_host, int64_t rows, int64_t cols,
+                      int64_t row_stride);
+
+/* The batching loop of ppgs.from_files_to_files / from_dataloader (ppgs/core.py:207-391)
+ * for the mel representation as ONE call: `reader_threads` threads decode 16-bit PCM
+ * 16 kHz WAVE files straight into pinned zero-padded int16 batches, the calling thread
+ * runs H2D -> pcm16_to_f32 -> mel + Transformer + softmax -> D2H on two device slots
+ * (copies on private streams, kernels on `stream`), `writer_threads` threads crop every
+ * row to samples/160 frames and write `<output>.pt`.  The threads live for the duration
+ * of the call only.
+ *   batch_sizes  : files per batch, n_batches entries (batch composition is the
+ *                  caller's: ppgs/data/sampler.py:46-82 semantics live in Python)
+ *   audio_files / output_files / file_samples : flat, in batch order; file_samples are
+ *                  the per-file sample counts from ppgs_wav_info
+ *   frames_done  : out, posteriorgram frames written
+ * PPGS_E_UNSUPPORTED when a file is not 16-bit PCM at 16 kHz (callers fall back to the
+ * per-batch API with ppgs_wav_read_f32 + ppgs_resample). */
+int ppgs_files_to_files(ppgs_engine* engine, int n_batches, const int32_t* batch_sizes,
+                        const char* const* audio_files, const char* const* output_files,
+                        const int64_t* file_samples, int reader_threads, int writer_threads,
+                        int legacy_mode, void* stream, int64_t* frames_done);
+
 #ifdef __cplusplus
 }
 #endif

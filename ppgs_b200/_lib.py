@@ -62,6 +62,17 @@ SYMBOLS = {
     'ppgs_engine_set_profiling': (_i, [_vp, _i]),
     'ppgs_engine_kernel_stat': (_i, [_vp, _i, _c.c_char_p, _sz, _c.POINTER(_c.c_double),
                                      _c.POINTER(_i64)]),
+    'ppgs_wav_info': (_i, [_c.c_char_p, _c.POINTER(_i64), _c.POINTER(_i), _c.POINTER(_i),
+                           _c.POINTER(_i), _c.POINTER(_i)]),
+    'ppgs_wav_read_f32': (_i, [_c.c_char_p, _vp, _i64, _c.POINTER(_i64), _c.POINTER(_i)]),
+    'ppgs_pcm16_to_f32': (_i, [_vp, _vp, _i64, _vp, _vp]),
+    'ppgs_resample_length': (_i64, [_i64, _i, _i]),
+    'ppgs_resample': (_i, [_vp, _vp, _i, _i64, _i64, _i, _i, _vp, _i64, _vp]),
+    'ppgs_resample_taps': (_i, [_i, _i, _vp, _i64, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
+    'ppgs_pt_write_f32': (_i, [_c.c_char_p, _vp, _i64, _i64, _i64]),
+    'ppgs_files_to_files': (_i, [_vp, _i, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_char_p),
+                                 _c.POINTER(_c.c_char_p), _c.POINTER(_i64), _i, _i, _i, _vp,
+                                 _c.POINTER(_i64)]),
 }
 
 

@@ -51,8 +51,9 @@ def from_audio(
     """
     if audio.dim() == 2:
         audio = audio.unsqueeze(0)
-    audio = resample(audio, sample_rate)
     engine = load.model(checkpoint, representation, gpu)
+    if sample_rate != config.SAMPLE_RATE:
+        audio = engine.resample(audio, sample_rate)
     if _fused_frontend(representation):
         # mel front-end + transformer in one C-ABI call; features stay on-chip
         # in the engine workspace (ppgs_from_audio)
@@ -91,7 +92,7 @@ def from_file(
 ) -> torch.Tensor:
     """Infer ppgs from an audio file (ppgs/core.py:131-168);
     returns shape=(len(ppgs.PHONEMES), frames)"""
-    audio = load.audio(file)
+    audio = load.audio(file, device=load.resolve_device(gpu))
     return from_audio(
         audio, config.SAMPLE_RATE, representation, checkpoint, gpu, legacy_mode
     ).squeeze(0)
@@ -132,14 +133,18 @@ def from_files_to_files(
             from_file_to_file(
                 audio_file, output_file, representation, checkpoint, gpu, legacy_mode)
         return
+    mapping = {
+        audio_file: output_file
+        for audio_file, output_file in zip(audio_files, output_files)}
     dataloader = data.loader(
         audio_files,
         features=['audio', 'length', 'audio_file'],
         num_workers=num_workers // 2,
         max_frames=max_frames)
-    mapping = {
-        audio_file: output_file
-        for audio_file, output_file in zip(audio_files, output_files)}
+    if _native_pipeline(dataloader, representation):
+        engine = load.model(checkpoint, representation, gpu)
+        dataloader.run_native(engine, mapping, num_workers // 2, legacy_mode)
+        return
     from_dataloader(
         dataloader, mapping, representation, checkpoint,
         save_workers=num_workers // 2, gpu=gpu, legacy_mode=legacy_mode)
@@ -261,12 +266,14 @@ def infer(
 
 
 def resample(audio, sample_rate, target_rate=config.SAMPLE_RATE):
-    """Perform audio resampling (ppgs/core.py:599-608)"""
+    """Perform audio resampling (ppgs/core.py:599-608): the arithmetic of
+    torchaudio.transforms.Resample(sample_rate, target_rate) as a CUDA kernel
+    (ppgs_resample).  The result lives where `audio` lives, like the reference's."""
     if sample_rate == target_rate:
         return audio
-    import torchaudio
-    resampler = torchaudio.transforms.Resample(sample_rate, target_rate)
-    return resampler.to(audio.device)(audio)
+    gpu = audio.device.index if audio.is_cuda else None
+    result = load.utility_engine(gpu).resample(audio, sample_rate, target_rate)
+    return result if audio.is_cuda else result.cpu()
 
 
 def representation_file_extension():
@@ -277,6 +284,16 @@ def representation_file_extension():
     if config.REPRESENTATION_KIND == 'ppg':
         return f'-{config.REPRESENTATION}-ppg.pt'
     return f'-{config.REPRESENTATION}.pt'
+
+
+def _native_pipeline(dataloader, representation):
+    """The whole loop runs inside libppgs_b200 (ppgs_files_to_files) when the
+    representation is mel and every file is 16-bit PCM at 16 kHz; otherwise the
+    batches come from the Python reader threads (same batches, same kernels).
+    PPGS_B200_NATIVE_FILES=0 forces the latter."""
+    if os.environ.get('PPGS_B200_NATIVE_FILES', '1') == '0':
+        return False
+    return _fused_frontend(representation) and dataloader.dataset.native
 
 
 def _fused_frontend(representation):

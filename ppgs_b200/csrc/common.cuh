@@ -197,6 +197,12 @@ struct LaunchScope {
 };
 int ensure_pinned(ppgs_engine* e, size_t bytes);
 
+// engine.cu, shared with io.cu: mel front-end + transformer on device buffers (`mel` = fp16
+// feature staging of batch x 80 x samples/160)
+extern "C" int ppgs_detail_from_audio_device(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                                             int64_t stride, const int64_t* lengths, int softmax,
+                                             int legacy_mode, float* out, __half* mel, cudaStream_t stream);
+
 // mel.cu
 int build_mel_tables(ppgs_engine* e, const float* basis_host /* [80][513] or null */);
 int launch_mel(ppgs_engine* e, const float* audio, int batch, int64_t samples,

@@ -689,9 +689,10 @@ static int ensure_io(ppgs_engine* e, size_t bytes) {
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-static int from_audio_device(ppgs_engine* e, const float* audio, int batch, int64_t samples,
-                             int64_t stride, const int64_t* lengths, int softmax,
-                             int legacy_mode, float* out, __half* mel, cudaStream_t stream) {
+// not part of the C ABI: shared with the file pipeline (io.cu)
+int ppgs_detail_from_audio_device(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                                  int64_t stride, const int64_t* lengths, int softmax,
+                                  int legacy_mode, float* out, __half* mel, cudaStream_t stream) {
     const int frames = (int)(samples / kHopSamples);
     if (frames <= 0) {
         set_error("from_audio: need at least %d samples", kHopSamples);
@@ -722,7 +723,7 @@ int ppgs_from_audio(ppgs_engine* e, const float* audio, int batch, int64_t sampl
     }
     const size_t mel_bytes = align256((size_t)batch * kMelChannels * (samples / kHopSamples) * 2);
     PPGS_CHECK(ensure_io(e, mel_bytes));
-    return from_audio_device(e, audio, batch, samples, stride, lengths, softmax, legacy_mode, out,
+    return ppgs_detail_from_audio_device(e, audio, batch, samples, stride, lengths, softmax, legacy_mode, out,
                              static_cast<__half*>(e->io_dev), static_cast<cudaStream_t>(stream));
 }
 
@@ -766,7 +767,7 @@ static int submit_host(ppgs_engine* e, const float* audio, int batch, int64_t sa
                               cudaMemcpyHostToDevice, e->copy_in));
     PPGS_CUDA(cudaEventRecord(slot.h2d_done, e->copy_in));
     PPGS_CUDA(cudaStreamWaitEvent(stream, slot.h2d_done, 0));
-    PPGS_CHECK(from_audio_device(e, audio_dev, batch, samples, samples, lengths, softmax,
+    PPGS_CHECK(ppgs_detail_from_audio_device(e, audio_dev, batch, samples, samples, lengths, softmax,
                                  legacy_mode, out_dev, mel_dev, stream));
     PPGS_CUDA(cudaEventRecord(slot.compute_done, stream));
     PPGS_CUDA(cudaStreamWaitEvent(e->copy_out, slot.compute_done, 0));

@@ -25,13 +25,23 @@ class Metadata:
     reference's warning."""
 
     def __init__(self, audio_files, max_frames=config.MAX_INFERENCE_FRAMES):
-        self.audio_files, self.lengths = [], []
+        self.audio_files, self.lengths, self.samples = [], [], {}
+        # every file is 16-bit PCM at 16 kHz: eligible for ppgs_files_to_files
+        self.native = True
         for audio_file in audio_files:
-            samples, sample_rate = load.wav_num_frames(audio_file)
+            info = load.wav_info(audio_file)
+            if info is None:
+                samples, sample_rate = load.wav_num_frames(audio_file)
+                self.native = False
+            else:
+                samples, sample_rate = info['samples'], info['sample_rate']
+                if info['bits'] != 16 or info['is_float'] or sample_rate != config.SAMPLE_RATE:
+                    self.native = False
             length = int(samples * (config.SAMPLE_RATE / sample_rate)) // config.HOPSIZE
             if length <= max_frames:
                 self.audio_files.append(audio_file)
                 self.lengths.append(length)
+                self.samples[audio_file] = samples
             else:
                 warnings.warn(
                     f'File {audio_file} of length {length} '
@@ -104,6 +114,15 @@ class Loader:
 
     def __len__(self):
         return len(self.batches)
+
+    def run_native(self, engine, output_files, workers=1, legacy_mode=False):
+        """This loader's batches through the native pipeline (reader / writer threads
+        and the GPU loop all inside ppgs_files_to_files).  Returns frames written."""
+        batches = [[self.dataset.audio_files[i] for i in batch] for batch in self.batches]
+        return engine.files_to_files(
+            batches, output_files, self.dataset.samples,
+            reader_threads=max(workers, 1), writer_threads=max(workers, 1),
+            legacy_mode=legacy_mode)
 
     def _load(self, batch):
         files = [self.dataset.audio_files[i] for i in batch]

@@ -1,6 +1,7 @@
 """Host-side handle of one packed model on one GPU (ppgs.load.model +
 ppgs.Model + the module the reference caches in ppgs/core.py:565-580)."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -239,6 +240,55 @@ class Engine:
             self._in_flight = (getattr(self, '_in_flight', None) or [])[-1:] + [(audio, out)]
         return out
 
+    # -- audio ingest / file pipeline ---------------------------------------
+    def resample(self, audio, sample_rate, target_rate=config.SAMPLE_RATE):
+        """torchaudio.transforms.Resample(sample_rate, target_rate) on the GPU
+        (ppgs/core.py:599-608): audio (..., samples) -> (..., ceil(samples * target / orig))
+        fp32 CUDA."""
+        sample_rate, target_rate = _integer_rate(sample_rate), _integer_rate(target_rate)
+        audio = self._on_device(audio, torch.float32)
+        shape = audio.shape
+        flat = audio.reshape(-1, shape[-1]).contiguous()
+        batch, samples = flat.shape
+        out_len = _lib.lib.ppgs_resample_length(samples, sample_rate, target_rate)
+        out = torch.empty(batch, out_len, dtype=torch.float32, device=self.device)
+        if batch and samples:
+            _lib.check(_lib.lib.ppgs_resample(
+                self._handle, ctypes.c_void_p(flat.data_ptr()), batch, samples, samples,
+                sample_rate, target_rate, ctypes.c_void_p(out.data_ptr()), out_len,
+                _stream_ptr(self.device)))
+        return out.reshape(shape[:-1] + (out_len,))
+
+    def pcm16_to_f32(self, pcm):
+        """int16 PCM CUDA tensor -> fp32 / 32768 (torchaudio.load's normalisation)."""
+        pcm = self._on_device(pcm, torch.int16).contiguous()
+        out = torch.empty(pcm.shape, dtype=torch.float32, device=self.device)
+        if pcm.numel():
+            _lib.check(_lib.lib.ppgs_pcm16_to_f32(
+                self._handle, ctypes.c_void_p(pcm.data_ptr()), pcm.numel(),
+                ctypes.c_void_p(out.data_ptr()), _stream_ptr(self.device)))
+        return out
+
+    def files_to_files(self, batches, output_files, samples, reader_threads=8, writer_threads=8,
+                       legacy_mode=False):
+        """The native file pipeline (ppgs_files_to_files): `batches` = list of lists of
+        audio file names (16-bit PCM, 16 kHz WAVE), `output_files` = {audio file: output
+        file}, `samples` = {audio file: sample count from the header}.  Returns the number
+        of posteriorgram frames written."""
+        flat = [file for batch in batches for file in batch]
+        if not flat:
+            return 0
+        sizes = (ctypes.c_int32 * len(batches))(*[len(batch) for batch in batches])
+        audio = (ctypes.c_char_p * len(flat))(*[os.fsencode(file) for file in flat])
+        outputs = (ctypes.c_char_p * len(flat))(*[os.fsencode(output_files[file]) for file in flat])
+        counts = (ctypes.c_int64 * len(flat))(*[int(samples[file]) for file in flat])
+        frames = ctypes.c_int64()
+        _lib.check(_lib.lib.ppgs_files_to_files(
+            self._handle, len(batches), sizes, audio, outputs, counts, int(reader_threads),
+            int(writer_threads), int(bool(legacy_mode)), _stream_ptr(self.device),
+            ctypes.byref(frames)))
+        return frames.value
+
     def check(self):
         """Synchronise and raise if a kernel reported a pipeline time-out (the device
         entry points are asynchronous and cannot report it themselves)."""
@@ -253,6 +303,14 @@ class Engine:
         if tensor.device != self.device or tensor.dtype != dtype:
             tensor = tensor.to(self.device, dtype)
         return tensor
+
+
+def _integer_rate(rate):
+    """torchaudio refuses non-integer rates (functional._get_sinc_resample_kernel)."""
+    if int(rate) != rate:
+        raise ValueError(
+            'Frequencies must be of integer type to ensure quality resampling computation.')
+    return int(rate)
 
 
 def _host_lengths(lengths, batch):

@@ -1,4 +1,5 @@
 """Loading utilities (ppgs/load.py:17-81)."""
+import ctypes
 import os
 import threading
 from pathlib import Path
@@ -6,6 +7,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
+from . import _lib
 from . import config
 from .engine import Engine
 
@@ -13,13 +15,40 @@ _engines = {}
 _lock = threading.Lock()
 
 
-def audio(file):
+def wav_info(file):
+    """Header of a RIFF/WAVE file through the native probe (ppgs_wav_info — the
+    torchaudio.info call of ppgs/data/dataset.py:187): dict(samples, sample_rate,
+    channels, bits, is_float), or None when the file is not a WAVE file the
+    library decodes."""
+    frames, rate = ctypes.c_int64(), ctypes.c_int()
+    channels, bits, is_float = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    code = _lib.lib.ppgs_wav_info(
+        os.fsencode(str(file)), ctypes.byref(frames), ctypes.byref(rate), ctypes.byref(channels),
+        ctypes.byref(bits), ctypes.byref(is_float))
+    if code == _lib.E_UNSUPPORTED:
+        return None
+    _lib.check(code)
+    return {'samples': frames.value, 'sample_rate': rate.value, 'channels': channels.value,
+            'bits': bits.value, 'is_float': bool(is_float.value)}
+
+
+def audio(file, device=None):
     """Load audio from disk as (channels, samples) fp32 at 16 kHz
-    (ppgs/load.py:17-30).  PCM / float WAV is decoded here with scipy
-    (torchaudio.load needs torchcodec); other containers go through
-    torchaudio when it can decode them."""
+    (ppgs/load.py:17-30).  Mono PCM / float WAVE files are decoded by the native
+    reader (ppgs_wav_read_f32; torchaudio.load needs torchcodec) and
+    resampled on the GPU; multi-channel WAVE files by scipy; other containers go
+    through torchaudio when it can decode them.  `device`: return the waveform on
+    that CUDA device instead of the CPU (saves a round trip after resampling)."""
     path = Path(file)
-    if path.suffix.lower() == '.wav':
+    info = wav_info(path) if path.suffix.lower() == '.wav' else None
+    if info is not None and info['channels'] == 1:
+        waveform = torch.empty(1, info['samples'], dtype=torch.float32)
+        frames, rate = ctypes.c_int64(), ctypes.c_int()
+        _lib.check(_lib.lib.ppgs_wav_read_f32(
+            os.fsencode(str(path)), ctypes.c_void_p(waveform.data_ptr()), waveform.numel(),
+            ctypes.byref(frames), ctypes.byref(rate)))
+        sample_rate = rate.value
+    elif path.suffix.lower() == '.wav':
         from scipy.io import wavfile
         sample_rate, data = wavfile.read(path)
         if data.dtype == np.int16:
@@ -30,10 +59,7 @@ def audio(file):
             data = (data.astype(np.float32) - 128.0) / 128.0
         else:
             data = data.astype(np.float32)
-        if data.ndim == 1:
-            data = data[None]
-        else:
-            data = data.T
+        data = data[None] if data.ndim == 1 else data.T
         waveform = torch.from_numpy(np.ascontiguousarray(data))
     else:
         import torchaudio
@@ -48,19 +74,19 @@ def audio(file):
                     'Failed to load mp3 file, make sure ffmpeg<=4.3 is installed')
             raise
     from .core import resample
+    if device is not None:
+        return resample(waveform.to(device), sample_rate)
     return resample(waveform, sample_rate)
 
 
 def wav_num_frames(file):
     """(samples, sample_rate) from the header only (torchaudio.info at
     ppgs/data/dataset.py:187)."""
-    import wave
-    try:
-        with wave.open(str(file), 'rb') as f:
-            return f.getnframes(), f.getframerate()
-    except (wave.Error, EOFError):
-        waveform = audio(file)
-        return waveform.shape[-1], config.SAMPLE_RATE
+    info = wav_info(file)
+    if info is not None:
+        return info['samples'], info['sample_rate']
+    waveform = audio(file)
+    return waveform.shape[-1], config.SAMPLE_RATE
 
 
 def state_dict(checkpoint=None, representation=None):
@@ -114,6 +140,18 @@ def model(checkpoint=None, representation=None, gpu=None, is_causal=None):
             if precision:
                 engine.precision = precision
             _engines[key] = engine
+    return engine
+
+
+def utility_engine(gpu=None):
+    """A weight-less engine on `gpu` for the ingest kernels (resampler, PCM decode)
+    when no model is involved; cached per device."""
+    device = resolve_device(gpu)
+    key = ('utility', device.index)
+    with _lock:
+        engine = _engines.get(key)
+        if engine is None:
+            engine = _engines[key] = Engine(device)
     return engine
 
 

@@ -96,8 +96,12 @@ def from_files_to_files(audio_files, output_files, representation=config.REPRESE
         audio_files, num_workers=max(num_workers // 2, 1), max_frames=max_frames,
         shard=(rank, world))
     mapping = dict(zip(audio_files, output_files))
-    core.from_dataloader(dataloader, mapping, representation, checkpoint,
-                         save_workers=max(num_workers // 2, 1), gpu=gpu,
-                         legacy_mode=legacy_mode)
+    if core._native_pipeline(dataloader, representation):
+        engine = load.model(checkpoint, representation, gpu)
+        dataloader.run_native(engine, mapping, max(num_workers // 2, 1), legacy_mode)
+    else:
+        core.from_dataloader(dataloader, mapping, representation, checkpoint,
+                             save_workers=max(num_workers // 2, 1), gpu=gpu,
+                             legacy_mode=legacy_mode)
     if world > 1:
         dist.barrier()

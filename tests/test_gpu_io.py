@@ -1,0 +1,191 @@
+"""Ingest / egress on the GPU through the C ABI: PCM decode and the sinc resampler against
+torchaudio (the reference's `ppgs.resample`, ppgs/core.py:599-608), and the native file
+pipeline `ppgs_files_to_files` against the per-batch API on the same batches (bitwise) and
+against the oracle (<= 1e-4)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from scipy.io import wavfile
+
+from oracle import ppg_oracle as O
+from test_host_logic import write_wav
+
+pytestmark = pytest.mark.gpu
+
+# fp32 dot products of <= 16 015 taps in a different summation order than conv1d
+RESAMPLE_TOL = 2e-6
+
+
+@pytest.fixture(scope='module')
+def ppgs_b200():
+    import ppgs_b200
+    return ppgs_b200
+
+
+@pytest.fixture(scope='module')
+def engine(ppgs_b200):
+    engine = ppgs_b200.Engine(0).load_state_dict(O.random_state_dict(5, peaky=True))
+    engine.precision = 'f16x2'
+    return engine
+
+
+@pytest.mark.parametrize('count', [1, 7, 8, 9, 4096, 160000 * 3 + 5])
+def test_pcm16_to_f32_is_exact(engine, count):
+    pcm = torch.randint(-32768, 32768, (count,), dtype=torch.int16)
+    pcm[0] = -32768
+    out = engine.pcm16_to_f32(pcm.cuda()).cpu()
+    assert torch.equal(out, pcm.float() / 32768.0)
+
+
+@pytest.mark.parametrize('orig,samples', [
+    (44100, 44100), (22050, 33333), (8000, 8000), (48000, 100001), (11025, 5000),
+    (32000, 433), (24000, 1)])
+def test_resample_matches_torchaudio(engine, orig, samples):
+    import torchaudio
+    audio = O.synthetic_audio(3, samples, orig)   # (3, 1, samples)
+    reference = torchaudio.transforms.Resample(orig, 16000)(audio)
+    got = engine.resample(audio.cuda(), orig).cpu()
+    assert got.shape == reference.shape
+    assert (got - reference).abs().max() <= RESAMPLE_TOL
+
+
+def test_public_resample_and_from_audio_at_other_rates(ppgs_b200, tmp_path):
+    """`ppgs.resample` keeps the tensor where it was; `from_audio(audio, 22050)` equals the
+    oracle on torchaudio-resampled audio."""
+    import torchaudio
+    sd = O.random_state_dict(5, peaky=True)
+    checkpoint = tmp_path / 'ckpt.pt'
+    torch.save({'model': sd}, checkpoint)
+    audio = O.synthetic_audio(2, 30000, 9)
+    reference = torchaudio.transforms.Resample(22050, 16000)(audio)
+    on_cpu = ppgs_b200.resample(audio, 22050)
+    assert on_cpu.device.type == 'cpu' and (on_cpu - reference).abs().max() <= RESAMPLE_TOL
+    assert ppgs_b200.resample(audio.cuda(), 22050).is_cuda
+    assert ppgs_b200.resample(audio, 16000) is audio
+    out = ppgs_b200.from_audio(audio, 22050, checkpoint=checkpoint, gpu=0).cpu()
+    expected = O.from_audio(sd, reference)
+    assert out.shape == expected.shape
+    assert (out - expected).abs().max() <= 1e-4
+    # a 22.05 kHz file goes through the native decoder + the GPU resampler
+    path = tmp_path / 'a.wav'
+    wavfile.write(path, 22050, audio[0, 0].numpy())
+    from_file = ppgs_b200.from_file(path, checkpoint=checkpoint, gpu=0).cpu()
+    assert (from_file - expected[0]).abs().max() <= 1e-4
+    with pytest.raises(ValueError, match='integer'):
+        ppgs_b200.resample(audio.cuda(), 22050.5)
+
+
+def make_files(tmp_path, lengths, channels=None):
+    files = []
+    for i, n in enumerate(lengths):
+        files.append(str(tmp_path / f'{i}.wav'))
+        write_wav(files[-1], n, seed=40 + i, channels=(channels or {}).get(i, 1))
+    return files
+
+
+def test_native_file_pipeline_equals_per_batch_api(ppgs_b200, tmp_path, monkeypatch):
+    """Same batches through ppgs_files_to_files (reader / writer threads in the library,
+    int16 over PCIe) and through the Python reader threads + from_dataloader: bitwise equal
+    `.pt` files, cropped like save_masked; <= 1e-4 from the oracle run file by file... the
+    oracle batch is the same zero-padded batch, so compare on the batch."""
+    sd = O.random_state_dict(6, peaky=True)
+    checkpoint = tmp_path / 'ckpt.pt'
+    torch.save({'model': sd}, checkpoint)
+    lengths = [16000, 40000, 90000, 8000, 16161, 32000, 64000, 433, 159999, 81000, 80160, 16000]
+    files = make_files(tmp_path, lengths, channels={2: 2, 7: 2})
+    native = [str(tmp_path / f'{i}-native.pt') for i in range(len(files))]
+    python = [str(tmp_path / f'{i}-python.pt') for i in range(len(files))]
+    calls = []
+    original = ppgs_b200.Engine.files_to_files
+    monkeypatch.setattr(ppgs_b200.Engine, 'files_to_files',
+                        lambda self, *a, **k: calls.append(1) or original(self, *a, **k))
+    ppgs_b200.from_files_to_files(files, native, checkpoint=checkpoint, num_workers=6, gpu=0,
+                                  max_frames=1500)
+    assert calls, 'the native pipeline was not used'
+    monkeypatch.setenv('PPGS_B200_NATIVE_FILES', '0')
+    ppgs_b200.from_files_to_files(files, python, checkpoint=checkpoint, num_workers=6, gpu=0,
+                                  max_frames=1500)
+    assert len(calls) == 1
+    for a, b, n in zip(native, python, lengths):
+        x, y = torch.load(a), torch.load(b)
+        assert x.shape == (40, n // 160) and x.dtype == torch.float32
+        assert torch.equal(x, y)
+    # one batch against the oracle: the batch that holds file 0
+    from ppgs_b200 import data
+    loader = data.loader(files, num_workers=0, max_frames=1500)
+    for audio, sample_lengths, names in loader:
+        if files[0] in names:
+            break
+    expected = O.from_audio(sd, audio, lengths=sample_lengths)
+    for row, name, n in zip(expected, names, sample_lengths.tolist()):
+        got = torch.load(native[files.index(name)])
+        assert (got - row[:, :n // 160]).abs().max() <= 1e-4
+
+
+def test_native_file_pipeline_many_batches(ppgs_b200, tmp_path):
+    """More batches than staging slots, one reader / one writer thread and many."""
+    sd = O.random_state_dict(6)
+    checkpoint = tmp_path / 'ckpt.pt'
+    torch.save({'model': sd}, checkpoint)
+    rng = np.random.default_rng(0)
+    lengths = [int(n) for n in rng.integers(3000, 30000, 60)]
+    files = make_files(tmp_path, lengths)
+    outputs = {}
+    for workers in (2, 16):
+        outputs[workers] = [str(tmp_path / f'{i}-{workers}.pt') for i in range(len(files))]
+        ppgs_b200.from_files_to_files(files, outputs[workers], checkpoint=checkpoint,
+                                      num_workers=workers, gpu=0, max_frames=400)
+    engine = ppgs_b200.load.model(checkpoint, 'mel', 0)
+    for i, n in enumerate(lengths):
+        a, b = torch.load(outputs[2][i]), torch.load(outputs[16][i])
+        assert a.shape == (40, n // 160) and torch.equal(a, b)
+    engine.check()
+
+
+def test_native_file_pipeline_reports_errors(ppgs_b200, tmp_path):
+    sd = O.random_state_dict(6)
+    engine = ppgs_b200.Engine(0).load_state_dict(sd)
+    files = make_files(tmp_path, [16000, 16000, 16000])
+    outputs = {file: file + '.pt' for file in files}
+    samples = {file: 16000 for file in files}
+    os.remove(files[1])
+    with pytest.raises(ValueError, match='cannot open'):
+        engine.files_to_files([[files[0]], [files[1]], [files[2]]], outputs, samples)
+    # header / announced length mismatch
+    write_wav(files[1], 8000)
+    with pytest.raises(RuntimeError, match='announced length'):
+        engine.files_to_files([[files[0], files[1]], [files[2]]], outputs, samples)
+    # unwritable output
+    write_wav(files[1], 16000)
+    outputs[files[2]] = str(tmp_path / 'missing-dir' / 'x.pt')
+    with pytest.raises(ValueError, match='cannot open for writing'):
+        engine.files_to_files([[files[0], files[1]], [files[2]]], outputs, samples)
+    # too short for the reflection padding
+    write_wav(files[0], 300)
+    with pytest.raises(ValueError, match='at least 433'):
+        engine.files_to_files([[files[0]]], outputs, {files[0]: 300})
+    # and the engine still works afterwards
+    assert engine.files_to_files([[files[1]]], outputs, samples) == 100
+
+
+def test_non_native_files_take_the_python_path(ppgs_b200, tmp_path):
+    """A float32 or 22.05 kHz file in the list: batches come from the Python readers
+    (native decode + GPU resampler per file), results still match the oracle."""
+    import torchaudio
+    sd = O.random_state_dict(6, peaky=True)
+    checkpoint = tmp_path / 'ckpt.pt'
+    torch.save({'model': sd}, checkpoint)
+    a = O.synthetic_audio(1, 22050, 1)[0, 0]
+    b = O.synthetic_audio(1, 16000, 2)[0, 0]
+    fa, fb = str(tmp_path / 'a.wav'), str(tmp_path / 'b.wav')
+    wavfile.write(fa, 22050, a.numpy())
+    wavfile.write(fb, 16000, b.numpy())
+    outs = [str(tmp_path / 'a.pt'), str(tmp_path / 'b.pt')]
+    ppgs_b200.from_files_to_files([fa, fb], outs, checkpoint=checkpoint, num_workers=2, gpu=0)
+    resampled = torchaudio.transforms.Resample(22050, 16000)(a[None])
+    assert resampled.shape[-1] == 16000
+    expected = O.from_audio(sd, torch.stack([resampled, b[None]]))
+    for out, row in zip(outs, expected):
+        assert (torch.load(out) - row).abs().max() <= 1e-4

@@ -1,0 +1,174 @@
+"""Host half of the ingest / egress C ABI (no GPU): the WAVE probe and decoder against
+scipy's reader with torchaudio.load's normalisation, the `.pt` writer against torch.load,
+and the resampler's filter table against torchaudio's own (bit-exact)."""
+import ctypes
+import math
+import struct
+import zipfile
+
+import numpy as np
+import pytest
+import torch
+from scipy.io import wavfile
+
+from test_host_logic import write_wav
+
+
+def probe(lib, path):
+    frames, rate = ctypes.c_int64(), ctypes.c_int()
+    channels, bits, is_float = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    code = lib.lib.ppgs_wav_info(str(path).encode(), frames, rate, channels, bits, is_float)
+    return code, (frames.value, rate.value, channels.value, bits.value, is_float.value)
+
+
+def decode(lib, path, capacity):
+    buffer = np.empty(capacity, np.float32)
+    frames, rate = ctypes.c_int64(), ctypes.c_int()
+    lib.check(lib.lib.ppgs_wav_read_f32(
+        str(path).encode(), buffer.ctypes.data, capacity, frames, rate))
+    return buffer[:frames.value], rate.value
+
+
+def normalised(data):
+    """torchaudio.load(normalize=True) of integer PCM."""
+    if data.dtype == np.int16:
+        return data.astype(np.float32) / 32768.0
+    if data.dtype == np.int32:
+        return data.astype(np.float32) / 2147483648.0
+    if data.dtype == np.uint8:
+        return (data.astype(np.float32) - 128.0) / 128.0
+    return data.astype(np.float32)
+
+
+@pytest.mark.parametrize('kind,rate', [
+    ('int16', 16000), ('int16-stereo', 44100), ('int32', 8000), ('uint8', 16000),
+    ('float32', 22050), ('float64', 16000)])
+def test_wav_probe_and_decode_match_scipy(library, tmp_path, kind, rate):
+    rng = np.random.default_rng(3)
+    n = 1237
+    data = {
+        'int16': lambda: rng.integers(-32768, 32768, n).astype(np.int16),
+        'int16-stereo': lambda: rng.integers(-32768, 32768, (n, 2)).astype(np.int16),
+        'int32': lambda: rng.integers(-2**31, 2**31, n).astype(np.int32),
+        'uint8': lambda: rng.integers(0, 256, n).astype(np.uint8),
+        'float32': lambda: rng.standard_normal(n).astype(np.float32),
+        'float64': lambda: rng.standard_normal(n),
+    }[kind]()
+    path = tmp_path / f'{kind}.wav'
+    wavfile.write(path, rate, data)
+    code, (frames, got_rate, channels, bits, is_float) = probe(library, path)
+    assert code == 0
+    assert (frames, got_rate) == (n, rate)
+    assert channels == (2 if data.ndim == 2 else 1)
+    assert bits == data.dtype.itemsize * 8 and is_float == int(data.dtype.kind == 'f')
+    audio, got_rate = decode(library, path, n)
+    channel0 = data if data.ndim == 1 else data[:, 0]
+    assert got_rate == rate and np.array_equal(audio, normalised(channel0))
+
+
+def test_wav_24bit_extensible_and_extra_chunks(library, tmp_path):
+    """24-bit PCM in a WAVE_FORMAT_EXTENSIBLE header, a LIST chunk of odd size before
+    `data` and trailing bytes after it."""
+    rng = np.random.default_rng(5)
+    values = rng.integers(-2**23, 2**23, 333)
+    payload = b''.join(struct.pack('<i', int(v))[:3] for v in values)
+    fmt = struct.pack('<HHIIHH', 0xFFFE, 1, 16000, 48000, 3, 24) + struct.pack('<HHI', 22, 24, 4)
+    fmt += struct.pack('<H', 1) + b'\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71'
+    body = b'WAVE' + b'fmt ' + struct.pack('<I', len(fmt)) + fmt
+    body += b'LIST' + struct.pack('<I', 5) + b'hello' + b'\x00'
+    body += b'data' + struct.pack('<I', len(payload)) + payload + b'\x00tail'
+    path = tmp_path / 'x.wav'
+    path.write_bytes(b'RIFF' + struct.pack('<I', len(body)) + body)
+    code, (frames, rate, channels, bits, is_float) = probe(library, path)
+    assert (code, frames, rate, channels, bits, is_float) == (0, 333, 16000, 1, 24, 0)
+    audio, _ = decode(library, path, 400)
+    assert np.array_equal(audio, (values * 256).astype(np.float32) / 2147483648.0)
+
+
+def test_wav_errors(library, tmp_path):
+    assert probe(library, tmp_path / 'missing.wav')[0] == library.E_INVALID
+    assert 'cannot open' in library.last_error()
+    other = tmp_path / 'not.wav'
+    other.write_bytes(b'ID3\x03' + bytes(64))
+    assert probe(library, other)[0] == library.E_UNSUPPORTED
+    short = tmp_path / 'short.wav'
+    write_wav(short, 100)
+    with pytest.raises(ValueError, match='do not fit'):
+        decode(library, short, 50)
+    from ppgs_b200 import load
+    assert load.wav_info(other) is None
+    assert load.wav_info(short) == {
+        'samples': 100, 'sample_rate': 16000, 'channels': 1, 'bits': 16, 'is_float': False}
+
+
+@pytest.mark.parametrize('cols', [0, 1, 255, 256, 1000, 1234])
+def test_pt_writer_is_torch_loadable(library, tmp_path, cols):
+    """ppgs_pt_write_f32 == torch.save(tensor[..., :length].clone()) for what torch.load
+    returns (ppgs/preprocess/core.py:219-221), also with weights_only and mmap."""
+    x = torch.randn(40, 1234)
+    path = tmp_path / f'ppg-{cols}.pt'
+    library.check(library.lib.ppgs_pt_write_f32(str(path).encode(), x.data_ptr(), 40, cols, 1234))
+    for kwargs in ({}, {'weights_only': True}, {'weights_only': False}, {'mmap': True}):
+        y = torch.load(path, **kwargs)
+        assert y.dtype == torch.float32 and y.shape == (40, cols) and y.is_contiguous()
+        assert torch.equal(y, x[:, :cols])
+    archive = zipfile.ZipFile(path)
+    assert archive.testzip() is None
+    names = archive.namelist()
+    assert names == [f'ppg-{cols}/data.pkl', f'ppg-{cols}/byteorder', f'ppg-{cols}/data/0',
+                     f'ppg-{cols}/version']
+    info = archive.getinfo(f'ppg-{cols}/data/0')
+    # storage starts 64-byte aligned, like torch's own writer (mmap-friendly)
+    with open(path, 'rb') as f:
+        f.seek(info.header_offset + 26)
+        name_len, extra_len = struct.unpack('<HH', f.read(4))
+    assert (info.header_offset + 30 + name_len + extra_len) % 64 == 0
+    # and a tensor saved by torch round-trips to the same values
+    reference = tmp_path / 'reference.pt'
+    torch.save(x[..., :cols].clone(), reference)
+    assert torch.equal(torch.load(reference), torch.load(path))
+
+
+def test_pt_writer_large_and_errors(library, tmp_path):
+    big = torch.randn(40, 70000)
+    path = tmp_path / 'big.pt'
+    library.check(library.lib.ppgs_pt_write_f32(str(path).encode(), big.data_ptr(), 40, 70000, 70000))
+    assert torch.equal(torch.load(path), big)
+    with pytest.raises(ValueError, match='bad shape'):
+        library.check(library.lib.ppgs_pt_write_f32(str(path).encode(), big.data_ptr(), 40, 10, 5))
+    with pytest.raises(ValueError, match='cannot open'):
+        library.check(library.lib.ppgs_pt_write_f32(
+            str(tmp_path / 'no' / 'dir.pt').encode(), big.data_ptr(), 40, 10, 10))
+
+
+@pytest.mark.parametrize('orig,new', [
+    (44100, 16000), (22050, 16000), (8000, 16000), (48000, 16000), (11025, 16000),
+    (32000, 16000), (24000, 16000), (16001, 16000)])
+def test_resample_taps_equal_torchaudio(library, orig, new):
+    """The filter bank of torchaudio.transforms.Resample(orig, new) (defaults), bit for bit."""
+    import torchaudio.functional as F
+    kernel, width = F.functional._get_sinc_resample_kernel(orig, new, math.gcd(orig, new))
+    ntaps, phases, got_width = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    library.check(library.lib.ppgs_resample_taps(orig, new, None, 0, ntaps, phases, got_width))
+    assert (phases.value, ntaps.value, got_width.value) == (kernel.shape[0], kernel.shape[2], width)
+    taps = np.empty((ntaps.value, phases.value), np.float32)
+    library.check(library.lib.ppgs_resample_taps(
+        orig, new, taps.ctypes.data, taps.size, ntaps, phases, got_width))
+    assert np.array_equal(taps, kernel[:, 0, :].numpy().T)
+    for samples in (0, 1, 159, 12345, 160000):
+        expected = math.ceil(new * samples / orig)
+        assert library.lib.ppgs_resample_length(samples, orig, new) == expected
+
+
+def test_metadata_flags_native_eligibility(tmp_path):
+    from ppgs_b200 import data
+    a, b, c = tmp_path / 'a.wav', tmp_path / 'b.wav', tmp_path / 'c.wav'
+    write_wav(a, 16000)
+    write_wav(b, 8000, channels=2)
+    assert data.Metadata([a, b]).native
+    assert data.Metadata([a, b]).samples == {a: 16000, b: 8000}
+    write_wav(c, 22050, rate=22050)
+    metadata = data.Metadata([a, c])
+    assert not metadata.native and metadata.lengths == [100, 100]
+    wavfile.write(c, 16000, np.zeros(1600, np.float32))
+    assert not data.Metadata([a, c]).native
