@@ -246,6 +246,33 @@ int ppgs_files_to_files(ppgs_engine* engine, int n_batches, const int32_t* batch
                         const int64_t* file_samples, int reader_threads, int writer_threads,
                         int legacy_mode, void* stream, int64_t* frames_done);
 
+/* ---- stateful streaming decoder for causal models (config/causal_transformer.py:18) ------
+ * The reference has no streaming state (ppgs/model/transformer.py:65-71 rebuilds the causal
+ * mask per call); this is the incremental form of its un-chunked causal forward
+ * (`legacy_mode=True`, IS_CAUSAL=True) over `streams` utterances that grow in lockstep.
+ * State per stream: the feature rows, and per layer the K / V rows of every frame pushed so
+ * far (the attention cache, read in place by the tcgen05 attention kernel).  A session holds
+ * ppgs_stream_capacity() = 510 frames; PPGS_E_TOO_LARGE beyond (ValueError('size is too
+ * large'), transformer.py:103-104) — restart with overlap like the reference's chunking.
+ *
+ * ppgs_stream_push appends `frames` feature frames (features_dev: (streams, input_channels,
+ * frames) fp16, contiguous) and writes the posteriorgram frames that became final — frames
+ * [emitted, length - 4): 2 + 2 frames of look-ahead of the two k=5 convolutions — to out_dev
+ * ((streams, output_channels, out_capacity) fp32; the first *frames_out frames of every row
+ * are valid).  `final` != 0 also emits the last 4 frames (zero padding beyond the end, as the
+ * reference pads) and closes the session until ppgs_stream_reset.  Every emitted frame equals
+ * the reference's value for the whole utterance. */
+typedef struct ppgs_stream ppgs_stream;
+int ppgs_stream_capacity(void);
+int ppgs_stream_create(ppgs_engine* engine, int streams, ppgs_stream** out);
+void ppgs_stream_destroy(ppgs_stream* stream_state);
+int ppgs_stream_reset(ppgs_stream* stream_state, void* stream);
+int ppgs_stream_length(const ppgs_stream* stream_state);
+int ppgs_stream_emitted(const ppgs_stream* stream_state);
+int ppgs_stream_push(ppgs_stream* stream_state, const void* features_dev, int frames, int final,
+                     int softmax, float* out_dev, int out_capacity, int* frames_out,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,13 @@ SYMBOLS = {
     'ppgs_files_to_files': (_i, [_vp, _i, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_char_p),
                                  _c.POINTER(_c.c_char_p), _c.POINTER(_i64), _i, _i, _i, _vp,
                                  _c.POINTER(_i64)]),
+    'ppgs_stream_capacity': (_i, []),
+    'ppgs_stream_create': (_i, [_vp, _i, _c.POINTER(_vp)]),
+    'ppgs_stream_destroy': (None, [_vp]),
+    'ppgs_stream_reset': (_i, [_vp, _vp]),
+    'ppgs_stream_length': (_i, [_vp]),
+    'ppgs_stream_emitted': (_i, [_vp]),
+    'ppgs_stream_push': (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _c.POINTER(_i), _vp]),
 }
 
 

@@ -158,6 +158,7 @@ struct AttnParams {
     float scale_log2e;
     __half* out;
     int64_t out_plane_stride;
+    int q_first_tile;   // streaming decoder: only query tiles >= this one are computed
     int* status;
     // cycle accounting (PPGS_B200_TRACE=1): MMA [0] wait q [1] wait k [2] wait p [3] wait v [4] total;
     // softmax warp 2: [8] wait s [9] row max [10] wait p_empty [11] chunk work [12] wait o [13] total [14] CTAs
@@ -198,7 +199,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
     __shared__ float row_part[2][128];   // per-row partial max / sum of the two halves
 
     const SeqInfo s = p.seqs[blockIdx.z];
-    const int q0 = blockIdx.x * 128, head = blockIdx.y;
+    const int q0 = ((int)blockIdx.x + p.q_first_tile) * 128, head = blockIdx.y;
     if (q0 >= s.tensor_len) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int nkeys = s.valid_len;
@@ -529,7 +530,7 @@ int launch_attention_planes(ppgs_engine* e, int head_dim, const __half* qkv, __h
 template <int D>
 static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows, int H, int heads,
                             int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, int q_first_tile, int q_tiles) {
     using Shape = AttnShape<D>;
     CUtensorMap map_qk, map_v, map_out;
     PPGS_CHECK(make_store_map(&map_out, out, H, rows, (uint64_t)rows * H));
@@ -552,8 +553,9 @@ static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int 
     p.out = out;
     p.out_plane_stride = (int64_t)rows * H;
     p.status = e->status_dev;
+    p.q_first_tile = q_first_tile;
     p.trace = e->trace_dev ? e->trace_dev + 80 : nullptr;
-    dim3 grid(max_pitch / 128, heads, (unsigned)nseq);
+    dim3 grid(q_tiles > 0 ? q_tiles : max_pitch / 128, heads, (unsigned)nseq);
     {
         LaunchScope scope(e, "tc_attention", stream);
         attention_tc_kernel<D><<<grid, kAttnThreads, Shape::kSmem, stream>>>(map_qk, map_v, map_out, p);
@@ -564,15 +566,22 @@ static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int 
 
 int launch_attention_any(ppgs_engine* e, const __half* qkv, __half* out, int rows, int H, int heads,
                          int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, int q_first_tile, int q_tiles) {
     const int D = H / heads;
     if (e->attention_impl == 1 && max_pitch <= 512 && max_pitch % 128 == 0 && e->status_dev) {
         if (D == 64)
-            return run_attention_tc<64>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream);
+            return run_attention_tc<64>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream,
+                                         q_first_tile, q_tiles);
         if (D == 128)
-            return run_attention_tc<128>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream);
+            return run_attention_tc<128>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream,
+                                         q_first_tile, q_tiles);
         if (D == 256)
-            return run_attention_tc<256>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream);
+            return run_attention_tc<256>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream,
+                                         q_first_tile, q_tiles);
+    }
+    if (q_first_tile || q_tiles) {
+        set_error("attention: the query-tile window needs the tcgen05 kernel (head_dim 64 / 128 / 256, pitch <= 512)");
+        return PPGS_E_UNSUPPORTED;
     }
     return launch_attention_planes(e, D, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes,
                                    stream);

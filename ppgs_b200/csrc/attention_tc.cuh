@@ -13,9 +13,11 @@ int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows
 
 // Same for any (hidden, heads): tcgen05 kernel when head_dim is 64 / 128 / 256 and the
 // pitch is <= 512 rows, CUDA-core kernel otherwise.
+// `q_first_tile` / `q_tiles` restrict the query tiles of every sequence (streaming decoder: the
+// keys of earlier tiles are the cache); 0 / 0 = all.
 int launch_attention_any(ppgs_engine* e, const __half* qkv, __half* out, int rows, int H, int heads,
                          int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
-                         cudaStream_t stream);
+                         cudaStream_t stream, int q_first_tile = 0, int q_tiles = 0);
 
 // CUDA-core attention over split planes for any (hidden, heads, head_dim in {64, 128, 256}):
 // used by the wav2vec2 encoder (12 heads x 64).

@@ -81,6 +81,13 @@ __device__ __forceinline__ void split32(const float (&y)[32], uint32_t (&h)[32],
     for (int i = 0; i < 16; ++i) split2_f16(y[2 * i], y[2 * i + 1], h[at + i], l[at + i]);
 }
 
+// work item -> row unit (GemmParams::win_*): identity unless a row-tile window is set
+__device__ __forceinline__ int window_unit(const GemmParams& p, int item) {
+    if (p.win_size == 0) return item;
+    const int seq = item / p.win_size;
+    return seq * p.win_stride + p.win_first + (item - seq * p.win_size);
+}
+
 template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -144,7 +151,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             long long t_wait = 0;
             const long long t_begin = clock64();
             for (int tile = worker; tile < total_tiles && ok; tile += workers) {
-                const int m_unit = tile / p.n_tiles, n_blk = tile - m_unit * p.n_tiles;
+                const int m_item = tile / p.n_tiles, n_blk = tile - m_item * p.n_tiles;
+                const int m_unit = window_unit(p, m_item);
                 const int m_blk = PAIR ? 2 * m_unit + (int)rank : m_unit;
                 const int a_row0 = m_blk * kBM * p.row_mul - p.half + n_blk * p.a_group_rows;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -274,7 +282,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         long long t_wait = 0;
         const long long t_begin = clock64();
         for (int tile = worker; tile < total_tiles; tile += workers, ++iter) {
-            const int m_unit = tile / p.n_tiles, n_blk = tile - m_unit * p.n_tiles;
+            const int m_item = tile / p.n_tiles, n_blk = tile - m_item * p.n_tiles;
+            const int m_unit = window_unit(p, m_item);
             const int m_blk = PAIR ? 2 * m_unit + (int)rank : m_unit;
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;

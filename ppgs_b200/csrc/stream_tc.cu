@@ -1,0 +1,352 @@
+// Stateful streaming decoder for causal models (config/causal_transformer.py: IS_CAUSAL =
+// True).  The reference cannot stream (ppgs/model/transformer.py:65-71 builds
+// the square mask per call and carries no state); this is the incremental form
+// of its un-chunked causal forward (legacy_mode=True) over a growing utterance.
+//
+// Semantics.  A session holds `streams` utterances that advance in lockstep.  After pushes
+// totalling L feature frames the state equals the reference forward over those L frames:
+//   * hidden position p depends on features <= p + 2 (input Conv1d k=5 'same') and, through
+//     the causal attention, on hidden positions <= p: final once L >= p + 3;
+//   * output frame q depends on hidden q-2 .. q+2 (output Conv1d k=5): final once L >= q + 5.
+// push() therefore emits frames [emitted, L - 4) (everything up to L when `final`), each
+// exactly the value the reference computes for the whole utterance (algorithmic latency: 4
+// frames = 40 ms).
+//
+// State = the activation matrices of the tensor-core path made persistent: every stream owns
+// 512 rows (510 frames + the 2 zero rows the k=5 convolutions read as padding) of the feature
+// matrix x0, the residual stream x, and ONE QKV MATRIX PER LAYER — the K / V columns of
+// rows < L are the attention cache, read in place by the tcgen05 attention kernel, whose
+// 512-key TMEM budget sets the session capacity (the reference's own chunked inference never
+// shows the model more than 500 frames either).  A push appends n feature rows and recomputes
+// only the 128-row tiles that hold a position >= L_old - 4 (GemmParams::win_*, AttnParams::
+// q_first_tile): positions whose look-ahead was incomplete are redone with the new frames,
+// earlier tiles keep their cached K / V.  Recomputing a tile is idempotent, so cached rows that
+// share a tile with new rows are rewritten with identical values.
+#include "attention_tc.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace ppgs {
+using namespace tc;
+
+constexpr int kStreamPitch = 512;       // rows per stream
+constexpr int kStreamCapacity = 510;    // frames per session
+constexpr int kStreamLookahead = 4;     // 2 (input conv) + 2 (output conv)
+
+// (B, C, n) fp16 feature frames -> rows [row0 + t0, row0 + t0 + n) of the time-major x0
+__global__ void stream_append_kernel(const __half* __restrict__ feats, int C, int n, int t0,
+                                     __half* __restrict__ x0) {
+    __shared__ __half tile[32][34];
+    const int b = blockIdx.z, f_base = blockIdx.x * 32, c_base = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c_base + i, f = f_base + tx;
+        tile[i][tx] = (c < C && f < n) ? feats[((int64_t)b * C + c) * n + f] : __float2half_rn(0.f);
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c_base + tx, f = f_base + i;
+        if (c < C && f < n) x0[((int64_t)b * kStreamPitch + t0 + f) * C + c] = tile[tx][i];
+    }
+}
+
+}  // namespace ppgs
+
+using namespace ppgs;
+
+struct ppgs_stream {
+    ppgs_engine* e = nullptr;
+    int streams = 0;
+    int length = 0;     // L: feature frames pushed so far
+    int emitted = 0;    // output frames returned so far
+    bool finished = false;
+    void* block = nullptr;   // one allocation
+    __half *x0 = nullptr, *xh = nullptr, *att = nullptr, *ff = nullptr;
+    std::vector<__half*> qkv;   // per layer
+    SeqInfo* seqs_dev = nullptr;
+    int* tile_seq_dev = nullptr;
+    size_t zero_bytes = 0;      // prefix of `block` that reset() clears (x0, x, qkv caches)
+};
+
+static int stream_reset_state(ppgs_stream* s, cudaStream_t stream) {
+    PPGS_CUDA(cudaMemsetAsync(s->block, 0, s->zero_bytes, stream));
+    s->length = 0;
+    s->emitted = 0;
+    s->finished = false;
+    return PPGS_OK;
+}
+
+extern "C" {
+
+int ppgs_stream_capacity(void) { return kStreamCapacity; }
+
+int ppgs_stream_create(ppgs_engine* e, int streams, ppgs_stream** out) {
+    if (!e || !out || streams <= 0) {
+        set_error("stream_create: bad argument");
+        return PPGS_E_INVALID;
+    }
+    *out = nullptr;
+    const ppgs_model_config& c = e->cfg;
+    if (!e->finalized) {
+        set_error("engine has no weights: call ppgs_engine_finalize first");
+        return PPGS_E_STATE;
+    }
+    if (!c.is_causal) {
+        set_error("stream_create: streaming needs a causal model (config/causal_transformer.py: IS_CAUSAL)");
+        return PPGS_E_INVALID;
+    }
+    if (c.hidden_channels != 256 || !tensor_core_shape(c) || c.kernel_size != 5) {
+        set_error("stream_create: the streaming decoder covers hidden 256 and kernel 5 (got hidden %d, "
+                  "kernel %d)", c.hidden_channels, c.kernel_size);
+        return PPGS_E_UNSUPPORTED;
+    }
+    if (e->precision == PPGS_PRECISION_FP32) {
+        set_error("stream_create: the streaming decoder runs the tensor-core path (precision f16x2 / f16)");
+        return PPGS_E_UNSUPPORTED;
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    PPGS_CUDA(cudaSetDevice(e->device));
+    ppgs_stream* s = new ppgs_stream();
+    s->e = e;
+    s->streams = streams;
+    const size_t rows = (size_t)streams * kStreamPitch;
+    const int C = c.input_channels, H = c.hidden_channels, F = c.ffn_channels;
+    Carver w;
+    const size_t o_x0 = w.take(rows * C * 2);
+    const size_t o_xh = w.take(2 * rows * H * 2);
+    std::vector<size_t> o_qkv(c.num_layers);
+    for (int l = 0; l < c.num_layers; ++l) o_qkv[l] = w.take(2 * rows * 3 * H * 2);
+    s->zero_bytes = w.off;
+    const size_t o_att = w.take(2 * rows * H * 2);
+    const size_t o_ff = w.take(2 * rows * F * 2);
+    const size_t o_seqs = w.take((size_t)streams * sizeof(SeqInfo));
+    const size_t o_tiles = w.take(rows / 128 * 4);
+    cudaError_t err = cudaMalloc(&s->block, w.off);
+    if (err != cudaSuccess) {
+        set_error("stream_create: cudaMalloc of %zu bytes failed: %s", w.off, cudaGetErrorString(err));
+        delete s;
+        if (prev >= 0) cudaSetDevice(prev);
+        return PPGS_E_CUDA;
+    }
+    char* base = static_cast<char*>(s->block);
+    s->x0 = reinterpret_cast<__half*>(base + o_x0);
+    s->xh = reinterpret_cast<__half*>(base + o_xh);
+    for (int l = 0; l < c.num_layers; ++l) s->qkv.push_back(reinterpret_cast<__half*>(base + o_qkv[l]));
+    s->att = reinterpret_cast<__half*>(base + o_att);
+    s->ff = reinterpret_cast<__half*>(base + o_ff);
+    s->seqs_dev = reinterpret_cast<SeqInfo*>(base + o_seqs);
+    s->tile_seq_dev = reinterpret_cast<int*>(base + o_tiles);
+    int rc = PPGS_OK;
+    if (cudaMemset(s->block, 0, w.off) != cudaSuccess) {
+        set_error("stream_create: cudaMemset failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = PPGS_E_CUDA;
+    }
+    if (rc == PPGS_OK) rc = build_weight_maps(e);
+    if (prev >= 0) cudaSetDevice(prev);
+    if (rc != PPGS_OK) {
+        cudaFree(s->block);
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return PPGS_OK;
+}
+
+void ppgs_stream_destroy(ppgs_stream* s) {
+    if (!s) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->e->device);
+    cudaDeviceSynchronize();
+    cudaFree(s->block);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete s;
+}
+
+int ppgs_stream_reset(ppgs_stream* s, void* stream) {
+    if (!s) {
+        set_error("stream is NULL");
+        return PPGS_E_INVALID;
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    PPGS_CUDA(cudaSetDevice(s->e->device));
+    const int rc = stream_reset_state(s, static_cast<cudaStream_t>(stream));
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+}
+
+int ppgs_stream_length(const ppgs_stream* s) { return s ? s->length : -1; }
+int ppgs_stream_emitted(const ppgs_stream* s) { return s ? s->emitted : -1; }
+
+int ppgs_stream_push(ppgs_stream* s, const void* features_dev, int frames, int final, int softmax,
+                     float* out_dev, int out_capacity, int* frames_out, void* stream_) {
+    if (!s) {
+        set_error("stream is NULL");
+        return PPGS_E_INVALID;
+    }
+    ppgs_engine* e = s->e;
+    const ppgs_model_config& c = e->cfg;
+    if (frames_out) *frames_out = 0;
+    if (frames < 0 || (frames > 0 && !features_dev) || out_capacity < 0 || (out_capacity > 0 && !out_dev)) {
+        set_error("stream_push: bad argument");
+        return PPGS_E_INVALID;
+    }
+    if (s->finished) {
+        set_error("stream_push: the session was finalised; call ppgs_stream_reset");
+        return PPGS_E_STATE;
+    }
+    if (s->length + frames > kStreamCapacity) {
+        // the positional-encoding limit of the reference is 5000 (transformer.py:103-104); here
+        // the cache capacity is the binding one
+        set_error("size is too large: a streaming session holds %d frames (%d pushed + %d new)",
+                  kStreamCapacity, s->length, frames);
+        return PPGS_E_TOO_LARGE;
+    }
+    const int t0 = s->length, L = t0 + frames;
+    const int keep_end = final ? L : (L - kStreamLookahead > s->emitted ? L - kStreamLookahead : s->emitted);
+    const int n_out = keep_end - s->emitted;
+    if (n_out > out_capacity) {
+        set_error("stream_push: %d output frames do not fit out_capacity %d", n_out, out_capacity);
+        return PPGS_E_INVALID;
+    }
+    if (e->precision == PPGS_PRECISION_FP32) {
+        set_error("stream_push: the streaming decoder runs the tensor-core path (precision f16x2 / f16)");
+        return PPGS_E_UNSUPPORTED;
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    PPGS_CUDA(cudaSetDevice(e->device));
+    struct Restore {
+        int prev;
+        ~Restore() {
+            if (prev >= 0) cudaSetDevice(prev);
+        }
+    } restore{prev};
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int C = c.input_channels, H = c.hidden_channels, F = c.ffn_channels, O = c.output_channels;
+    const int k = c.kernel_size, B = s->streams;
+    const int rows = B * kStreamPitch;
+    const int planes = e->precision == PPGS_PRECISION_F16X2 ? 2 : 1;
+
+    if (frames > 0) {
+        dim3 grid((frames + 31) / 32, (C + 31) / 32, B);
+        LaunchScope scope(e, "stream_append", stream);
+        stream_append_kernel<<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __half*>(features_dev), C, frames,
+                                                                t0, s->x0);
+    }
+    PPGS_CUDA(cudaGetLastError());
+    s->length = L;
+    if (final) s->finished = true;
+    if (L == 0 || (frames == 0 && n_out == 0)) return PPGS_OK;
+
+    // tiles to (re)compute: every position >= max(t0 - 4, 0) (incomplete look-ahead, and the
+    // rows the output convolution of the first emitted frame reads), in units of tile pairs
+    const int first_pos = s->emitted < t0 - kStreamLookahead ? s->emitted
+                                                               : (t0 - kStreamLookahead > 0 ? t0 - kStreamLookahead : 0);
+    int tile_first = (first_pos / 128) & ~1;
+    int tile_end = ((L - 1) / 128 + 2) & ~1;   // exclusive, even
+    const int tiles_per_seq = kStreamPitch / 128;
+    if (tile_end > tiles_per_seq) tile_end = tiles_per_seq;
+    const int win_tiles = tile_end - tile_first;
+
+    ForwardPlan plan;
+    plan.rows = rows;
+    plan.max_pitch = kStreamPitch;
+    plan.batch = B;
+    plan.frames = n_out;
+    plan.seqs.resize(B);
+    for (int b = 0; b < B; ++b) {
+        SeqInfo& q = plan.seqs[b];
+        q.row0 = b * kStreamPitch;
+        q.tensor_len = L;
+        q.valid_len = L;
+        q.batch = b;
+        q.src_start = 0;
+        q.keep_begin = s->emitted;
+        q.keep_end = keep_end;
+        q.out_start = 0;
+    }
+    PPGS_CHECK(upload_plan(e, plan, s->seqs_dev, s->tile_seq_dev, stream));
+
+    CUtensorMap map_x0, map_x, map_att, map_ff, out_x, out_ff;
+    PPGS_CHECK(make_plane_map(&map_x0, s->x0, false, C, rows, 1, 1, C, 0, (uint64_t)rows * C, 128, 1));
+    PPGS_CHECK(make_plane_map(&map_x, s->xh, false, H, rows, 1, 2, H, 0, (uint64_t)rows * H, 128, planes));
+    PPGS_CHECK(make_plane_map(&map_att, s->att, false, H, rows, 1, 2, H, 0, (uint64_t)rows * H, 128, planes));
+    PPGS_CHECK(make_plane_map(&map_ff, s->ff, false, F, rows, 1, 2, F, 0, (uint64_t)rows * F, 128, planes));
+    PPGS_CHECK(make_store_map(&out_x, s->xh, H, rows, (uint64_t)rows * H));
+    PPGS_CHECK(make_store_map(&out_ff, s->ff, F, rows, (uint64_t)rows * F));
+
+    GemmParams base;
+    base.m_tiles = B * win_tiles;
+    base.seqs = s->seqs_dev;
+    base.tile_seq = s->tile_seq_dev;
+    base.status = e->status_dev;
+    base.eps = c.layer_norm_eps;
+    base.b_planes = planes;
+    base.pair = 1;
+    base.win_size = win_tiles / 2;          // units of tile pairs
+    base.win_stride = tiles_per_seq / 2;
+    base.win_first = tile_first / 2;
+    auto wmap = [&](TcWeight& w) -> const CUtensorMap& { return w.maps[planes - 1].bn128; };
+
+    {
+        GemmParams p = base;
+        p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = (C + 63) / 64; p.a_planes = 1;
+        p.N = H; p.scale = e->tc_conv_in.inv_scale; p.bias = e->conv_in_b; p.pe = e->pe;
+        PPGS_CHECK(launch_gemm_tc(e, "tc_conv_in", 256, kEpiConvIn, map_x0, wmap(e->tc_conv_in), &out_x, p, stream));
+    }
+    for (int layer = 0; layer < c.num_layers; ++layer) {
+        const LayerWeights& Lw = e->layers[layer];
+        TcLayer& T = e->tc_layers[layer];
+        CUtensorMap out_qkv;
+        PPGS_CHECK(make_store_map(&out_qkv, s->qkv[layer], 3 * H, rows, (uint64_t)rows * 3 * H));
+        {
+            GemmParams p = base;
+            p.n_tiles = 3 * H / 256; p.cblocks = H / 64; p.a_planes = planes;
+            p.N = 3 * H; p.scale = T.in_w.inv_scale; p.bias = Lw.in_b;
+            PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, wmap(T.in_w), &out_qkv, p, stream));
+        }
+        PPGS_CHECK(launch_attention_any(e, s->qkv[layer], s->att, rows, H, c.num_heads, kStreamPitch, B,
+                                        s->seqs_dev, 1, planes, stream, tile_first, win_tiles));
+        {
+            GemmParams p = base;
+            p.n_tiles = 1; p.cblocks = H / 64; p.a_planes = planes;
+            p.N = H; p.scale = T.out_w.inv_scale; p.bias = Lw.out_b;
+            p.residual = s->xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
+            p.gamma = Lw.n1_w; p.beta = Lw.n1_b;
+            PPGS_CHECK(launch_gemm_tc(e, "tc_out_proj_ln", 256, kEpiResLN, map_att, wmap(T.out_w), &out_x, p, stream));
+        }
+        {
+            GemmParams p = base;
+            p.n_tiles = F / 256; p.cblocks = H / 64; p.a_planes = planes;
+            p.N = F; p.scale = T.l1_w.inv_scale; p.bias = Lw.l1_b; p.relu = 1;
+            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn1", 256, kEpiPlanes, map_x, wmap(T.l1_w), &out_ff, p, stream));
+        }
+        {
+            GemmParams p = base;
+            p.n_tiles = 1; p.cblocks = F / 64; p.a_planes = planes;
+            p.N = H; p.scale = T.l2_w.inv_scale; p.bias = Lw.l2_b;
+            p.residual = s->xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
+            p.gamma = Lw.n2_w; p.beta = Lw.n2_b;
+            PPGS_CHECK(launch_gemm_tc(e, "tc_ffn2_ln", 256, kEpiResLN, map_ff, wmap(T.l2_w), &out_x, p, stream));
+        }
+    }
+    if (n_out > 0) {
+        GemmParams p = base;
+        p.pair = 0;                       // the BN = 64 kernel is single-CTA: window in tiles
+        p.win_size = win_tiles; p.win_stride = tiles_per_seq; p.win_first = tile_first;
+        p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = H / 64; p.a_planes = planes;
+        p.N = O; p.O = O; p.scale = e->tc_conv_out.inv_scale; p.bias = e->conv_out_b;
+        p.ppg = out_dev; p.T = out_capacity; p.softmax = softmax;
+        PPGS_CHECK(launch_gemm_tc(e, "tc_conv_out_softmax", 64, kEpiConvOut, map_x,
+                                  e->tc_conv_out.maps[planes - 1].bn64, nullptr, p, stream));
+    }
+    s->emitted = keep_end;
+    if (frames_out) *frames_out = n_out;
+    return PPGS_OK;
+}
+
+}  // extern "C"

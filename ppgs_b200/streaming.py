@@ -1,0 +1,107 @@
+"""Stateful streaming inference for causal models (`config/causal_transformer.py`:
+IS_CAUSAL = True) — BASELINE config 4 with state.  The reference cannot stream (SURVEY.md
+F8); `Streamer` is the incremental form of its un-chunked causal forward: every frame it
+emits equals `ppgs.from_features(..., legacy_mode=True)` of the whole utterance, 4 frames
+(40 ms) after the frame was pushed."""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import config
+from .engine import _stream_ptr
+
+
+class Streamer:
+    """`streams` utterances decoded in lockstep on one engine (C ABI: ppgs_stream_*)."""
+
+    LOOKAHEAD = 4
+
+    def __init__(self, engine, streams):
+        self.engine = engine
+        self.streams = int(streams)
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.lib.ppgs_stream_create(engine._handle, self.streams, ctypes.byref(handle)))
+        self._handle = handle
+        self._audio = None       # (streams, samples) fp32 tail for push_audio
+        self._frames_in = 0      # mel frames already handed to push()
+        self._samples_seen = 0
+
+    def __del__(self):
+        handle = getattr(self, '_handle', None)
+        lib = getattr(_lib, 'lib', None) if _lib is not None else None
+        if handle is not None and handle.value and lib is not None:
+            lib.ppgs_stream_destroy(handle)
+            self._handle = None
+
+    capacity = property(lambda self: _lib.lib.ppgs_stream_capacity())
+    length = property(lambda self: _lib.lib.ppgs_stream_length(self._handle))
+    emitted = property(lambda self: _lib.lib.ppgs_stream_emitted(self._handle))
+
+    def reset(self):
+        _lib.check(_lib.lib.ppgs_stream_reset(self._handle, _stream_ptr(self.engine.device)))
+        self._audio, self._frames_in, self._samples_seen = None, 0, 0
+
+    def push(self, features=None, final=False, softmax=True):
+        """features (streams, channels, n) fp16 (or None / n = 0 with `final` to flush)
+        -> posteriorgram frames that became final, (streams, 40, m) fp32 CUDA."""
+        device = self.engine.device
+        if features is None:
+            features = torch.empty(self.streams, self.engine.cfg.input_channels, 0,
+                                   dtype=torch.float16, device=device)
+        features = self.engine._on_device(features, torch.float16).contiguous()
+        if features.dim() != 3 or features.shape[0] != self.streams:
+            raise ValueError(f'expected features of shape ({self.streams}, channels, frames)')
+        if features.shape[1] != self.engine.cfg.input_channels:
+            raise ValueError(f'expected {self.engine.cfg.input_channels} feature channels')
+        frames = features.shape[-1]
+        capacity = frames + self.LOOKAHEAD
+        out = torch.empty(self.streams, self.engine.cfg.output_channels, capacity,
+                          dtype=torch.float32, device=device)
+        produced = ctypes.c_int()
+        _lib.check(_lib.lib.ppgs_stream_push(
+            self._handle, ctypes.c_void_p(features.data_ptr()), frames, int(bool(final)),
+            int(bool(softmax)), ctypes.c_void_p(out.data_ptr()), capacity, ctypes.byref(produced),
+            _stream_ptr(device)))
+        return out[..., :produced.value]
+
+    def push_audio(self, audio, final=False, softmax=True):
+        """16 kHz audio (streams, 1, n) appended to the session.  Mel frame t reads samples
+        [160 t - 432, 160 t + 592) of the reflect-padded utterance (ppgs/preprocess/
+        spectrogram.py:27-43), so a frame is computed once its window is complete (or at
+        `final`, with the reference's reflection at the end); the front-end runs on the
+        buffered tail only."""
+        hop, left = config.HOPSIZE, (config.NUM_FFT - config.HOPSIZE) // 2   # 160, 432
+        device = self.engine.device
+        if audio.dim() == 3:
+            audio = audio.squeeze(1)
+        audio = self.engine._on_device(audio, torch.float32)
+        if audio.shape[0] != self.streams:
+            raise ValueError(f'expected audio of shape ({self.streams}, 1, samples)')
+        first = self._frames_in
+        # the tail starts 3 hops before the next frame: its first 3 frames absorb the
+        # artificial reflection at the cut (3 * 160 >= 432), except at the true start
+        skip = min(first, 3)
+        start = (first - skip) * hop
+        if self._audio is None:
+            self._audio, self._offset = audio, 0
+        else:
+            self._audio = torch.cat((self._audio, audio), dim=-1)
+        self._samples_seen += audio.shape[-1]
+        self._audio = self._audio[:, start - self._offset:]
+        self._offset = start
+        total = self._samples_seen
+        if final:
+            last = total // hop                                   # frames = samples // 160
+        else:
+            last = max((total - (config.NUM_FFT - left)) // hop + 1, first)   # 160 t + 592 <= total
+            last = min(last, total // hop)
+        if last > first and self._audio.shape[-1] > left:
+            mel = self.engine.mel(self._audio.contiguous())
+            features = mel[..., skip:skip + (last - first)]
+        else:
+            last = first
+            features = torch.empty(self.streams, config.NUM_MELS, 0, dtype=torch.float16,
+                                   device=device)
+        self._frames_in = last
+        return self.push(features, final=final, softmax=softmax)

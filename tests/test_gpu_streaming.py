@@ -1,0 +1,138 @@
+"""Stateful streaming decoder (ppgs_stream_*) against the oracle: every
+frame a session emits equals the reference's un-chunked causal forward
+(`legacy_mode=True`, IS_CAUSAL=True; ppgs/model/transformer.py:65-81) of the WHOLE
+utterance, whatever the push sizes — to the north-star tolerance of 1e-4."""
+import pytest
+import torch
+
+from oracle import ppg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PPG_TOL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def ppgs_b200():
+    import ppgs_b200
+    return ppgs_b200
+
+
+@pytest.fixture(scope='module')
+def state():
+    return O.random_state_dict(7, peaky=True)
+
+
+@pytest.fixture(scope='module')
+def engine(ppgs_b200, state):
+    engine = ppgs_b200.Engine(0, is_causal=True).load_state_dict(state)
+    engine.precision = 'f16x2'
+    return engine
+
+
+def features_and_reference(state, streams, frames, seed):
+    audio = O.synthetic_audio(streams, frames * 160, seed)
+    features = O.mel_from_audios(audio)
+    lengths = torch.full((streams,), frames, dtype=torch.long)
+    reference = O.from_features(state, features, lengths, is_causal=True, legacy_mode=True)
+    return audio, features, reference
+
+
+@pytest.mark.parametrize('streams,pushes', [
+    (4, [160, 160, 160]),                       # BASELINE config 4: 160-frame chunks
+    (2, [128, 128, 128, 126]),                  # tile-aligned pushes up to the capacity
+    (3, [1, 2, 3, 4, 5, 37, 200, 1, 130, 127]),  # ragged pushes, odd stream count
+    (1, [510]),                                 # one push
+    (2, [300, 0, 0, 100]),                      # empty pushes
+])
+def test_streaming_equals_full_causal_forward(ppgs_b200, engine, state, streams, pushes):
+    total = sum(pushes)
+    _, features, reference = features_and_reference(state, streams, total, seed=total + streams)
+    streamer = ppgs_b200.Streamer(engine, streams)
+    assert streamer.capacity == 510
+    at, pieces = 0, []
+    for i, n in enumerate(pushes):
+        final = i + 1 == len(pushes)
+        out = streamer.push(features[..., at:at + n].cuda(), final=final)
+        at += n
+        expected_end = at if final else max(at - 4, 0)
+        assert streamer.length == at and streamer.emitted == expected_end
+        begin = expected_end - out.shape[-1]
+        # every partial result is already the whole-utterance value (causality + look-ahead)
+        if out.shape[-1]:
+            assert (out.cpu() - reference[..., begin:expected_end]).abs().max() <= PPG_TOL
+        pieces.append(out)
+    result = torch.cat(pieces, dim=-1).cpu()
+    assert result.shape == reference.shape
+    assert (result - reference).abs().max() <= PPG_TOL
+    assert (result.sum(1) - 1).abs().max() <= 1e-5
+    engine.check()
+
+
+def test_streaming_flush_reset_and_errors(ppgs_b200, engine, state):
+    _, features, reference = features_and_reference(state, 2, 200, seed=3)
+    streamer = ppgs_b200.Streamer(engine, 2)
+    first = streamer.push(features[..., :200].cuda())
+    assert first.shape[-1] == 196
+    tail = streamer.push(None, final=True)            # flush: the last 4 frames
+    assert tail.shape[-1] == 4
+    result = torch.cat((first, tail), dim=-1).cpu()
+    assert (result - reference).abs().max() <= PPG_TOL
+    with pytest.raises(RuntimeError, match='finalised'):
+        streamer.push(features[..., :10].cuda())
+    # the same session object serves the next utterance after reset, bit for bit
+    streamer.reset()
+    again = torch.cat((streamer.push(features.cuda()), streamer.push(None, final=True)), dim=-1).cpu()
+    assert torch.equal(again, result)
+    # logits instead of posteriors
+    streamer.reset()
+    logits = streamer.push(features.cuda(), final=True, softmax=False).cpu()
+    expected = O.from_features(state, features, torch.tensor([200, 200]), softmax=False,
+                               is_causal=True, legacy_mode=True)
+    assert (logits - expected).abs().max() <= 2e-3
+    assert (torch.softmax(logits, 1) - reference).abs().max() <= PPG_TOL
+    # capacity: ValueError('size is too large') like ppgs/model/transformer.py:103-104
+    streamer.reset()
+    streamer.push(torch.zeros(2, 80, 500, dtype=torch.float16).cuda())
+    with pytest.raises(ValueError, match='size is too large'):
+        streamer.push(torch.zeros(2, 80, 11, dtype=torch.float16).cuda())
+    with pytest.raises(ValueError, match='expected features'):
+        streamer.push(torch.zeros(3, 80, 1, dtype=torch.float16).cuda())
+    # streaming needs a causal model
+    plain = ppgs_b200.Engine(0).load_state_dict(state)
+    with pytest.raises(ValueError, match='causal'):
+        ppgs_b200.Streamer(plain, 2)
+
+
+def test_streaming_is_incremental(ppgs_b200, engine, state):
+    """A push recomputes only the row tiles from 4 frames before the previous end: the
+    launch count of a late push equals an early push's, and sessions do not disturb the
+    engine's batch API."""
+    _, features, reference = features_and_reference(state, 2, 480, seed=5)
+    streamer = ppgs_b200.Streamer(engine, 2)
+    engine.set_profiling(True)
+    streamer.push(features[..., :160].cuda())
+    streamer.push(features[..., 160:320].cuda())
+    batch = engine.transformer(features.cuda(), torch.tensor([480, 480]), legacy_mode=True).cpu()
+    out = streamer.push(features[..., 320:].cuda(), final=True).cpu()
+    stats = engine.kernel_stats()
+    engine.set_profiling(False)
+    assert (out - reference[..., 316:]).abs().max() <= PPG_TOL
+    assert (batch - reference).abs().max() <= PPG_TOL
+    assert stats['stream_append'][1] == 3 and stats['tc_conv_out_softmax'][1] == 4
+
+
+def test_streaming_from_audio(ppgs_b200, engine, state):
+    """push_audio: mel frames are produced as their 1024-sample windows complete; the
+    concatenated result equals the oracle's from_audio of the whole utterance."""
+    audio, features, reference = features_and_reference(state, 2, 300, seed=11)
+    streamer = ppgs_b200.Streamer(engine, 2)
+    cuts = [0, 100, 1000, 1700, 16000, 16001, 30000, 47999, 48000]
+    pieces = []
+    for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        pieces.append(streamer.push_audio(audio[..., a:b].cuda(), final=i + 2 == len(cuts)))
+    result = torch.cat(pieces, dim=-1).cpu()
+    assert result.shape == reference.shape
+    assert (result - reference).abs().max() <= PPG_TOL
+    # and the streamed features are the batch front-end's, bit for bit
+    assert streamer.length == 300
