@@ -81,11 +81,15 @@ __device__ __forceinline__ void split32(const float (&y)[32], uint32_t (&h)[32],
     for (int i = 0; i < 16; ++i) split2_f16(y[2 * i], y[2 * i + 1], h[at + i], l[at + i]);
 }
 
-// work item -> row unit (GemmParams::win_*): identity unless a row-tile window is set
-__device__ __forceinline__ int window_unit(const GemmParams& p, int item) {
-    if (p.win_size == 0) return item;
-    const int seq = item / p.win_size;
-    return seq * p.win_stride + p.win_first + (item - seq * p.win_size);
+// work item (row tile, or tile pair in the CTA-pair kernel) -> row tile of this CTA; identity
+// unless a row-tile window is set (GemmParams::win_*, in tiles).  A pair is two ADJACENT tiles;
+// it need not start at an even tile.
+template <bool PAIR>
+__device__ __forceinline__ int window_tile(const GemmParams& p, int item, int rank) {
+    if (p.win_size == 0) return PAIR ? 2 * item + rank : item;
+    const int per_seq = PAIR ? p.win_size / 2 : p.win_size;
+    const int seq = item / per_seq, u = item - seq * per_seq;
+    return seq * p.win_stride + p.win_first + (PAIR ? 2 * u + rank : u);
 }
 
 template <int BN, int EPI, bool PAIR>
@@ -152,8 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const long long t_begin = clock64();
             for (int tile = worker; tile < total_tiles && ok; tile += workers) {
                 const int m_item = tile / p.n_tiles, n_blk = tile - m_item * p.n_tiles;
-                const int m_unit = window_unit(p, m_item);
-                const int m_blk = PAIR ? 2 * m_unit + (int)rank : m_unit;
+                const int m_blk = window_tile<PAIR>(p, m_item, (int)rank);
                 const int a_row0 = m_blk * kBM * p.row_mul - p.half + n_blk * p.a_group_rows;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
@@ -283,8 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const long long t_begin = clock64();
         for (int tile = worker; tile < total_tiles; tile += workers, ++iter) {
             const int m_item = tile / p.n_tiles, n_blk = tile - m_item * p.n_tiles;
-            const int m_unit = window_unit(p, m_item);
-            const int m_blk = PAIR ? 2 * m_unit + (int)rank : m_unit;
+            const int m_blk = window_tile<PAIR>(p, m_item, (int)rank);
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
             // ResLN: the residual loads of the first two column chunks are in flight while

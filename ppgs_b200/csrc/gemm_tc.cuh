@@ -25,9 +25,9 @@ struct GemmParams {
     // grouped GEMM (block-diagonal weights): n tile g reads A rows shifted by g * a_group_rows
     // and owns output columns [g * group_cols, (g + 1) * group_cols) (kEpiF32 only)
     int a_group_rows = 0, group_cols = 0;
-    // row-tile window (streaming decoder): work unit u (a tile, or a tile pair in the CTA-pair
-    // kernel) maps to unit (u / win_size) * win_stride + win_first + u % win_size, i.e. only
-    // `win_size` units of every sequence of `win_stride` units are computed; 0 = all rows
+    // row-tile window (streaming decoder): only tiles [win_first, win_first + win_size) of every
+    // sequence of `win_stride` tiles are computed (m_tiles = sequences * win_size; win_size even
+    // for the CTA-pair kernel); 0 = all rows
     int win_size = 0, win_stride = 0, win_first = 0;
     int a_planes = 2, b_planes = 2;
     int pair = 0;                // 1: CTA-pair kernel (cta_group::2); W map must have box rows BN/2

@@ -243,13 +243,16 @@ int ppgs_stream_push(ppgs_stream* s, const void* features_dev, int frames, int f
     if (L == 0 || (frames == 0 && n_out == 0)) return PPGS_OK;
 
     // tiles to (re)compute: every position >= max(t0 - 4, 0) (incomplete look-ahead, and the
-    // rows the output convolution of the first emitted frame reads), in units of tile pairs
+    // rows the output convolution of the first emitted frame reads)
     const int first_pos = s->emitted < t0 - kStreamLookahead ? s->emitted
                                                                : (t0 - kStreamLookahead > 0 ? t0 - kStreamLookahead : 0);
-    int tile_first = (first_pos / 128) & ~1;
-    int tile_end = ((L - 1) / 128 + 2) & ~1;   // exclusive, even
     const int tiles_per_seq = kStreamPitch / 128;
-    if (tile_end > tiles_per_seq) tile_end = tiles_per_seq;
+    int tile_first = first_pos / 128;
+    int tile_end = (L - 1) / 128 + 1;          // exclusive
+    if ((tile_end - tile_first) & 1) {         // the CTA-pair GEMMs take an even number of tiles
+        if (tile_end < tiles_per_seq) ++tile_end;
+        else --tile_first;
+    }
     const int win_tiles = tile_end - tile_first;
 
     ForwardPlan plan;
@@ -287,9 +290,9 @@ int ppgs_stream_push(ppgs_stream* s, const void* features_dev, int frames, int f
     base.eps = c.layer_norm_eps;
     base.b_planes = planes;
     base.pair = 1;
-    base.win_size = win_tiles / 2;          // units of tile pairs
-    base.win_stride = tiles_per_seq / 2;
-    base.win_first = tile_first / 2;
+    base.win_size = win_tiles;
+    base.win_stride = tiles_per_seq;
+    base.win_first = tile_first;
     auto wmap = [&](TcWeight& w) -> const CUtensorMap& { return w.maps[planes - 1].bn128; };
 
     {
@@ -336,8 +339,7 @@ int ppgs_stream_push(ppgs_stream* s, const void* features_dev, int frames, int f
     }
     if (n_out > 0) {
         GemmParams p = base;
-        p.pair = 0;                       // the BN = 64 kernel is single-CTA: window in tiles
-        p.win_size = win_tiles; p.win_stride = tiles_per_seq; p.win_first = tile_first;
+        p.pair = 0;                       // the BN = 64 kernel is single-CTA
         p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = H / 64; p.a_planes = planes;
         p.N = O; p.O = O; p.scale = e->tc_conv_out.inv_scale; p.bias = e->conv_out_b;
         p.ppg = out_dev; p.T = out_capacity; p.softmax = softmax;
