@@ -273,6 +273,31 @@ int ppgs_stream_push(ppgs_stream* stream_state, const void* features_dev, int fr
                      int softmax, float* out_dev, int out_capacity, int* frames_out,
                      void* stream);
 
+/* ---- posteriorgram post-processing on the device (the step after the hot path) ----------- */
+
+/* ppgs.distance (ppgs/core.py:399-469): x, y = (phonemes, frames) fp32 with row strides;
+ * similarity_dev = (phonemes, phonemes) row-major similarity matrix (the reference's
+ * assets/balanced_similarity.pt) or NULL for normalize=False; reduction 0 'none' (out:
+ * frames floats), 1 'mean', 2 'sum' (out: one float). */
+int ppgs_ppg_distance(ppgs_engine* engine, const float* x_dev, const float* y_dev, int phonemes,
+                      int64_t frames, int64_t x_stride, int64_t y_stride,
+                      const float* similarity_dev, float exponent, int reduction, float* out_dev,
+                      void* stream);
+/* ppgs.interpolate (ppgs/core.py:475-496): (1 - w) x + w y over (rows, frames) contiguous;
+ * interp_dev = per-frame weights or NULL for the scalar. */
+int ppgs_ppg_interpolate(ppgs_engine* engine, const float* x_dev, const float* y_dev,
+                         const float* interp_dev, float interp_scalar, int64_t rows,
+                         int64_t frames, float* out_dev, void* stream);
+/* ppgs.edit.grid.sample (ppgs/edit/grid.py:13-50): ppg (phonemes, frames) contiguous, grid of
+ * float frame indices -> out (phonemes, grid_len). */
+int ppgs_ppg_grid_sample(ppgs_engine* engine, const float* ppg_dev, int phonemes, int64_t frames,
+                         const float* grid_dev, int64_t grid_len, float* out_dev, void* stream);
+/* ppgs.sparsify (ppgs/core.py:504-543): ppg (batch, phonemes, frames) contiguous; method 0
+ * 'constant', 1 'percentile' (threshold = q), 2 'topk' (threshold = k); renormalised with
+ * softmax(log(ppg + 1e-8)). */
+int ppgs_ppg_sparsify(ppgs_engine* engine, const float* ppg_dev, int batch, int phonemes,
+                      int64_t frames, int method, float threshold, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,8 @@ from .engine import Engine  # noqa: F401
 from .streaming import Streamer  # noqa: F401
 from .core import (  # noqa: F401
     from_audio, from_features, from_file, from_file_to_file, from_files_to_files,
-    from_dataloader, infer, resample, representation_file_extension)
+    from_dataloader, infer, resample, representation_file_extension,
+    distance, interpolate, sparsify)
+from . import edit  # noqa: F401
 
 __version__ = '0.1.0'

@@ -37,6 +37,11 @@ BUCKETS = 1
 RANDOM_SEED = 1234
 MAX_INFERENCE_FRAMES = float('inf')
 
+# PPG distance (defaults.py:93,214): the reference ships assets/balanced_similarity.pt; set
+# SIMILARITY_MATRIX_PATH to that file (or pass `similarity=` to ppgs_b200.distance)
+SIMILARITY_MATRIX_PATH = None
+SIMILARITY_EXPONENT = 1.2
+
 # Per-representation model kwargs (ppgs/load.py:35-50, ppgs/config/w2v2fb.py:7-10)
 MODEL_KWARGS = {
     'mel': {},

@@ -244,6 +244,147 @@ class _Writer:
 
 
 ###############################################################################
+# PPG distance, interpolation, sparsification (device kernels, csrc/postops.cu)
+###############################################################################
+
+
+def _post_engine(tensor):
+    return load.utility_engine(tensor.device.index if tensor.is_cuda else None)
+
+
+def _stream(engine):
+    import ctypes
+    return ctypes.c_void_p(torch.cuda.current_stream(engine.device).cuda_stream)
+
+
+def _f32(engine, tensor):
+    return tensor.to(engine.device, torch.float32).contiguous()
+
+
+def _back(result, like):
+    """Results live where the (first) input lives, like the reference's."""
+    return result if like.is_cuda else result.cpu()
+
+
+def distance(
+    ppgX: torch.Tensor,
+    ppgY: torch.Tensor,
+    reduction: str = 'mean',
+    normalize: bool = True,
+    exponent: float = None,
+    similarity: Optional[torch.Tensor] = None
+) -> torch.Tensor:
+    """Compute the pronunciation distance between two aligned PPGs
+    (ppgs/core.py:399-469): similarity-weighted Jensen-Shannon distance, one CUDA kernel.
+
+    ppgX, ppgY: shape=(len(ppgs.PHONEMES), frames); reduction in ['mean', 'none', 'sum'];
+    `similarity`: the (phonemes, phonemes) similarity matrix — default: the tensor stored
+    at config.SIMILARITY_MATRIX_PATH (the reference's assets/balanced_similarity.pt)."""
+    import ctypes
+    from . import _lib
+    if reduction is None:
+        reduction = 'none'
+    if reduction not in ('mean', 'none', 'sum'):
+        raise ValueError(f'Reduction method {reduction} not defined')
+    if exponent is None:
+        exponent = config.SIMILARITY_EXPONENT
+    engine = _post_engine(ppgX)
+    x, y = _f32(engine, ppgX), _f32(engine, ppgY)
+    if x.dim() != 2 or x.shape != y.shape:
+        raise ValueError('ppgX and ppgY must both have shape (phonemes, frames)')
+    weights = None
+    if normalize:
+        if similarity is None:
+            if config.SIMILARITY_MATRIX_PATH is None:
+                raise ValueError(
+                    'distance(normalize=True) needs the phoneme similarity matrix: pass '
+                    'similarity= or set ppgs_b200.config.SIMILARITY_MATRIX_PATH')
+            key = (str(config.SIMILARITY_MATRIX_PATH), engine.device.index)
+            if getattr(distance, 'key', None) != key:    # the cache of ppgs/core.py:436-442
+                distance.similarity_matrix = torch.load(config.SIMILARITY_MATRIX_PATH)
+                distance.key = key
+            similarity = distance.similarity_matrix
+        weights = _f32(engine, similarity)
+        if weights.shape != (x.shape[0], x.shape[0]):
+            raise ValueError('similarity must have shape (phonemes, phonemes)')
+    phonemes, frames = x.shape
+    out = torch.empty(frames if reduction == 'none' else 1, dtype=torch.float32, device=engine.device)
+    _lib.check(_lib.lib.ppgs_ppg_distance(
+        engine._handle, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()), phonemes,
+        frames, x.stride(0), y.stride(0),
+        ctypes.c_void_p(weights.data_ptr()) if weights is not None else None, float(exponent),
+        {'none': 0, 'mean': 1, 'sum': 2}[reduction], ctypes.c_void_p(out.data_ptr()),
+        _stream(engine)))
+    return _back(out if reduction == 'none' else out[0], ppgX)
+
+
+def interpolate(
+    ppgX: torch.Tensor,
+    ppgY: torch.Tensor,
+    interp: Union[float, torch.Tensor]
+) -> torch.Tensor:
+    """Linear interpolation (ppgs/core.py:475-496): (1 - interp) * ppgX + interp * ppgY,
+    interp a scalar or shape=(frames,)."""
+    import ctypes
+    from . import _lib
+    engine = _post_engine(ppgX)
+    x, y = _f32(engine, ppgX), _f32(engine, ppgY)
+    if x.shape != y.shape:
+        raise ValueError('ppgX and ppgY must have the same shape')
+    frames = x.shape[-1]
+    weights, scalar = None, 0.0
+    if torch.is_tensor(interp) and interp.dim() > 0:
+        if interp.shape != (frames,):
+            raise ValueError('interp must be a scalar or have shape (frames,)')
+        weights = _f32(engine, interp)
+    else:
+        scalar = float(interp)
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib.ppgs_ppg_interpolate(
+        engine._handle, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()),
+        ctypes.c_void_p(weights.data_ptr()) if weights is not None else None, scalar,
+        x.numel() // max(frames, 1), frames, ctypes.c_void_p(out.data_ptr()), _stream(engine)))
+    return _back(out, ppgX)
+
+
+def sparsify(
+    ppg: torch.Tensor,
+    method: str = 'percentile',
+    threshold: Union[float, int, torch.Tensor] = 0.85
+) -> torch.Tensor:
+    """Make phonetic posteriorgrams sparse (ppgs/core.py:504-543).
+
+    ppg: shape=(batch, len(ppgs.PHONEMES), frames); method in ['constant', 'percentile',
+    'topk'].  Like the reference, a 1-element *tensor* threshold with 'percentile' adds a
+    leading axis to the result (torch.quantile keeps the q axis); 'topk' treats every batch
+    row like the reference treats a single-row batch."""
+    import ctypes
+    from . import _lib
+    methods = {'constant': 0, 'percentile': 1, 'topk': 2}
+    if method not in methods:
+        raise ValueError(f'Sparsification method {method} not defined')
+    engine = _post_engine(ppg)
+    x = _f32(engine, ppg)
+    squeeze = x.dim() == 2
+    if squeeze:
+        x = x[None]
+    if x.dim() != 3:
+        raise ValueError('ppg must have shape (batch, phonemes, frames)')
+    extra_axis = method == 'percentile' and torch.is_tensor(threshold) and threshold.dim() > 0
+    value = float(threshold.reshape(-1)[0]) if torch.is_tensor(threshold) else float(threshold)
+    batch, phonemes, frames = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib.ppgs_ppg_sparsify(
+        engine._handle, ctypes.c_void_p(x.data_ptr()), batch, phonemes, frames, methods[method],
+        value, ctypes.c_void_p(out.data_ptr()), _stream(engine)))
+    if squeeze:
+        out = out[0]
+    if extra_axis:
+        out = out[None]
+    return _back(out, ppg)
+
+
+###############################################################################
 # Inference
 ###############################################################################
 

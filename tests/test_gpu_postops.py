@@ -1,0 +1,134 @@
+"""Device post-processing (csrc/postops.cu) through the public API against golden outputs of
+the reference's ppgs.distance / sparsify / interpolate / edit.grid.sample and the oracle.
+
+Tolerances: interpolate / grid sample bit-exact (products and sums are not fused);
+sparsify <= 1e-6 (logf / expf); distance <= 5e-4 absolute per frame on values of O(1) — the
+square root of near-zero fp32 divergences amplifies last-bit differences of logf (the
+reference's own fp32 result is as far from an fp64 evaluation)."""
+import pytest
+import torch
+
+from conftest import golden
+from oracle import postops_oracle as P
+
+pytestmark = pytest.mark.gpu
+
+CASES = ['postops_s0', 'postops_s1']
+DISTANCE_TOL = 5e-4
+
+
+@pytest.fixture(scope='module')
+def ppgs_b200():
+    import ppgs_b200
+    return ppgs_b200
+
+
+def tensors(name):
+    return {k: torch.from_numpy(v) for k, v in golden(name).items()}
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_distance_vs_reference_golden(ppgs_b200, name):
+    g = tensors(name)
+    x, y, similarity = g['x'], g['y'], g['similarity']
+    frames = x.shape[-1]
+    for device in ('cpu', 'cuda'):
+        a, b = x.to(device), y.to(device)
+        got = ppgs_b200.distance(a, b, reduction='none', similarity=similarity)
+        assert got.device.type == device and got.shape == (frames,)
+        assert (got.cpu() - g['distance_none']).abs().max() <= DISTANCE_TOL
+        got = ppgs_b200.distance(a, b, reduction='none', normalize=False)
+        assert (got.cpu() - g['distance_raw_none']).abs().max() <= DISTANCE_TOL
+    for reduction, scale in (('mean', 1), ('sum', frames)):
+        got = ppgs_b200.distance(x.cuda(), y.cuda(), reduction=reduction, similarity=similarity)
+        assert got.dim() == 0
+        assert abs(got.item() - g[f'distance_{reduction}'].item()) <= DISTANCE_TOL * scale
+        got = ppgs_b200.distance(x, y, reduction=reduction, normalize=False)
+        assert abs(got.item() - g[f'distance_raw_{reduction}'].item()) <= DISTANCE_TOL * scale
+    got = ppgs_b200.distance(x, y, exponent=2.0, similarity=similarity)
+    assert abs(got.item() - g['distance_exp2'].item()) <= DISTANCE_TOL
+    # fp64 ground truth: as close as the reference's own fp32 evaluation
+    truth = P.distance(x.double(), y.double(), 'none', similarity=similarity.double())
+    mine = ppgs_b200.distance(x, y, reduction='none', similarity=similarity).double()
+    assert (mine - truth).abs().max() <= DISTANCE_TOL
+    # identical PPGs are at distance ~0, strided inputs are accepted
+    assert ppgs_b200.distance(x, x, normalize=False).item() <= 1e-3
+    wide = torch.cat((x, y), dim=-1).cuda()
+    strided = ppgs_b200.distance(wide[:, :frames], wide[:, frames:], 'none', normalize=False)
+    assert (strided.cpu() - g['distance_raw_none']).abs().max() <= DISTANCE_TOL
+
+
+def test_distance_errors_and_config_path(ppgs_b200, tmp_path):
+    g = tensors('postops_s1')
+    with pytest.raises(ValueError, match='not defined'):
+        ppgs_b200.distance(g['x'], g['y'], reduction='median', normalize=False)
+    with pytest.raises(ValueError, match='similarity'):
+        ppgs_b200.distance(g['x'], g['y'])
+    path = tmp_path / 'similarity.pt'
+    torch.save(g['similarity'], path)
+    ppgs_b200.config.SIMILARITY_MATRIX_PATH = path       # the reference's asset location
+    try:
+        got = ppgs_b200.distance(g['x'], g['y'])
+    finally:
+        ppgs_b200.config.SIMILARITY_MATRIX_PATH = None
+    assert abs(got.item() - g['distance_mean'].item()) <= DISTANCE_TOL
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_sparsify_vs_reference_golden(ppgs_b200, name):
+    g = tensors(name)
+    batch = g['batch']
+    cases = [
+        (('percentile', torch.tensor([0.85])), g['sparse_percentile']),   # leading q axis kept
+        (('percentile', torch.tensor([0.5])), g['sparse_percentile50']),
+        (('percentile', 0.85), g['sparse_percentile'][0]),
+        (('constant', torch.tensor([0.1])), g['sparse_constant']),
+        (('constant', 0.1), g['sparse_constant']),
+        (('topk', 3), g['sparse_topk']),
+    ]
+    for (method, threshold), expected in cases:
+        for device in ('cpu', 'cuda'):
+            got = ppgs_b200.sparsify(batch.to(device), method, threshold)
+            assert got.device.type == device and got.shape == expected.shape
+            assert (got.cpu() - expected).abs().max() <= 1e-6
+            assert ((got.cpu() > 1e-6) == (expected > 1e-6)).all()   # same support
+    # batch > 1: every row like a single-row batch
+    many = P.random_ppg(3, 19, batch=5)
+    got = ppgs_b200.sparsify(many.cuda(), 'topk', 4).cpu()
+    assert (got - P.sparsify(many, 'topk', 4)).abs().max() <= 1e-6
+    got = ppgs_b200.sparsify(many.cuda(), 'percentile', 0.9).cpu()
+    assert (got - P.sparsify(many, 'percentile', 0.9)).abs().max() <= 1e-6
+    with pytest.raises(ValueError, match='not defined'):
+        ppgs_b200.sparsify(many, 'median')
+    with pytest.raises(ValueError, match='range'):
+        ppgs_b200.sparsify(many, 'percentile', 1.5)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_interpolate_and_grid_sample_vs_reference_golden(ppgs_b200, name):
+    g = tensors(name)
+    x, y = g['x'], g['y']
+    assert torch.equal(ppgs_b200.interpolate(x.cuda(), y.cuda(), g['interp']).cpu(),
+                       g['interpolate_vector'])
+    assert torch.equal(ppgs_b200.interpolate(x, y, 0.3), g['interpolate_scalar'])
+    assert torch.equal(ppgs_b200.edit.grid.sample(x.cuda(), g['grid'].cuda()).cpu(), g['grid_sample'])
+    assert torch.equal(ppgs_b200.edit.grid.sample(x, g['grid']), g['grid_sample'])
+    # time-stretch to twice the length and back keeps every original frame
+    grid = ppgs_b200.edit.grid.constant(x, 0.5)
+    stretched = ppgs_b200.edit.grid.sample(x, grid)
+    assert stretched.shape == (40, round(x.shape[-1] / 0.5 + 1e-4))
+    assert torch.equal(stretched, P.grid_sample(x, grid))
+
+
+def test_postops_follow_the_hot_path_on_device(ppgs_b200):
+    """from_audio -> sparsify / distance without leaving the GPU."""
+    from oracle import ppg_oracle as O
+    sd = O.random_state_dict(0, peaky=True)
+    engine = ppgs_b200.Engine(0).load_state_dict(sd)
+    audio = O.synthetic_audio(2, 32000, 4)
+    ppg = engine.from_audio(audio.cuda())
+    reference = O.from_audio(sd, audio)
+    sparse = ppgs_b200.sparsify(ppg, 'topk', 2)
+    assert sparse.is_cuda and (sparse.cpu() - P.sparsify(reference, 'topk', 2)).abs().max() <= 2e-4
+    d = ppgs_b200.distance(ppg[0], ppg[1], normalize=False)
+    assert d.is_cuda and abs(d.item() - P.distance(reference[0], reference[1], normalize=False).item()) <= 2e-3
