@@ -28,7 +28,8 @@ constexpr int kMaxBandWeights = 2048;
 struct MelSmem {
     alignas(16) float audio[kTileSamples];
     alignas(16) float window[kNfft];
-    alignas(16) cf tw512[kHalf];
+    alignas(16) cf tw_pass1[7 * 8];     // [r - 1][k]      = tw512[8 k r]
+    alignas(16) cf tw_pass2[7 * 64];    // [r - 1][k]      = tw512[k r]
     alignas(16) cf tw1024[kBins + 3];
     alignas(16) cf zb[kMelWarps][kZPad];
     alignas(16) float band_weights[kMaxBandWeights];
@@ -105,8 +106,8 @@ __device__ __forceinline__ void frame_to_mel(const float* a, MelSmem& s, cf* zb,
         v0[r] = zb[zpad(lane + 64 * r)];
         v1[r] = zb[zpad(lane + 32 + 64 * r)];
     }
-    stockham_twiddle<1>(v0, lane, s.tw512);
-    stockham_twiddle<1>(v1, lane + 32, s.tw512);
+    stockham_twiddle_table<1>(v0, lane, s.tw_pass1);
+    stockham_twiddle_table<1>(v1, lane + 32, s.tw_pass1);
     dft8(v0);
     dft8(v1);
     __syncwarp();
@@ -125,8 +126,8 @@ __device__ __forceinline__ void frame_to_mel(const float* a, MelSmem& s, cf* zb,
         v0[r] = zb[zpad(lane + 64 * r)];
         v1[r] = zb[zpad(lane + 32 + 64 * r)];
     }
-    stockham_twiddle<2>(v0, lane, s.tw512);
-    stockham_twiddle<2>(v1, lane + 32, s.tw512);
+    stockham_twiddle_table<2>(v0, lane, s.tw_pass2);
+    stockham_twiddle_table<2>(v1, lane + 32, s.tw_pass2);
     dft8(v0);
     dft8(v1);
     __syncwarp();
@@ -176,7 +177,14 @@ mel_kernel(const float* __restrict__ audio, int64_t samples, int64_t stride, int
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int i = tid; i < kNfft; i += kMelThreads) s.window[i] = t.window[i];
-    for (int i = tid; i < kHalf; i += kMelThreads) s.tw512[i] = {t.tw512[i].x, t.tw512[i].y};
+    for (int i = tid; i < 7 * 8; i += kMelThreads) {
+        const int r = i / 8 + 1, k = i & 7;
+        s.tw_pass1[i] = {t.tw512[k * r * 8].x, t.tw512[k * r * 8].y};
+    }
+    for (int i = tid; i < 7 * 64; i += kMelThreads) {
+        const int r = i / 64 + 1, k = i & 63;
+        s.tw_pass2[i] = {t.tw512[k * r].x, t.tw512[k * r].y};
+    }
     for (int i = tid; i < kBins; i += kMelThreads) s.tw1024[i] = {t.tw1024[i].x, t.tw1024[i].y};
     for (int i = tid; i < kMels * 3; i += kMelThreads) s.band_meta[i] = t.band_meta[i];
     for (int i = tid; i < t.band_weight_count; i += kMelThreads)

@@ -31,13 +31,19 @@ constexpr int kHalf = 512;          // complex FFT length
 constexpr int kBins = 513;
 constexpr int kMels = 80;
 constexpr int kReflect = (kNfft - kHop) / 2;   // 432
-constexpr int kZPad = kHalf + kHalf / 8;       // padded complex buffer length (576)
+constexpr int kZPad = kHalf;                   // complex FFT buffer length (swizzled, no padding)
 
 struct cf {
     float x, y;
 };
 
-PPGS_HD int zpad(int i) { return i + (i >> 3); }
+// Physical slot of complex element i in the shared FFT buffer: an XOR swizzle inside aligned
+// blocks of 16 elements (8-byte elements, 16 "double banks" per half-warp wavefront).  Every
+// access pattern of the transform is then conflict-free per half-warp: consecutive elements
+// (a permutation of one block), the stride-8 scatter of pass 0 (index 8 l + r: the low three
+// bits are XORed with l / 2, bit 3 with l >> 3) and the two-groups-64-apart scatter of pass 1
+// (bit 3 is XORed with bit 6 of the index, which separates the groups).
+PPGS_HD int zpad(int i) { return i ^ (((i >> 4) & 7) | (((i >> 6) & 1) << 3)); }
 
 PPGS_HD cf cadd(cf a, cf b) { return {a.x + b.x, a.y + b.y}; }
 PPGS_HD cf csub(cf a, cf b) { return {a.x - b.x, a.y - b.y}; }
@@ -80,6 +86,18 @@ PPGS_HD void stockham_twiddle(cf* v, int j, const cf* tw512) {
     const int k = j & (Ns - 1);
 #pragma unroll
     for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], tw512[k * r * step]);
+}
+
+// Same twiddles from per-pass tables laid out [r - 1][k] (k = j mod Ns), so that the lanes
+// of a warp read consecutive entries (pass 2) or eight consecutive entries broadcast (pass 1)
+// instead of the strided tw512[k r step]: table[(r - 1) Ns + k] == tw512[k r step].
+template <int PASS>
+PPGS_HD void stockham_twiddle_table(cf* v, int j, const cf* table) {
+    if (PASS == 0) return;
+    constexpr int Ns = (PASS == 1) ? 8 : 64;
+    const int k = j & (Ns - 1);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], table[(r - 1) * Ns + k]);
 }
 
 template <int PASS>
