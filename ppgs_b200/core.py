@@ -118,16 +118,22 @@ def from_files_to_files(
     representation: str = config.REPRESENTATION,
     checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
     num_workers: int = 0,
-    gpu: Optional[int] = None,
+    gpu: Optional[Union[int, List[int]]] = None,
     max_frames: int = config.MAX_INFERENCE_FRAMES,
     legacy_mode: bool = False
 ) -> None:
     """Infer ppgs from audio files and save to torch tensor files
     (ppgs/core.py:207-272).  `num_workers` == 0: one file per call like the
     reference; > 0: frame-budget batches from `data.loader` (reader threads) and
-    `num_workers // 2` writer threads."""
+    `num_workers // 2` writer threads.  `gpu` may be a list of CUDA ordinals: the
+    batch list is dealt round-robin to one pipeline per GPU (BASELINE config 5 from
+    a single process; `parallel.from_files_to_files` is the torchrun form)."""
     if len(audio_files) != len(output_files):
         raise ValueError('audio_files and output_files must have equal lengths')
+    if isinstance(gpu, (list, tuple)):
+        return _from_files_to_files_sharded(
+            audio_files, output_files, representation, checkpoint, num_workers, list(gpu),
+            max_frames, legacy_mode)
     if num_workers == 0:
         for audio_file, output_file in zip(audio_files, output_files):
             from_file_to_file(
@@ -150,6 +156,62 @@ def from_files_to_files(
         save_workers=num_workers // 2, gpu=gpu, legacy_mode=legacy_mode)
 
 
+def _from_files_to_files_sharded(audio_files, output_files, representation, checkpoint,
+                                 num_workers, gpus, max_frames, legacy_mode):
+    """One pipeline thread per GPU over batches i::len(gpus) of the SAME deterministic
+    batch list (so every posterior equals the single-GPU run).  The checkpoint is read
+    once; the other GPUs adopt the first engine's packed weight blob through one
+    device-to-device copy each (the single-process form of the NCCL broadcast)."""
+    if not gpus:
+        raise ValueError('gpu: empty list of devices')
+    workers = max(num_workers // 2, 1)
+    mapping = dict(zip(audio_files, output_files))
+    first = load.model(checkpoint, representation, gpus[0])
+    engines = [first]
+    for gpu in gpus[1:]:
+        key = load.cache_key(representation, checkpoint, gpu)
+        with load._lock:
+            engine = load._engines.get(key)
+        if engine is None or engine is first:
+            from .engine import Engine
+            engine = Engine(gpu, is_causal=bool(first.cfg.is_causal),
+                            **load.model_kwargs(representation))
+            engine.blob().copy_(first.blob())
+            torch.cuda.synchronize(engine.device)
+            engine.adopt_blob()
+            engine.precision = first.precision
+            if gpu != gpus[0]:
+                with load._lock:
+                    load._engines[key] = engine
+        engines.append(engine)
+    loaders = []
+    for rank in range(len(gpus)):
+        loaders.append(data.loader(
+            audio_files, num_workers=workers, max_frames=max_frames, shard=(rank, len(gpus)),
+            dataset=loaders[0].dataset if loaders else None))
+    errors = []
+
+    def run(engine, dataloader):
+        try:
+            with torch.cuda.device(engine.device):
+                if _native_pipeline(dataloader, representation):
+                    dataloader.run_native(engine, mapping, workers, legacy_mode)
+                else:
+                    from_dataloader(dataloader, mapping, representation, checkpoint,
+                                    save_workers=workers, gpu=engine.device.index,
+                                    legacy_mode=legacy_mode, engine=engine)
+        except Exception as error:      # surfaced after every shard has stopped
+            errors.append(error)
+
+    threads = [threading.Thread(target=run, args=pair) for pair in zip(engines, loaders)]
+    for thread in threads:
+        thread.start()
+    for thread in threads:
+        thread.join()
+    if errors:
+        raise errors[0]
+
+
 ###############################################################################
 # Batched file inference
 ###############################################################################
@@ -164,14 +226,16 @@ def from_dataloader(
     checkpoint: Union[str, bytes, os.PathLike] = None,
     save_workers: int = 1,
     gpu: Optional[int] = None,
-    legacy_mode: bool = False
+    legacy_mode: bool = False,
+    engine=None
 ) -> None:
     """Infer ppgs from a dataloader yielding (audio, length, audio_filename)
     batches (ppgs/core.py:280-391).  The reference pickles every result to a
     spawn Pool; here writer *threads* take (pinned host tensor, filename,
     frames) items from a bounded queue, so the D2H copy of batch i overlaps the
     kernels of batch i+1."""
-    engine = load.model(checkpoint, representation, gpu)
+    if engine is None:
+        engine = load.model(checkpoint, representation, gpu)
     writer = _Writer(save_workers)
     try:
         for audios, lengths, audio_files in dataloader:

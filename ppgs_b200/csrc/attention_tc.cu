@@ -538,11 +538,10 @@ static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int 
                               (uint64_t)rows * 3 * H, 128, planes));
     PPGS_CHECK(make_plane_map(&map_v, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
                               (uint64_t)rows * 3 * H, 64, planes));
-    static bool attr_tc = false;
-    if (!attr_tc) {
+    static PerDeviceOnce attr_tc;
+    if (attr_tc.first(e->device)) {
         PPGS_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Shape::kSmem));
-        attr_tc = true;
     }
     AttnParams p;
     p.seqs = seqs_dev;

@@ -18,6 +18,18 @@ constexpr int kMelChannels = 80;   // ppgs.NUM_MELS
 
 void set_error(const char* fmt, ...);
 
+// Function attributes (opt-in dynamic shared memory) are per DEVICE: one flag per device
+// and kernel instantiation, so a process driving several GPUs configures each of them.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first(int device) {
+        if (device < 0 || device >= 64) return true;
+        const bool was = done[device];
+        done[device] = true;
+        return !was;
+    }
+};
+
 #define PPGS_CUDA(expr)                                                          \
     do {                                                                         \
         cudaError_t err__ = (expr);                                              \

@@ -416,11 +416,10 @@ int launch_ffn_fused(ppgs_engine* e, const CUtensorMap& map_x, const CUtensorMap
         set_error("ffn_fused: needs an even number of row tiles");
         return PPGS_E_INVALID;
     }
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first(e->device)) {
         PPGS_CUDA(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kFfnSmem));
-        attr = true;
     }
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attrs[1];

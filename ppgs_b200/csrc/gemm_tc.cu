@@ -671,12 +671,11 @@ static int launch_one(ppgs_engine* e, const char* name, const CUtensorMap& map_a
                       const CUtensorMap& map_b, const CUtensorMap& map_out, const GemmParams& p,
                       cudaStream_t stream) {
     using Shape = GemmShape<BN, PAIR>;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first(e->device)) {
         PPGS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, PAIR>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Shape::kSmemBytes));
-        attr = true;
     }
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attrs[1];

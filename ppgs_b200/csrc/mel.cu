@@ -360,11 +360,10 @@ int launch_mel(ppgs_engine* e, const float* audio, int batch, int64_t samples, i
         set_error("too many mel tiles");
         return PPGS_E_TOO_LARGE;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first(e->device)) {
         PPGS_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(MelSmem)));
-        attr_set = true;
     }
     // bulk copies need 16-byte aligned sources: base, row stride and tile offset
     // (160*4 and 432*4 are multiples of 16).

@@ -421,11 +421,10 @@ static int launch_attention(ppgs_engine* e, const float* qkv, const ForwardPlan&
                             const SeqInfo* seqs, float* out, cudaStream_t stream) {
     const int H = e->cfg.hidden_channels;
     const size_t smem = (size_t)(32 * D + 32 * (D + 1) + 32 * D) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first(e->device)) {
         PPGS_CUDA(cudaFuncSetAttribute(attention_fp32_kernel<D>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
     }
     dim3 grid(plan.max_pitch / 32, e->cfg.num_heads, (unsigned)plan.seqs.size());
     {

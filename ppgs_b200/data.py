@@ -102,8 +102,9 @@ class Loader:
     `num_workers` reader threads decode files; up to `prefetch` batches ahead."""
 
     def __init__(self, audio_files, num_workers=0, max_frames=config.MAX_INFERENCE_FRAMES,
-                 prefetch=2, shard=None):
-        self.dataset = Metadata(audio_files, max_frames)
+                 prefetch=2, shard=None, dataset=None):
+        # `dataset`: reuse the header probe of another shard's loader
+        self.dataset = dataset if dataset is not None else Metadata(audio_files, max_frames)
         self.batches = frame_budget_batches(self.dataset.lengths, max_frames)
         if shard is not None:
             rank, world = shard
@@ -147,10 +148,10 @@ class Loader:
 
 
 def loader(audio_files, features=('audio', 'length', 'audio_file'), num_workers=0,
-           max_frames=config.MAX_INFERENCE_FRAMES, shard=None):
+           max_frames=config.MAX_INFERENCE_FRAMES, shard=None, dataset=None):
     """ppgs.data.loader for the inference feature set."""
     if list(features) != ['audio', 'length', 'audio_file']:
         raise ValueError(
             "ppgs_b200.data.loader serves the inference path only: "
             "features must be ['audio', 'length', 'audio_file']")
-    return Loader(audio_files, num_workers, max_frames, shard=shard)
+    return Loader(audio_files, num_workers, max_frames, shard=shard, dataset=dataset)

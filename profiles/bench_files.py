@@ -2,7 +2,7 @@
 16 kHz int16 WAVE files (tmpfs when available), native pipeline (ppgs_files_to_files) vs the
 Python reader / writer threads on the same batches.  Prints one JSON line per arm.
 
-    python profiles/bench_files.py [files=2048] [workers=16]
+    python profiles/bench_files.py [files=2048] [workers=16] [gpus=1]
 """
 import json
 import os
@@ -21,6 +21,8 @@ from oracle import ppg_oracle as O  # noqa: E402
 
 files = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 workers = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+gpus = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+device = 0 if gpus == 1 else list(range(gpus))
 root = tempfile.mkdtemp(dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
 try:
     rng = np.random.default_rng(0)
@@ -40,18 +42,18 @@ try:
     engine = ppgs_b200.load.model(checkpoint, 'mel', 0)
     for arm in ('native', 'python'):
         os.environ['PPGS_B200_NATIVE_FILES'] = '1' if arm == 'native' else '0'
-        ppgs_b200.from_files_to_files(audio_files[:128], output_files[:128], checkpoint=checkpoint,
-                                      num_workers=workers, gpu=0, max_frames=64000)   # warm-up
+        ppgs_b200.from_files_to_files(audio_files[:128 * gpus], output_files[:128 * gpus], checkpoint=checkpoint,
+                                      num_workers=workers, gpu=device, max_frames=64000)   # warm-up
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ppgs_b200.from_files_to_files(audio_files, output_files, checkpoint=checkpoint,
-                                      num_workers=workers, gpu=0, max_frames=64000)
+                                      num_workers=workers, gpu=device, max_frames=64000)
         torch.cuda.synchronize()
         seconds = time.perf_counter() - t0
         sample = torch.load(output_files[-1])
         assert sample.shape == (40, 1000)
         print(json.dumps({
-            'arm': arm, 'files': files, 'workers': workers, 'seconds': round(seconds, 3),
+            'arm': arm, 'gpus': gpus, 'files': files, 'workers': workers, 'seconds': round(seconds, 3),
             'files_per_sec': round(files / seconds, 1),
             'ppg_frames_per_sec': round(files * 1000 / seconds),
             'audio_hours_per_hour': round(files * 10 / seconds),

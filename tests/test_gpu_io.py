@@ -189,3 +189,25 @@ def test_non_native_files_take_the_python_path(ppgs_b200, tmp_path):
     expected = O.from_audio(sd, torch.stack([resampled, b[None]]))
     for out, row in zip(outs, expected):
         assert (torch.load(out) - row).abs().max() <= 1e-4
+
+
+def test_files_sharded_over_a_gpu_list(ppgs_b200, tmp_path):
+    """`gpu=[...]`: one pipeline thread per listed device over batches i::n of the same batch
+    list (here the same device twice = two engines sharing a blob copy): results equal the
+    single-pipeline run bit for bit."""
+    sd = O.random_state_dict(8)
+    checkpoint = tmp_path / 'ckpt.pt'
+    torch.save({'model': sd}, checkpoint)
+    rng = np.random.default_rng(1)
+    lengths = [int(n) for n in rng.integers(3000, 40000, 30)]
+    files = make_files(tmp_path, lengths)
+    single = [str(tmp_path / f'{i}-single.pt') for i in range(len(files))]
+    sharded = [str(tmp_path / f'{i}-sharded.pt') for i in range(len(files))]
+    ppgs_b200.from_files_to_files(files, single, checkpoint=checkpoint, num_workers=4, gpu=0,
+                                  max_frames=500)
+    devices = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    ppgs_b200.from_files_to_files(files, sharded, checkpoint=checkpoint, num_workers=4, gpu=devices,
+                                  max_frames=500)
+    for a, b, n in zip(single, sharded, lengths):
+        x, y = torch.load(a), torch.load(b)
+        assert x.shape == (40, n // 160) and torch.equal(x, y)
