@@ -67,10 +67,9 @@ def ncu_traffic(kernel):
     None when the kernel has no capture."""
     path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if not os.path.exists(path):
-        return None
+        return None, None
     entry = json.load(open(path)).get('kernels', {}).get(kernel)
-    return None if entry is None else {'bytes_per_launch': entry['dram_bytes'],
-                                       'source': entry['source']}
+    return (None, None) if entry is None else (entry['dram_bytes'], entry['source'])
 
 
 class ClockSampler:
@@ -175,6 +174,120 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_other_workload(args):
+    """BASELINE configs[2] / configs[3] on one GPU, same JSON keys (not the headline line)."""
+    import torch
+    import ppgs_b200
+    from oracle import ppg_oracle as O   # synthetic inputs only
+    steps, warmup = max(args.steps, 1), max(args.warmup, 3)
+    device = torch.device('cuda', 0)
+    torch.cuda.set_device(device)
+    peaks = load_peaks()
+
+    def timed(fn, n):
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        start.record()
+        for i in range(n):
+            fn(i)
+        stop.record()
+        torch.cuda.synchronize(device)
+        return start.elapsed_time(stop)
+
+    if args.workload == 'w2v2fb':
+        from oracle import w2v2_oracle as W
+        batch = 32
+        front = ppgs_b200.Engine(0).load_state_dict(O.random_state_dict(0))
+        front.load_w2v2_state_dict(W.random_state_dict(0))
+        head = ppgs_b200.Engine(0, input_channels=768, hidden_channels=512).load_state_dict(
+            O.random_state_dict(1, input_channels=768, hidden_channels=512, peaky=True))
+        rotate = 4
+        host = [O.synthetic_audio(batch, SAMPLES, 200 + i).squeeze(1).pin_memory() for i in range(rotate)]
+        dev = [h.to(device) for h in host]
+        lengths = torch.full((batch,), FRAMES)
+        out_host = torch.empty(batch, O_OUT, FRAMES, dtype=torch.float32).pin_memory()
+
+        def device_step(i):
+            return head.transformer(front.w2v2fb(dev[i % rotate]), lengths)
+
+        def host_step(i):
+            audio = host[i % rotate].to(device, non_blocking=True)
+            out_host.copy_(head.transformer(front.w2v2fb(audio), lengths), non_blocking=True)
+
+        frames_per_step, flops_per_frame = batch * FRAMES, 198.6e6
+        workload = 'w2v2fb (wav2vec2-base front-end + hidden-512 PPG Transformer), batch=32x10s synthetic 16 kHz'
+        engines = (front, head)
+    else:
+        streams, chunk, pushes = 256, 160, 3
+        engine = ppgs_b200.Engine(0, is_causal=True).load_state_dict(O.random_state_dict(2, peaky=True))
+        engine.precision = 'f16x2'
+        features = O.mel_from_audios(O.synthetic_audio(8, chunk * pushes * 160, 0))
+        features = features.repeat(streams // 8, 1, 1).contiguous()
+        host = [features[..., i * chunk:(i + 1) * chunk].contiguous().pin_memory() for i in range(pushes)]
+        dev = [h.to(device) for h in host]
+        streamer = ppgs_b200.Streamer(engine, streams)
+        out_host = torch.empty(streams, O_OUT, chunk + 4, dtype=torch.float32).pin_memory()
+
+        def device_step(i):   # one step = one session: three 160-frame pushes with state
+            streamer.reset()
+            for j in range(pushes):
+                streamer.push(dev[j], final=j + 1 == pushes)
+
+        def host_step(i):
+            streamer.reset()
+            for j in range(pushes):
+                out = streamer.push(host[j].to(device, non_blocking=True), final=j + 1 == pushes)
+                out_host[..., :out.shape[-1]].copy_(out, non_blocking=True)
+
+        frames_per_step = streams * chunk * pushes
+        # dense 13.414 MFLOP per computed frame + causal attention over the growing context
+        attention = sum(LAYERS * 4 * H * (t + 1) for t in range(chunk * pushes)) / (chunk * pushes)
+        flops_per_frame = DENSE_PER_FRAME + attention
+        workload = ('config/causal_transformer.py, stateful streaming: 256 sessions x three 160-frame '
+                    'pushes (480-frame context), mel features in')
+        engines = (engine,)
+
+    for i in range(warmup):
+        device_step(i)
+        host_step(i)
+    sampler = ClockSampler(0)
+    sampler.start()
+    before = sum(e.launches for e in engines)
+    device_ms = timed(device_step, steps)
+    launches = sum(e.launches for e in engines) - before
+    e2e_ms = timed(host_step, steps)
+    clocks = sampler.stop()
+    for e in engines:
+        e.set_profiling(True)
+    timed(device_step, steps)
+    stats = {}
+    for e in engines:
+        for k, (ms, n) in e.kernel_stats().items():
+            stats[k] = round(stats.get(k, 0.0) + ms / steps, 4)
+        e.set_profiling(False)
+    value = frames_per_step / (device_ms / steps / 1e3)
+    tflops = value * flops_per_frame / 1e12
+    in_bytes = sum(h.numel() * h.element_size() for h in host) if args.workload != 'w2v2fb' \
+        else host[0].numel() * 4
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': steps, 'warmup': warmup,
+        'ms_per_step': device_ms / steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f16x2-split tcgen05 MMA, f32 accumulate', 'data': 'synthetic',
+        'config': {'workload': workload, 'l2': 'rotating inputs; activation traffic per step exceeds L2'},
+        'e2e': {'value': frames_per_step / (e2e_ms / steps / 1e3), 'unit': UNIT,
+                'ms_per_step': e2e_ms / steps, 'h2d_bytes_per_step': in_bytes,
+                'd2h_bytes_per_step': frames_per_step * O_OUT * 4,
+                'api': 'Engine / Streamer public API, pinned host tensors in, pinned host tensor out'},
+        'gpu_launches': launches, 'clocks': clocks,
+        'roofline': {'kernel': 'whole step', 'bound': 'tensor', 'achieved': tflops,
+                     'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s',
+                     'frac': tflops / peaks['tflops_sustained'], 'traffic': None,
+                     'algorithmic_flops_per_frame': flops_per_frame, 'kernels_ms_per_step': stats},
+        'cpu_baseline': None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
@@ -183,6 +296,9 @@ def main():
     parser.add_argument('--impl', default='ppgs_b200', choices=['ppgs_b200', 'reference'])
     parser.add_argument('--precision', default=os.environ.get('PPGS_B200_PRECISION', 'auto'))
     parser.add_argument('--no-cpu-baseline', action='store_true')
+    parser.add_argument('--workload', default='mel', choices=['mel', 'w2v2fb', 'causal-stream'],
+                        help="mel = BASELINE configs[1] (the headline; default); w2v2fb = configs[2]; "
+                             "causal-stream = configs[3] with state (extra lines, N=1 only)")
     args = parser.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -191,6 +307,10 @@ def main():
 
     if args.impl == 'reference':
         run_reference(args, rank)
+        return
+    if args.workload != 'mel':
+        if rank == 0:
+            run_other_workload(args)
         return
 
     import torch
@@ -319,8 +439,10 @@ def main():
         'ffn': 2 * FFN_FLOPS_PER_LAUNCH_HALF * computed, 'qkv': 2 * 3 * H * H * computed,
         'out_proj': 2 * H * H * computed, 'conv_in': 2 * KSIZE * C_IN * H * computed,
         'conv_out': 2 * KSIZE * H * O_OUT * computed, 'attention': BATCH * ATTN_PER_UTT / LAYERS}
+    traffic, traffic_source = ncu_traffic(name)
     roofline = {'kernel': name, 'share_of_step': kernel_ms / total_kernel_ms,
-                'ms_per_launch': per_launch_ms, 'traffic': ncu_traffic(name)}
+                'ms_per_launch': per_launch_ms, 'traffic': traffic, 'traffic_unit': 'bytes per launch',
+                'traffic_source': traffic_source}
     key = next((k for k in sorted(flops_by_kernel, key=len, reverse=True) if k in name), None)
     if key is not None:
         achieved = flops_by_kernel[key] / (per_launch_ms * 1e-3) / 1e12
@@ -329,7 +451,9 @@ def main():
                          'frac': achieved / peak,
                          'peak_source': f"{peaks['source']} bf16 cuBLAS sustained (kernel timed "
                                         'inside a long step)',
-                         'algorithmic_flops_per_launch': flops_by_kernel[key]})
+                         'algorithmic_flops_per_launch': flops_by_kernel[key],
+                         'mma_passes_per_algorithmic_mma': 3 if precision == 'f16x2' else 1,
+                         'executed_frac': achieved / peak * (3 if precision == 'f16x2' else 1)})
     else:   # mel front-end
         bytes_per_launch = BATCH * FRAMES * 800
         achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
