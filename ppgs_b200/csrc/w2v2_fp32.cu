@@ -89,23 +89,81 @@ groupnorm_gelu_kernel(float* __restrict__ x, int T0, int64_t P0, const double* _
     }
 }
 
-// same, but the activation leaves as split-fp16 planes [2][B*P0][512] (tensor-core convs)
+// ---- tensor-core path: conv0 is 10 MACs per output, so the 2.1 GB fp32 activation of a
+// 32 x 10 s batch is never materialised: the statistics pass and the normalise + GELU +
+// split pass both recompute it from the audio (same fmaf chain as conv0_kernel, same
+// accumulation order as groupnorm_stats_kernel -> same values), thread = channel.
+__device__ __forceinline__ void conv0_stage(const float* __restrict__ audio, int64_t stride, int samples, int b,
+                                            int t0, int frames, float* xs) {
+    for (int i = threadIdx.x; i < frames * 5 + 5; i += blockDim.x) {
+        const int64_t pos = (int64_t)t0 * 5 + i - kW2v2Pad;
+        xs[i] = (pos >= 0 && pos < samples) ? audio[(int64_t)b * stride + pos] : 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(512)
-groupnorm_gelu_planes_kernel(const float* __restrict__ x, int T0, int64_t P0, int64_t plane_stride,
-                             const double* __restrict__ sums, const float* __restrict__ gamma,
-                             const float* __restrict__ beta, float eps, __half* __restrict__ planes) {
-    const int b = blockIdx.y, c = threadIdx.x;
-    const double mean = sums[((int64_t)b * kConvDim + c) * 2] / T0;
-    const double var = sums[((int64_t)b * kConvDim + c) * 2 + 1] / T0 - mean * mean;
-    const float m = (float)mean, r = (float)(1.0 / sqrt(var + (double)eps));
-    const float g = gamma[c], be = beta[c];
-    const int t_begin = blockIdx.x * 64, t_end = (int)min((int64_t)t_begin + 64, P0);
+conv0_stats_kernel(const float* __restrict__ audio, int64_t stride, int samples, int T0,
+                   const float* __restrict__ w /* [512][10] */, double* __restrict__ sums) {
+    __shared__ float xs[256 * 5 + 5];
+    const int b = blockIdx.y, c = threadIdx.x, t_begin = blockIdx.x * 256;
+    const int frames = min(256, T0 - t_begin);
+    conv0_stage(audio, stride, samples, b, t_begin, frames, xs);
+    float wc[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) wc[j] = w[c * 10 + j];
+    __syncthreads();
+    float s = 0.f, q = 0.f;
+    for (int tt = 0; tt < frames; ++tt) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) v = fmaf(wc[j], xs[tt * 5 + j], v);
+        s += v;
+        q = fmaf(v, v, q);
+    }
+    atomicAdd(&sums[((int64_t)b * kConvDim + c) * 2], (double)s);
+    atomicAdd(&sums[((int64_t)b * kConvDim + c) * 2 + 1], (double)q);
+}
+
+// thread = channel pair (half2 stores: 128 contiguous bytes per warp, row and plane)
+__global__ void __launch_bounds__(256)
+conv0_groupnorm_gelu_planes_kernel(const float* __restrict__ audio, int64_t stride, int samples, int T0,
+                                   int64_t P0, int64_t plane_stride, const float* __restrict__ w,
+                                   const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, __half* __restrict__ planes) {
+    __shared__ float xs[64 * 5 + 5];
+    const int b = blockIdx.y, c = 2 * threadIdx.x, t_begin = blockIdx.x * 64;
+    const int t_end = (int)min((int64_t)t_begin + 64, P0);
+    conv0_stage(audio, stride, samples, b, t_begin, 64, xs);
+    float wc[2][10], m[2], r[2], g[2], be[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) wc[h][j] = w[(c + h) * 10 + j];
+        const double mean = sums[((int64_t)b * kConvDim + c + h) * 2] / T0;
+        const double var = sums[((int64_t)b * kConvDim + c + h) * 2 + 1] / T0 - mean * mean;
+        m[h] = (float)mean;
+        r[h] = (float)(1.0 / sqrt(var + (double)eps));
+        g[h] = gamma[c + h];
+        be[h] = beta[c + h];
+    }
+    __syncthreads();
+#pragma unroll 2
     for (int t = t_begin; t < t_end; ++t) {   // rows [T0, P0) -> 0: finite inputs for the junk rows
         const int64_t at = ((int64_t)b * P0 + t) * kConvDim + c;
-        __half hi = __float2half_rn(0.f), lo = hi;
-        if (t < T0) tc::split_f16(gelu_exact((x[at] - m) * r * g + be), hi, lo);
-        planes[at] = hi;
-        planes[plane_stride + at] = lo;
+        uint32_t hi2 = 0u, lo2 = 0u;
+        if (t < T0) {
+            float y[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v = 0.f;
+#pragma unroll
+                for (int j = 0; j < 10; ++j) v = fmaf(wc[h][j], xs[(t - t_begin) * 5 + j], v);
+                y[h] = gelu_exact((v - m[h]) * r[h] * g[h] + be[h]);
+            }
+            tc::split2_f16(y[0], y[1], hi2, lo2);
+        }
+        *reinterpret_cast<uint32_t*>(planes + at) = hi2;
+        *reinterpret_cast<uint32_t*>(planes + plane_stride + at) = lo2;
     }
 }
 
@@ -644,14 +702,20 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
 
     // ---- feature encoder: conv0 + GroupNorm + GELU on the CUDA cores, then six stride-2
     // convolutions as GEMMs (tensor cores: taps = k-blocks, A boxes take every 2nd row)
-    PPGS_CUDA(cudaMemsetAsync(act[0], 0, act_bytes, stream));
+    // fp32 path: junk rows of the conv activations must be finite.  The tensor-core path writes
+    // every row a TMA load can see (maps are bounded by the row count, stores are clipped)
+    if (!use_tc) PPGS_CUDA(cudaMemsetAsync(act[0], 0, act_bytes, stream));
     PPGS_CUDA(cudaMemsetAsync(sums, 0, (size_t)batch * kConvDim * 2 * sizeof(double), stream));
-    {
-        LaunchScope scope(e, "w2v2_conv0", stream);
-        conv0_kernel<<<dim3((T[0] + 31) / 32, batch), 256, 0, stream>>>(audio, stride, (int)samples, T[0],
-                                                                          Q[0], w.conv_w[0], act[0]);
-    }
-    {
+    if (use_tc) {
+        LaunchScope scope(e, "w2v2_conv0_stats", stream);
+        conv0_stats_kernel<<<dim3((T[0] + 255) / 256, batch), 512, 0, stream>>>(audio, stride, (int)samples, T[0],
+                                                                               w.conv_w[0], sums);
+    } else {
+        {
+            LaunchScope scope(e, "w2v2_conv0", stream);
+            conv0_kernel<<<dim3((T[0] + 31) / 32, batch), 256, 0, stream>>>(audio, stride, (int)samples, T[0],
+                                                                              Q[0], w.conv_w[0], act[0]);
+        }
         LaunchScope scope(e, "w2v2_groupnorm_stats", stream);
         groupnorm_stats_kernel<<<dim3((T[0] + 255) / 256, batch), 512, 0, stream>>>(act[0], T[0], Q[0], sums);
     }
@@ -662,9 +726,10 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
         __half* bufs[2] = {reinterpret_cast<__half*>(act[0]), reinterpret_cast<__half*>(act[1])};
         const int64_t rows0 = (int64_t)batch * Q[0];
         {
-            LaunchScope scope(e, "w2v2_groupnorm_gelu", stream);
-            groupnorm_gelu_planes_kernel<<<dim3((unsigned)((Q[0] + 63) / 64), batch), 512, 0, stream>>>(
-                act[0], T[0], Q[0], rows0 * kConvDim, sums, w.gn_w, w.gn_b, 1e-5f, bufs[1]);
+            LaunchScope scope(e, "w2v2_conv0_groupnorm_gelu", stream);
+            conv0_groupnorm_gelu_planes_kernel<<<dim3((unsigned)((Q[0] + 63) / 64), batch), 256, 0, stream>>>(
+                audio, stride, (int)samples, T[0], Q[0], rows0 * kConvDim, w.conv_w[0], sums, w.gn_w, w.gn_b,
+                1e-5f, bufs[1]);
         }
         PPGS_CUDA(cudaGetLastError());
         int cur = 1;
