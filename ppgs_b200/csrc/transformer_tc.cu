@@ -168,6 +168,9 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     // hidden 256: one GEMM tile spans a full row and the residual + LayerNorm live in the
     // epilogue; wider models store the projection and normalise in a separate pass
     const bool fused_ln = H == 256;
+    // experiment (PPGS_B200_SPLIT_OUT_PROJ_LN=1): the K = 256 out-projection is epilogue-bound
+    // with the fused LayerNorm; run it with the plain epilogue + the standalone LayerNorm pass
+    static const bool split_out_proj = [] { const char* v = getenv("PPGS_B200_SPLIT_OUT_PROJ_LN"); return v && atoi(v) != 0; }();
     PPGS_CHECK(build_weight_maps(e));
     const int planes = e->precision == PPGS_PRECISION_F16X2 ? 2 : 1;
 
@@ -177,7 +180,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     const size_t o_qkv = w.take((size_t)2 * rows * 3 * H * 2);
     const size_t o_att = w.take((size_t)2 * rows * H * 2);
     const size_t o_ff = w.take((size_t)2 * rows * F * 2);
-    const size_t o_y = w.take(fused_ln ? 0 : (size_t)2 * rows * H * 2);
+    const size_t o_y = w.take(fused_ln && !split_out_proj ? 0 : (size_t)2 * rows * H * 2);
     const size_t o_seqs = w.take(plan.seqs.size() * sizeof(SeqInfo));
     const size_t o_tiles = w.take((size_t)(rows / 128) * 4);
     PPGS_CHECK(ensure_workspace(e, w.off));
@@ -201,7 +204,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     // output tensor maps (TMA stores of the epilogues)
     CUtensorMap out_x, out_qkv, out_ff, out_y;
     PPGS_CHECK(make_store_map(&out_x, xh, H, rows, (uint64_t)rows * H));
-    if (!fused_ln) PPGS_CHECK(make_store_map(&out_y, yh, H, rows, (uint64_t)rows * H));
+    if (!fused_ln || split_out_proj) PPGS_CHECK(make_store_map(&out_y, yh, H, rows, (uint64_t)rows * H));
     PPGS_CHECK(make_store_map(&out_qkv, qkv, 3 * H, rows, (uint64_t)rows * 3 * H));
     PPGS_CHECK(make_store_map(&out_ff, ff, F, rows, (uint64_t)rows * F));
 
@@ -255,7 +258,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             GemmParams p = base;
             p.cblocks = cblocks; p.a_planes = planes;
             p.N = H; p.scale = wt.inv_scale; p.bias = bias; p.trace = trace(slot);
-            if (fused_ln) {
+            if (fused_ln && !(split_out_proj && slot == 2)) {
                 p.n_tiles = 1; p.trace_ln = trace(slot_ln);
                 p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
                 p.gamma = gamma; p.beta = beta;
@@ -264,7 +267,10 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             p.n_tiles = H / 256;
             PPGS_CHECK(launch_gemm_tc(e, name, 256, kEpiPlanes, map_a, wmap(wt), &out_y, p, stream));
             LaunchScope scope(e, "residual_layernorm_planes", stream);
-            if (H == 512)
+            if (H == 256)
+                residual_layernorm_planes_kernel<256><<<(rows + 7) / 8, 256, 0, stream>>>(
+                    xh, yh, (int64_t)rows * H, gamma, beta, c.layer_norm_eps, seqs_dev, tile_seq_dev, rows);
+            else if (H == 512)
                 residual_layernorm_planes_kernel<512><<<(rows + 7) / 8, 256, 0, stream>>>(
                     xh, yh, (int64_t)rows * H, gamma, beta, c.layer_norm_eps, seqs_dev, tile_seq_dev, rows);
             else if (H == 768)
