@@ -147,7 +147,7 @@ def utility_engine(gpu=None):
     """A weight-less engine on `gpu` for the ingest kernels (resampler, PCM decode)
     when no model is involved; cached per device."""
     device = resolve_device(gpu)
-    key = ('utility', device.index)
+    key = ('utility', '', device.index, False)
     with _lock:
         engine = _engines.get(key)
         if engine is None:

@@ -12,7 +12,7 @@ def _frontend_engine(gpu):
     # any finalised engine on the device owns the mel tables; prefer a cached one
     with load._lock:
         for key, engine in load._engines.items():
-            if key[2] == load.resolve_device(gpu).index:
+            if key[0] != 'utility' and key[2] == load.resolve_device(gpu).index:
                 return engine
     return _standalone(load.resolve_device(gpu))
 
