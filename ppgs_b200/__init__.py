@@ -10,7 +10,7 @@ from .config import configure  # noqa: F401
 from .phonemes import PHONEMES, PHONEME_TO_INDEX_MAPPING, SILENCE  # noqa: F401
 from . import config, data, load, preprocess, parallel  # noqa: F401
 from .engine import Engine  # noqa: F401
-from .streaming import Streamer  # noqa: F401
+from .streaming import LongStreamer, Streamer  # noqa: F401
 from .core import (  # noqa: F401
     from_audio, from_features, from_file, from_file_to_file, from_files_to_files,
     from_dataloader, infer, resample, representation_file_extension,

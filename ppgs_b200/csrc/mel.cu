@@ -34,7 +34,9 @@ struct MelSmem {
     alignas(16) cf zb[kMelWarps][kZPad];
     alignas(16) float band_weights[kMaxBandWeights];
     int32_t band_meta[kMels * 3];
-    alignas(16) __half out[kMels][kTileFrames];
+    // rows padded to 34 halves (68 B): the per-frame column store out[m][f] of lanes m = 0..31
+    // then hits 32 different banks (17 m mod 32) instead of two
+    alignas(16) __half out[kMels][kTileFrames + 2];
     alignas(8) unsigned long long mbar;
 };
 

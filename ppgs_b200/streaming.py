@@ -105,3 +105,96 @@ class Streamer:
                                    device=device)
         self._frames_in = last
         return self.push(features, final=final, softmax=softmax)
+
+
+class LongStreamer:
+    """Unbounded streaming for causal models: the reference's CHUNKED inference
+    (ppgs/model/transformer.py:49-64: 500-frame chunks every 400 frames over the input
+    left-padded with 50 replicas of its first frame, the middle 400 frames of every chunk
+    kept), computed incrementally.  Chunk i is a `Streamer` session over padded frames
+    [400 i, 400 i + 454): by causality its kept outputs (local frames 50..449) never see a
+    later frame, so the session stops there and its state is recycled for chunk i + 2; two
+    sessions alternate, and the 54 frames they share are pushed to both.  Every emitted
+    frame equals `ppgs.from_features(whole_utterance)` (legacy_mode=False) of the causal
+    model for utterances longer than one chunk (the reference only chunks when
+    frames > 500; shorter utterances are what `Streamer` computes)."""
+
+    def __init__(self, engine, streams):
+        self.engine = engine
+        self.streams = int(streams)
+        self.chunk = config.CHUNK_LENGTH
+        self.overlap = config.CHUNK_OVERLAP
+        self.stride = self.chunk - 2 * self.overlap
+        # a session consumes the kept frames + the look-ahead of the two convolutions
+        self.consumed = self.chunk - self.overlap + Streamer.LOOKAHEAD
+        self.sessions = [Streamer(engine, streams), Streamer(engine, streams)]
+        self.reset()
+
+    def reset(self):
+        for session in self.sessions:
+            session.reset()
+        self.frames = 0          # feature frames pushed so far (un-padded axis)
+        self.emitted = 0
+        self.first_frame = None  # replicated 50 times in front of the stream
+        self.closed = False
+
+    def _session_input(self, index, features, begin, end):
+        """Slice of padded frames [begin, end) that chunk `index` still has to see."""
+        lo = max(begin, index * self.stride)
+        hi = min(end, index * self.stride + self.consumed)
+        return lo, hi
+
+    def push(self, features=None, final=False, softmax=True):
+        """features (streams, channels, n) fp16 -> (streams, 40, m) fp32: the frames that
+        became final, in order."""
+        if self.closed:
+            raise RuntimeError('the stream was finalised; call reset()')
+        device = self.engine.device
+        channels = self.engine.cfg.input_channels
+        if features is None:
+            features = torch.empty(self.streams, channels, 0, dtype=torch.float16, device=device)
+        features = self.engine._on_device(features, torch.float16)
+        if features.dim() != 3 or features.shape[0] != self.streams or features.shape[1] != channels:
+            raise ValueError(f'expected features of shape ({self.streams}, {channels}, frames)')
+        n = features.shape[-1]
+        if self.first_frame is None and n:
+            self.first_frame = features[..., :1]
+            features = torch.cat((self.first_frame.expand(-1, -1, self.overlap), features), dim=-1)
+            begin = 0                               # padded axis = un-padded + 50
+        else:
+            begin = self.frames + self.overlap if self.first_frame is not None else 0
+        end = begin + features.shape[-1]
+        self.frames += n
+        if final:
+            self.closed = True
+        pieces = []
+        # chunks that overlap [begin, end) on the padded axis, oldest first
+        first = max((begin - self.consumed) // self.stride + 1, 0) if begin >= self.consumed else 0
+        last = max((end - 1) // self.stride, 0) if end > 0 else 0
+        if final and self.frames:
+            # the reference runs ceil(frames / 400) chunks
+            last = min(last, -(-self.frames // self.stride) - 1)
+        for index in range(first, last + 1):
+            session = self.sessions[index % 2]
+            lo, hi = self._session_input(index, features, begin, end)
+            start = index * self.stride
+            if lo == start and hi > lo and session.length:   # recycle the state of chunk index - 2
+                session.reset()
+            chunk_final = final and index * self.stride + self.consumed > end
+            piece = features[..., lo - begin:hi - begin] if hi > lo else None
+            if piece is None and not chunk_final:
+                continue
+            local_before = session.emitted
+            out = session.push(piece, final=chunk_final, softmax=softmax)
+            # keep local frames [50, 450)
+            keep_lo = max(self.overlap - local_before, 0)
+            keep_hi = min(self.chunk - self.overlap - local_before, out.shape[-1])
+            if keep_hi > keep_lo:
+                pieces.append(out[..., keep_lo:keep_hi])
+        if pieces:
+            result = torch.cat(pieces, dim=-1)
+        else:
+            result = torch.empty(self.streams, self.engine.cfg.output_channels, 0,
+                                 dtype=torch.float32, device=device)
+        self.emitted += result.shape[-1]
+        return result

@@ -136,3 +136,37 @@ def test_streaming_from_audio(ppgs_b200, engine, state):
     assert (result - reference).abs().max() <= PPG_TOL
     # and the streamed features are the batch front-end's, bit for bit
     assert streamer.length == 300
+
+
+@pytest.mark.parametrize('total,pushes', [
+    (501, [501]),
+    (801, [160] * 5 + [1]),
+    (1234, [400, 54, 46, 300, 434]),
+    (1700, [37] * 45 + [35]),
+])
+def test_long_streamer_equals_chunked_reference(ppgs_b200, engine, state, total, pushes):
+    """Unbounded streaming = the reference's chunked inference (500 / 400 / 50,
+    ppgs/model/transformer.py:49-64) computed incrementally by two alternating sessions."""
+    assert sum(pushes) == total
+    audio = O.synthetic_audio(2, total * 160, total)
+    features = O.mel_from_audios(audio)
+    lengths = torch.full((2,), total, dtype=torch.long)
+    reference = O.from_features(state, features, lengths, is_causal=True)   # chunked
+    streamer = ppgs_b200.LongStreamer(engine, 2)
+    at, pieces = 0, []
+    for i, n in enumerate(pushes):
+        out = streamer.push(features[..., at:at + n].cuda(), final=i + 1 == len(pushes))
+        begin = streamer.emitted - out.shape[-1]
+        if out.shape[-1]:
+            assert (out.cpu() - reference[..., begin:streamer.emitted]).abs().max() <= PPG_TOL
+        at += n
+        pieces.append(out)
+    result = torch.cat(pieces, dim=-1).cpu()
+    assert result.shape == reference.shape
+    assert (result - reference).abs().max() <= PPG_TOL
+    with pytest.raises(RuntimeError, match='finalised'):
+        streamer.push(features[..., :1].cuda())
+    # the batch API on the same features agrees too (same chunking, folded into the batch axis)
+    batch = engine.transformer(features.cuda(), lengths).cpu()
+    assert (batch - result).abs().max() <= 2e-5
+    engine.check()
