@@ -473,7 +473,7 @@ def main():
     roofline['kernels_ms_per_step'] = {k: round(ms / steps, 4) for k, (ms, _) in sorted(stats.items())}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N = 1 only
         cpu, _ = cpu_reference_rate(steps=3, warmup=1, budget_s=20.0)
 
     dtype = {'fp32': 'f32 (CUDA-core FFMA)', 'f16x2': 'f16x2-split tcgen05 MMA, f32 accumulate',
