@@ -176,6 +176,14 @@ int ppgs_engine_wait(ppgs_engine* engine);
  * (bench.py's `gpu_launches`). */
 int64_t ppgs_engine_launch_count(const ppgs_engine* engine);
 
+/* Steady-state loops of ppgs_from_audio / ppgs_from_audio_host* / ppgs_files_to_files (same
+ * shapes, lengths and buffers as an earlier call, engine workspace untouched in between) are
+ * replayed as one CUDA graph instead of 29 launches.  Kernels inside a replay still count in
+ * ppgs_engine_launch_count.  On by default (tensor-core precisions, profiling off);
+ * PPGS_B200_GRAPHS=0 or ppgs_engine_set_graphs(engine, 0) keeps the launch path. */
+int64_t ppgs_engine_graph_replays(const ppgs_engine* engine);
+int ppgs_engine_set_graphs(ppgs_engine* engine, int enabled);
+
 /* Per-kernel device timing for bench.py's roofline: when enabled, every launch is
  * bracketed by CUDA events on its stream and accumulated under the kernel's
  * name.  `ppgs_engine_kernel_stat(e, i, ...)` enumerates the names (returns

@@ -58,6 +58,8 @@ SYMBOLS = {
     'ppgs_from_audio_host_submit': (_i, [_vp, _vp, _i, _i64, _c.POINTER(_i64), _i, _i, _vp, _vp]),
     'ppgs_engine_wait': (_i, [_vp]),
     'ppgs_engine_launch_count': (_i64, [_vp]),
+    'ppgs_engine_graph_replays': (_i64, [_vp]),
+    'ppgs_engine_set_graphs': (_i, [_vp, _i]),
     'ppgs_engine_workspace_bytes': (_sz, [_vp]),
     'ppgs_engine_set_profiling': (_i, [_vp, _i]),
     'ppgs_engine_kernel_stat': (_i, [_vp, _i, _c.c_char_p, _sz, _c.POINTER(_c.c_double),

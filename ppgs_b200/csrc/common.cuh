@@ -180,6 +180,29 @@ struct ppgs_engine {
 
     int64_t launches = 0;
 
+    // CUDA-graph cache of the fused from_audio forward (engine.cu): steady-state loops replay
+    // the 29 launches as one graph.  An entry is valid while `graph_generation` is unchanged
+    // (weights, precision, workspace block, profiling) and may be replayed only while the
+    // workspace still holds the plan tables of its plan (`ws_owner`; every other workspace
+    // user resets it through ensure_workspace).
+    struct GraphEntry {
+        std::vector<int64_t> key;
+        cudaGraphExec_t exec = nullptr;
+        uint64_t generation = 0;
+        int plan_id = 0;
+        int64_t launches = 0;
+        uint64_t last_used = 0;
+    };
+    std::vector<GraphEntry> graphs;
+    std::map<std::vector<int64_t>, int> plan_ids;
+    std::vector<std::vector<int64_t>> uncapturable;
+    uint64_t graph_generation = 1, graph_clock = 0;
+    int ws_owner = 0, next_plan_id = 1;
+    bool capturing = false;
+    int graphs_enabled = 1;          // PPGS_B200_GRAPHS=0 disables
+    cudaStream_t capture_stream = nullptr;
+    int64_t graph_replays = 0;
+
     // optional per-kernel timing (ppgs_engine_set_profiling): CUDA events on the
     // launch stream around every launch, accumulated per kernel name
     bool profiling = false;

@@ -26,7 +26,13 @@ void set_error(const char* fmt, ...) {
 }
 
 int ensure_workspace(ppgs_engine* e, size_t bytes) {
+    e->ws_owner = 0;   // whoever asks for the workspace is about to overwrite it
     if (bytes <= e->workspace_bytes) return PPGS_OK;
+    if (e->capturing) {
+        set_error("workspace growth during graph capture");
+        return PPGS_E_STATE;
+    }
+    e->graph_generation += 1;
     if (e->workspace) {
         PPGS_CUDA(cudaDeviceSynchronize());   // earlier launches may still use the old block
         PPGS_CUDA(cudaFree(e->workspace));
@@ -105,6 +111,10 @@ int upload_plan(ppgs_engine* e, const ForwardPlan& plan, SeqInfo* seqs_dev, int*
     if (e->cached_plan_dev == seqs_dev && e->cached_plan.size() == plan.seqs.size() &&
         memcmp(e->cached_plan.data(), plan.seqs.data(), seq_bytes) == 0)
         return PPGS_OK;
+    if (e->capturing) {   // a copy from the shared staging buffer must not become a graph node
+        set_error("plan tables are not resident during graph capture");
+        return PPGS_E_STATE;
+    }
     // the pinned staging buffer is reused: the previous upload must have been consumed
     if (!e->plan_uploaded) PPGS_CUDA(cudaEventCreateWithFlags(&e->plan_uploaded, cudaEventDisableTiming));
     else PPGS_CUDA(cudaEventSynchronize(e->plan_uploaded));
@@ -426,6 +436,9 @@ void ppgs_engine_destroy(ppgs_engine* e) {
     if (e->copy_in) cudaStreamDestroy(e->copy_in);
     if (e->copy_out) cudaStreamDestroy(e->copy_out);
     if (e->plan_uploaded) cudaEventDestroy(e->plan_uploaded);
+    for (auto& g : e->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
     cudaFreeHost(e->pinned);
     cudaFree(e->mel.window);
     cudaFree(e->mel.tw512);
@@ -527,6 +540,8 @@ int ppgs_engine_finalize(ppgs_engine* e) {
         else i = e->weights.erase(i);
     }
     e->finalized = true;
+    e->graph_generation += 1;   // packed weights moved: cached graphs are stale
+    e->ws_owner = 0;
     pick_default_precision(e);
     return PPGS_OK;
 }
@@ -556,6 +571,8 @@ int ppgs_engine_adopt_blob(ppgs_engine* e) {
     if (it != e->weights.end()) basis = it->second.data.data();
     PPGS_CHECK(build_mel_tables(e, basis));
     e->finalized = true;
+    e->graph_generation += 1;   // packed weights moved: cached graphs are stale
+    e->ws_owner = 0;
     pick_default_precision(e);
     return PPGS_OK;
 }
@@ -593,6 +610,7 @@ int ppgs_engine_set_precision(ppgs_engine* e, int precision) {
     }
     e->precision = precision;
     e->precision_chosen = true;
+    e->graph_generation += 1;
     return PPGS_OK;
 }
 
@@ -600,11 +618,23 @@ int ppgs_engine_get_precision(const ppgs_engine* e) { return e ? e->precision : 
 
 int64_t ppgs_engine_launch_count(const ppgs_engine* e) { return e ? e->launches : 0; }
 
+int64_t ppgs_engine_graph_replays(const ppgs_engine* e) { return e ? e->graph_replays : 0; }
+
+int ppgs_engine_set_graphs(ppgs_engine* e, int enabled) {
+    if (!e) {
+        set_error("engine is NULL");
+        return PPGS_E_INVALID;
+    }
+    e->graphs_enabled = enabled != 0;
+    return PPGS_OK;
+}
+
 int ppgs_engine_set_profiling(ppgs_engine* e, int enabled) {
     PPGS_ENTER(e);
     drain_stats(e);
     e->stats.clear();
     e->profiling = enabled != 0;
+    e->graph_generation += 1;
     return PPGS_OK;
 }
 
@@ -689,10 +719,9 @@ static int ensure_io(ppgs_engine* e, size_t bytes) {
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-// not part of the C ABI: shared with the file pipeline (io.cu)
-int ppgs_detail_from_audio_device(ppgs_engine* e, const float* audio, int batch, int64_t samples,
-                                  int64_t stride, const int64_t* lengths, int softmax,
-                                  int legacy_mode, float* out, __half* mel, cudaStream_t stream) {
+static int from_audio_device_launch(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                                    int64_t stride, const int64_t* lengths, int softmax,
+                                    int legacy_mode, float* out, __half* mel, cudaStream_t stream) {
     const int frames = (int)(samples / kHopSamples);
     if (frames <= 0) {
         set_error("from_audio: need at least %d samples", kHopSamples);
@@ -705,6 +734,104 @@ int ppgs_detail_from_audio_device(ppgs_engine* e, const float* audio, int batch,
     PPGS_CHECK(build_plan(e, batch, frames, frame_lengths.data(), legacy_mode, &plan));
     PPGS_CHECK(launch_mel(e, audio, batch, samples, stride, mel, stream));
     return run_transformer(e, mel, plan, softmax, out, stream);
+}
+
+static const size_t kMaxGraphs = 16;
+
+// not part of the C ABI: shared with the file pipeline (io.cu).  Steady-state loops (same
+// shapes, lengths and buffers as an earlier call, workspace untouched in between) replay the
+// forward as one CUDA graph; everything else takes the launch path.
+int ppgs_detail_from_audio_device(ppgs_engine* e, const float* audio, int batch, int64_t samples,
+                                  int64_t stride, const int64_t* lengths, int softmax,
+                                  int legacy_mode, float* out, __half* mel, cudaStream_t stream) {
+    static const bool env_enabled = [] { const char* v = getenv("PPGS_B200_GRAPHS"); return !v || atoi(v) != 0; }();
+    if (!env_enabled || !e->graphs_enabled || e->profiling || e->trace_dev || e->capturing ||
+        e->precision == PPGS_PRECISION_FP32)
+        return from_audio_device_launch(e, audio, batch, samples, stride, lengths, softmax, legacy_mode, out,
+                                        mel, stream);
+    std::vector<int64_t> plan_key = {batch, samples, stride, softmax, legacy_mode, e->precision,
+                                     (int64_t)(lengths != nullptr)};
+    if (lengths) plan_key.insert(plan_key.end(), lengths, lengths + batch);
+    auto found = e->plan_ids.find(plan_key);
+    if (found == e->plan_ids.end()) {
+        if (e->plan_ids.size() > 256) e->plan_ids.clear();   // ids only matter for the last few calls
+        found = e->plan_ids.emplace(plan_key, e->next_plan_id++).first;
+    }
+    const int plan_id = found->second;
+    std::vector<int64_t> key = {(int64_t)(intptr_t)audio, (int64_t)(intptr_t)out, (int64_t)(intptr_t)mel};
+    key.insert(key.end(), plan_key.begin(), plan_key.end());
+    e->graph_clock += 1;
+    ppgs_engine::GraphEntry* entry = nullptr;
+    for (auto& g : e->graphs)
+        if (g.generation == e->graph_generation && g.key == key) entry = &g;
+    if (entry && e->ws_owner == plan_id) {
+        PPGS_CUDA(cudaGraphLaunch(entry->exec, stream));
+        entry->last_used = e->graph_clock;
+        e->launches += entry->launches;
+        e->graph_replays += 1;
+        return PPGS_OK;
+    }
+    bool capturable = !entry && e->ws_owner == plan_id;   // tables resident: same plan ran last
+    for (const auto& bad : e->uncapturable)
+        if (bad == key) capturable = false;
+    if (capturable) {
+        if (!e->capture_stream &&
+            cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            capturable = false;
+        }
+    }
+    if (capturable) {
+        const int64_t launches_before = e->launches;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        bool ok = cudaStreamBeginCapture(e->capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            e->capturing = true;
+            const int rc = from_audio_device_launch(e, audio, batch, samples, stride, lengths, softmax,
+                                                    legacy_mode, out, mel, e->capture_stream);
+            e->capturing = false;
+            const cudaError_t end = cudaStreamEndCapture(e->capture_stream, &graph);
+            ok = rc == PPGS_OK && end == cudaSuccess && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        const int64_t captured = e->launches - launches_before;
+        e->launches = launches_before;
+        if (ok) {
+            if (e->graphs.size() >= kMaxGraphs) {   // evict stale generations first, then the LRU entry
+                size_t victim = 0;
+                for (size_t i = 0; i < e->graphs.size(); ++i) {
+                    const bool stale_i = e->graphs[i].generation != e->graph_generation;
+                    const bool stale_v = e->graphs[victim].generation != e->graph_generation;
+                    if ((stale_i && !stale_v) || (stale_i == stale_v && e->graphs[i].last_used < e->graphs[victim].last_used))
+                        victim = i;
+                }
+                cudaGraphExecDestroy(e->graphs[victim].exec);
+                e->graphs.erase(e->graphs.begin() + victim);
+            }
+            ppgs_engine::GraphEntry g;
+            g.key = key;
+            g.exec = exec;
+            g.generation = e->graph_generation;
+            g.plan_id = plan_id;
+            g.launches = captured;
+            g.last_used = e->graph_clock;
+            e->graphs.push_back(g);
+            e->ws_owner = plan_id;   // the capture ran no kernel: the tables are still this plan's
+            PPGS_CUDA(cudaGraphLaunch(exec, stream));
+            e->launches += captured;
+            e->graph_replays += 1;
+            return PPGS_OK;
+        }
+        cudaGetLastError();   // capture refused (e.g. a table upload was needed): launch path from now on
+        if (exec) cudaGraphExecDestroy(exec);
+        if (e->uncapturable.size() < 64) e->uncapturable.push_back(key);
+    }
+    const int rc = from_audio_device_launch(e, audio, batch, samples, stride, lengths, softmax, legacy_mode, out,
+                                            mel, stream);
+    if (rc == PPGS_OK) e->ws_owner = plan_id;
+    return rc;
 }
 
 int ppgs_from_audio(ppgs_engine* e, const float* audio, int batch, int64_t samples,

@@ -140,6 +140,14 @@ class Engine:
     def launches(self):
         return _lib.lib.ppgs_engine_launch_count(self._handle)
 
+    @property
+    def graph_replays(self):
+        """Forwards replayed as one CUDA graph (steady-state loops of from_audio*)."""
+        return _lib.lib.ppgs_engine_graph_replays(self._handle)
+
+    def set_graphs(self, enabled):
+        _lib.check(_lib.lib.ppgs_engine_set_graphs(self._handle, int(bool(enabled))))
+
     def set_profiling(self, enabled):
         """Per-kernel CUDA-event timing (bench.py roofline); clears the stats."""
         _lib.check(_lib.lib.ppgs_engine_set_profiling(self._handle, int(bool(enabled))))

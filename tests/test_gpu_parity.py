@@ -346,3 +346,56 @@ def test_config5_sharded_files_two_ranks(ppgs_b200, tmp_path):
         x, y = torch.load(a), torch.load(b)
         assert x.shape == (40, n // 160)
         assert torch.equal(x, y)
+
+
+def test_cuda_graph_replay_is_bitwise_the_launch_path(ppgs_b200):
+    """Steady-state loops replay the forward as one CUDA graph: same bits as 29 launches, the
+    replay stops as soon as anything else touches the workspace or the inputs change, and
+    launches keep being counted."""
+    sd = O.random_state_dict(9, peaky=True)
+    engine = make_engine(ppgs_b200, sd, 'f16x2')
+    audio = O.synthetic_audio(3, 160 * 620, 21).cuda()
+    other = O.synthetic_audio(3, 160 * 620, 22).cuda()
+    engine.set_graphs(False)
+    want, want_other = engine.from_audio(audio), engine.from_audio(other)
+    per_forward = engine.launches
+    engine.from_audio(audio)
+    per_forward = engine.launches - per_forward
+    engine.set_graphs(True)
+    out = torch.empty_like(want)
+
+    def forward(x):
+        # fixed output buffer, like a serving loop (the public wrapper allocates per call)
+        from ppgs_b200 import _lib
+        _lib.check(_lib.lib.ppgs_from_audio(
+            engine._handle, ctypes.c_void_p(x.data_ptr()), 3, x.shape[-1], x.shape[-1], None, 1, 0,
+            ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out.clone()
+
+    x = audio.squeeze(1).contiguous()
+    y = other.squeeze(1).contiguous()
+    assert torch.equal(forward(x), want)            # launch path, makes the plan resident
+    assert engine.graph_replays == 0
+    before = engine.launches
+    assert torch.equal(forward(x), want)            # captured + launched as a graph
+    assert torch.equal(forward(x), want)            # replayed
+    assert engine.graph_replays == 2 and engine.launches - before == 2 * per_forward
+    x.copy_(y)                                      # same buffers, new contents: still a replay
+    assert torch.equal(forward(x), want_other)
+    assert engine.graph_replays == 3
+    assert torch.equal(forward(y), want_other)      # other input buffer: its own graph
+    # something else uses the workspace (other shape): the next call must not replay blindly
+    engine.from_audio(O.synthetic_audio(1, 160 * 100, 3).cuda())
+    replays = engine.graph_replays
+    assert torch.equal(forward(y), want_other) and engine.graph_replays == replays
+    assert torch.equal(forward(y), want_other) and engine.graph_replays == replays + 1
+    # profiling and precision changes drop back to launches
+    engine.set_profiling(True)
+    assert torch.equal(forward(y), want_other) and engine.graph_replays == replays + 1
+    engine.set_profiling(False)
+    engine.precision = 'f16'
+    loose = forward(y)
+    assert (loose - want_other).abs().max() > 0
+    engine.precision = 'f16x2'
+    assert torch.equal(forward(y), want_other)
+    engine.check()
