@@ -257,7 +257,7 @@ int ppgs_files_to_files(ppgs_engine* engine, int n_batches, const int32_t* batch
 /* ---- stateful streaming decoder for causal models (config/causal_transformer.py:18) ------
  * The reference has no streaming state (ppgs/model/transformer.py:65-71 rebuilds the causal
  * mask per call); this is the incremental form of its un-chunked causal forward
- * (`legacy_mode=True`, IS_CAUSAL=True) over `streams` utterances that grow in lockstep.
+ * (`legacy_mode=True`, IS_CAUSAL=True) over `streams` independent utterances.
  * State per stream: the feature rows, and per layer the K / V rows of every frame pushed so
  * far (the attention cache, read in place by the tcgen05 attention kernel).  A session holds
  * ppgs_stream_capacity() = 510 frames; PPGS_E_TOO_LARGE beyond (ValueError('size is too
@@ -280,6 +280,17 @@ int ppgs_stream_emitted(const ppgs_stream* stream_state);
 int ppgs_stream_push(ppgs_stream* stream_state, const void* features_dev, int frames, int final,
                      int softmax, float* out_dev, int out_capacity, int* frames_out,
                      void* stream);
+/* Independent streams (serving): stream b brings frames[b] <= max_frames frames (the first
+ * frames[b] columns of row b of features_dev, (streams, input_channels, max_frames) fp16), may
+ * be finalised on its own (final[b], NULL = none) and emits frames_out[b] frames into row b of
+ * out_dev.  ppgs_stream_reset_streams clears the flagged streams for their next utterance
+ * while the others keep their state; ppgs_stream_state reports per-stream lengths / emitted
+ * frames (either pointer may be NULL).  ppgs_stream_push is the lockstep special case. */
+int ppgs_stream_push_ragged(ppgs_stream* stream_state, const void* features_dev, int max_frames,
+                            const int32_t* frames, const int32_t* final, int softmax,
+                            float* out_dev, int out_capacity, int32_t* frames_out, void* stream);
+int ppgs_stream_reset_streams(ppgs_stream* stream_state, const int32_t* flags, void* stream);
+int ppgs_stream_state(const ppgs_stream* stream_state, int32_t* lengths, int32_t* emitted);
 
 /* ---- posteriorgram post-processing on the device (the step after the hot path) ----------- */
 

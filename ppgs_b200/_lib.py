@@ -82,6 +82,10 @@ SYMBOLS = {
     'ppgs_stream_length': (_i, [_vp]),
     'ppgs_stream_emitted': (_i, [_vp]),
     'ppgs_stream_push': (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _c.POINTER(_i), _vp]),
+    'ppgs_stream_push_ragged': (_i, [_vp, _vp, _i, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32), _i,
+                                     _vp, _i, _c.POINTER(_c.c_int32), _vp]),
+    'ppgs_stream_reset_streams': (_i, [_vp, _c.POINTER(_c.c_int32), _vp]),
+    'ppgs_stream_state': (_i, [_vp, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
     'ppgs_ppg_distance': (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i64, _vp, _c.c_float, _i, _vp, _vp]),
     'ppgs_ppg_interpolate': (_i, [_vp, _vp, _vp, _vp, _c.c_float, _i64, _i64, _vp, _vp]),
     'ppgs_ppg_grid_sample': (_i, [_vp, _vp, _i, _i64, _vp, _i64, _vp, _vp]),

@@ -159,6 +159,7 @@ struct AttnParams {
     __half* out;
     int64_t out_plane_stride;
     int q_first_tile;   // streaming decoder: only query tiles >= this one are computed
+    int q_first_per_seq;   // 1: per sequence, from SeqInfo::src_start
     int* status;
     // cycle accounting (PPGS_B200_TRACE=1): MMA [0] wait q [1] wait k [2] wait p [3] wait v [4] total;
     // softmax warp 2: [8] wait s [9] row max [10] wait p_empty [11] chunk work [12] wait o [13] total [14] CTAs
@@ -199,7 +200,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
     __shared__ float row_part[2][128];   // per-row partial max / sum of the two halves
 
     const SeqInfo s = p.seqs[blockIdx.z];
-    const int q0 = ((int)blockIdx.x + p.q_first_tile) * 128, head = blockIdx.y;
+    const int q0 = ((int)blockIdx.x + (p.q_first_per_seq ? s.src_start : p.q_first_tile)) * 128, head = blockIdx.y;
     if (q0 >= s.tensor_len) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int nkeys = s.valid_len;
@@ -532,6 +533,7 @@ static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int 
                             int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
                             cudaStream_t stream, int q_first_tile, int q_tiles) {
     using Shape = AttnShape<D>;
+    const bool per_seq = q_first_tile < 0;   // -1: first query tile per sequence (SeqInfo::src_start)
     CUtensorMap map_qk, map_v, map_out;
     PPGS_CHECK(make_store_map(&map_out, out, H, rows, (uint64_t)rows * H));
     PPGS_CHECK(make_plane_map(&map_qk, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
@@ -552,7 +554,8 @@ static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int 
     p.out = out;
     p.out_plane_stride = (int64_t)rows * H;
     p.status = e->status_dev;
-    p.q_first_tile = q_first_tile;
+    p.q_first_tile = per_seq ? 0 : q_first_tile;
+    p.q_first_per_seq = per_seq ? 1 : 0;
     p.trace = e->trace_dev ? e->trace_dev + 80 : nullptr;
     dim3 grid(q_tiles > 0 ? q_tiles : max_pitch / 128, heads, (unsigned)nseq);
     {

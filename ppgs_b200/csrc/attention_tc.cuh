@@ -14,7 +14,8 @@ int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows
 // Same for any (hidden, heads): tcgen05 kernel when head_dim is 64 / 128 / 256 and the
 // pitch is <= 512 rows, CUDA-core kernel otherwise.
 // `q_first_tile` / `q_tiles` restrict the query tiles of every sequence (streaming decoder: the
-// keys of earlier tiles are the cache); 0 / 0 = all.
+// keys of earlier tiles are the cache); 0 / 0 = all; q_first_tile = -1: the first query tile of
+// every sequence comes from its SeqInfo::src_start.
 int launch_attention_any(ppgs_engine* e, const __half* qkv, __half* out, int rows, int H, int heads,
                          int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
                          cudaStream_t stream, int q_first_tile = 0, int q_tiles = 0);

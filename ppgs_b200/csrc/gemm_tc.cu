@@ -89,7 +89,8 @@ __device__ __forceinline__ int window_tile(const GemmParams& p, int item, int ra
     if (p.win_size == 0) return PAIR ? 2 * item + rank : item;
     const int per_seq = PAIR ? p.win_size / 2 : p.win_size;
     const int seq = item / per_seq, u = item - seq * per_seq;
-    return seq * p.win_stride + p.win_first + (PAIR ? 2 * u + rank : u);
+    const int first = p.win_per_seq ? p.seqs[seq].src_start : p.win_first;
+    return seq * p.win_stride + first + (PAIR ? 2 * u + rank : u);
 }
 
 template <int BN, int EPI, bool PAIR>

@@ -29,6 +29,7 @@ struct GemmParams {
     // sequence of `win_stride` tiles are computed (m_tiles = sequences * win_size; win_size even
     // for the CTA-pair kernel); 0 = all rows
     int win_size = 0, win_stride = 0, win_first = 0;
+    int win_per_seq = 0;         // 1: the first tile of sequence s is seqs[s].src_start instead of win_first
     int a_planes = 2, b_planes = 2;
     int pair = 0;                // 1: CTA-pair kernel (cta_group::2); W map must have box rows BN/2
     int N = 0;                   // real output columns

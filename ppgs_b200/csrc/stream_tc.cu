@@ -3,8 +3,10 @@
 // the square mask per call and carries no state); this is the incremental form
 // of its un-chunked causal forward (legacy_mode=True) over a growing utterance.
 //
-// Semantics.  A session holds `streams` utterances that advance in lockstep.  After pushes
-// totalling L feature frames the state equals the reference forward over those L frames:
+// Semantics.  A session holds `streams` independent utterances; every push may bring a
+// different number of frames (including none) to each of them, and streams can be finalised
+// and reset one by one while the others keep going.  After pushes totalling L feature frames
+// a stream's state equals the reference forward over those L frames:
 //   * hidden position p depends on features <= p + 2 (input Conv1d k=5 'same') and, through
 //     the causal attention, on hidden positions <= p: final once L >= p + 3;
 //   * output frame q depends on hidden q-2 .. q+2 (output Conv1d k=5): final once L >= q + 5.
@@ -22,6 +24,8 @@
 // q_first_tile): positions whose look-ahead was incomplete are redone with the new frames,
 // earlier tiles keep their cached K / V.  Recomputing a tile is idempotent, so cached rows that
 // share a tile with new rows are rewritten with identical values.
+#include <algorithm>
+
 #include "attention_tc.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -34,20 +38,41 @@ constexpr int kStreamPitch = 512;       // rows per stream
 constexpr int kStreamCapacity = 510;    // frames per session
 constexpr int kStreamLookahead = 4;     // 2 (input conv) + 2 (output conv)
 
-// (B, C, n) fp16 feature frames -> rows [row0 + t0, row0 + t0 + n) of the time-major x0
-__global__ void stream_append_kernel(const __half* __restrict__ feats, int C, int n, int t0,
-                                     __half* __restrict__ x0) {
+// (B, C, n) fp16 feature frames -> rows [row0 + t0_b, row0 + t0_b + n_b) of the time-major x0;
+// counts[b] = {t0_b, n_b}
+__global__ void stream_append_kernel(const __half* __restrict__ feats, int C, int n,
+                                     const int2* __restrict__ counts, __half* __restrict__ x0) {
     __shared__ __half tile[32][34];
     const int b = blockIdx.z, f_base = blockIdx.x * 32, c_base = blockIdx.y * 32;
+    const int2 at = counts[b];
+    if (f_base >= at.y) return;
     const int tx = threadIdx.x, ty = threadIdx.y;
     for (int i = ty; i < 32; i += 8) {
         const int c = c_base + i, f = f_base + tx;
-        tile[i][tx] = (c < C && f < n) ? feats[((int64_t)b * C + c) * n + f] : __float2half_rn(0.f);
+        tile[i][tx] = (c < C && f < at.y) ? feats[((int64_t)b * C + c) * n + f] : __float2half_rn(0.f);
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int c = c_base + tx, f = f_base + i;
-        if (c < C && f < n) x0[((int64_t)b * kStreamPitch + t0 + f) * C + c] = tile[tx][i];
+        if (c < C && f < at.y) x0[((int64_t)b * kStreamPitch + at.x + f) * C + c] = tile[tx][i];
+    }
+}
+
+// reset of single streams: the feature rows and the residual stream must read as zero beyond
+// the (new) length; the K / V caches may keep stale finite values (masked by the key count)
+__global__ void stream_clear_kernel(const int2* __restrict__ flags, __half* __restrict__ x0, int C,
+                                    __half* __restrict__ xh, int H, int64_t plane_stride) {
+    const int b = blockIdx.y;
+    if (!flags[b].x) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n0 = (int64_t)kStreamPitch * C / 2, n1 = (int64_t)kStreamPitch * H / 2;
+    uint32_t* a = reinterpret_cast<uint32_t*>(x0 + (int64_t)b * kStreamPitch * C);
+    uint32_t* h0 = reinterpret_cast<uint32_t*>(xh + (int64_t)b * kStreamPitch * H);
+    uint32_t* h1 = reinterpret_cast<uint32_t*>(xh + plane_stride + (int64_t)b * kStreamPitch * H);
+    if (i < n0) a[i] = 0u;
+    if (i < n1) {
+        h0[i] = 0u;
+        h1[i] = 0u;
     }
 }
 
@@ -58,22 +83,33 @@ using namespace ppgs;
 struct ppgs_stream {
     ppgs_engine* e = nullptr;
     int streams = 0;
-    int length = 0;     // L: feature frames pushed so far
-    int emitted = 0;    // output frames returned so far
-    bool finished = false;
-    void* block = nullptr;   // one allocation
+    std::vector<int> length;     // L_b: feature frames pushed so far
+    std::vector<int> emitted;    // output frames returned so far
+    std::vector<char> finished;
+    void* block = nullptr;       // one allocation
     __half *x0 = nullptr, *xh = nullptr, *att = nullptr, *ff = nullptr;
-    std::vector<__half*> qkv;   // per layer
+    std::vector<__half*> qkv;    // per layer
     SeqInfo* seqs_dev = nullptr;
     int* tile_seq_dev = nullptr;
-    size_t zero_bytes = 0;      // prefix of `block` that reset() clears (x0, x, qkv caches)
+    int2* counts_dev = nullptr;  // per stream {t0, n} of the push / reset flags
+    int2* counts_host = nullptr; // pinned staging of the same
+    cudaEvent_t counts_used = nullptr;
+    size_t zero_bytes = 0;       // prefix of `block` that a full reset clears (x0, x, qkv caches)
 };
 
 static int stream_reset_state(ppgs_stream* s, cudaStream_t stream) {
     PPGS_CUDA(cudaMemsetAsync(s->block, 0, s->zero_bytes, stream));
-    s->length = 0;
-    s->emitted = 0;
-    s->finished = false;
+    std::fill(s->length.begin(), s->length.end(), 0);
+    std::fill(s->emitted.begin(), s->emitted.end(), 0);
+    std::fill(s->finished.begin(), s->finished.end(), 0);
+    return PPGS_OK;
+}
+
+// pinned staging -> device, after the previous use of the staging buffer has been consumed
+static int upload_counts(ppgs_stream* s, cudaStream_t stream) {
+    PPGS_CUDA(cudaMemcpyAsync(s->counts_dev, s->counts_host, (size_t)s->streams * sizeof(int2),
+                              cudaMemcpyHostToDevice, stream));
+    PPGS_CUDA(cudaEventRecord(s->counts_used, stream));
     return PPGS_OK;
 }
 
@@ -111,6 +147,9 @@ int ppgs_stream_create(ppgs_engine* e, int streams, ppgs_stream** out) {
     ppgs_stream* s = new ppgs_stream();
     s->e = e;
     s->streams = streams;
+    s->length.assign(streams, 0);
+    s->emitted.assign(streams, 0);
+    s->finished.assign(streams, 0);
     const size_t rows = (size_t)streams * kStreamPitch;
     const int C = c.input_channels, H = c.hidden_channels, F = c.ffn_channels;
     Carver w;
@@ -123,6 +162,7 @@ int ppgs_stream_create(ppgs_engine* e, int streams, ppgs_stream** out) {
     const size_t o_ff = w.take(2 * rows * F * 2);
     const size_t o_seqs = w.take((size_t)streams * sizeof(SeqInfo));
     const size_t o_tiles = w.take(rows / 128 * 4);
+    const size_t o_counts = w.take((size_t)streams * sizeof(int2));
     cudaError_t err = cudaMalloc(&s->block, w.off);
     if (err != cudaSuccess) {
         set_error("stream_create: cudaMalloc of %zu bytes failed: %s", w.off, cudaGetErrorString(err));
@@ -138,7 +178,14 @@ int ppgs_stream_create(ppgs_engine* e, int streams, ppgs_stream** out) {
     s->ff = reinterpret_cast<__half*>(base + o_ff);
     s->seqs_dev = reinterpret_cast<SeqInfo*>(base + o_seqs);
     s->tile_seq_dev = reinterpret_cast<int*>(base + o_tiles);
+    s->counts_dev = reinterpret_cast<int2*>(base + o_counts);
     int rc = PPGS_OK;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&s->counts_host), (size_t)streams * sizeof(int2),
+                      cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->counts_used, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("stream_create: pinned staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = PPGS_E_CUDA;
+    }
     if (cudaMemset(s->block, 0, w.off) != cudaSuccess) {
         set_error("stream_create: cudaMemset failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = PPGS_E_CUDA;
@@ -147,6 +194,8 @@ int ppgs_stream_create(ppgs_engine* e, int streams, ppgs_stream** out) {
     if (prev >= 0) cudaSetDevice(prev);
     if (rc != PPGS_OK) {
         cudaFree(s->block);
+        if (s->counts_host) cudaFreeHost(s->counts_host);
+        if (s->counts_used) cudaEventDestroy(s->counts_used);
         delete s;
         return rc;
     }
@@ -161,6 +210,8 @@ void ppgs_stream_destroy(ppgs_stream* s) {
     cudaSetDevice(s->e->device);
     cudaDeviceSynchronize();
     cudaFree(s->block);
+    cudaFreeHost(s->counts_host);
+    cudaEventDestroy(s->counts_used);
     if (prev >= 0) cudaSetDevice(prev);
     delete s;
 }
@@ -178,43 +229,109 @@ int ppgs_stream_reset(ppgs_stream* s, void* stream) {
     return rc;
 }
 
-int ppgs_stream_length(const ppgs_stream* s) { return s ? s->length : -1; }
-int ppgs_stream_emitted(const ppgs_stream* s) { return s ? s->emitted : -1; }
+int ppgs_stream_length(const ppgs_stream* s) { return s && !s->length.empty() ? s->length[0] : -1; }
+int ppgs_stream_emitted(const ppgs_stream* s) { return s && !s->emitted.empty() ? s->emitted[0] : -1; }
 
-int ppgs_stream_push(ppgs_stream* s, const void* features_dev, int frames, int final, int softmax,
-                     float* out_dev, int out_capacity, int* frames_out, void* stream_) {
+int ppgs_stream_state(const ppgs_stream* s, int32_t* lengths, int32_t* emitted) {
+    if (!s) {
+        set_error("stream is NULL");
+        return PPGS_E_INVALID;
+    }
+    for (int b = 0; b < s->streams; ++b) {
+        if (lengths) lengths[b] = s->length[b];
+        if (emitted) emitted[b] = s->emitted[b];
+    }
+    return PPGS_OK;
+}
+
+int ppgs_stream_reset_streams(ppgs_stream* s, const int32_t* flags, void* stream_) {
+    if (!s || !flags) {
+        set_error("stream_reset_streams: bad argument");
+        return PPGS_E_INVALID;
+    }
+    ppgs_engine* e = s->e;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    PPGS_CUDA(cudaSetDevice(e->device));
+    struct Restore {
+        int prev;
+        ~Restore() {
+            if (prev >= 0) cudaSetDevice(prev);
+        }
+    } restore{prev};
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PPGS_CUDA(cudaEventSynchronize(s->counts_used));
+    bool any = false;
+    for (int b = 0; b < s->streams; ++b) {
+        s->counts_host[b] = make_int2(flags[b] ? 1 : 0, 0);
+        if (flags[b]) {
+            any = true;
+            s->length[b] = s->emitted[b] = 0;
+            s->finished[b] = 0;
+        }
+    }
+    if (!any) return PPGS_OK;
+    PPGS_CHECK(upload_counts(s, stream));
+    const ppgs_model_config& c = e->cfg;
+    const int64_t widest = (int64_t)kStreamPitch * (c.hidden_channels > c.input_channels ? c.hidden_channels
+                                                                                          : c.input_channels) / 2;
+    {
+        LaunchScope scope(e, "stream_clear", stream);
+        stream_clear_kernel<<<dim3((unsigned)((widest + 255) / 256), s->streams), 256, 0, stream>>>(
+            s->counts_dev, s->x0, c.input_channels, s->xh, c.hidden_channels,
+            (int64_t)s->streams * kStreamPitch * c.hidden_channels);
+    }
+    PPGS_CUDA(cudaGetLastError());
+    return PPGS_OK;
+}
+
+int ppgs_stream_push_ragged(ppgs_stream* s, const void* features_dev, int max_frames, const int32_t* frames,
+                            const int32_t* final, int softmax, float* out_dev, int out_capacity,
+                            int32_t* frames_out, void* stream_) {
     if (!s) {
         set_error("stream is NULL");
         return PPGS_E_INVALID;
     }
     ppgs_engine* e = s->e;
     const ppgs_model_config& c = e->cfg;
-    if (frames_out) *frames_out = 0;
-    if (frames < 0 || (frames > 0 && !features_dev) || out_capacity < 0 || (out_capacity > 0 && !out_dev)) {
+    const int B = s->streams;
+    if (frames_out)
+        for (int b = 0; b < B; ++b) frames_out[b] = 0;
+    if (max_frames < 0 || !frames || (max_frames > 0 && !features_dev) || out_capacity < 0 ||
+        (out_capacity > 0 && !out_dev)) {
         set_error("stream_push: bad argument");
-        return PPGS_E_INVALID;
-    }
-    if (s->finished) {
-        set_error("stream_push: the session was finalised; call ppgs_stream_reset");
-        return PPGS_E_STATE;
-    }
-    if (s->length + frames > kStreamCapacity) {
-        // the positional-encoding limit of the reference is 5000 (transformer.py:103-104); here
-        // the cache capacity is the binding one
-        set_error("size is too large: a streaming session holds %d frames (%d pushed + %d new)",
-                  kStreamCapacity, s->length, frames);
-        return PPGS_E_TOO_LARGE;
-    }
-    const int t0 = s->length, L = t0 + frames;
-    const int keep_end = final ? L : (L - kStreamLookahead > s->emitted ? L - kStreamLookahead : s->emitted);
-    const int n_out = keep_end - s->emitted;
-    if (n_out > out_capacity) {
-        set_error("stream_push: %d output frames do not fit out_capacity %d", n_out, out_capacity);
         return PPGS_E_INVALID;
     }
     if (e->precision == PPGS_PRECISION_FP32) {
         set_error("stream_push: the streaming decoder runs the tensor-core path (precision f16x2 / f16)");
         return PPGS_E_UNSUPPORTED;
+    }
+    // validate everything before any state changes
+    for (int b = 0; b < B; ++b) {
+        const int n = frames[b];
+        if (n < 0 || n > max_frames) {
+            set_error("stream_push: stream %d brings %d frames, the feature tensor holds %d", b, n, max_frames);
+            return PPGS_E_INVALID;
+        }
+        if (s->finished[b] && (n > 0 || (final && final[b]))) {
+            set_error("stream_push: stream %d was finalised; reset it first", b);
+            return PPGS_E_STATE;
+        }
+        if (s->length[b] + n > kStreamCapacity) {
+            // the positional-encoding limit of the reference is 5000 (transformer.py:103-104); here
+            // the cache capacity is the binding one
+            set_error("size is too large: a streaming session holds %d frames (stream %d: %d pushed + %d new)",
+                      kStreamCapacity, b, s->length[b], n);
+            return PPGS_E_TOO_LARGE;
+        }
+        const int L = s->length[b] + n;
+        const bool fin = final && final[b];
+        const int keep_end = fin ? L : (L - kStreamLookahead > s->emitted[b] ? L - kStreamLookahead : s->emitted[b]);
+        if (keep_end - s->emitted[b] > out_capacity) {
+            set_error("stream_push: %d output frames of stream %d do not fit out_capacity %d",
+                      keep_end - s->emitted[b], b, out_capacity);
+            return PPGS_E_INVALID;
+        }
     }
     int prev = -1;
     cudaGetDevice(&prev);
@@ -227,50 +344,71 @@ int ppgs_stream_push(ppgs_stream* s, const void* features_dev, int frames, int f
     } restore{prev};
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int C = c.input_channels, H = c.hidden_channels, F = c.ffn_channels, O = c.output_channels;
-    const int k = c.kernel_size, B = s->streams;
+    const int k = c.kernel_size;
     const int rows = B * kStreamPitch;
     const int planes = e->precision == PPGS_PRECISION_F16X2 ? 2 : 1;
-
-    if (frames > 0) {
-        dim3 grid((frames + 31) / 32, (C + 31) / 32, B);
-        LaunchScope scope(e, "stream_append", stream);
-        stream_append_kernel<<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __half*>(features_dev), C, frames,
-                                                                t0, s->x0);
-    }
-    PPGS_CUDA(cudaGetLastError());
-    s->length = L;
-    if (final) s->finished = true;
-    if (L == 0 || (frames == 0 && n_out == 0)) return PPGS_OK;
-
-    // tiles to (re)compute: every position >= max(t0 - 4, 0) (incomplete look-ahead, and the
-    // rows the output convolution of the first emitted frame reads)
-    const int first_pos = s->emitted < t0 - kStreamLookahead ? s->emitted
-                                                               : (t0 - kStreamLookahead > 0 ? t0 - kStreamLookahead : 0);
     const int tiles_per_seq = kStreamPitch / 128;
-    int tile_first = first_pos / 128;
-    int tile_end = (L - 1) / 128 + 1;          // exclusive
-    if ((tile_end - tile_first) & 1) {         // the CTA-pair GEMMs take an even number of tiles
-        if (tile_end < tiles_per_seq) ++tile_end;
-        else --tile_first;
-    }
-    const int win_tiles = tile_end - tile_first;
 
+    // per-stream bookkeeping: new length, frames to emit, tiles to (re)compute — every position
+    // >= max(t0 - 4, 0): incomplete look-ahead, and the rows the output convolution of the
+    // first emitted frame reads
     ForwardPlan plan;
     plan.rows = rows;
     plan.max_pitch = kStreamPitch;
     plan.batch = B;
-    plan.frames = n_out;
     plan.seqs.resize(B);
+    std::vector<int> tile_first(B, 0), tile_end(B, 0);
+    PPGS_CUDA(cudaEventSynchronize(s->counts_used));
+    int win_tiles = 0, max_new = 0, max_out = 0;
+    bool any_work = false;
     for (int b = 0; b < B; ++b) {
+        const int n = frames[b], t0 = s->length[b], L = t0 + n;
+        const bool fin = final && final[b];
+        const int keep_end = fin ? L : (L - kStreamLookahead > s->emitted[b] ? L - kStreamLookahead : s->emitted[b]);
+        const int n_out = keep_end - s->emitted[b];
+        s->counts_host[b] = make_int2(t0, n);
         SeqInfo& q = plan.seqs[b];
         q.row0 = b * kStreamPitch;
         q.tensor_len = L;
         q.valid_len = L;
         q.batch = b;
-        q.src_start = 0;
-        q.keep_begin = s->emitted;
+        q.keep_begin = s->emitted[b];
         q.keep_end = keep_end;
         q.out_start = 0;
+        const bool work = L > 0 && (n > 0 || n_out > 0);
+        if (work) {
+            const int lookback = t0 - kStreamLookahead > 0 ? t0 - kStreamLookahead : 0;
+            const int first_pos = s->emitted[b] < lookback ? s->emitted[b] : lookback;
+            tile_first[b] = first_pos / 128;
+            tile_end[b] = (L - 1) / 128 + 1;
+            win_tiles = std::max(win_tiles, tile_end[b] - tile_first[b]);
+            any_work = true;
+        }
+        max_new = std::max(max_new, n);
+        max_out = std::max(max_out, n_out);
+        if (frames_out) frames_out[b] = n_out;
+        s->length[b] = L;
+        s->emitted[b] = keep_end;
+        if (fin) s->finished[b] = 1;
+    }
+    if (max_new > 0) {
+        PPGS_CHECK(upload_counts(s, stream));
+        dim3 grid((max_new + 31) / 32, (C + 31) / 32, B);
+        LaunchScope scope(e, "stream_append", stream);
+        stream_append_kernel<<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __half*>(features_dev), C,
+                                                                max_frames, s->counts_dev, s->x0);
+    }
+    PPGS_CUDA(cudaGetLastError());
+    if (!any_work) return PPGS_OK;
+
+    // one window size for every stream (the CTA-pair GEMMs take an even number of tiles); a
+    // stream that needs fewer tiles recomputes neighbours, which is idempotent
+    win_tiles = (win_tiles + 1) & ~1;
+    if (win_tiles > tiles_per_seq) win_tiles = tiles_per_seq;
+    for (int b = 0; b < B; ++b) {
+        int first = tile_first[b];
+        if (first + win_tiles > tiles_per_seq) first = tiles_per_seq - win_tiles;
+        plan.seqs[b].src_start = first;   // GemmParams::win_per_seq / attention q_first_tile = -1
     }
     PPGS_CHECK(upload_plan(e, plan, s->seqs_dev, s->tile_seq_dev, stream));
 
@@ -292,7 +430,7 @@ int ppgs_stream_push(ppgs_stream* s, const void* features_dev, int frames, int f
     base.pair = 1;
     base.win_size = win_tiles;
     base.win_stride = tiles_per_seq;
-    base.win_first = tile_first;
+    base.win_per_seq = 1;
     auto wmap = [&](TcWeight& w) -> const CUtensorMap& { return w.maps[planes - 1].bn128; };
 
     {
@@ -313,7 +451,7 @@ int ppgs_stream_push(ppgs_stream* s, const void* features_dev, int frames, int f
             PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, wmap(T.in_w), &out_qkv, p, stream));
         }
         PPGS_CHECK(launch_attention_any(e, s->qkv[layer], s->att, rows, H, c.num_heads, kStreamPitch, B,
-                                        s->seqs_dev, 1, planes, stream, tile_first, win_tiles));
+                                        s->seqs_dev, 1, planes, stream, -1, win_tiles));
         {
             GemmParams p = base;
             p.n_tiles = 1; p.cblocks = H / 64; p.a_planes = planes;
@@ -337,7 +475,7 @@ int ppgs_stream_push(ppgs_stream* s, const void* features_dev, int frames, int f
             PPGS_CHECK(launch_gemm_tc(e, "tc_ffn2_ln", 256, kEpiResLN, map_ff, wmap(T.l2_w), &out_x, p, stream));
         }
     }
-    if (n_out > 0) {
+    if (max_out > 0) {
         GemmParams p = base;
         p.pair = 0;                       // the BN = 64 kernel is single-CTA
         p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = H / 64; p.a_planes = planes;
@@ -346,8 +484,24 @@ int ppgs_stream_push(ppgs_stream* s, const void* features_dev, int frames, int f
         PPGS_CHECK(launch_gemm_tc(e, "tc_conv_out_softmax", 64, kEpiConvOut, map_x,
                                   e->tc_conv_out.maps[planes - 1].bn64, nullptr, p, stream));
     }
-    s->emitted = keep_end;
-    if (frames_out) *frames_out = n_out;
+    return PPGS_OK;
+}
+
+int ppgs_stream_push(ppgs_stream* s, const void* features_dev, int frames, int final, int softmax,
+                     float* out_dev, int out_capacity, int* frames_out, void* stream) {
+    if (!s) {
+        set_error("stream is NULL");
+        return PPGS_E_INVALID;
+    }
+    if (frames_out) *frames_out = 0;
+    if (frames < 0) {
+        set_error("stream_push: bad argument");
+        return PPGS_E_INVALID;
+    }
+    std::vector<int32_t> counts(s->streams, frames), finals(s->streams, final ? 1 : 0), produced(s->streams, 0);
+    PPGS_CHECK(ppgs_stream_push_ragged(s, features_dev, frames, counts.data(), finals.data(), softmax, out_dev,
+                                       out_capacity, produced.data(), stream));
+    if (frames_out) *frames_out = produced[0];
     return PPGS_OK;
 }
 

@@ -38,13 +38,32 @@ class Streamer:
     length = property(lambda self: _lib.lib.ppgs_stream_length(self._handle))
     emitted = property(lambda self: _lib.lib.ppgs_stream_emitted(self._handle))
 
-    def reset(self):
-        _lib.check(_lib.lib.ppgs_stream_reset(self._handle, _stream_ptr(self.engine.device)))
-        self._audio, self._frames_in, self._samples_seen = None, 0, 0
+    def reset(self, streams=None):
+        """Start over: every stream, or only the listed ones (the others keep their state)."""
+        if streams is None:
+            _lib.check(_lib.lib.ppgs_stream_reset(self._handle, _stream_ptr(self.engine.device)))
+            self._audio, self._frames_in, self._samples_seen = None, 0, 0
+            return
+        flags = (ctypes.c_int32 * self.streams)(*[0] * self.streams)
+        for index in streams:
+            flags[index] = 1
+        _lib.check(_lib.lib.ppgs_stream_reset_streams(
+            self._handle, flags, _stream_ptr(self.engine.device)))
 
-    def push(self, features=None, final=False, softmax=True):
+    def state(self):
+        """(lengths, emitted) per stream."""
+        lengths = (ctypes.c_int32 * self.streams)()
+        emitted = (ctypes.c_int32 * self.streams)()
+        _lib.check(_lib.lib.ppgs_stream_state(self._handle, lengths, emitted))
+        return list(lengths), list(emitted)
+
+    def push(self, features=None, final=False, softmax=True, lengths=None):
         """features (streams, channels, n) fp16 (or None / n = 0 with `final` to flush)
-        -> posteriorgram frames that became final, (streams, 40, m) fp32 CUDA."""
+        -> posteriorgram frames that became final, (streams, 40, m) fp32 CUDA.
+
+        Independent streams: `lengths` = frames each stream brings (the first lengths[b]
+        columns of its row) and `final` may be a per-stream sequence; the result is then
+        (out, produced) with produced[b] valid frames in row b."""
         device = self.engine.device
         if features is None:
             features = torch.empty(self.streams, self.engine.cfg.input_channels, 0,
@@ -58,12 +77,30 @@ class Streamer:
         capacity = frames + self.LOOKAHEAD
         out = torch.empty(self.streams, self.engine.cfg.output_channels, capacity,
                           dtype=torch.float32, device=device)
-        produced = ctypes.c_int()
-        _lib.check(_lib.lib.ppgs_stream_push(
-            self._handle, ctypes.c_void_p(features.data_ptr()), frames, int(bool(final)),
-            int(bool(softmax)), ctypes.c_void_p(out.data_ptr()), capacity, ctypes.byref(produced),
+        ragged = lengths is not None or not isinstance(final, (bool, int))
+        if not ragged:
+            produced = ctypes.c_int()
+            _lib.check(_lib.lib.ppgs_stream_push(
+                self._handle, ctypes.c_void_p(features.data_ptr()), frames, int(bool(final)),
+                int(bool(softmax)), ctypes.c_void_p(out.data_ptr()), capacity, ctypes.byref(produced),
+                _stream_ptr(device)))
+            return out[..., :produced.value]
+        if lengths is None:
+            lengths = [frames] * self.streams
+        if torch.is_tensor(lengths):
+            lengths = lengths.tolist()
+        finals = [bool(final)] * self.streams if isinstance(final, (bool, int)) else list(final)
+        if len(lengths) != self.streams or len(finals) != self.streams:
+            raise ValueError(f'expected {self.streams} lengths / final flags')
+        counts = (ctypes.c_int32 * self.streams)(*[int(n) for n in lengths])
+        flags = (ctypes.c_int32 * self.streams)(*[int(bool(f)) for f in finals])
+        produced = (ctypes.c_int32 * self.streams)()
+        _lib.check(_lib.lib.ppgs_stream_push_ragged(
+            self._handle, ctypes.c_void_p(features.data_ptr()), frames, counts, flags,
+            int(bool(softmax)), ctypes.c_void_p(out.data_ptr()), capacity, produced,
             _stream_ptr(device)))
-        return out[..., :produced.value]
+        produced = list(produced)
+        return out[..., :max(produced) if produced else 0], produced
 
     def push_audio(self, audio, final=False, softmax=True):
         """16 kHz audio (streams, 1, n) appended to the session.  Mel frame t reads samples

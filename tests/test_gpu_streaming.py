@@ -170,3 +170,66 @@ def test_long_streamer_equals_chunked_reference(ppgs_b200, engine, state, total,
     batch = engine.transformer(features.cuda(), lengths).cpu()
     assert (batch - result).abs().max() <= 2e-5
     engine.check()
+
+
+def test_independent_streams_join_finish_and_restart(ppgs_b200, engine, state):
+    """Serving: four streams with their own utterances, push sizes, end points and restarts.
+    Whatever the interleaving, each utterance's frames equal its own whole-utterance causal
+    forward."""
+    import random
+    random.seed(4)
+    streams = 4
+    streamer = ppgs_b200.Streamer(engine, streams)
+    totals = [[300, 77], [510], [40, 40, 200], [129, 256]]          # utterances per stream
+    features, references = {}, {}
+    for b, lengths in enumerate(totals):
+        for u, total in enumerate(lengths):
+            _, f, r = features_and_reference(state, 1, total, seed=100 * b + u)
+            features[b, u], references[b, u] = f[0], r[0]
+    utterance = [0] * streams                     # current utterance of each stream
+    position = [0] * streams
+    collected = {key: [] for key in features}
+    steps = 0
+    while any(utterance[b] < len(totals[b]) for b in range(streams)):
+        steps += 1
+        counts, finals = [], []
+        for b in range(streams):
+            if utterance[b] >= len(totals[b]):
+                counts.append(0)
+                finals.append(False)
+                continue
+            total = totals[b][utterance[b]]
+            n = min(random.choice([0, 1, 7, 33, 64, 128, 160]), total - position[b])
+            counts.append(n)
+            finals.append(position[b] + n == total)
+        width = max(max(counts), 1)
+        chunk = torch.zeros(streams, 80, width, dtype=torch.float16)
+        for b, n in enumerate(counts):
+            if n:
+                chunk[b, :, :n] = features[b, utterance[b]][:, position[b]:position[b] + n]
+        out, produced = streamer.push(chunk.cuda(), final=finals, lengths=counts)
+        lengths_now, emitted_now = streamer.state()
+        finished = []
+        for b in range(streams):
+            if utterance[b] >= len(totals[b]):
+                assert produced[b] == 0
+                continue
+            position[b] += counts[b]
+            assert lengths_now[b] == position[b]
+            collected[b, utterance[b]].append(out[b, :, :produced[b]].cpu())
+            if finals[b]:
+                assert emitted_now[b] == totals[b][utterance[b]]
+                finished.append(b)
+        if finished:                                # those streams start their next utterance
+            streamer.reset(streams=finished)
+            for b in finished:
+                utterance[b] += 1
+                position[b] = 0
+    assert steps > 10
+    for key, pieces in collected.items():
+        result = torch.cat(pieces, dim=-1)
+        assert result.shape == references[key].shape
+        assert (result - references[key]).abs().max() <= PPG_TOL, key
+    with pytest.raises(ValueError, match='brings'):
+        streamer.push(torch.zeros(streams, 80, 2, dtype=torch.float16).cuda(), lengths=[3, 0, 0, 0])
+    engine.check()
