@@ -211,3 +211,28 @@ def test_files_sharded_over_a_gpu_list(ppgs_b200, tmp_path):
     for a, b, n in zip(single, sharded, lengths):
         x, y = torch.load(a), torch.load(b)
         assert x.shape == (40, n // 160) and torch.equal(x, y)
+
+
+def test_native_file_pipeline_uniform_batches_replay_graphs(ppgs_b200, tmp_path, monkeypatch):
+    """Equal-length files: every batch has the same plan, so the pipeline's forwards are
+    replayed from the engine's CUDA-graph cache — the files still equal the per-batch API's."""
+    sd = O.random_state_dict(10, peaky=True)
+    checkpoint = tmp_path / 'ckpt.pt'
+    torch.save({'model': sd}, checkpoint)
+    files = make_files(tmp_path, [16000] * 50)
+    native = [str(tmp_path / f'{i}-native.pt') for i in range(len(files))]
+    python = [str(tmp_path / f'{i}-python.pt') for i in range(len(files))]
+    engine = ppgs_b200.load.model(checkpoint, 'mel', 0)
+    before = engine.graph_replays
+    ppgs_b200.from_files_to_files(files, native, checkpoint=checkpoint, num_workers=4, gpu=0,
+                                  max_frames=500)      # 5 files per batch, 10 equal batches
+    assert engine.graph_replays - before == 9
+    monkeypatch.setenv('PPGS_B200_NATIVE_FILES', '0')
+    engine.set_graphs(False)
+    try:
+        ppgs_b200.from_files_to_files(files, python, checkpoint=checkpoint, num_workers=4, gpu=0,
+                                      max_frames=500)
+    finally:
+        engine.set_graphs(True)
+    for a, b in zip(native, python):
+        assert torch.equal(torch.load(a), torch.load(b))
