@@ -206,8 +206,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
     int nkeys = s.valid_len;
     if (p.causal) nkeys = min(nkeys, q0 + 128);
     const int64_t out_row0 = (int64_t)(s.row0 + q0);
+    pdl_launch_dependents();
     if (nkeys <= 0) {
         // every key masked (chunk_lengths == 0 rows of transformer.py:59-60): zeros
+        pdl_wait();
         for (int i = threadIdx.x; i < 128 * D; i += kAttnThreads) {
             const int r = i / D, d = i - r * D;
             __half* dst = p.out + (out_row0 + r) * p.H + head * D + d;
@@ -239,6 +241,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    pdl_wait();   // Q / K / V of the previous kernel are needed from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -560,7 +563,19 @@ static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int 
     dim3 grid(q_tiles > 0 ? q_tiles : max_pitch / 128, heads, (unsigned)nseq);
     {
         LaunchScope scope(e, "tc_attention", stream);
-        attention_tc_kernel<D><<<grid, kAttnThreads, Shape::kSmem, stream>>>(map_qk, map_v, map_out, p);
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attrs[1];
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kAttnThreads);
+        cfg.dynamicSmemBytes = Shape::kSmem;
+        cfg.stream = stream;
+        if (pdl_enabled()) {
+            attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attrs[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attrs;
+            cfg.numAttrs = 1;
+        }
+        PPGS_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<D>, map_qk, map_v, map_out, p));
     }
     PPGS_CUDA(cudaGetLastError());
     return PPGS_OK;

@@ -143,6 +143,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    // the set-up above may overlap the previous kernel; its results are needed from here on
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------ producer
@@ -584,6 +587,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+bool pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("PPGS_B200_PDL"); return v && atoi(v) != 0; }();
+    return on;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -679,7 +687,7 @@ static int launch_one(ppgs_engine* e, const char* name, const CUtensorMap& map_a
                                        (int)Shape::kSmemBytes));
     }
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attrs[1];
+    cudaLaunchAttribute attrs[2];
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Shape::kSmemBytes;
     cfg.stream = stream;
@@ -698,6 +706,12 @@ static int launch_one(ppgs_engine* e, const char* name, const CUtensorMap& map_a
         cfg.numAttrs = 1;
     } else {
         cfg.gridDim = dim3(std::min(p.m_tiles * p.n_tiles, e->sm_count));
+    }
+    if (pdl_enabled()) {
+        cfg.attrs = attrs;
+        attrs[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs += 1;
     }
     {
         LaunchScope scope(e, name, stream);

@@ -71,6 +71,10 @@ int make_plane_map(CUtensorMap* map, const __half* base, bool rank4, uint64_t in
 // of a strided convolution over time-major activations (rank-3 maps only).
 
 // BN in {256, 128, 64}.  Launches a persistent grid of min(tiles, SMs) CTAs.
+// PPGS_B200_PDL=1: GEMM and attention kernels are launched with programmatic stream serialisation
+// (their prologues overlap the previous kernel's tail; see pdl_wait in tc_common.cuh)
+bool pdl_enabled();
+
 // Store map over output planes [2][rows][inner]: box {64, 128, 1 plane}, 128-byte
 // swizzle (the epilogue's staging layout).
 int make_store_map(CUtensorMap* map, __half* base, uint64_t inner, uint64_t rows,
