@@ -41,7 +41,7 @@ def from_audio(
     Arguments
         audio: batched audio, shape=(batch, 1, samples) (or (1, samples))
         sample_rate: audio sampling rate
-        representation: 'mel' (w2v2fb: not built yet)
+        representation: 'mel' or 'w2v2fb'
         checkpoint: the checkpoint file
         gpu: CUDA ordinal
         legacy_mode: use legacy (unchunked) inference

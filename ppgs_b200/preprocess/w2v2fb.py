@@ -1,5 +1,6 @@
 """w2v2fb representation (ppgs/preprocess/w2v2fb/core.py:32-94): wav2vec2-base latents at
-the PPG frame rate, computed by the CUDA library (fp32 CUDA-core arithmetic this round)."""
+the PPG frame rate, computed by the CUDA library (split-fp16 tcgen05 GEMMs / attention,
+fp32 GroupNorm / LayerNorm; PPGS_B200_W2V2_TC=0 keeps everything in fp32 on the CUDA cores)."""
 import os
 
 import torch

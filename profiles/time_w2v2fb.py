@@ -1,5 +1,5 @@
 """BASELINE config 3 (w2v2fb, batch = 32 x 10 s) timing of the CUDA front-end + d=512 PPG
-head (both fp32 CUDA-core arithmetic this round) — context for DESIGN.md, not the headline."""
+head, per-kernel — context for DESIGN.md, not the headline (see `bench.py --workload w2v2fb`)."""
 import os
 import sys
 import time
