@@ -399,3 +399,33 @@ def test_cuda_graph_replay_is_bitwise_the_launch_path(ppgs_b200):
     engine.precision = 'f16x2'
     assert torch.equal(forward(y), want_other)
     engine.check()
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_from_audio_random_batches_vs_oracle(ppgs_b200, seed):
+    """Seeded random batch shapes (1-7 utterances, ragged lengths from 3 frames to 3.2 chunks,
+    sample counts that are not multiples of the hop) against the oracle, device and host
+    entry points, repeated so that the CUDA-graph cache is exercised on odd shapes too."""
+    rng = np.random.default_rng(1000 + seed)
+    batch = int(rng.integers(1, 8))
+    longest = int(rng.choice([437, 160 * 37 + 5, 160 * 400, 160 * 500 + 159, 160 * 777 + 80, 160 * 1600]))
+    lengths = [longest] + [int(rng.integers(433, longest + 1)) for _ in range(batch - 1)]
+    order = rng.permutation(batch)
+    lengths = [lengths[i] for i in order]
+    sd = O.random_state_dict(50 + seed, peaky=bool(seed % 2))
+    engine = make_engine(ppgs_b200, sd, 'f16x2')
+    audio = O.synthetic_audio(batch, longest, 70 + seed)
+    for row, n in enumerate(lengths):
+        audio[row, :, n:] = 0                      # zero padding, like the reference collate
+    sample_lengths = torch.tensor(lengths)
+    ref = O.from_audio(sd, audio, lengths=sample_lengths)
+    frames = [n // 160 for n in lengths]
+    pinned = audio.squeeze(1).contiguous().pin_memory()
+    for repeat in range(3):
+        out = engine.from_audio(audio.cuda(), lengths=sample_lengths).cpu()
+        host = engine.from_audio_host(pinned, lengths=sample_lengths)
+        assert out.shape == ref.shape == host.shape
+        for row, n in enumerate(frames):
+            assert (out[row, :, :n] - ref[row, :, :n]).abs().max() <= PPG_TOL
+            assert torch.equal(host[row, :, :n], out[row, :, :n])
+    engine.check()
