@@ -67,9 +67,10 @@ def ncu_traffic(kernel):
     None when the kernel has no capture."""
     path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if not os.path.exists(path):
-        return None, None
+        return None, None, None
     entry = json.load(open(path)).get('kernels', {}).get(kernel)
-    return (None, None) if entry is None else (entry['dram_bytes'], entry['source'])
+    return (None, None, None) if entry is None else (
+        entry['dram_bytes'], entry['source'], entry.get('tensor_pipe_active_pct'))
 
 
 class ClockSampler:
@@ -439,10 +440,12 @@ def main():
         'ffn': 2 * FFN_FLOPS_PER_LAUNCH_HALF * computed, 'qkv': 2 * 3 * H * H * computed,
         'out_proj': 2 * H * H * computed, 'conv_in': 2 * KSIZE * C_IN * H * computed,
         'conv_out': 2 * KSIZE * H * O_OUT * computed, 'attention': BATCH * ATTN_PER_UTT / LAYERS}
-    traffic, traffic_source = ncu_traffic(name)
+    traffic, traffic_source, tensor_pipe = ncu_traffic(name)
     roofline = {'kernel': name, 'share_of_step': kernel_ms / total_kernel_ms,
                 'ms_per_launch': per_launch_ms, 'traffic': traffic, 'traffic_unit': 'bytes per launch',
-                'traffic_source': traffic_source}
+                'traffic_source': traffic_source,
+                # committed ncu capture of this kernel (not measured in this run)
+                'ncu_tensor_pipe_active_pct': tensor_pipe}
     key = next((k for k in sorted(flops_by_kernel, key=len, reverse=True) if k in name), None)
     if key is not None:
         achieved = flops_by_kernel[key] / (per_launch_ms * 1e-3) / 1e12
