@@ -95,6 +95,21 @@ def collate(audios, pin_memory=False):
     return padded, lengths
 
 
+# Engine workspace per output frame at the default model: activations of 1.25 computed frames
+# (x, QKV, attention output, FFN hidden as split planes) + features + posteriors
+WORKSPACE_BYTES_PER_FRAME = 16 * 1024
+
+
+def bounded_max_frames(max_frames):
+    """The reference's default `max_frames` is infinite (ppgs/config/static.py:22): every file
+    lands in ONE batch, which cannot work for a corpus.  An infinite budget is replaced by
+    what a quarter of the free GPU memory holds (warned once); finite budgets are kept."""
+    if max_frames != float('inf') or not torch.cuda.is_available():
+        return max_frames
+    free, _ = torch.cuda.mem_get_info()
+    return max(int(free // 4 // WORKSPACE_BYTES_PER_FRAME), 1000)
+
+
 class Loader:
     """Iterable of (audio (B,1,max_samples) pinned fp32, lengths (B,) int64
     samples, [audio_file]) — what `ppgs.data.loader(files, ['audio','length',
@@ -105,6 +120,12 @@ class Loader:
                  prefetch=2, shard=None, dataset=None):
         # `dataset`: reuse the header probe of another shard's loader
         self.dataset = dataset if dataset is not None else Metadata(audio_files, max_frames)
+        budget = bounded_max_frames(max_frames)
+        if budget != max_frames and sum(self.dataset.lengths) > budget:
+            warnings.warn(
+                f'max_frames is unbounded and the files hold {sum(self.dataset.lengths)} frames: '
+                f'batching with max_frames={budget} (a quarter of the free GPU memory)')
+            max_frames = budget
         self.batches = frame_budget_batches(self.dataset.lengths, max_frames)
         if shard is not None:
             rank, world = shard
