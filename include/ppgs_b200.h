@@ -204,6 +204,12 @@ size_t ppgs_engine_workspace_bytes(const ppgs_engine* engine);
 int ppgs_wav_info(const char* path, int64_t* frames, int* sample_rate, int* channels,
                   int* bits, int* is_float);
 
+/* The same probe over a file list on `threads` host threads (the Metadata loop of
+ * ppgs/data/dataset.py:180-198 for a corpus); status[i] is the per-file PPGS_* code. */
+int ppgs_wav_info_many(const char* const* paths, int64_t count, int threads, int64_t* frames,
+                       int32_t* sample_rate, int32_t* channels, int32_t* bits, int32_t* is_float,
+                       int32_t* status);
+
 /* torchaudio.load as used by ppgs/load.py:17-30, for WAVE files: channel 0 (what
  * ppgs/data/collate.py:27 keeps) as fp32 normalised to [-1, 1) (int16 / 32768 ...). */
 int ppgs_wav_read_f32(const char* path, float* dst_host, int64_t capacity, int64_t* frames,

@@ -66,6 +66,9 @@ SYMBOLS = {
                                      _c.POINTER(_i64)]),
     'ppgs_wav_info': (_i, [_c.c_char_p, _c.POINTER(_i64), _c.POINTER(_i), _c.POINTER(_i),
                            _c.POINTER(_i), _c.POINTER(_i)]),
+    'ppgs_wav_info_many': (_i, [_c.POINTER(_c.c_char_p), _i64, _i, _c.POINTER(_i64),
+                                _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32),
+                                _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
     'ppgs_wav_read_f32': (_i, [_c.c_char_p, _vp, _i64, _c.POINTER(_i64), _c.POINTER(_i)]),
     'ppgs_pcm16_to_f32': (_i, [_vp, _vp, _i64, _vp, _vp]),
     'ppgs_resample_length': (_i64, [_i64, _i, _i]),

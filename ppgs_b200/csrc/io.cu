@@ -695,6 +695,37 @@ int ppgs_wav_info(const char* path, int64_t* frames, int* sample_rate, int* chan
     return PPGS_OK;
 }
 
+int ppgs_wav_info_many(const char* const* paths, int64_t count, int threads, int64_t* frames,
+                       int32_t* sample_rate, int32_t* channels, int32_t* bits, int32_t* is_float,
+                       int32_t* status) {
+    if (!paths || count < 0 || !frames || !sample_rate || !channels || !bits || !is_float || !status) {
+        set_error("wav_info_many: bad argument");
+        return PPGS_E_INVALID;
+    }
+    threads = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+    if (count < 64) threads = 1;
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= count) return;
+            int rate = 0, ch = 0, b = 0, f = 0;
+            int64_t n = 0;
+            status[i] = ppgs_wav_info(paths[i], &n, &rate, &ch, &b, &f);
+            frames[i] = n;
+            sample_rate[i] = rate;
+            channels[i] = ch;
+            bits[i] = b;
+            is_float[i] = f;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    return PPGS_OK;
+}
+
 int ppgs_wav_read_f32(const char* path, float* dst, int64_t capacity, int64_t* frames, int* sample_rate) {
     if (!path || !dst) {
         set_error("wav_read_f32: bad argument");

@@ -28,8 +28,8 @@ class Metadata:
         self.audio_files, self.lengths, self.samples = [], [], {}
         # every file is 16-bit PCM at 16 kHz: eligible for ppgs_files_to_files
         self.native = True
-        for audio_file in audio_files:
-            info = load.wav_info(audio_file)
+        audio_files = list(audio_files)
+        for audio_file, info in zip(audio_files, load.wav_info_many(audio_files)):
             if info is None:
                 samples, sample_rate = load.wav_num_frames(audio_file)
                 self.native = False

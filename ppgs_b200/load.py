@@ -32,6 +32,29 @@ def wav_info(file):
             'bits': bits.value, 'is_float': bool(is_float.value)}
 
 
+def wav_info_many(files, threads=16):
+    """`wav_info` of every file in one native call (header probes on `threads` host threads);
+    entries are None for files the library does not decode."""
+    count = len(files)
+    if count == 0:
+        return []
+    paths = (ctypes.c_char_p * count)(*[os.fsencode(str(file)) for file in files])
+    frames = (ctypes.c_int64 * count)()
+    arrays = [(ctypes.c_int32 * count)() for _ in range(5)]   # rate, channels, bits, is_float, status
+    _lib.check(_lib.lib.ppgs_wav_info_many(paths, count, int(threads), frames, *arrays))
+    rate, channels, bits, is_float, status = arrays
+    infos = []
+    for i in range(count):
+        if status[i] == _lib.E_UNSUPPORTED:
+            infos.append(None)
+        elif status[i] != 0:
+            infos.append(wav_info(files[i]))     # raises with the file's own message
+        else:
+            infos.append({'samples': frames[i], 'sample_rate': rate[i], 'channels': channels[i],
+                          'bits': bits[i], 'is_float': bool(is_float[i])})
+    return infos
+
+
 def audio(file, device=None):
     """Load audio from disk as (channels, samples) fp32 at 16 kHz
     (ppgs/load.py:17-30).  Mono PCM / float WAVE files are decoded by the native

@@ -172,3 +172,21 @@ def test_metadata_flags_native_eligibility(tmp_path):
     assert not metadata.native and metadata.lengths == [100, 100]
     wavfile.write(c, 16000, np.zeros(1600, np.float32))
     assert not data.Metadata([a, c]).native
+
+
+def test_wav_info_many_matches_single_probe(library, tmp_path):
+    from ppgs_b200 import load
+    files = []
+    for i in range(130):      # > 64: the threaded path
+        files.append(tmp_path / f'{i}.wav')
+        write_wav(files[-1], 100 + i, rate=16000 if i % 3 else 8000, channels=1 + i % 2)
+    other = tmp_path / 'x.mp3'
+    other.write_bytes(b'ID3' + bytes(40))
+    files.insert(7, other)
+    infos = load.wav_info_many(files, threads=8)
+    assert infos[7] is None
+    for file, info in zip(files, infos):
+        assert info == load.wav_info(file)
+    with pytest.raises(ValueError, match='cannot open'):
+        load.wav_info_many(files + [tmp_path / 'missing.wav'])
+    assert load.wav_info_many([]) == []
