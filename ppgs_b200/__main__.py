@@ -16,8 +16,9 @@ def parse_args(argv=None):
     parser.add_argument('--checkpoint', type=Path, help='The checkpoint file')
     parser.add_argument('--num-workers', type=int, default=0,
                         help='Number of CPU threads for reading / saving')
-    parser.add_argument('--gpu', type=int,
-                        help='The index of the GPU to use for inference (default: current)')
+    parser.add_argument('--gpu', type=int, nargs='+',
+                        help='The index of the GPU to use for inference (default: current); '
+                             'several indices shard the file list over those GPUs')
     parser.add_argument('--max-frames', type=float, default=ppgs_b200.MAX_INFERENCE_FRAMES,
                         help='Maximum number of frames in a batch')
     parser.add_argument('--legacy-mode', action='store_true',
@@ -31,6 +32,10 @@ def main(argv=None):
     args = vars(parse_args(argv))
     for file in args.pop('config', None) or []:
         ppgs_b200.configure(file)
+    if args['gpu'] is not None and len(args['gpu']) == 1:
+        args['gpu'] = args['gpu'][0]
+    if isinstance(args['gpu'], list) and args['num_workers'] == 0:
+        args['num_workers'] = 2 * len(args['gpu'])     # the sharded path is the batched one
     ppgs_b200.from_files_to_files(**args)
 
 
