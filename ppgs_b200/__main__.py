@@ -25,15 +25,16 @@ def parse_args(argv=None):
                         help='Use legacy (unchunked) inference')
     parser.add_argument('--config', type=Path, nargs='*',
                         help='yapecs-style configuration files (UPPER_CASE overrides)')
-    return parser.parse_args(argv)
+    args = parser.parse_args(argv)
+    if args.gpu is not None and len(args.gpu) == 1:
+        args.gpu = args.gpu[0]          # one index: the reference's `--gpu N`
+    return args
 
 
 def main(argv=None):
     args = vars(parse_args(argv))
     for file in args.pop('config', None) or []:
         ppgs_b200.configure(file)
-    if args['gpu'] is not None and len(args['gpu']) == 1:
-        args['gpu'] = args['gpu'][0]
     if isinstance(args['gpu'], list) and args['num_workers'] == 0:
         args['num_workers'] = 2 * len(args['gpu'])     # the sharded path is the batched one
     ppgs_b200.from_files_to_files(**args)

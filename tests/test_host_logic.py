@@ -89,6 +89,8 @@ def test_cli_flags_match_reference():
     assert [str(p) for p in args.audio_files] == ['a.wav', 'b.wav']
     assert args.num_workers == 4 and args.gpu == 1 and args.legacy_mode
     assert args.representation == 'mel' and args.max_frames == 64000
+    sharded = parse_args(['--audio_files', 'a.wav', '--output_files', 'a.pt', '--gpu', '0', '1', '3'])
+    assert sharded.gpu == [0, 1, 3]
 
 
 def test_unknown_representation_raises_value_error():
