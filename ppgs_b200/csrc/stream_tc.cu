@@ -58,22 +58,23 @@ __global__ void stream_append_kernel(const __half* __restrict__ feats, int C, in
     }
 }
 
-// reset of single streams: the feature rows and the residual stream must read as zero beyond
-// the (new) length; the K / V caches may keep stale finite values (masked by the key count)
-__global__ void stream_clear_kernel(const int2* __restrict__ flags, __half* __restrict__ x0, int C,
-                                    __half* __restrict__ xh, int H, int64_t plane_stride) {
-    const int b = blockIdx.y;
-    if (!flags[b].x) return;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t n0 = (int64_t)kStreamPitch * C / 2, n1 = (int64_t)kStreamPitch * H / 2;
-    uint32_t* a = reinterpret_cast<uint32_t*>(x0 + (int64_t)b * kStreamPitch * C);
-    uint32_t* h0 = reinterpret_cast<uint32_t*>(xh + (int64_t)b * kStreamPitch * H);
-    uint32_t* h1 = reinterpret_cast<uint32_t*>(xh + plane_stride + (int64_t)b * kStreamPitch * H);
-    if (i < n0) a[i] = 0u;
-    if (i < n1) {
-        h0[i] = 0u;
-        h1[i] = 0u;
-    }
+// reset of single streams: every region of the stream's state reads as zero afterwards (the
+// feature rows and the residual stream must be zero beyond the new length; the K / V caches
+// are cleared too so that non-finite values of an earlier utterance cannot leak through the
+// masked tail of a key block)
+struct ClearRegions {
+    uint32_t* base[16];       // region start of stream 0, as 32-bit words
+    int64_t words[16];        // words per stream in that region
+    int count;
+};
+
+__global__ void stream_clear_kernel(const int2* __restrict__ flags, ClearRegions regions) {
+    const int b = blockIdx.y, r = blockIdx.z;
+    if (!flags[b].x || r >= regions.count) return;
+    uint4* dst = reinterpret_cast<uint4*>(regions.base[r] + (int64_t)b * regions.words[r]);
+    const int64_t n = regions.words[r] / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 }  // namespace ppgs
@@ -273,13 +274,24 @@ int ppgs_stream_reset_streams(ppgs_stream* s, const int32_t* flags, void* stream
     if (!any) return PPGS_OK;
     PPGS_CHECK(upload_counts(s, stream));
     const ppgs_model_config& c = e->cfg;
-    const int64_t widest = (int64_t)kStreamPitch * (c.hidden_channels > c.input_channels ? c.hidden_channels
-                                                                                          : c.input_channels) / 2;
+    const int64_t rows = (int64_t)s->streams * kStreamPitch;
+    ClearRegions regions;
+    regions.count = 0;
+    auto add = [&](__half* base, int64_t halves_per_stream) {
+        regions.base[regions.count] = reinterpret_cast<uint32_t*>(base);
+        regions.words[regions.count] = halves_per_stream / 2;
+        regions.count += 1;
+    };
+    add(s->x0, (int64_t)kStreamPitch * c.input_channels);
+    for (int plane = 0; plane < 2; ++plane)
+        add(s->xh + plane * rows * c.hidden_channels, (int64_t)kStreamPitch * c.hidden_channels);
+    for (size_t layer = 0; layer < s->qkv.size() && regions.count + 2 <= 16; ++layer)
+        for (int plane = 0; plane < 2; ++plane)
+            add(s->qkv[layer] + plane * rows * 3 * c.hidden_channels,
+                (int64_t)kStreamPitch * 3 * c.hidden_channels);
     {
         LaunchScope scope(e, "stream_clear", stream);
-        stream_clear_kernel<<<dim3((unsigned)((widest + 255) / 256), s->streams), 256, 0, stream>>>(
-            s->counts_dev, s->x0, c.input_channels, s->xh, c.hidden_channels,
-            (int64_t)s->streams * kStreamPitch * c.hidden_channels);
+        stream_clear_kernel<<<dim3(48, s->streams, regions.count), 256, 0, stream>>>(s->counts_dev, regions);
     }
     PPGS_CUDA(cudaGetLastError());
     return PPGS_OK;

@@ -233,3 +233,24 @@ def test_independent_streams_join_finish_and_restart(ppgs_b200, engine, state):
     with pytest.raises(ValueError, match='brings'):
         streamer.push(torch.zeros(streams, 80, 2, dtype=torch.float16).cuda(), lengths=[3, 0, 0, 0])
     engine.check()
+
+
+def test_stream_reset_isolates_utterances(ppgs_b200, engine, state):
+    """Non-finite features in one utterance neither reach the other stream nor the next
+    utterance of the same stream after its reset."""
+    _, features, reference = features_and_reference(state, 2, 200, seed=17)
+    streamer = ppgs_b200.Streamer(engine, 2)
+    poisoned = features.clone()
+    poisoned[0, :, 60:90] = float('nan')
+    out, produced = streamer.push(poisoned.cuda(), final=[True, True], lengths=[200, 200])
+    assert produced == [200, 200]
+    assert not torch.isfinite(out[0]).all()
+    assert (out[1].cpu() - reference[1]).abs().max() <= PPG_TOL      # the neighbour is untouched
+    streamer.reset(streams=[0])
+    out, produced = streamer.push(features[:, :, :130].cuda(), final=[True, False], lengths=[130, 0])
+    assert produced == [130, 0]
+    _, _, short = features_and_reference(state, 2, 200, seed=17)
+    expected = O.from_features(state, features[:1, :, :130], torch.tensor([130]), is_causal=True,
+                               legacy_mode=True)
+    assert (out[0, :, :130].cpu() - expected[0]).abs().max() <= PPG_TOL
+    engine.check()
