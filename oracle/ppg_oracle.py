@@ -9,7 +9,7 @@ Parity pin: the reference ships NO tests, golden vectors or fixtures
 (SURVEY.md §4), so this oracle is pinned against *outputs of the reference's own
 modules run in the dev container* under `oracle/refshim.py` (script:
 `oracle/make_golden.py`; committed fixtures: `tests/golden/*.npz`; live check:
-`tests/test_oracle_vs_reference.py`, which runs whenever `/root/reference`
+`tests/test_oracle_golden.py::test_oracle_vs_live_reference`, which runs whenever `/root/reference`
 exists).  Third-party boundaries that remain unpinned: `torchutil.inference
 .context` (restated, package absent) and `librosa.filters.mel` (restated from the
 published Slaney construction, checked against torchaudio's implementation).

@@ -1,7 +1,7 @@
 """Import the UNMODIFIED reference (`/root/reference/ppgs`) in the dev container.
 
 TEST INFRASTRUCTURE ONLY.  Used by `oracle/make_golden.py` (and by
-`tests/test_oracle_vs_reference.py` when `/root/reference` exists) to pin the
+`tests/test_oracle_golden.py::test_oracle_vs_live_reference` when `/root/reference` exists) to pin the
 oracle restatement against the reference's own modules.  Never imported by the
 product package, by `-m gpu` tests, by `smoke()` or by `bench.py` — the
 reference tree does not exist on the GPU box.
