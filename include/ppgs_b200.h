@@ -240,6 +240,10 @@ int ppgs_resample_taps(int orig_rate, int target_rate, float* taps, int64_t capa
  * batch row is a strided read). */
 int ppgs_pt_write_f32(const char* path, const float* data_host, int64_t rows, int64_t cols,
                       int64_t row_stride);
+/* Same for an fp16 tensor (torch.HalfStorage): the feature files of `python -m ppgs.preprocess`
+ * (ppgs/preprocess/core.py:105-190 saves the fp16 representations with save_masked). */
+int ppgs_pt_write_f16(const char* path, const void* data_host, int64_t rows, int64_t cols,
+                      int64_t row_stride);
 
 /* The batching loop of ppgs.from_files_to_files / from_dataloader (ppgs/core.py:207-391)
  * for the mel representation as ONE call: `reader_threads` threads decode 16-bit PCM

@@ -36,6 +36,7 @@ LAYER_NORM_EPS = 1e-5            # torch.nn.TransformerEncoderLayer default
 BUCKETS = 1
 RANDOM_SEED = 1234
 MAX_INFERENCE_FRAMES = float('inf')
+MAX_PREPROCESS_FRAMES = 10000    # defaults.py:188
 
 # PPG distance (defaults.py:93,214): the reference ships assets/balanced_similarity.pt; set
 # SIMILARITY_MATRIX_PATH to that file (or pass `similarity=` to ppgs_b200.distance)

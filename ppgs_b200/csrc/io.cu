@@ -264,14 +264,14 @@ static void pickle_unicode(ByteSink& s, const char* text) {
 
 // The pickle torch.save emits for one contiguous fp32 CPU tensor of shape (rows, cols)
 // (memo PUTs omitted; the unpickler does not need them).
-static void tensor_pickle(ByteSink& s, int64_t rows, int64_t cols) {
+static void tensor_pickle(ByteSink& s, int64_t rows, int64_t cols, const char* storage_global) {
     s.u8(0x80);
     s.u8(2);
     s.str("ctorch._utils\n_rebuild_tensor_v2\n");
     s.u8('(');
     s.u8('(');
     pickle_unicode(s, "storage");
-    s.str("ctorch\nFloatStorage\n");
+    s.str(storage_global);
     pickle_unicode(s, "0");
     pickle_unicode(s, "cpu");
     pickle_int(s, rows * cols);
@@ -384,25 +384,28 @@ static std::string archive_stem(const char* path) {
 
 // `data`: rows x cols fp32, row stride `row_stride` elements (cropping a padded batch row
 // is a strided read here, the file always holds the contiguous tensor).
-static int pt_write(const char* path, const float* data, int64_t rows, int64_t cols, int64_t row_stride,
-                    std::vector<float>& contiguous, ByteSink& head) {
+// `elem` = bytes per element (4: torch.FloatStorage, 2: torch.HalfStorage)
+static int pt_write(const char* path, const void* data_, int64_t rows, int64_t cols, int64_t row_stride,
+                    std::vector<float>& contiguous, ByteSink& head, int elem = 4) {
+    const char* data = static_cast<const char*>(data_);
     if (rows < 0 || cols < 0 || row_stride < cols || rows * cols > (int64_t)0x3FFFFFFF) {
         set_error("pt_write: bad shape (%lld, %lld)", (long long)rows, (long long)cols);
         return PPGS_E_INVALID;
     }
-    const float* payload = data;
+    const char* payload = data;
     if (row_stride != cols) {
-        contiguous.resize((size_t)(rows * cols));
+        contiguous.resize((size_t)(rows * cols * elem + 3) / 4);
+        char* packed = reinterpret_cast<char*>(contiguous.data());
         for (int64_t r = 0; r < rows; ++r)
-            memcpy(contiguous.data() + r * cols, data + r * row_stride, (size_t)cols * 4);
-        payload = contiguous.data();
+            memcpy(packed + r * cols * elem, data + r * row_stride * elem, (size_t)cols * elem);
+        payload = packed;
     }
-    const size_t payload_bytes = (size_t)(rows * cols) * 4;
+    const size_t payload_bytes = (size_t)(rows * cols) * elem;
     const std::string stem = archive_stem(path);
     head.b.clear();
     std::vector<ZipEntry> dir;
     ByteSink pkl;
-    tensor_pickle(pkl, rows, cols);
+    tensor_pickle(pkl, rows, cols, elem == 2 ? "ctorch\nHalfStorage\n" : "ctorch\nFloatStorage\n");
     zip_local(head, dir, stem + "/data.pkl", pkl.b.data(), pkl.b.size(), crc32_bytes(pkl.b.data(), pkl.b.size()),
               false, true);
     zip_local(head, dir, stem + "/byteorder", "little", 6, crc32_bytes("little", 6), false, true);
@@ -762,6 +765,16 @@ int ppgs_pt_write_f32(const char* path, const float* data, int64_t rows, int64_t
     std::vector<float> contiguous;
     ByteSink head;
     return pt_write(path, data, rows, cols, row_stride, contiguous, head);
+}
+
+int ppgs_pt_write_f16(const char* path, const void* data, int64_t rows, int64_t cols, int64_t row_stride) {
+    if (!path || (!data && rows * cols > 0)) {
+        set_error("pt_write_f16: bad argument");
+        return PPGS_E_INVALID;
+    }
+    std::vector<float> contiguous;
+    ByteSink head;
+    return pt_write(path, data, rows, cols, row_stride, contiguous, head, 2);
 }
 
 int64_t ppgs_resample_length(int64_t samples, int orig_rate, int target_rate) {

@@ -236,3 +236,28 @@ def test_native_file_pipeline_uniform_batches_replay_graphs(ppgs_b200, tmp_path,
         engine.set_graphs(True)
     for a, b in zip(native, python):
         assert torch.equal(torch.load(a), torch.load(b))
+
+
+def test_preprocess_from_files_to_files(ppgs_b200, tmp_path):
+    """ppgs.preprocess.from_files_to_files (ppgs/preprocess/core.py:63-97): fp16 feature files,
+    cropped per file, equal to the batch front-end's rows and within 1 fp16 ulp of the oracle."""
+    from test_mel_emulation import ulp_distance
+    from ppgs_b200 import data, preprocess
+    lengths = [16000, 40000, 24321, 8000, 16161, 32000]
+    files = make_files(tmp_path, lengths)
+    outputs = [str(tmp_path / f'{i}-{{}}.pt') for i in range(len(files))]
+    preprocess.from_files_to_files(files, outputs, ['mel'], num_workers=4, gpu=0)
+    loader = data.loader(files, num_workers=0, max_frames=ppgs_b200.config.MAX_PREPROCESS_FRAMES)
+    seen = 0
+    for audio, sample_lengths, names in loader:
+        expected = ppgs_b200.preprocess.mel.from_audios(audio.cuda(), sample_lengths, gpu=0).cpu()
+        oracle = O.mel_from_audios(audio)
+        for row, reference, name, n in zip(expected, oracle, names, sample_lengths.tolist()):
+            got = torch.load(str(tmp_path / f'{files.index(name)}-mel.pt'))
+            assert got.dtype == torch.float16 and got.shape == (80, n // 160)
+            assert torch.equal(got, row[:, :n // 160])
+            assert ulp_distance(got.numpy(), reference[:, :n // 160].numpy()).max() <= 1
+            seen += 1
+    assert seen == len(files)
+    with pytest.raises(ValueError, match='not supported'):
+        preprocess.from_files_to_files(files, outputs, ['bottleneck'], gpu=0)

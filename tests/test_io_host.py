@@ -190,3 +190,19 @@ def test_wav_info_many_matches_single_probe(library, tmp_path):
     with pytest.raises(ValueError, match='cannot open'):
         load.wav_info_many(files + [tmp_path / 'missing.wav'])
     assert load.wav_info_many([]) == []
+
+
+def test_pt_writer_fp16_and_save_masked(library, tmp_path):
+    """fp16 feature tensors (torch.HalfStorage) and the save_masked wrapper."""
+    from ppgs_b200 import preprocess
+    x = torch.randn(80, 333).half()
+    for cols in (0, 1, 100, 333):
+        path = tmp_path / f'mel-{cols}.pt'
+        library.check(library.lib.ppgs_pt_write_f16(str(path).encode(), x.data_ptr(), 80, cols, 333))
+        for kwargs in ({}, {'weights_only': True}):
+            y = torch.load(path, **kwargs)
+            assert y.dtype == torch.float16 and y.shape == (80, cols) and torch.equal(y, x[:, :cols])
+    for tensor in (x, x.float(), torch.randn(2, 3, 10), torch.arange(12).reshape(3, 4)):
+        path = tmp_path / 'masked.pt'
+        preprocess.save_masked(tensor, path, 3)         # native for 2-D fp16 / fp32, torch.save otherwise
+        assert torch.equal(torch.load(path), tensor[..., :3])
