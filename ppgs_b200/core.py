@@ -109,7 +109,7 @@ def from_file_to_file(
     """Infer ppg from an audio file and save to a torch tensor file
     (ppgs/core.py:171-204)"""
     result = from_file(audio_file, representation, checkpoint, gpu, legacy_mode)
-    torch.save(result.detach().cpu(), output_file)
+    preprocess.save_masked(result.detach().cpu(), output_file, result.shape[-1])
 
 
 def from_files_to_files(
