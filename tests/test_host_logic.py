@@ -146,3 +146,26 @@ def test_configure_applies_yapecs_style_overrides(tmp_path):
     finally:
         ppgs_b200.configure({'IS_CAUSAL': False})
     assert ppgs_b200.config.IS_CAUSAL is False
+
+
+def test_bounded_max_frames_keeps_finite_budgets():
+    from ppgs_b200 import data
+    assert data.bounded_max_frames(64000) == 64000
+    assert data.bounded_max_frames(1) == 1
+    if not torch.cuda.is_available():      # nothing to derive a budget from: unchanged
+        assert data.bounded_max_frames(float('inf')) == float('inf')
+
+
+def test_loader_reuses_a_header_probe(tmp_path):
+    from ppgs_b200 import data
+    files = []
+    for i, n in enumerate([16000, 8000, 12000, 4000]):
+        files.append(tmp_path / f'{i}.wav')
+        write_wav(files[-1], n, seed=i)
+    first = data.loader(files, num_workers=0, max_frames=120, shard=(0, 2))
+    second = data.loader(files, num_workers=0, max_frames=120, shard=(1, 2), dataset=first.dataset)
+    assert second.dataset is first.dataset
+    together = sorted(i for batch in first.batches + second.batches for i in batch)
+    assert together == [0, 1, 2, 3]
+    everything = data.loader(files, num_workers=0, max_frames=120)
+    assert everything.batches[0::2] == first.batches and everything.batches[1::2] == second.batches
