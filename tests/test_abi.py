@@ -82,3 +82,24 @@ def test_no_cpu_fallback_in_python_host():
     import ppgs_b200
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         ppgs_b200.from_audio(torch.zeros(1, 1, 16000), 16000)
+
+
+def test_plain_c_consumer_links_and_runs(library, tmp_path):
+    """tests/csrc/abi_smoke.c: a C program built against include/ppgs_b200.h and linked to the
+    shared library runs the host-side entry points (no GPU) — the boundary is usable from C."""
+    import torch
+    from test_host_logic import write_wav
+    lib_dir = os.path.dirname(library.LIBRARY_PATH)
+    exe = tmp_path / 'abi_smoke'
+    subprocess.check_call([
+        'gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'),
+        os.path.join(ROOT, 'tests', 'csrc', 'abi_smoke.c'), '-o', str(exe),
+        '-L', lib_dir, '-lppgs_b200', f'-Wl,-rpath,{lib_dir}'])
+    wav, out = tmp_path / 'a.wav', tmp_path / 'a.pt'
+    raw = write_wav(wav, 6400 * 40, seed=3)
+    result = subprocess.run([str(exe), str(wav), str(out)], check=True, capture_output=True, text=True)
+    assert result.stdout.split() == ['256000', '16000', '1', '16', '0', '475', '160', '17', '1600']
+    tensor = torch.load(out)
+    assert tensor.shape == (40, 1600)
+    expected = torch.from_numpy(raw[:, 0].astype('float32') / 32768.0)[:64000].reshape(40, 1600)
+    assert torch.equal(tensor, expected)
