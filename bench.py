@@ -16,9 +16,14 @@ pass of the hot path (fused STFT+mel -> Transformer -> softmax) over one batch.
          HOST buffers: H2D + compute + D2H inside the timed region;
   roofline    the dominant kernel (per-kernel CUDA events, a second timed pass
          over the same steps with the library's launch profiling enabled);
-  cpu_baseline / --impl reference    the reference's CPU path as shipped (stock
-         torch modules under bf16 autocast, oracle.AsShipped — the reference
-         tree itself cannot travel to the GPU box) on the host cores.
+  cpu_baseline / --impl reference    the reference's OWN code (oracle/_ref, the
+         travelled byte-identical copy made by oracle/build_ref.py, imported under
+         oracle/refshim.py) as shipped: gpu=None, bf16 autocast, all host cores
+         (`kind: "reference"`; falls back to the oracle port when the copy is absent);
+  torch_gpu_baseline   the same reference code on the same B200 (gpu=0: PyTorch eager,
+         fp16 autocast = oracle mode O2; and its modules in fp32 with TF32 off = O3),
+         timed outside the headline region — the library baseline the kernels must beat;
+  spread    the K-step window is repeated and the median reported (min / max beside it).
 """
 import argparse
 import json
@@ -129,30 +134,87 @@ def cpu_reference_rate(steps, warmup, utterances=None, budget_s=20.0):
     from_features (ppgs/core.py:333-352; from_audio itself fails for B>1)."""
     import torch
     from oracle import ppg_oracle as O
+    from oracle import ref_arm
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = O.AsShipped(O.random_state_dict(0))
+    sd = O.random_state_dict(0)
+    if ref_arm.available():
+        # the reference's own code: mel.from_audios + ppgs.from_features(gpu=None)
+        ckpt = ref_arm.checkpoint_for(sd)
+        run = lambda audio: ref_arm.from_audios(audio, ckpt, gpu=None)   # noqa: E731
+        what = ("reference's own ppgs.preprocess.mel.from_audios + ppgs.from_features(gpu=None) "
+                '(oracle/_ref, bf16 autocast as shipped)')
+    else:
+        run = O.AsShipped(sd).from_audios
+        what = 'oracle port (as-shipped bf16-autocast torch modules; oracle/_ref absent)'
     probe = O.synthetic_audio(2, SAMPLES, 0)
-    model.from_audios(probe)
+    run(probe)
     t0 = time.perf_counter()
-    model.from_audios(probe)
+    run(probe)
     per_utt = (time.perf_counter() - t0) / 2
     if utterances is None:
         utterances = int(max(2, min(BATCH, budget_s / max(steps + warmup, 1) / per_utt)))
     audio = O.synthetic_audio(utterances, SAMPLES, 1)
     for _ in range(warmup):
-        model.from_audios(audio)
+        run(audio)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        out = model.from_audios(audio)
+        out = run(audio)
         times.append(time.perf_counter() - t0)
     assert out.shape == (utterances, O_OUT, FRAMES)
     mean = sum(times) / len(times)
     return {'value': utterances * FRAMES / mean, 'unit': UNIT, 'cores': torch.get_num_threads(),
-            'kind': 'port',
+            'kind': ref_arm.kind(),
             'sample': f'{utterances}x10s utterances per step, {steps} steps (+{warmup} warm-up), '
-                      f'as-shipped bf16-autocast torch modules, dtype {out.dtype}'.replace('torch.', '')}, mean
+                      f'{what}, output dtype {out.dtype}'.replace('torch.', '')}, mean
+
+
+def torch_gpu_baseline(device, audio_dev, audio_host, steps=5, warmup=3):
+    """The bar on the same box: the reference's own code on
+    this GPU.  O2 = as shipped with gpu=0 (PyTorch eager, fp16 autocast: cuBLAS / cuDNN /
+    SDPA kernels); O3 = its modules in fp32 with autocast and TF32 off (the numerics class of
+    the 1e-4 target).  Same 64 x 10 s batch, inputs resident on the device, CUDA events,
+    outside the headline timed region."""
+    import torch
+    from oracle import ppg_oracle as O
+    from oracle import ref_arm
+    if not ref_arm.available():
+        return {'unavailable': 'oracle/_ref absent (run python -m oracle.build_ref in the dev container)'}
+    sd = O.random_state_dict(0, peaky=True)
+    ckpt = ref_arm.checkpoint_for(sd)
+    ref = O.from_audio(sd, audio_host[:2].unsqueeze(1))
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    result = {'batch': f'{BATCH}x10s, device-resident audio', 'steps': steps, 'warmup': warmup,
+              'torch': torch.__version__}
+    try:
+        fp32 = ref_arm.modules_fp32(ckpt, device)
+        arms = {
+            'fp16_autocast_as_shipped': lambda a: ref_arm.from_audios(a, ckpt, gpu=device.index),
+            'fp32_tf32_off': fp32,
+        }
+        audio3 = audio_dev.unsqueeze(1)
+        for name, fn in arms.items():
+            for _ in range(warmup):
+                out = fn(audio3)
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(device)
+            start.record()
+            for _ in range(steps):
+                out = fn(audio3)
+            stop.record()
+            torch.cuda.synchronize(device)
+            ms = start.elapsed_time(stop) / steps
+            result[name] = {'ms_per_step': ms, 'frames_per_sec': BATCH * FRAMES / (ms / 1e3),
+                            'max_abs_vs_oracle': (out[:2].float().cpu() - ref).abs().max().item(),
+                            'output_dtype': str(out.dtype).replace('torch.', '')}
+            del out
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return result
 
 
 def run_reference(args, rank):
@@ -176,11 +238,15 @@ def run_reference(args, rank):
 
 
 def run_other_workload(args):
+    print(json.dumps(measure_other_workload(args.workload, max(args.steps, 1), max(args.warmup, 3))),
+          flush=True)
+
+
+def measure_other_workload(workload_name, steps, warmup):
     """BASELINE configs[2] / configs[3] on one GPU, same JSON keys (not the headline line)."""
     import torch
     import ppgs_b200
     from oracle import ppg_oracle as O   # synthetic inputs only
-    steps, warmup = max(args.steps, 1), max(args.warmup, 3)
     device = torch.device('cuda', 0)
     torch.cuda.set_device(device)
     peaks = load_peaks()
@@ -195,7 +261,7 @@ def run_other_workload(args):
         torch.cuda.synchronize(device)
         return start.elapsed_time(stop)
 
-    if args.workload == 'w2v2fb':
+    if workload_name == 'w2v2fb':
         from oracle import w2v2_oracle as W
         batch = 32
         front = ppgs_b200.Engine(0).load_state_dict(O.random_state_dict(0))
@@ -268,7 +334,7 @@ def run_other_workload(args):
         e.set_profiling(False)
     value = frames_per_step / (device_ms / steps / 1e3)
     tflops = value * flops_per_frame / 1e12
-    in_bytes = sum(h.numel() * h.element_size() for h in host) if args.workload != 'w2v2fb' \
+    in_bytes = sum(h.numel() * h.element_size() for h in host) if workload_name != 'w2v2fb' \
         else host[0].numel() * 4
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': steps, 'warmup': warmup,
@@ -286,7 +352,7 @@ def run_other_workload(args):
                      'algorithmic_flops_per_frame': flops_per_frame, 'kernels_ms_per_step': stats},
         'cpu_baseline': None,
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def main():
@@ -297,6 +363,10 @@ def main():
     parser.add_argument('--impl', default='ppgs_b200', choices=['ppgs_b200', 'reference'])
     parser.add_argument('--precision', default=os.environ.get('PPGS_B200_PRECISION', 'auto'))
     parser.add_argument('--no-cpu-baseline', action='store_true')
+    parser.add_argument('--no-torch-baseline', action='store_true')
+    parser.add_argument('--no-other-configs', action='store_true')
+    parser.add_argument('--windows', type=int, default=10,
+                        help='repeats of the K-step timed window (median reported, min / max in "spread")')
     parser.add_argument('--workload', default='mel', choices=['mel', 'w2v2fb', 'causal-stream'],
                         help="mel = BASELINE configs[1] (the headline; default); w2v2fb = configs[2]; "
                              "causal-stream = configs[3] with state (extra lines, N=1 only)")
@@ -369,7 +439,15 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    device_step = lambda i: engine.from_audio(dev[i % rotate])                      # noqa: E731
+    def timed_windows(fn, n, windows):
+        """`windows` back-to-back timed regions of exactly `n` steps each (every one bracketed
+        by barrier + synchronize, max over ranks); the headline is the median window."""
+        return [timed(fn, n) for _ in range(windows)]
+
+    # device-resident step through the C ABI (ppgs_from_audio) into a fixed output buffer:
+    # no allocation and no host work besides the call itself inside the timed region
+    out_dev = torch.empty(BATCH, O_OUT, FRAMES, dtype=torch.float32, device=device)
+    device_step = lambda i: engine.from_audio(dev[i % rotate], out=out_dev)         # noqa: E731
     # reference-facing call with HOST buffers; requests are pipelined two deep (the
     # H2D of step i+1 and the D2H of step i-1 overlap the kernels of step i), every
     # step still copies its own input in and its own result out
@@ -385,10 +463,12 @@ def main():
     if rank == 0:
         sampler.start()
     launches_before = engine.launches
-    device_ms = timed(device_step, steps)
-    launches = engine.launches - launches_before
-    e2e_ms = timed(host_step, steps)
+    device_windows = timed_windows(device_step, steps, args.windows)
+    launches = (engine.launches - launches_before) // args.windows
+    e2e_windows = timed_windows(host_step, steps, max(1, args.windows // 2))
     clocks = sampler.stop() if rank == 0 else None
+    device_ms = statistics.median(device_windows)
+    e2e_ms = statistics.median(e2e_windows)
 
     # roofline pass: same steps with per-kernel CUDA events (library profiling)
     engine.set_profiling(True)
@@ -479,6 +559,35 @@ def main():
     if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N = 1 only
         cpu, _ = cpu_reference_rate(steps=3, warmup=1, budget_s=20.0)
 
+    # the same-box library baseline (outside every timed region of the product)
+    torch_gpu = None
+    if not args.no_torch_baseline and world == 1:
+        try:
+            torch_gpu = torch_gpu_baseline(device, dev[0], host[0])
+            for arm in ('fp16_autocast_as_shipped', 'fp32_tf32_off'):
+                if arm in torch_gpu:
+                    torch_gpu[arm]['ppgs_b200_speedup'] = torch_gpu[arm]['ms_per_step'] / (device_ms / steps)
+            if single_pass and 'fp16_autocast_as_shipped' in torch_gpu:
+                torch_gpu['fp16_autocast_as_shipped']['ppgs_b200_f16_single_pass_speedup'] = (
+                    torch_gpu['fp16_autocast_as_shipped']['ms_per_step'] / single_pass['ms_per_step'])
+        except Exception as error:   # a baseline must never take the headline down
+            torch_gpu = {'unavailable': f'{type(error).__name__}: {error}'[:300]}
+
+    # BASELINE configs[2] / configs[3] in short form (their own full lines: --workload ...)
+    others = None
+    if not args.no_other_configs and world == 1:
+        others = {}
+        torch.cuda.empty_cache()
+        for name in ('w2v2fb', 'causal-stream'):
+            try:
+                full = measure_other_workload(name, steps=5, warmup=3)
+                others[name] = {'value': full['value'], 'unit': UNIT, 'ms_per_step': full['ms_per_step'],
+                                'e2e_value': full['e2e']['value'], 'workload': full['config']['workload'],
+                                'roofline_frac_whole_step': full['roofline']['frac'],
+                                'gpu_launches': full['gpu_launches']}
+            except Exception as error:
+                others[name] = {'unavailable': f'{type(error).__name__}: {error}'[:300]}
+
     dtype = {'fp32': 'f32 (CUDA-core FFMA)', 'f16x2': 'f16x2-split tcgen05 MMA, f32 accumulate',
              'f16': 'f16 tcgen05 MMA, f32 accumulate'}.get(precision, precision)
     line = {
@@ -499,6 +608,15 @@ def main():
         'clocks': clocks,
         'roofline': roofline,
         'cpu_baseline': cpu,
+        'spread': {'windows': len(device_windows), 'steps_per_window': steps, 'statistic': 'median',
+                   'ms_per_step_min': min(device_windows) / steps,
+                   'ms_per_step_median': device_ms / steps,
+                   'ms_per_step_max': max(device_windows) / steps,
+                   'e2e_windows': len(e2e_windows),
+                   'e2e_ms_per_step_min': min(e2e_windows) / steps,
+                   'e2e_ms_per_step_max': max(e2e_windows) / steps},
+        'torch_gpu_baseline': torch_gpu,
+        'other_configs': others,
         'single_pass_f16_context': single_pass,
     }
     print(json.dumps(line), flush=True)

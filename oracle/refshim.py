@@ -1,10 +1,12 @@
-"""Import the UNMODIFIED reference (`/root/reference/ppgs`) in the dev container.
+"""Import the UNMODIFIED reference (`/root/reference/ppgs`, or its travelled copy
+`oracle/_ref/ppgs` made by `oracle/build_ref.py`).
 
-TEST INFRASTRUCTURE ONLY.  Used by `oracle/make_golden.py` (and by
-`tests/test_oracle_golden.py::test_oracle_vs_live_reference` when `/root/reference` exists) to pin the
-oracle restatement against the reference's own modules.  Never imported by the
-product package, by `-m gpu` tests, by `smoke()` or by `bench.py` — the
-reference tree does not exist on the GPU box.
+TEST / BENCH INFRASTRUCTURE ONLY.  Used by `oracle/make_golden*.py` (and by
+`tests/test_oracle_golden.py::test_oracle_vs_live_reference`) to pin the oracle
+restatement against the reference's own modules, and by `oracle/ref_arm.py` for
+`bench.py --impl reference` / `cpu_baseline` / `torch_gpu_baseline` (the reference's own
+code timed beside the product).  Never imported by the product package, by `-m gpu`
+tests or by `smoke()`.
 
 The reference cannot be imported as-is: `yapecs`, `torchutil`,
 `pypar`, `librosa`, `matplotlib`, `moviepy`, `espnet`, ... are not installed and
@@ -27,7 +29,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('PPGS_REFERENCE_ROOT', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# The travelled copy made by `oracle/build_ref.py` (byte-identical *.py files of the reference
+# package; git-ignored, ships to the GPU box) is used when the reference tree itself is absent.
+TRAVELLED_ROOT = os.path.join(_HERE, '_ref')
+
+
+def _pick_root():
+    env = os.environ.get('PPGS_REFERENCE_ROOT')
+    for root in ([env] if env else []) + ['/root/reference', TRAVELLED_ROOT]:
+        if os.path.isdir(os.path.join(root, 'ppgs')):
+            return root
+    return env or '/root/reference'
+
+
+REFERENCE_ROOT = _pick_root()
 
 _AUTO_STUB_ROOTS = (
     'espnet', 'torch_complex', 'nltk', 'gdown', 'humanfriendly', 'dac',

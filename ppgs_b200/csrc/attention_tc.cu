@@ -154,7 +154,8 @@ struct AttnShape {
 
 struct AttnParams {
     const SeqInfo* seqs;
-    int H, causal, planes;
+    int H, causal, planes;   // planes: V operand and output planes
+    int qk_planes, p_planes; // Q / K and P operands: 2 = hi + lo, 1 = hi only (fewer MMA passes)
     float scale_log2e;
     __half* out;
     int64_t out_plane_stride;
@@ -183,8 +184,9 @@ __device__ __forceinline__ int chunk_order(int i, int nchunks) {
 
 template <int D>
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_v,
-                    const __grid_constant__ CUtensorMap map_out, const AttnParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_out,
+                    const AttnParams p) {
     using Shape = AttnShape<D>;
     constexpr int DC = Shape::kDC, KB = Shape::kKB, NP = Shape::kNP, NK = Shape::kNK, NV = Shape::kNV;
     constexpr int SAFE = Shape::kSafeChunks;
@@ -193,7 +195,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* q_smem = smem;                      // later: P ring, output staging
     unsigned char* k_ring = smem + Shape::kABytes;     // later: V ring
-    __shared__ __align__(8) uint64_t q_full, s_full, o_full;
+    __shared__ __align__(8) uint64_t q_full, o_full, s_full[8];   // s_full[j]: scores of key block j
     __shared__ __align__(8) uint64_t k_full[2], k_empty[2], p_full[4], p_empty[4];
     __shared__ __align__(8) uint64_t v_full[4], v_empty[4];
     __shared__ uint32_t tmem_slot;
@@ -222,8 +224,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
 
     if (threadIdx.x == 0) {
         mbar_init(&q_full, 1);
-        mbar_init(&s_full, 1);
         mbar_init(&o_full, 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&s_full[i], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&k_full[i], 1);
             mbar_init(&k_empty[i], 1);
@@ -245,23 +247,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            prefetch_tensormap(&map_qk);
+            prefetch_tensormap(&map_q);
+            prefetch_tensormap(&map_k);
             prefetch_tensormap(&map_v);
             const int col_q = head * D, col_k = p.H + head * D, col_v = 2 * p.H + head * D;
-            const CUtensorMap* map_k = KB == 128 ? &map_qk : &map_v;   // box of KB rows
             bool ok = true;
-            mbar_arrive_expect_tx(&q_full, p.planes * DC * kTile16K);
+            mbar_arrive_expect_tx(&q_full, p.qk_planes * DC * kTile16K);
             for (int dc = 0; dc < DC; ++dc)
-                tma_load_3d(q_smem + dc * 2 * kTile16K, &map_qk, &q_full, col_q + dc * 64, s.row0 + q0, 0);
+                tma_load_3d(q_smem + dc * 2 * kTile16K, &map_q, &q_full, col_q + dc * 64, s.row0 + q0, 0);
             for (int j = 0; j < nb && ok; ++j) {
                 const int slot = j % NK;
                 if (!mbar_wait(&k_empty[slot], ((j / NK) & 1) ^ 1)) { ok = false; break; }
-                mbar_arrive_expect_tx(&k_full[slot], p.planes * DC * Shape::kKTile);
+                mbar_arrive_expect_tx(&k_full[slot], p.qk_planes * DC * Shape::kKTile);
                 for (int dc = 0; dc < DC; ++dc)
-                    tma_load_3d(k_ring + slot * Shape::kKSlotBytes + dc * 2 * Shape::kKTile, map_k,
+                    tma_load_3d(k_ring + slot * Shape::kKSlotBytes + dc * 2 * Shape::kKTile, &map_k,
                                 &k_full[slot], col_k + dc * 64, s.row0 + j * KB, 0);
             }
-            if (ok && !mbar_wait(&s_full, 0)) ok = false;   // K ring is dead: reuse it for V
+            if (ok && !mbar_wait(&s_full[nb - 1], 0)) ok = false;   // K ring is dead: reuse it for V
             for (int i = 0; i < nchunks && ok; ++i) {
                 const int c = chunk_order<SAFE>(i, nchunks), slot = i % NV;
                 if (!mbar_wait(&v_empty[slot], ((i / NV) & 1) ^ 1)) { ok = false; break; }
@@ -299,14 +301,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
                                         (ks & 3) * 32;
                     const uint64_t dq0 = smem_desc_kmajor_sw128(qa), dk0 = smem_desc_kmajor_sw128(kb);
                     umma_f16(d_tmem, dq0, dk0, idesc_s, ks > 0);
-                    if (p.planes == 2) {
+                    if (p.qk_planes == 2) {
                         umma_f16(d_tmem, dq0, smem_desc_kmajor_sw128(kb + Shape::kKTile), idesc_s, 1);
                         umma_f16(d_tmem, smem_desc_kmajor_sw128(qa + kTile16K), dk0, idesc_s, 1);
                     }
                 }
                 umma_commit(&k_empty[slot]);
+                umma_commit(&s_full[j]);   // the softmax warps start their row-max pass on block j
             }
-            if (ok) umma_commit(&s_full);
             const uint32_t o_tmem = tmem_base + Shape::kOCol;
             const int pre = nchunks > SAFE ? nchunks - SAFE : 0;
             for (int i = 0; i < nchunks && ok; ++i) {
@@ -326,11 +328,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
                     const uint64_t dp0 = smem_desc_kmajor_sw128(pa);
                     const uint64_t dv0 = smem_desc_mnmajor_sw128(vb, 2 * kVPlaneBytes);
                     umma_f16(o_tmem, dp0, dv0, idesc_o, (i > 0 || ks > 0) ? 1u : 0u);
-                    if (p.planes == 2) {
+                    if (p.planes == 2)
                         umma_f16(o_tmem, dp0, smem_desc_mnmajor_sw128(vb + kVPlaneBytes, 2 * kVPlaneBytes),
                                  idesc_o, 1);
+                    if (p.p_planes == 2)
                         umma_f16(o_tmem, smem_desc_kmajor_sw128(pa + kTile16K), dv0, idesc_o, 1);
-                    }
                 }
                 umma_commit(&p_empty[ps]);
                 umma_commit(&v_empty[vs]);
@@ -351,15 +353,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
         uint32_t raw[32];
         const long long ts0 = clock64();
-        bool ok = mbar_wait(&s_full, 0);
-        const long long ts1 = clock64();
-        long long t_pempty = 0;
-        tcgen05_fence_after();
+        bool ok = true;
+        long long t_pempty = 0, ts1 = ts0;
         float mx = -FLT_MAX;
-        if (ok) {
+        {
+            // row max, block by block as the S MMAs retire (the first wait is the exposed one)
             const int ngroups = (nkeys + 31) >> 5;
+            int ready = -1;
 #pragma unroll 1
-            for (int g = half; g < ngroups; g += 2) {
+            for (int g = half; g < ngroups && ok; g += 2) {
+                const int blk = (g * 32) / KB;
+                if (blk > ready) {
+                    ok = mbar_wait(&s_full[blk], 0);
+                    if (ready < 0) ts1 = clock64();
+                    ready = blk;
+                    tcgen05_fence_after();
+                    if (!ok) break;
+                }
                 tmem_ld_32x32(t_row + g * 32, raw);
                 tmem_wait_ld();
                 const bool full = g * 32 + 32 <= nkeys && (!p.causal || g * 32 + 31 <= q0);
@@ -376,6 +386,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
                 }
             }
         }
+        // every thread has observed the completion of ALL score MMAs before the exp pass
+        // (a thread whose groups ended early never waited for the last block)
+        if (ok) ok = mbar_wait(&s_full[nb - 1], 0);
+        tcgen05_fence_after();
         row_part[half][r] = mx;
         named_bar_sync(1, 256);
         mx = fmaxf(row_part[0][r], row_part[1][r]);
@@ -396,7 +410,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
                 tmem_ld_32x32(t_row + chunk_order<SAFE>(i + 1, nchunks) * 64 + half * 32, nxt);
             uint32_t h[16], l[16];
             const bool full = key0 + 32 <= nkeys && (!p.causal || key0 + 31 <= q0);
-            if (full) {
+            if (full && p.p_planes == 1) {
+                // single-plane P: the row sum is taken over the ROUNDED numerators, so the
+                // weights the P.V MMA applies sum to one exactly
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float e0 = fast_exp2(fmaf(__uint_as_float(cur[2 * j]), p.scale_log2e, -mc));
+                    const float e1 = fast_exp2(fmaf(__uint_as_float(cur[2 * j + 1]), p.scale_log2e, -mc));
+                    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(e1), "f"(e0));
+                    const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+                    sum += back.x + back.y;
+                }
+            } else if (full) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float e0 = fast_exp2(fmaf(__uint_as_float(cur[2 * j]), p.scale_log2e, -mc));
@@ -415,8 +440,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
                         const float e = fast_exp2(fmaf(__uint_as_float(cur[2 * j + q]), p.scale_log2e, -mc));
                         pv[q] = allowed ? e : 0.f;
                     }
-                    sum += pv[0] + pv[1];
-                    split2_f16(pv[0], pv[1], h[j], l[j]);
+                    if (p.p_planes == 1) {
+                        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(pv[1]), "f"(pv[0]));
+                        const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+                        sum += back.x + back.y;
+                    } else {
+                        sum += pv[0] + pv[1];
+                        split2_f16(pv[0], pv[1], h[j], l[j]);
+                    }
                 }
             }
             {
@@ -431,7 +462,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
                 const uint32_t unit = (uint32_t)(half * 4 + u) ^ sw;
                 const uint32_t addr = p_slot + row_off + unit * 16;
                 st_shared_v4(addr, h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
-                st_shared_v4(addr + kTile16K, l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
+                if (p.p_planes == 2)
+                    st_shared_v4(addr + kTile16K, l[4 * u], l[4 * u + 1], l[4 * u + 2], l[4 * u + 3]);
             }
             fence_proxy_async_smem();
             tcgen05_fence_before();
@@ -534,13 +566,15 @@ int launch_attention_planes(ppgs_engine* e, int head_dim, const __half* qkv, __h
 template <int D>
 static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows, int H, int heads,
                             int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
-                            cudaStream_t stream, int q_first_tile, int q_tiles) {
+                            cudaStream_t stream, int q_first_tile, int q_tiles, int qk_planes, int p_planes) {
     using Shape = AttnShape<D>;
     const bool per_seq = q_first_tile < 0;   // -1: first query tile per sequence (SeqInfo::src_start)
-    CUtensorMap map_qk, map_v, map_out;
+    CUtensorMap map_q, map_k, map_v, map_out;
     PPGS_CHECK(make_store_map(&map_out, out, H, rows, (uint64_t)rows * H));
-    PPGS_CHECK(make_plane_map(&map_qk, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
-                              (uint64_t)rows * 3 * H, 128, planes));
+    PPGS_CHECK(make_plane_map(&map_q, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
+                              (uint64_t)rows * 3 * H, 128, qk_planes));
+    PPGS_CHECK(make_plane_map(&map_k, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
+                              (uint64_t)rows * 3 * H, Shape::kKB, qk_planes));
     PPGS_CHECK(make_plane_map(&map_v, qkv, false, 3 * H, rows, 1, 2, 3 * H, 0,
                               (uint64_t)rows * 3 * H, 64, planes));
     static PerDeviceOnce attr_tc;
@@ -553,6 +587,8 @@ static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int 
     p.H = H;
     p.causal = causal;
     p.planes = planes;
+    p.qk_planes = qk_planes;
+    p.p_planes = p_planes;
     p.scale_log2e = 1.4426950408889634f / sqrtf((float)D);
     p.out = out;
     p.out_plane_stride = (int64_t)rows * H;
@@ -575,7 +611,7 @@ static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int 
             cfg.attrs = attrs;
             cfg.numAttrs = 1;
         }
-        PPGS_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<D>, map_qk, map_v, map_out, p));
+        PPGS_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<D>, map_q, map_k, map_v, map_out, p));
     }
     PPGS_CUDA(cudaGetLastError());
     return PPGS_OK;
@@ -583,18 +619,20 @@ static int run_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int 
 
 int launch_attention_any(ppgs_engine* e, const __half* qkv, __half* out, int rows, int H, int heads,
                          int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
-                         cudaStream_t stream, int q_first_tile, int q_tiles) {
+                         cudaStream_t stream, int q_first_tile, int q_tiles, int qk_planes, int p_planes) {
     const int D = H / heads;
+    qk_planes = (qk_planes == 1 || planes == 1) ? 1 : 2;
+    p_planes = (p_planes == 1 || planes == 1) ? 1 : 2;
     if (e->attention_impl == 1 && max_pitch <= 512 && max_pitch % 128 == 0 && e->status_dev) {
         if (D == 64)
             return run_attention_tc<64>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream,
-                                         q_first_tile, q_tiles);
+                                         q_first_tile, q_tiles, qk_planes, p_planes);
         if (D == 128)
             return run_attention_tc<128>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream,
-                                         q_first_tile, q_tiles);
+                                         q_first_tile, q_tiles, qk_planes, p_planes);
         if (D == 256)
             return run_attention_tc<256>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream,
-                                         q_first_tile, q_tiles);
+                                         q_first_tile, q_tiles, qk_planes, p_planes);
     }
     if (q_first_tile || q_tiles) {
         set_error("attention: the query-tile window needs the tcgen05 kernel (head_dim 64 / 128 / 256, pitch <= 512)");
@@ -608,7 +646,8 @@ int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows
                         const ForwardPlan& plan, const SeqInfo* seqs_dev, int planes,
                         cudaStream_t stream) {
     return launch_attention_any(e, qkv, out, rows, e->cfg.hidden_channels, e->cfg.num_heads, plan.max_pitch,
-                                (int)plan.seqs.size(), seqs_dev, e->cfg.is_causal, planes, stream);
+                                (int)plan.seqs.size(), seqs_dev, e->cfg.is_causal, planes, stream, 0, 0,
+                                e->attn_qk_planes, e->attn_p_planes);
 }
 
 }  // namespace ppgs

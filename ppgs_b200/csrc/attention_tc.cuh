@@ -18,7 +18,10 @@ int launch_attention_tc(ppgs_engine* e, const __half* qkv, __half* out, int rows
 // every sequence comes from its SeqInfo::src_start.
 int launch_attention_any(ppgs_engine* e, const __half* qkv, __half* out, int rows, int H, int heads,
                          int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
-                         cudaStream_t stream, int q_first_tile = 0, int q_tiles = 0);
+                         cudaStream_t stream, int q_first_tile = 0, int q_tiles = 0,
+                         int qk_planes = 2, int p_planes = 2);
+// `qk_planes` / `p_planes` = 1: Q, K / the softmax numerators P enter their MMAs as one fp16
+// plane (S in one pass instead of three, P.V in two); ignored when `planes` is 1.
 
 // CUDA-core attention over split planes for any (hidden, heads, head_dim in {64, 128, 256}):
 // used by the wav2vec2 encoder (12 heads x 64).

@@ -208,15 +208,20 @@ class Engine:
             _stream_ptr(self.device)))
         return out
 
-    def from_audio(self, audio, lengths=None, softmax=True, legacy_mode=False):
+    def from_audio(self, audio, lengths=None, softmax=True, legacy_mode=False, out=None):
         """Fused mel + transformer on device buffers. audio (B,1,samples) CUDA;
-        lengths in SAMPLES (None = full)."""
+        lengths in SAMPLES (None = full).  `out`: optional preallocated (B,40,frames) fp32
+        CUDA tensor (steady-state loops: no allocation per call)."""
         if audio.dim() == 3:
             audio = audio.squeeze(1)
         audio = self._on_device(audio, torch.float32).contiguous()
         batch, samples = audio.shape
-        out = torch.empty(batch, self.cfg.output_channels, samples // config.HOPSIZE,
-                          dtype=torch.float32, device=self.device)
+        shape = (batch, self.cfg.output_channels, samples // config.HOPSIZE)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        elif (tuple(out.shape) != shape or out.dtype != torch.float32 or out.device != self.device
+              or not out.is_contiguous()):
+            raise ValueError(f'out must be a contiguous fp32 tensor of shape {shape} on {self.device}')
         lengths_host = None if lengths is None else _host_lengths(lengths, batch)
         _lib.check(_lib.lib.ppgs_from_audio(
             self._handle, ctypes.c_void_p(audio.data_ptr()), batch, samples, samples,
