@@ -6,6 +6,12 @@ import ppgs_b200
 
 
 def parse_args(argv=None):
+    # --config first: it decides the defaults of the other flags (the reference's yapecs reads
+    # it at import time, before `ppgs.REPRESENTATION` is looked at)
+    early = argparse.ArgumentParser(add_help=False)
+    early.add_argument('--config', type=Path, nargs='*')
+    for file in early.parse_known_args(argv)[0].config or []:
+        ppgs_b200.configure(file)
     parser = argparse.ArgumentParser(description='Phonetic posteriorgram inference')
     parser.add_argument('--audio_files', nargs='+', type=Path, required=True,
                         help='Paths to audio files')
@@ -33,8 +39,7 @@ def parse_args(argv=None):
 
 def main(argv=None):
     args = vars(parse_args(argv))
-    for file in args.pop('config', None) or []:
-        ppgs_b200.configure(file)
+    args.pop('config', None)   # applied by parse_args, before the defaults were read
     if isinstance(args['gpu'], list) and args['num_workers'] == 0:
         args['num_workers'] = 2 * len(args['gpu'])     # the sharded path is the batched one
     ppgs_b200.from_files_to_files(**args)

@@ -59,6 +59,29 @@ W2V2FB_CONFIG = 'facebook/wav2vec2-base'
 W2V2FB_CHECKPOINT = None
 
 
+class Live:
+    """Default argument that is read from the LIVE configuration when the function is called,
+    not when it was defined: `def f(representation=config.live('REPRESENTATION'))` +
+    `representation = config.resolve(representation)` sees `configure()` / `--config`
+    overrides made after import (the reference gets the same effect from yapecs rewriting
+    ppgs.config.defaults before the package body runs)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return f'config.{self.name}'
+
+
+def live(name):
+    return Live(name)
+
+
+def resolve(value):
+    import sys
+    return getattr(sys.modules[__name__], value.name) if isinstance(value, Live) else value
+
+
 def configure(source):
     """Apply a yapecs-style configuration (the reference reads `--config file.py` at import,
     ppgs/__init__.py:7-15): every UPPER_CASE name of a python file (or dict) overrides the

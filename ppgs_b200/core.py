@@ -31,7 +31,7 @@ from . import preprocess
 def from_audio(
     audio: torch.Tensor,
     sample_rate: Union[int, float],
-    representation: str = config.REPRESENTATION,
+    representation: str = config.live('REPRESENTATION'),
     checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
     gpu: Optional[int] = None,
     legacy_mode: bool = False
@@ -49,6 +49,7 @@ def from_audio(
     Returns
         ppgs, shape=(batch, len(ppgs.PHONEMES), frames), fp32 on the GPU
     """
+    representation = config.resolve(representation)
     if audio.dim() == 2:
         audio = audio.unsqueeze(0)
     engine = load.model(checkpoint, representation, gpu)
@@ -69,7 +70,7 @@ def from_audio(
 def from_features(
     features: torch.Tensor,
     lengths: torch.Tensor,
-    representation: str = config.REPRESENTATION,
+    representation: str = config.live('REPRESENTATION'),
     checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
     gpu: Optional[int] = None,
     softmax: bool = True,
@@ -79,19 +80,21 @@ def from_features(
 
     features: shape=(batch, channels, frames); lengths: shape=(batch,)
     """
+    representation = config.resolve(representation)
     return infer(features, lengths, representation, checkpoint, softmax,
                  legacy_mode, gpu=gpu)
 
 
 def from_file(
     file: Union[str, bytes, os.PathLike],
-    representation: str = config.REPRESENTATION,
+    representation: str = config.live('REPRESENTATION'),
     checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
     gpu: Optional[int] = None,
     legacy_mode: bool = False
 ) -> torch.Tensor:
     """Infer ppgs from an audio file (ppgs/core.py:131-168);
     returns shape=(len(ppgs.PHONEMES), frames)"""
+    representation = config.resolve(representation)
     audio = load.audio(file, device=load.resolve_device(gpu))
     return from_audio(
         audio, config.SAMPLE_RATE, representation, checkpoint, gpu, legacy_mode
@@ -101,13 +104,14 @@ def from_file(
 def from_file_to_file(
     audio_file: Union[str, bytes, os.PathLike],
     output_file: Union[str, bytes, os.PathLike],
-    representation: str = config.REPRESENTATION,
+    representation: str = config.live('REPRESENTATION'),
     checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
     gpu: Optional[int] = None,
     legacy_mode: bool = False
 ) -> None:
     """Infer ppg from an audio file and save to a torch tensor file
     (ppgs/core.py:171-204)"""
+    representation = config.resolve(representation)
     result = from_file(audio_file, representation, checkpoint, gpu, legacy_mode)
     preprocess.save_masked(result.detach().cpu(), output_file, result.shape[-1])
 
@@ -115,11 +119,11 @@ def from_file_to_file(
 def from_files_to_files(
     audio_files: List[Union[str, bytes, os.PathLike]],
     output_files: List[Union[str, bytes, os.PathLike]],
-    representation: str = config.REPRESENTATION,
+    representation: str = config.live('REPRESENTATION'),
     checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
     num_workers: int = 0,
     gpu: Optional[Union[int, List[int]]] = None,
-    max_frames: int = config.MAX_INFERENCE_FRAMES,
+    max_frames: int = config.live('MAX_INFERENCE_FRAMES'),
     legacy_mode: bool = False
 ) -> None:
     """Infer ppgs from audio files and save to torch tensor files
@@ -128,6 +132,8 @@ def from_files_to_files(
     `num_workers // 2` writer threads.  `gpu` may be a list of CUDA ordinals: the
     batch list is dealt round-robin to one pipeline per GPU (BASELINE config 5 from
     a single process; `parallel.from_files_to_files` is the torchrun form)."""
+    representation = config.resolve(representation)
+    max_frames = config.resolve(max_frames)
     if len(audio_files) != len(output_files):
         raise ValueError('audio_files and output_files must have equal lengths')
     if isinstance(gpu, (list, tuple)):
@@ -146,7 +152,8 @@ def from_files_to_files(
         audio_files,
         features=['audio', 'length', 'audio_file'],
         num_workers=num_workers // 2,
-        max_frames=max_frames)
+        max_frames=max_frames,
+        device=gpu)
     if _native_pipeline(dataloader, representation):
         engine = load.model(checkpoint, representation, gpu)
         dataloader.run_native(engine, mapping, num_workers // 2, legacy_mode)
@@ -188,7 +195,7 @@ def _from_files_to_files_sharded(audio_files, output_files, representation, chec
     for rank in range(len(gpus)):
         loaders.append(data.loader(
             audio_files, num_workers=workers, max_frames=max_frames, shard=(rank, len(gpus)),
-            dataset=loaders[0].dataset if loaders else None))
+            dataset=loaders[0].dataset if loaders else None, device=gpus[rank]))
     errors = []
 
     def run(engine, dataloader):
@@ -222,7 +229,7 @@ def from_dataloader(
     output_files: Dict[
         Union[str, bytes, os.PathLike],
         Union[str, bytes, os.PathLike]],
-    representation: str = config.REPRESENTATION,
+    representation: str = config.live('REPRESENTATION'),
     checkpoint: Union[str, bytes, os.PathLike] = None,
     save_workers: int = 1,
     gpu: Optional[int] = None,
@@ -234,6 +241,7 @@ def from_dataloader(
     spawn Pool; here writer *threads* take (pinned host tensor, filename,
     frames) items from a bounded queue, so the D2H copy of batch i overlaps the
     kernels of batch i+1."""
+    representation = config.resolve(representation)
     if engine is None:
         engine = load.model(checkpoint, representation, gpu)
     writer = _Writer(save_workers)
@@ -456,7 +464,7 @@ def sparsify(
 def infer(
     features,
     lengths,
-    representation=config.REPRESENTATION,
+    representation=config.live('REPRESENTATION'),
     checkpoint=None,
     softmax=True,
     legacy_mode=False,
@@ -464,6 +472,7 @@ def infer(
 ):
     """Perform model inference (ppgs/core.py:551-596): cached engine per
     (representation, checkpoint, device); logits -> softmax(dim=1) in-kernel."""
+    representation = config.resolve(representation)
     if gpu is None and features.is_cuda:
         gpu = features.device.index
     engine = load.model(checkpoint, representation, gpu)

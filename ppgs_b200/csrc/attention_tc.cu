@@ -623,6 +623,12 @@ int launch_attention_any(ppgs_engine* e, const __half* qkv, __half* out, int row
     const int D = H / heads;
     qk_planes = (qk_planes == 1 || planes == 1) ? 1 : 2;
     p_planes = (p_planes == 1 || planes == 1) ? 1 : 2;
+    // default model (head_dim 128): two query tiles per CTA, K / V streamed in 128-key blocks
+    // (any sequence length), single-plane Q / K / P
+    if (e->attention_impl == 1 && e->attn_dual && e->status_dev &&
+        attention_dual_supported(D, max_pitch, qk_planes, p_planes))
+        return launch_attention_dual(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream,
+                                     q_first_tile, q_tiles);
     if (e->attention_impl == 1 && max_pitch <= 512 && max_pitch % 128 == 0 && e->status_dev) {
         if (D == 64)
             return run_attention_tc<64>(e, qkv, out, rows, H, heads, max_pitch, nseq, seqs_dev, causal, planes, stream,

@@ -29,4 +29,11 @@ int launch_attention_planes(ppgs_engine* e, int head_dim, const __half* qkv, __h
                             int H, int heads, int max_pitch, int nseq, const SeqInfo* seqs_dev,
                             int causal, int planes, cudaStream_t stream);
 
+// Two query tiles per CTA sharing every K / V block, single-plane Q / K / P (attention_dual_tc.cu):
+// head_dim 128 only.  Same arguments as launch_attention_any.
+bool attention_dual_supported(int D, int max_pitch, int qk_planes, int p_planes);
+int launch_attention_dual(ppgs_engine* e, const __half* qkv, __half* out, int rows, int H, int heads,
+                          int max_pitch, int nseq, const SeqInfo* seqs_dev, int causal, int planes,
+                          cudaStream_t stream, int q_first_tile, int q_tiles);
+
 }  // namespace ppgs

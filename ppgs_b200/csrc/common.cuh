@@ -140,8 +140,12 @@ struct ppgs_engine {
     bool tc_maps_ready = false;
     int* status_dev = nullptr;   // kernels report barrier time-outs here
     int attention_impl = 1;      // 1 = tcgen05 kernel, 0 = CUDA-core kernel (validation)
-    int attn_qk_planes = 2;      // 1: attention scores from the hi planes of Q / K only (PPGS_B200_ATTN_QK_PLANES)
-    int attn_p_planes = 2;       // 1: softmax numerators as one fp16 plane (PPGS_B200_ATTN_P_PLANES)
+    // attention operand planes of the PPG Transformer (not the wav2vec2 encoder): Q / K and the
+    // softmax numerators P enter their MMAs as one fp16 plane (S in one pass, P.V in two; measured
+    // +1e-5 on the posteriorgram, profiles/r02_attn_planes.jsonl); 2 = hi + lo like every other operand
+    int attn_qk_planes = 1;      // PPGS_B200_ATTN_QK_PLANES
+    int attn_p_planes = 1;       // PPGS_B200_ATTN_P_PLANES
+    int attn_dual = 1;           // head_dim 128: two query tiles per CTA (attention_dual_tc.cu; PPGS_B200_ATTN_DUAL)
     int gemm_pair = 1;           // 1 = CTA-pair (cta_group::2) GEMMs at BN = 256
     int fused_ffn = 0;           // 1 = one fused kernel for linear1 + ReLU + linear2 + LN (PPGS_B200_FUSED_FFN;
                                  // parity-green but shared-memory-bound and slower than the two GEMMs)

@@ -121,8 +121,11 @@ extern "C" int ppgs_debug_attention(ppgs_engine* e, const float* qkv_host, int r
     PPGS_CUDA(cudaMemcpy(seq_dev.ptr, &s, sizeof(SeqInfo), cudaMemcpyHostToDevice));
     const int saved = e->attention_impl;
     e->attention_impl = use_tensor_cores ? 1 : 0;
+    // use_tensor_cores == 2: Q / K / P as single fp16 planes (head_dim 128: the two-tile kernel)
+    const int operand_planes = use_tensor_cores == 2 ? 1 : 2;
     const int rc = launch_attention_any(e, qkv_dev.as<__half>(), out_dev.as<__half>(), rows, H, heads, rows, 1,
-                                        seq_dev.as<SeqInfo>(), causal, planes, nullptr);
+                                        seq_dev.as<SeqInfo>(), causal, planes, nullptr, 0, 0, operand_planes,
+                                        operand_planes);
     e->attention_impl = saved;
     PPGS_CHECK(rc);
     PPGS_CUDA(cudaDeviceSynchronize());

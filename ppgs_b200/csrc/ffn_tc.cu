@@ -3,52 +3,51 @@
 //
 //     x <- LayerNorm2(x + W2 relu(W1 x + b1) + b2)
 //
-// in ONE kernel per layer: the (rows x 2048) hidden activation never leaves the SM.
-// Unfused it costs 0.6 GB of HBM writes and 0.75 GB of reads per layer at the bench
-// shape, and those stores were what bounded the linear1 GEMM.
+// in ONE kernel per layer: the (rows x 2048) hidden activation never leaves the SM.  Unfused
+// it is written and read back as split-fp16 planes, 8 KB per row and layer = 6.7 GB per
+// 64 x 10 s batch — more than half of the step's HBM traffic, on a part that runs at its power
+// cap (profiles/r02_power_probe.jsonl: the step without those stores is 28 % shorter).
 //
-// A CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256) owns 256 rows:
-//   X tile       [4 k-blocks][hi|lo][128 rows][64]  128 KB per CTA, loaded once per tile
-//   per 64-wide hidden chunk c (32 chunks):
-//     G1_c   Hacc[c&1] = X . W1_c^T          N = 64,  K = 256   (TMEM cols 256 + 64 (c&1))
-//     E_c    relu(Hacc * s1 + b1) -> split fp16 -> H1 smem tile [hi|lo][128][64] (A operand)
-//     G2_c   Y += H1 . W2_c^T                N = 256, K = 64    (TMEM cols 0..255)
-//   LayerNorm epilogue on Y (+ b2 + residual), planes out through TMA stores
-// The MMA issuer runs G1_{c+1} before G2_c so the tensor pipe is busy while the
-// epilogue warps turn Hacc_c into H1.  Weights stream through small rings: four 8 KB
-// W1 k-block slots and one 32 KB W2 slot per CTA (each CTA holds half of the N rows).
+// A CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256) owns 256 rows; per 128-wide hidden
+// chunk c (16 chunks):
+//     G1_c   Hacc[c & 1] = X . W1_c^T        N = 128, K = 256   (TMEM cols 256 + 128 (c & 1))
+//     E_c    relu(Hacc * s1 + b1) -> split fp16 -> H1 smem tile [kc 2][hi|lo][128 rows][64]
+//     G2_c   Y += H1 . W2_c^T                N = 256, K = 128   (TMEM cols 0..255)
+// issued as G1_0, G1_1, G2_0, G1_2, G2_1, ... so that the epilogue warps turn Hacc_c into H1
+// while the tensor pipe runs G1_{c+1} / G2_{c-1}.  Round 1's version used 64-wide chunks: at
+// N = 64 the MMAs re-read their 4 KB A slice every 32 cycles and shared memory, not the
+// tensor pipe, set the pace (it was 40 % slower than the two GEMMs and off by default).  With
+// N = 128 the operand reads need 96 B/clk of the 128 B/clk port.
 //
-// Warp roles (352 threads): 0 X + W1 producer, 1 MMA issuer (leader CTA) + TMEM
-// allocation, 2-9 epilogue (two threads per row), 10 W2 producer.
+// Everything streams through ONE ring of three 48 KB slots filled by one producer warp in the
+// order the MMA warp consumes it: a G1 slot = X k-block (hi|lo, 32 KB) + this CTA's half of
+// the W1 k-block (64 rows, hi|lo, 16 KB); a G2 slot = this CTA's half of the W2 k-block
+// (128 rows, hi|lo, 32 KB).  X is re-read from L2 per chunk (the resident X tile of round 1
+// would leave no room for a 128-wide H1 tile).
+//
+// LayerNorm epilogue (per tile): the Y accumulator is read ONCE into registers (128 values per
+// thread, two threads per row) and released at once, so the next tile's MMAs start while
+// bias + residual + LayerNorm + split + TMA stores run from registers.  The residual tile
+// comes by TMA into the dead H1 tile.
+//
+// Warp roles (384 threads): 0 producer, 1 MMA issuer (leader CTA) + TMEM allocation, 2-3
+// idle, 4-11 epilogue (two threads per row); setmaxnreg moves registers to the epilogue.
 #include "gemm_tc.cuh"
 
 namespace ppgs {
 namespace tc {
 
-constexpr int kFfnThreads = 352;
-constexpr int kFC = 64;                        // hidden-chunk width
-constexpr int kTileBytes = 16384;              // [128 rows][64] fp16
-constexpr int kXBytes = 4 * 2 * kTileBytes;    // 128 KB
-constexpr int kW1SubBytes = 2 * 32 * 128;      // [hi|lo][32 rows][64] = 8 KB
-constexpr int kW1Bytes = 4 * kW1SubBytes;      // 32 KB
-constexpr int kW2Bytes = 2 * kTileBytes;       // [hi|lo][128 rows][64] = 32 KB
-constexpr int kH1Bytes = 2 * kTileBytes;       // 32 KB
-constexpr size_t kFfnSmem = kXBytes + kW1Bytes + kW2Bytes + kH1Bytes;   // 224 KB
+namespace {
+
+constexpr int kFfnThreads = 384;
+constexpr int kFC = 128;                        // hidden-chunk width
+constexpr int kTileBytes = 16384;               // [128 rows][64] fp16, 128-byte swizzle
+constexpr int kSlotBytes = 3 * kTileBytes;      // 48 KB
+constexpr int kStages = 3;
+constexpr int kW1PlaneBytes = 64 * 128;         // [64 rows][64] = 8 KB
+constexpr int kH1Off = kStages * kSlotBytes;    // [kc 2][hi|lo][128 rows][64] = 64 KB
+constexpr size_t kFfnSmem = kH1Off + 4 * kTileBytes;   // 208 KB
 constexpr int kYCol = 0, kHaccCol = 256;
-
-__device__ __forceinline__ bool timed_wait(uint64_t* bar, uint32_t parity, long long& acc) {
-    const long long t0 = clock64();
-    const bool ok = mbar_wait(bar, parity);
-    acc += clock64() - t0;
-    return ok;
-}
-
-__device__ __forceinline__ void stage_row128(uint32_t tile, int row, const uint32_t (&w)[32]) {
-    const uint32_t base = tile + (uint32_t)row * 128, sw = (uint32_t)row & 7;
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-        st_shared_v4(base + (((uint32_t)u ^ sw) << 4), w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
-}
 
 __device__ __forceinline__ void load_row32(const float* src, float (&out)[32]) {
 #pragma unroll
@@ -61,17 +60,32 @@ __device__ __forceinline__ void load_row32(const float* src, float (&out)[32]) {
     }
 }
 
+// one 128-byte row of a 128B-swizzled [128 rows][64 fp16] tile <- 32 packed words
+__device__ __forceinline__ void stage_row128(uint32_t tile, int row, const uint32_t (&w)[32]) {
+    const uint32_t base = tile + (uint32_t)row * 128, sw = (uint32_t)row & 7;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        st_shared_v4(base + (((uint32_t)u ^ sw) << 4), w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+}
+
+__device__ __forceinline__ void load_row128(uint32_t tile, int row, uint32_t (&w)[32]) {
+    const uint32_t base = tile + (uint32_t)row * 128, sw = (uint32_t)row & 7;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w[4 * u]), "=r"(w[4 * u + 1]), "=r"(w[4 * u + 2]), "=r"(w[4 * u + 3])
+                     : "r"(base + (((uint32_t)u ^ sw) << 4)));
+}
+
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_out,
-                 const FfnParams p) {
+                 const __grid_constant__ CUtensorMap map_res, const FfnParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* x_smem = smem;
-    unsigned char* w1_smem = x_smem + kXBytes;
-    unsigned char* w2_smem = w1_smem + kW1Bytes;
-    unsigned char* h1_smem = w2_smem + kW2Bytes;
-    __shared__ __align__(8) uint64_t x_full, x_empty, w2_full, w2_empty, h1_full, h1_empty, y_full, y_empty;
-    __shared__ __align__(8) uint64_t w1_full[4], w1_empty[4], hacc_full[2], hacc_empty[2];
+    unsigned char* h1_smem = smem + kH1Off;
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
+    __shared__ __align__(8) uint64_t hacc_full[2], hacc_empty[2], h1_full, h1_empty, y_full, y_empty;
+    __shared__ __align__(8) uint64_t res_full[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float ln_part[2][kBM];
 
@@ -85,22 +99,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
 
     if (threadIdx.x == 0) {
-        mbar_init(&x_full, 1);
-        mbar_init(&x_empty, 8);     // this CTA's epilogue warps, after the residual was read from X
-        mbar_init(&w2_full, 1);
-        mbar_init(&w2_empty, 1);
-        mbar_init(&h1_full, 2);     // one elected epilogue thread per CTA
-        mbar_init(&h1_empty, 1);
-        mbar_init(&y_full, 1);
-        mbar_init(&y_empty, 16);
-        for (int i = 0; i < 4; ++i) {
-            mbar_init(&w1_full[i], 1);
-            mbar_init(&w1_empty[i], 1);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&hacc_full[i], 1);
-            mbar_init(&hacc_empty[i], 8);   // the 4 warps of the owning epilogue set, both CTAs
+            mbar_init(&hacc_empty[i], 16);   // epilogue warps of both CTAs
+            mbar_init(&res_full[i], 1);
         }
+        mbar_init(&h1_full, 16);
+        mbar_init(&h1_empty, 1);
+        mbar_init(&y_full, 1);
+        mbar_init(&y_empty, 16);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_pair<512>(&tmem_slot);
@@ -108,96 +119,102 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
-    if (warp == 0) {
-        // ------------------------------------------------ producer: X tile + W1 chunks
-        if (lane == 0) {
-            prefetch_tensormap(&map_x);
-            prefetch_tensormap(&map_w1);
-            bool ok = true;
-            int it = 0;
-            for (int pt = worker; pt < pair_tiles && ok; pt += workers, ++it) {
-                const int m_blk = 2 * pt + (int)rank;
-                if (!mbar_wait(&x_empty, (uint32_t)(it & 1) ^ 1)) { ok = false; break; }
-                if (rank == 0) mbar_arrive_expect_tx(&x_full, 2u * p.planes * 4 * kTileBytes);
-                const uint32_t x_bar = map_to_cta(&x_full, 0);
-                for (int kb = 0; kb < 4; ++kb)
-                    tma_load_3d_pair(x_smem + kb * 2 * kTileBytes, &map_x, x_bar, kb * kBK, m_blk * kBM, 0);
-                for (int c = 0; c < NC && ok; ++c) {
-                    const uint32_t g = (uint32_t)(it * NC + c);
-                    for (int kb = 0; kb < 4; ++kb) {
-                        if (!mbar_wait(&w1_empty[kb], (g & 1) ^ 1)) { ok = false; break; }
-                        if (rank == 0) mbar_arrive_expect_tx(&w1_full[kb], 2u * p.planes * 32 * 128);
-                        tma_load_4d_pair(w1_smem + kb * kW1SubBytes, &map_w1, map_to_cta(&w1_full[kb], 0),
-                                         kb * kBK, c * kFC + (int)rank * 32, 0, 0);
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (warp == 0) {
+            // ------------------------------------------------ producer: one ring, MMA order
+            if (lane == 0) {
+                prefetch_tensormap(&map_x);
+                prefetch_tensormap(&map_w1);
+                prefetch_tensormap(&map_w2);
+                const uint32_t g1_tx = 2u * (p.planes * kTileBytes + p.planes * kW1PlaneBytes);
+                const uint32_t g2_tx = 2u * p.planes * kTileBytes;
+                int stage = 0;
+                uint32_t phase = 0;
+                bool ok = true;
+                auto acquire = [&](uint32_t tx) -> unsigned char* {
+                    if (!mbar_wait(&empty_bar[stage], phase ^ 1)) {
+                        ok = false;
+                        return nullptr;
+                    }
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
+                    return smem + stage * kSlotBytes;
+                };
+                auto advance = [&]() {
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                };
+                for (int pt = worker; pt < pair_tiles && ok; pt += workers) {
+                    const int m_blk = 2 * pt + (int)rank;
+                    auto load_g1 = [&](int c) {
+                        for (int kb = 0; kb < 4 && ok; ++kb) {
+                            unsigned char* slot = acquire(g1_tx);
+                            if (!slot) return;
+                            const uint32_t bar = map_to_cta(&full_bar[stage], 0);
+                            tma_load_3d_pair(slot, &map_x, bar, kb * kBK, m_blk * kBM, 0);
+                            tma_load_4d_pair(slot + 2 * kTileBytes, &map_w1, bar, kb * kBK, c * kFC + (int)rank * 64, 0, 0);
+                            advance();
+                        }
+                    };
+                    auto load_g2 = [&](int c) {
+                        for (int kb = 0; kb < 2 && ok; ++kb) {
+                            unsigned char* slot = acquire(g2_tx);
+                            if (!slot) return;
+                            const uint32_t bar = map_to_cta(&full_bar[stage], 0);
+                            tma_load_4d_pair(slot, &map_w2, bar, c * kFC + kb * kBK, (int)rank * 128, 0, 0);
+                            advance();
+                        }
+                    };
+                    load_g1(0);
+                    for (int c = 0; c < NC && ok; ++c) {
+                        if (c + 1 < NC) load_g1(c + 1);
+                        load_g2(c);
                     }
                 }
+                if (!ok) atomicExch(p.status, kStatusProducerTimeout);
             }
-            if (!ok) atomicExch(p.status, kStatusProducerTimeout);
-        }
-    } else if (warp == 10) {
-        // ------------------------------------------------ producer: W2 chunks
-        if (lane == 0) {
-            prefetch_tensormap(&map_w2);
-            bool ok = true;
-            int it = 0;
-            for (int pt = worker; pt < pair_tiles && ok; pt += workers, ++it) {
-                for (int c = 0; c < NC; ++c) {
-                    const uint32_t g = (uint32_t)(it * NC + c);
-                    if (!mbar_wait(&w2_empty, (g & 1) ^ 1)) { ok = false; break; }
-                    if (rank == 0) mbar_arrive_expect_tx(&w2_full, 2u * p.planes * kTileBytes);
-                    tma_load_4d_pair(w2_smem, &map_w2, map_to_cta(&w2_full, 0), c * kFC,
-                                     (int)rank * 128, 0, 0);
-                }
-            }
-            if (!ok) atomicExch(p.status, kStatusProducerTimeout);
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer (leader CTA)
-        if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc1 = make_idesc_f16(2 * kBM, kFC);
-            constexpr uint32_t idesc2 = make_idesc_f16(2 * kBM, 256);
-            const uint32_t x_addr = smem_u32(x_smem), w1_addr = smem_u32(w1_smem);
-            const uint32_t w2_addr = smem_u32(w2_smem), h1_addr = smem_u32(h1_smem);
-            const bool two = p.planes == 2;
-            bool ok = true;
-            int it = 0;
-            long long tw[6] = {0, 0, 0, 0, 0, 0};
-            const long long t_begin = clock64();
-            // G2 of chunk (gg = global index, cc = index inside the tile)
-            auto issue_g2 = [&](uint32_t gg, int cc) -> bool {
-                if (cc == 0 && !timed_wait(&y_empty, (uint32_t)(it & 1) ^ 1, tw[5])) return false;
-                if (!timed_wait(&h1_full, gg & 1, tw[3])) return false;
-                if (!timed_wait(&w2_full, gg & 1, tw[4])) return false;
-                tcgen05_fence_after();
-                const uint32_t d = tmem_base + kYCol;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t koff = k * 32;
-                    const uint64_t da0 = smem_desc_kmajor_sw128(h1_addr + koff);
-                    const uint64_t db0 = smem_desc_kmajor_sw128(w2_addr + koff);
-                    umma_f16_pair(d, da0, db0, idesc2, (cc > 0 || k > 0) ? 1u : 0u);
-                    if (two) {
-                        umma_f16_pair(d, da0, smem_desc_kmajor_sw128(w2_addr + kTileBytes + koff), idesc2, 1);
-                        umma_f16_pair(d, smem_desc_kmajor_sw128(h1_addr + kTileBytes + koff), db0, idesc2, 1);
+        } else if (warp == 1) {
+            // ------------------------------------------------ MMA issuer (leader CTA)
+            if (lane == 0 && rank == 0) {
+                constexpr uint32_t idesc1 = make_idesc_f16(2 * kBM, kFC);
+                constexpr uint32_t idesc2 = make_idesc_f16(2 * kBM, 256);
+                const uint32_t h1_addr = smem_u32(h1_smem);
+                const bool two = p.planes == 2;
+                int stage = 0;
+                uint32_t phase = 0;
+                bool ok = true;
+                uint32_t g = 0;    // chunks issued by G1 so far (all tiles)
+                uint32_t g2 = 0;   // chunks issued by G2 so far
+                int it = 0;
+                auto next_slot = [&]() -> uint32_t {
+                    if (!mbar_wait(&full_bar[stage], phase)) {
+                        ok = false;
+                        return 0;
                     }
-                }
-                umma_commit_pair(&h1_empty);
-                umma_commit_pair(&w2_empty);
-                return true;
-            };
-            for (int pt = worker; pt < pair_tiles && ok; pt += workers, ++it) {
-                if (!timed_wait(&x_full, (uint32_t)(it & 1), tw[0])) { ok = false; break; }
-                for (int c = 0; c < NC && ok; ++c) {
-                    const uint32_t g = (uint32_t)(it * NC + c);
+                    tcgen05_fence_after();
+                    return smem_u32(smem + stage * kSlotBytes);
+                };
+                auto release_slot = [&]() {
+                    umma_commit_pair(&empty_bar[stage]);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                };
+                auto issue_g1 = [&]() {
                     const int hb = (int)(g & 1);
-                    if (!timed_wait(&hacc_empty[hb], ((g >> 1) & 1) ^ 1, tw[1])) { ok = false; break; }
+                    if (!mbar_wait(&hacc_empty[hb], ((g >> 1) & 1) ^ 1)) { ok = false; return; }
+                    tcgen05_fence_after();
                     const uint32_t d = tmem_base + kHaccCol + hb * kFC;
                     for (int kb = 0; kb < 4 && ok; ++kb) {
-                        if (!timed_wait(&w1_full[kb], g & 1, tw[2])) { ok = false; break; }
-                        tcgen05_fence_after();
-                        const uint32_t a0 = x_addr + kb * 2 * kTileBytes;
-                        const uint32_t b0 = w1_addr + kb * kW1SubBytes;
+                        const uint32_t a0 = next_slot();
+                        if (!ok) return;
+                        const uint32_t b0 = a0 + 2 * kTileBytes;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint32_t koff = k * 32;
@@ -205,199 +222,208 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                             const uint64_t db0 = smem_desc_kmajor_sw128(b0 + koff);
                             umma_f16_pair(d, da0, db0, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
                             if (two) {
-                                umma_f16_pair(d, da0, smem_desc_kmajor_sw128(b0 + 32 * 128 + koff), idesc1, 1);
+                                umma_f16_pair(d, da0, smem_desc_kmajor_sw128(b0 + kW1PlaneBytes + koff), idesc1, 1);
                                 umma_f16_pair(d, smem_desc_kmajor_sw128(a0 + kTileBytes + koff), db0, idesc1, 1);
                             }
                         }
-                        umma_commit_pair(&w1_empty[kb]);
+                        release_slot();
                     }
-                    if (!ok) break;
                     umma_commit_pair(&hacc_full[hb]);
-                    if (c >= 1 && !issue_g2(g - 1, c - 1)) { ok = false; break; }
+                    ++g;
+                };
+                auto issue_g2 = [&](int c) {
+                    if (c == 0 && !mbar_wait(&y_empty, (uint32_t)(it & 1) ^ 1)) { ok = false; return; }
+                    if (!mbar_wait(&h1_full, g2 & 1)) { ok = false; return; }
+                    tcgen05_fence_after();
+                    const uint32_t d = tmem_base + kYCol;
+                    for (int kb = 0; kb < 2 && ok; ++kb) {
+                        const uint32_t b0 = next_slot();
+                        if (!ok) return;
+                        const uint32_t a0 = h1_addr + kb * 2 * kTileBytes;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t koff = k * 32;
+                            const uint64_t da0 = smem_desc_kmajor_sw128(a0 + koff);
+                            const uint64_t db0 = smem_desc_kmajor_sw128(b0 + koff);
+                            umma_f16_pair(d, da0, db0, idesc2, (c > 0 || kb > 0 || k > 0) ? 1u : 0u);
+                            if (two) {
+                                umma_f16_pair(d, da0, smem_desc_kmajor_sw128(b0 + kTileBytes + koff), idesc2, 1);
+                                umma_f16_pair(d, smem_desc_kmajor_sw128(a0 + kTileBytes + koff), db0, idesc2, 1);
+                            }
+                        }
+                        release_slot();
+                    }
+                    umma_commit_pair(&h1_empty);
+                    ++g2;
+                };
+                for (int pt = worker; pt < pair_tiles && ok; pt += workers, ++it) {
+                    issue_g1();
+                    for (int c = 0; c < NC && ok; ++c) {
+                        if (c + 1 < NC) issue_g1();
+                        if (ok) issue_g2(c);
+                    }
+                    if (ok) umma_commit_pair(&y_full);
                 }
-                if (ok && !issue_g2((uint32_t)(it * NC + NC - 1), NC - 1)) ok = false;
-                if (ok) umma_commit_pair(&y_full);
-            }
-            if (!ok) atomicExch(p.status, kStatusMmaTimeout);
-            if (p.trace) {
-                for (int i = 0; i < 6; ++i) atomicAdd(p.trace + i, (unsigned long long)tw[i]);
-                atomicAdd(p.trace + 6, (unsigned long long)(clock64() - t_begin));
+                if (!ok) atomicExch(p.status, kStatusMmaTimeout);
             }
         }
     } else {
-        // ------------------------------------------------ epilogue warps 2..9
-        const int set = (warp - 2) >> 2;          // which 32 of a chunk's 64 columns / column half of Y
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        // ------------------------------------------------ epilogue warps 4..11
+        const int set = (warp - 4) >> 2;          // 64-column half of a hidden chunk / 128-column half of Y
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const bool elected = (warp - 2) == 4 * set && lane == 0;
+        const bool elected = quad == 0 && lane == 0;          // one thread per set
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
         const uint32_t h1_addr = smem_u32(h1_smem);
         const uint32_t hacc_empty_remote[2] = {map_to_cta(&hacc_empty[0], 0), map_to_cta(&hacc_empty[1], 0)};
         const uint32_t h1_full_remote = map_to_cta(&h1_full, 0);
         const uint32_t y_empty_remote = map_to_cta(&y_empty, 0);
         const float scale1 = *p.scale1, scale2 = *p.scale2;
-        uint32_t raw[32], h[32], l[32];
-        float y[32];
         bool ok = true;
         int it = 0;
-        long long te[4] = {0, 0, 0, 0};
-        const long long t_begin = clock64();
+        uint32_t g = 0;
         for (int pt = worker; pt < pair_tiles && ok; pt += workers, ++it) {
             const int m_blk = 2 * pt + (int)rank;
             const int m0 = m_blk * kBM;
             const int64_t m = (int64_t)m0 + row;
-            // ---- hidden chunks: Hacc -> relu -> split -> H1 (A operand of G2).  Epilogue set s
-            // (4 warps, one row per thread) owns the chunks with c % 2 == s, i.e. always the
-            // accumulator buffer Hacc[s]; the per-chunk synchronisation cost is paid by 4 warps
-            // every other chunk instead of 8 warps every chunk.
-            float bias2nd[32];
+            // ---- hidden chunks: Hacc -> relu -> split -> H1 (A operand of G2); this thread owns
+            // 64 columns (kc = set) of its row
 #pragma unroll 1
-            for (int c = set; c < NC; c += 2) {
-                const uint32_t g = (uint32_t)(it * NC + c);
-                // the bias loads (L2 latency) are in flight while this set waits for its chunk
-                load_row32(p.bias1 + c * kFC, y);
-                load_row32(p.bias1 + c * kFC + 32, bias2nd);
-                if (!timed_wait(&hacc_full[set], (g >> 1) & 1, te[0])) { ok = false; break; }
+            for (int c = 0; c < NC; ++c, ++g) {
+                const int hb = (int)(g & 1);
+                uint32_t raw[2][32], h[32], l[32];
+                float b[32];
+                if (!mbar_wait(&hacc_full[hb], (g >> 1) & 1)) { ok = false; break; }
                 tcgen05_fence_after();
-                uint32_t raw2[32];
-                tmem_ld_32x32(t_lane + kHaccCol + set * kFC, raw);
-                tmem_ld_32x32(t_lane + kHaccCol + set * kFC + 32, raw2);
+                const uint32_t col = kHaccCol + hb * kFC + set * 64;
+                tmem_ld_32x32(t_lane + col, raw[0]);
+                tmem_ld_32x32(t_lane + col + 32, raw[1]);
+                load_row32(p.bias1 + c * kFC + set * 64, b);
                 tmem_wait_ld();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster_relaxed(hacc_empty_remote[set]);
+                if (lane == 0) mbar_arrive_cluster_relaxed(hacc_empty_remote[hb]);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float v0 = fmaxf(fmaf(__uint_as_float(raw[2 * j]), scale1, y[2 * j]), 0.f);
-                    const float v1 = fmaxf(fmaf(__uint_as_float(raw[2 * j + 1]), scale1, y[2 * j + 1]), 0.f);
-                    split2_f16(v0, v1, h[j], l[j]);
-                    const float v2 = fmaxf(fmaf(__uint_as_float(raw2[2 * j]), scale1, bias2nd[2 * j]), 0.f);
-                    const float v3 = fmaxf(fmaf(__uint_as_float(raw2[2 * j + 1]), scale1, bias2nd[2 * j + 1]), 0.f);
-                    split2_f16(v2, v3, h[16 + j], l[16 + j]);
-                }
-                if (!timed_wait(&h1_empty, (g & 1) ^ 1, te[1])) { ok = false; break; }
-                stage_row128(h1_addr, row, h);
-                stage_row128(h1_addr + kTileBytes, row, l);
+                for (int j = 0; j < 16; ++j)
+                    split2_f16(fmaxf(fmaf(__uint_as_float(raw[0][2 * j]), scale1, b[2 * j]), 0.f),
+                               fmaxf(fmaf(__uint_as_float(raw[0][2 * j + 1]), scale1, b[2 * j + 1]), 0.f), h[j], l[j]);
+                load_row32(p.bias1 + c * kFC + set * 64 + 32, b);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    split2_f16(fmaxf(fmaf(__uint_as_float(raw[1][2 * j]), scale1, b[2 * j]), 0.f),
+                               fmaxf(fmaf(__uint_as_float(raw[1][2 * j + 1]), scale1, b[2 * j + 1]), 0.f), h[16 + j],
+                               l[16 + j]);
+                // the H1 tile is free once G2 of the previous chunk has retired
+                if (!mbar_wait(&h1_empty, (g & 1) ^ 1)) { ok = false; break; }
+                stage_row128(h1_addr + set * 2 * kTileBytes, row, h);
+                stage_row128(h1_addr + set * 2 * kTileBytes + kTileBytes, row, l);
                 fence_proxy_async_smem();
-                named_bar_sync(1 + set, 128);
-                if (elected) mbar_arrive_cluster(h1_full_remote);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(h1_full_remote);
             }
             if (!ok) break;
-            // ---- LayerNorm epilogue on Y: set s owns columns [128 s, 128 s + 128)
-            if (!timed_wait(&y_full, (uint32_t)(it & 1), te[2])) { ok = false; break; }
+            // ---- LayerNorm epilogue: Y -> registers (and released), + bias2 + residual
+            if (!mbar_wait(&y_full, (uint32_t)(it & 1))) { ok = false; break; }
             tcgen05_fence_after();
-            const long long t_ln = clock64();
-            const uint32_t t_acc = t_lane + kYCol;
-            const SeqInfo s = p.seqs[p.tile_seq[m_blk]];
-            const bool in_tensor = (int)(m - s.row0) < s.tensor_len;
-            const int c_first = set * 4;
-            float sum = 0.f;
-            // the residual IS the X tile still resident in shared memory (128B-swizzled
-            // [k-block][hi|lo][128 rows][64]): no global re-read
-            const uint32_t x_row = smem_u32(x_smem) + (uint32_t)row * 128;
-            const uint32_t xsw = (uint32_t)row & 7;
+            float v[128];
+            {
+                uint32_t raw[32];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = c_first + i;
-                tmem_ld_32x32(t_acc + c * 32, raw);
-                load_row32(p.bias2 + c * 32, y);
-                uint4 rh[4], rl[4];
-                const uint32_t tile = x_row + (uint32_t)(c >> 1) * 2 * kTileBytes;
+                for (int i = 0; i < 4; ++i) {
+                    tmem_ld_32x32(t_lane + kYCol + set * 128 + i * 32, raw);
+                    tmem_wait_ld();
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t addr = tile + (((uint32_t)((c & 1) * 4 + u) ^ xsw) << 4);
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(rh[u].x), "=r"(rh[u].y), "=r"(rh[u].z), "=r"(rh[u].w)
-                                 : "r"(addr));
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(rl[u].x), "=r"(rl[u].y), "=r"(rl[u].z), "=r"(rl[u].w)
-                                 : "r"(addr + kTileBytes));
+                    for (int j = 0; j < 32; ++j) v[i * 32 + j] = __uint_as_float(raw[j]) * scale2;
                 }
-                tmem_wait_ld();
-                const uint32_t* rhw = reinterpret_cast<const uint32_t*>(rh);
-                const uint32_t* rlw = reinterpret_cast<const uint32_t*>(rl);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&rhw[j]));
-                    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&rlw[j]));
-                    const float v0 = fmaf(__uint_as_float(raw[2 * j]), scale2, y[2 * j]) + (fh.x + fl.x);
-                    const float v1 = fmaf(__uint_as_float(raw[2 * j + 1]), scale2, y[2 * j + 1]) + (fh.y + fl.y);
-                    sum += v0 + v1;
-                    raw[2 * j] = __float_as_uint(v0);
-                    raw[2 * j + 1] = __float_as_uint(v1);
-                }
-                tmem_st_32x32(t_acc + c * 32, raw);
             }
-            // X is dead now (all G1 MMAs completed before y_full): let the producer refill it
+            tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&x_empty);
-            tmem_wait_st();
+            if (lane == 0) mbar_arrive_cluster_relaxed(y_empty_remote);   // the next tile may overwrite Y
+            // residual rows: TMA into the dead H1 tile, one 64-column group (hi|lo, 32 KB) per set
+            // at a time; y_full implies the last G2 has read H1
+            const uint32_t res_tile = h1_addr + set * 2 * kTileBytes;
+            float sum = 0.f;
+#pragma unroll
+            for (int gq = 0; gq < 2; ++gq) {
+                named_bar_sync(1 + set, 128);   // previous group consumed by all rows of the set
+                if (elected) {
+                    mbar_arrive_expect_tx(&res_full[set], 2 * kTileBytes);
+                    tma_load_3d(h1_smem + set * 2 * kTileBytes, &map_res, &res_full[set], set * 128 + gq * 64, m0, 0);
+                }
+                float b[32];
+                uint32_t rh[32], rl[32];
+                if (!mbar_wait(&res_full[set], (uint32_t)((2 * it + gq) & 1))) { ok = false; break; }
+                load_row128(res_tile, row, rh);
+                load_row128(res_tile + kTileBytes, row, rl);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    load_row32(p.bias2 + set * 128 + gq * 64 + half * 32, b);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&rh[half * 16 + j]));
+                        const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&rl[half * 16 + j]));
+                        const int at = gq * 64 + half * 32 + 2 * j;
+                        v[at] = (v[at] + b[2 * j]) + (fh.x + fl.x);
+                        v[at + 1] = (v[at + 1] + b[2 * j + 1]) + (fh.y + fl.y);
+                        sum += v[at] + v[at + 1];
+                    }
+                }
+            }
+            if (!ok) break;
             ln_part[set][row] = sum;
             named_bar_sync(3, 256);
             const float mean = (ln_part[0][row] + ln_part[1][row]) * (1.f / 256);
             named_bar_sync(3, 256);
             float sq = 0.f;
-#pragma unroll 1
-            for (int c = c_first; c < c_first + 4; ++c) {
-                tmem_ld_32x32(t_acc + c * 32, raw);
-                tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float d = __uint_as_float(raw[j]) - mean;
-                    sq = fmaf(d, d, sq);
-                }
+            for (int i = 0; i < 128; ++i) {
+                const float d = v[i] - mean;
+                sq = fmaf(d, d, sq);
             }
             ln_part[set][row] = sq;
             named_bar_sync(3, 256);
             const float rstd = rsqrtf((ln_part[0][row] + ln_part[1][row]) * (1.f / 256) + p.eps);
-            named_bar_sync(3, 256);
-            unsigned char* stage = h1_smem + set * kTileBytes;   // H1 is dead until the next tile
-#pragma unroll 1
+            named_bar_sync(3, 256);   // also: every row of both sets has consumed its residual tile
+            const SeqInfo s = p.seqs[p.tile_seq[m_blk]];
+            const bool in_tensor = (int)(m - s.row0) < s.tensor_len;
+            // normalise + split + stage (hi -> first 16 KB tile of the set, lo -> second) + TMA store
+#pragma unroll
             for (int gq = 0; gq < 2; ++gq) {
-                const int n0 = (c_first + 2 * gq) * 32;
+                uint32_t h[32], l[32];
+                float gamma[32], beta[32];
+                const int n0 = set * 128 + gq * 64;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    float gamma[32];
-                    tmem_ld_32x32(t_acc + n0 + half * 32, raw);
                     load_row32(p.gamma + n0 + half * 32, gamma);
-                    load_row32(p.beta + n0 + half * 32, y);
-                    tmem_wait_ld();
-                    if (gq == 1 && half == 1) {   // Y has been read: the next tile may overwrite it
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster_relaxed(y_empty_remote);
-                    }
+                    load_row32(p.beta + n0 + half * 32, beta);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float v0 = fmaf((__uint_as_float(raw[2 * j]) - mean) * rstd, gamma[2 * j], y[2 * j]);
-                        const float v1 = fmaf((__uint_as_float(raw[2 * j + 1]) - mean) * rstd, gamma[2 * j + 1], y[2 * j + 1]);
+                        const int at = gq * 64 + half * 32 + 2 * j;
+                        const float v0 = fmaf((v[at] - mean) * rstd, gamma[2 * j], beta[2 * j]);
+                        const float v1 = fmaf((v[at + 1] - mean) * rstd, gamma[2 * j + 1], beta[2 * j + 1]);
                         split2_f16(in_tensor ? v0 : 0.f, in_tensor ? v1 : 0.f, h[half * 16 + j], l[half * 16 + j]);
                     }
                 }
-#pragma unroll
-                for (int plane = 0; plane < 2; ++plane) {
-                    if (elected) bulk_wait_read_all();
+                if (gq == 1) {
+                    if (elected) bulk_wait_read_all();   // group 0's stores have drained the tiles
                     named_bar_sync(1 + set, 128);
-                    stage_row128(smem_u32(stage), row, plane == 0 ? h : l);
-                    fence_proxy_async_smem();
-                    named_bar_sync(1 + set, 128);
-                    if (elected) {
-                        tma_store_3d(&map_out, stage, n0, m0, plane);
-                        bulk_commit_group();
-                    }
+                }
+                stage_row128(res_tile, row, h);
+                stage_row128(res_tile + kTileBytes, row, l);
+                fence_proxy_async_smem();
+                named_bar_sync(1 + set, 128);
+                if (elected) {
+                    tma_store_3d(&map_out, h1_smem + set * 2 * kTileBytes, n0, m0, 0);
+                    tma_store_3d(&map_out, h1_smem + set * 2 * kTileBytes + kTileBytes, n0, m0, 1);
+                    bulk_commit_group();
                 }
             }
             // the staging tiles alias H1: drain the stores before the next tile's chunks
             if (elected) bulk_wait_read_all();
             named_bar_sync(3, 256);
-            te[3] += clock64() - t_ln;
         }
         if (elected) bulk_wait_all();
-        if (p.trace && warp == 2 && lane == 0) {
-            for (int i = 0; i < 4; ++i) atomicAdd(p.trace + 8 + i, (unsigned long long)te[i]);
-            atomicAdd(p.trace + 12, (unsigned long long)(clock64() - t_begin));
-            atomicAdd(p.trace + 13, 1ull);
-        }
         if (!ok) atomicExch(p.status, kStatusEpilogueTimeout);
     }
 
@@ -409,9 +435,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
 }
 
+}  // namespace
+
 int launch_ffn_fused(ppgs_engine* e, const CUtensorMap& map_x, const CUtensorMap& map_w1,
-                     const CUtensorMap& map_w2, const CUtensorMap& map_out, const FfnParams& p,
-                     cudaStream_t stream) {
+                     const CUtensorMap& map_w2, const CUtensorMap& map_out, const CUtensorMap& map_res,
+                     const FfnParams& p, cudaStream_t stream) {
     if (p.m_tiles <= 0 || p.m_tiles % 2 || p.num_chunks <= 0) {
         set_error("ffn_fused: needs an even number of row tiles");
         return PPGS_E_INVALID;
@@ -422,7 +450,7 @@ int launch_ffn_fused(ppgs_engine* e, const CUtensorMap& map_x, const CUtensorMap
                                        (int)kFfnSmem));
     }
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attrs[1];
+    cudaLaunchAttribute attrs[2];
     cfg.blockDim = dim3(kFfnThreads);
     cfg.dynamicSmemBytes = kFfnSmem;
     cfg.stream = stream;
@@ -433,9 +461,14 @@ int launch_ffn_fused(ppgs_engine* e, const CUtensorMap& map_x, const CUtensorMap
     attrs[0].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
+    if (pdl_enabled()) {
+        attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    }
     {
         LaunchScope scope(e, "tc_ffn_fused_ln", stream);
-        PPGS_CUDA(cudaLaunchKernelEx(&cfg, ffn_fused_kernel, map_x, map_w1, map_w2, map_out, p));
+        PPGS_CUDA(cudaLaunchKernelEx(&cfg, ffn_fused_kernel, map_x, map_w1, map_w2, map_out, map_res, p));
     }
     PPGS_CUDA(cudaGetLastError());
     return PPGS_OK;

@@ -383,7 +383,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         split32(y, h, l, half * 16);
                     }
                     stage_store_plane(&map_out, stage, set, row, elected, h, n0, m0, 0, p.debug_flags);
-                    stage_store_plane(&map_out, stage, set, row, elected, l, n0, m0, 1, p.debug_flags);
+                    // columns below `hi_only_cols` are consumed as single fp16 planes (attention Q / K):
+                    // their lo plane is never read, so it is not written (warp-uniform)
+                    if (n0 >= p.hi_only_cols)
+                        stage_store_plane(&map_out, stage, set, row, elected, l, n0, m0, 1, p.debug_flags);
                 }
             } else if (EPI == kEpiConvIn) {
                 const SeqInfo s = p.seqs[p.tile_seq[m_blk]];

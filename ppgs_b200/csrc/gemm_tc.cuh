@@ -48,6 +48,7 @@ struct GemmParams {
     const SeqInfo* seqs = nullptr;
     const int* tile_seq = nullptr;
     int relu = 0;                // kEpiPlanes activation: 0 none, 1 ReLU, 2 exact GELU
+    int hi_only_cols = 0;        // kEpiPlanes: output columns [0, hi_only_cols) keep only their hi plane (multiple of 64)
     float* ppg = nullptr;   // kEpiConvOut
     int T = 0, O = 0, softmax = 1;
     int* status = nullptr;

@@ -463,7 +463,8 @@ int ppgs_stream_push_ragged(ppgs_stream* s, const void* features_dev, int max_fr
             PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, wmap(T.in_w), &out_qkv, p, stream));
         }
         PPGS_CHECK(launch_attention_any(e, s->qkv[layer], s->att, rows, H, c.num_heads, kStreamPitch, B,
-                                        s->seqs_dev, 1, planes, stream, -1, win_tiles));
+                                        s->seqs_dev, 1, planes, stream, -1, win_tiles, e->attn_qk_planes,
+                                        e->attn_p_planes));
         {
             GemmParams p = base;
             p.n_tiles = 1; p.cblocks = H / 64; p.a_planes = planes;

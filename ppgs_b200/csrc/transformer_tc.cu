@@ -247,6 +247,11 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             GemmParams p = base;
             p.n_tiles = 3 * H / 256; p.cblocks = H / 64; p.a_planes = planes;
             p.N = 3 * H; p.scale = T.in_w.inv_scale; p.bias = L.in_b; p.trace = trace(1);
+            // Q / K enter the attention MMAs as their hi planes only: skip the lo-plane stores
+            if (planes == 2 && e->attn_qk_planes == 1 && e->attention_impl == 1 &&
+                (H / c.num_heads == 128 ? e->attn_dual != 0 || plan.max_pitch <= 512 : plan.max_pitch <= 512) &&
+                plan.max_pitch % 128 == 0)
+                p.hi_only_cols = 2 * H;
             PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, wmap(T.in_w), &out_qkv,
                                       p, stream));
         }

@@ -24,7 +24,8 @@ class Metadata:
     list-of-files branch).  Files longer than `max_frames` are skipped with the
     reference's warning."""
 
-    def __init__(self, audio_files, max_frames=config.MAX_INFERENCE_FRAMES):
+    def __init__(self, audio_files, max_frames=config.live('MAX_INFERENCE_FRAMES')):
+        max_frames = config.resolve(max_frames)
         self.audio_files, self.lengths, self.samples = [], [], {}
         # every file is 16-bit PCM at 16 kHz: eligible for ppgs_files_to_files
         self.native = True
@@ -100,13 +101,14 @@ def collate(audios, pin_memory=False):
 WORKSPACE_BYTES_PER_FRAME = 16 * 1024
 
 
-def bounded_max_frames(max_frames):
+def bounded_max_frames(max_frames, device=None):
     """The reference's default `max_frames` is infinite (ppgs/config/static.py:22): every file
     lands in ONE batch, which cannot work for a corpus.  An infinite budget is replaced by
-    what a quarter of the free GPU memory holds (warned once); finite budgets are kept."""
+    what a quarter of the free memory of `device` (the GPU that will run the batches; None =
+    the current one) holds (warned once); finite budgets are kept."""
     if max_frames != float('inf') or not torch.cuda.is_available():
         return max_frames
-    free, _ = torch.cuda.mem_get_info()
+    free, _ = torch.cuda.mem_get_info(device)
     return max(int(free // 4 // WORKSPACE_BYTES_PER_FRAME), 1000)
 
 
@@ -116,11 +118,13 @@ class Loader:
     'audio_file'], num_workers, max_frames)` yields (ppgs/data/loader.py:20-43).
     `num_workers` reader threads decode files; up to `prefetch` batches ahead."""
 
-    def __init__(self, audio_files, num_workers=0, max_frames=config.MAX_INFERENCE_FRAMES,
-                 prefetch=2, shard=None, dataset=None):
-        # `dataset`: reuse the header probe of another shard's loader
+    def __init__(self, audio_files, num_workers=0, max_frames=config.live('MAX_INFERENCE_FRAMES'),
+                 prefetch=2, shard=None, dataset=None, device=None):
+        # `dataset`: reuse the header probe of another shard's loader; `device`: the GPU the
+        # batches will run on (sizes an unbounded frame budget from ITS free memory)
+        max_frames = config.resolve(max_frames)
         self.dataset = dataset if dataset is not None else Metadata(audio_files, max_frames)
-        budget = bounded_max_frames(max_frames)
+        budget = bounded_max_frames(max_frames, device)
         if budget != max_frames and sum(self.dataset.lengths) > budget:
             warnings.warn(
                 f'max_frames is unbounded and the files hold {sum(self.dataset.lengths)} frames: '
@@ -169,10 +173,10 @@ class Loader:
 
 
 def loader(audio_files, features=('audio', 'length', 'audio_file'), num_workers=0,
-           max_frames=config.MAX_INFERENCE_FRAMES, shard=None, dataset=None):
+           max_frames=config.live('MAX_INFERENCE_FRAMES'), shard=None, dataset=None, device=None):
     """ppgs.data.loader for the inference feature set."""
     if list(features) != ['audio', 'length', 'audio_file']:
         raise ValueError(
             "ppgs_b200.data.loader serves the inference path only: "
             "features must be ['audio', 'length', 'audio_file']")
-    return Loader(audio_files, num_workers, max_frames, shard=shard, dataset=dataset)
+    return Loader(audio_files, num_workers, max_frames, shard=shard, dataset=dataset, device=device)

@@ -46,13 +46,18 @@ def _stream_ptr(device):
 class Engine:
     """One ppgs_engine: packed weights + workspace on `device`."""
 
-    def __init__(self, device, input_channels=config.INPUT_CHANNELS,
-                 hidden_channels=config.HIDDEN_CHANNELS,
-                 num_hidden_layers=config.NUM_HIDDEN_LAYERS,
-                 output_channels=config.OUTPUT_CHANNELS,
-                 kernel_size=config.KERNEL_SIZE,
-                 attention_heads=config.ATTENTION_HEADS,
-                 is_causal=config.IS_CAUSAL, max_len=config.MAX_LEN):
+    def __init__(self, device, input_channels=config.live('INPUT_CHANNELS'),
+                 hidden_channels=config.live('HIDDEN_CHANNELS'),
+                 num_hidden_layers=config.live('NUM_HIDDEN_LAYERS'),
+                 output_channels=config.live('OUTPUT_CHANNELS'),
+                 kernel_size=config.live('KERNEL_SIZE'),
+                 attention_heads=config.live('ATTENTION_HEADS'),
+                 is_causal=config.live('IS_CAUSAL'), max_len=config.live('MAX_LEN')):
+        # defaults come from the configuration as it is NOW (configure() / --config)
+        input_channels, hidden_channels = config.resolve(input_channels), config.resolve(hidden_channels)
+        num_hidden_layers, output_channels = config.resolve(num_hidden_layers), config.resolve(output_channels)
+        kernel_size, attention_heads = config.resolve(kernel_size), config.resolve(attention_heads)
+        is_causal, max_len = config.resolve(is_causal), config.resolve(max_len)
         self.device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('ppgs_b200 runs on CUDA devices only (no CPU fallback)')

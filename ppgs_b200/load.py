@@ -170,7 +170,7 @@ def utility_engine(gpu=None):
     """A weight-less engine on `gpu` for the ingest kernels (resampler, PCM decode)
     when no model is involved; cached per device."""
     device = resolve_device(gpu)
-    key = ('utility', '', device.index, False)
+    key = ('utility', '', device.index, False, ())
     with _lock:
         engine = _engines.get(key)
         if engine is None:
@@ -180,7 +180,10 @@ def utility_engine(gpu=None):
 
 def cache_key(representation, checkpoint, gpu, is_causal=None):
     causal = config.IS_CAUSAL if is_causal is None else bool(is_causal)
-    return (str(representation), str(checkpoint), resolve_device(gpu).index, causal)
+    # the live model configuration is part of the identity of a cached engine
+    shape = (config.INPUT_CHANNELS, config.HIDDEN_CHANNELS, config.NUM_HIDDEN_LAYERS,
+             config.ATTENTION_HEADS, config.KERNEL_SIZE, config.OUTPUT_CHANNELS)
+    return (str(representation), str(checkpoint), resolve_device(gpu).index, causal, shape)
 
 
 def clear_cache():

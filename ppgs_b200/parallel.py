@@ -40,7 +40,10 @@ def broadcast_engine(state_dict=None, representation=None, gpu=None, src=0, **kw
     function of the model config) goes to every other rank in ONE NCCL broadcast
     over NVLink, and those ranks adopt it without touching the checkpoint."""
     gpu = local_device() if gpu is None else gpu
-    engine = Engine(gpu, **{**load.model_kwargs(representation), **kwargs})
+    # the live configuration (configure() / --config), not import-time defaults: every rank
+    # must build the engine load.cache_key() will describe
+    kwargs = {'is_causal': config.IS_CAUSAL, **load.model_kwargs(representation), **kwargs}
+    engine = Engine(gpu, **kwargs)
     rank = dist.get_rank() if dist.is_initialized() else 0
     if rank == src:
         if state_dict is None:
@@ -78,13 +81,14 @@ def shard_by_frames(frame_lengths, world):
     return [sorted(p) for p in parts]
 
 
-def from_files_to_files(audio_files, output_files, representation=config.REPRESENTATION,
+def from_files_to_files(audio_files, output_files, representation=config.live('REPRESENTATION'),
                         checkpoint=None, num_workers=2, max_frames=64000, legacy_mode=False):
     """Sharded `from_files_to_files` under torchrun: every rank builds the same
     deterministic batch list (data.frame_budget_batches) and takes batches
     rank::world, so batch composition — and therefore every posterior — is
     identical to a single-GPU run."""
     from . import core, data
+    representation = config.resolve(representation)
     rank, world = init()
     gpu = local_device()
     if world > 1:
@@ -94,7 +98,7 @@ def from_files_to_files(audio_files, output_files, representation=config.REPRESE
             load._engines[load.cache_key(representation, checkpoint, gpu)] = engine
     dataloader = data.loader(
         audio_files, num_workers=max(num_workers // 2, 1), max_frames=max_frames,
-        shard=(rank, world))
+        shard=(rank, world), device=gpu)
     mapping = dict(zip(audio_files, output_files))
     if core._native_pipeline(dataloader, representation):
         engine = load.model(checkpoint, representation, gpu)

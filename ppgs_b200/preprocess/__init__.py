@@ -22,9 +22,10 @@ def get(representation):
     return REGISTRY[representation]
 
 
-def from_audio(audio, representation=config.REPRESENTATION,
+def from_audio(audio, representation=config.live('REPRESENTATION'),
                sample_rate=config.SAMPLE_RATE, gpu=None):
     """Preprocess audio (ppgs/preprocess/core.py:194-216)."""
+    representation = config.resolve(representation)
     from ..core import resample
     audio = resample(audio, sample_rate)
     features = get(representation).from_audio(

@@ -92,6 +92,49 @@ def test_tcgen05_gemm(engine, case, planes):
     assert err <= tol, f'relative error {err:.3e}'
 
 
+def attention_reference(qkv, rows, H, heads, valid_len, causal):
+    q, k, v = [t.double().reshape(rows, heads, H // heads).transpose(0, 1) for t in qkv.split(H, 1)]
+    scores = q @ k.transpose(1, 2) / (H // heads) ** 0.5
+    scores[:, :, valid_len:] = float('-inf')
+    if causal:
+        scores = scores.masked_fill(torch.ones(rows, rows).triu(1).bool(), float('-inf'))
+    p = torch.softmax(scores, -1) if valid_len else torch.zeros_like(scores)
+    return (p @ v).transpose(0, 1).reshape(rows, H)
+
+
+@pytest.mark.parametrize('tensor_len,valid_len', [(126, 126), (500, 500), (500, 317), (250, 1), (300, 0),
+                                                  (380, 300), (1200, 1111)])
+@pytest.mark.parametrize('causal', [0, 1])
+@pytest.mark.parametrize('growth', [0.0, 3.0])
+def test_attention_two_tile_kernel(engine, tensor_len, valid_len, causal, growth):
+    """The default model's attention (head_dim 128, attention_dual_tc.cu): two query tiles per
+    CTA over shared K / V blocks, Q / K / P as single fp16 planes, online softmax.  Odd tile
+    counts (380 -> 3 tiles: one idle lane), sequences longer than the old 512-key limit, causal
+    masks (the earlier tile needs fewer key blocks than its partner) and key norms that GROW
+    along the sequence (`growth`), so that later blocks exceed the running max by far more than
+    the 2^8 slack and the accumulator is rescaled in TMEM.  Tolerance: the fp16 rounding of
+    Q, K (scores) and P, i.e. the reference's own fp16-autocast numerics for this product."""
+    lib = debug_lib()
+    H, heads = 256, 2
+    rows = (tensor_len + 2 + 127) // 128 * 128
+    g = torch.Generator().manual_seed(tensor_len + valid_len + causal)
+    qkv = torch.randn(rows, 3 * H, generator=g)
+    qkv[:, :H] *= 2.0
+    qkv[:, H:2 * H] *= (1.0 + growth * torch.arange(rows) / rows)[:, None] ** 2
+    out = torch.empty(rows, H)
+    lib.check(lib.lib.ppgs_debug_attention(
+        engine._handle, qkv.data_ptr(), rows, tensor_len, valid_len, H, heads, causal, 2, 2, out.data_ptr()))
+    # reference on the operands the kernel is specified to see: Q, K rounded to fp16
+    seen = qkv.clone()
+    seen[:, :2 * H] = seen[:, :2 * H].half().float()
+    ref = attention_reference(seen, rows, H, heads, valid_len, causal)
+    err = (out.double() - ref)[:tensor_len].abs().max().item()
+    assert err <= 2e-3, f'max-abs {err:.3e}'
+    if not growth:   # and against the unrounded operands at the fp16-autocast class of error
+        exact = attention_reference(qkv, rows, H, heads, valid_len, causal)
+        assert (out.double() - exact)[:tensor_len].abs().max().item() <= 5e-3
+
+
 @pytest.mark.parametrize('tensor_len,valid_len', [(126, 126), (500, 500), (500, 317), (250, 1), (300, 0)])
 @pytest.mark.parametrize('impl', [0, 1])
 @pytest.mark.parametrize('H,heads,causal', [(256, 2, 0), (128, 2, 0), (512, 2, 0), (768, 12, 0), (256, 2, 1),
