@@ -147,8 +147,8 @@ struct ppgs_engine {
     int attn_p_planes = 1;       // PPGS_B200_ATTN_P_PLANES
     int attn_dual = 1;           // head_dim 128: two query tiles per CTA (attention_dual_tc.cu; PPGS_B200_ATTN_DUAL)
     int gemm_pair = 1;           // 1 = CTA-pair (cta_group::2) GEMMs at BN = 256
-    int fused_ffn = 0;           // 1 = one fused kernel for linear1 + ReLU + linear2 + LN (PPGS_B200_FUSED_FFN;
-                                 // parity-green but shared-memory-bound and slower than the two GEMMs)
+    int fused_ffn = 1;           // 1 = one fused kernel for linear1 + ReLU + linear2 + residual + LN (ffn_tc.cu): the
+                                 // hidden activation never leaves the SM; 0 (PPGS_B200_FUSED_FFN=0) = two GEMMs
     unsigned long long* trace_dev = nullptr;   // [8 kernel kinds][8] cycle counters (PPGS_B200_TRACE=1)
 
     // wav2vec2-base front-end of the `w2v2fb` representation (optional)

@@ -105,10 +105,12 @@ struct FfnParams {
     unsigned long long* trace;
 };
 // map_x: activation planes {256, rows, 2}, box {64, 128, planes}; map_w1: linear1 planes,
-// box rows 32; map_w2: linear2 planes, box rows 128; map_out: store map of the x planes.
+// box rows 64; map_w2: linear2 planes, box rows 128; map_out: store map of the x planes;
+// map_res: the x planes again with both planes in the box (residual rows of the epilogue).
+// num_chunks = ffn_channels / 128.
 int launch_ffn_fused(ppgs_engine* e, const CUtensorMap& map_x, const CUtensorMap& map_w1,
-                     const CUtensorMap& map_w2, const CUtensorMap& map_out, const FfnParams& p,
-                     cudaStream_t stream);
+                     const CUtensorMap& map_w2, const CUtensorMap& map_out, const CUtensorMap& map_res,
+                     const FfnParams& p, cudaStream_t stream);
 
 }  // namespace tc
 }  // namespace ppgs

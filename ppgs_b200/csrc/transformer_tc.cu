@@ -201,6 +201,9 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     PPGS_CHECK(make_plane_map(&map_x, xh, false, H, rows, 1, 2, H, 0, (uint64_t)rows * H, 128, planes));
     PPGS_CHECK(make_plane_map(&map_att, att, false, H, rows, 1, 2, H, 0, (uint64_t)rows * H, 128, planes));
     PPGS_CHECK(make_plane_map(&map_ff, ff, false, F, rows, 1, 2, F, 0, (uint64_t)rows * F, 128, planes));
+    // residual rows of the fused FFN's LayerNorm epilogue: always both planes of x
+    CUtensorMap map_res;
+    PPGS_CHECK(make_plane_map(&map_res, xh, false, H, rows, 1, 2, H, 0, (uint64_t)rows * H, 128, 2));
     // output tensor maps (TMA stores of the epilogues)
     CUtensorMap out_x, out_qkv, out_ff, out_y;
     PPGS_CHECK(make_store_map(&out_x, xh, H, rows, (uint64_t)rows * H));
@@ -289,16 +292,16 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
         };
         PPGS_CHECK(project_ln(fused_ln ? "tc_out_proj_ln" : "tc_out_proj", map_att, T.out_w, H / 64, L.out_b,
                               L.n1_w, L.n1_b, 2, 6));
-        if (pair && e->fused_ffn && fused_ln && F % 64 == 0) {
+        if (pair && e->fused_ffn && fused_ln && F % 128 == 0) {
             FfnParams f;
-            f.m_tiles = rows / 128; f.num_chunks = F / 64; f.planes = planes;
+            f.m_tiles = rows / 128; f.num_chunks = F / 128; f.planes = planes;
             f.scale1 = T.l1_w.inv_scale; f.scale2 = T.l2_w.inv_scale;
             f.bias1 = L.l1_b; f.bias2 = L.l2_b; f.gamma = L.n2_w; f.beta = L.n2_b;
             f.eps = c.layer_norm_eps; f.seqs = seqs_dev; f.tile_seq = tile_seq_dev;
             f.status = e->status_dev;
             f.trace = e->trace_dev ? e->trace_dev + 64 : nullptr;   // counters 64..79
-            PPGS_CHECK(launch_ffn_fused(e, map_x, T.l1_w.maps[planes - 1].bn32, T.l2_w.maps[planes - 1].bn128, out_x, f,
-                                        stream));
+            PPGS_CHECK(launch_ffn_fused(e, map_x, T.l1_w.maps[planes - 1].bn64, T.l2_w.maps[planes - 1].bn128, out_x,
+                                        map_res, f, stream));
         } else {
             {
                 GemmParams p = base;

@@ -161,10 +161,12 @@ def test_single_pass_f16_mode_is_the_autocast_numerics_class(ppgs_b200):
     assert err['f16x2'] <= PPG_TOL < err['f16'] <= 2e-2
 
 
-@pytest.mark.parametrize('switch', ['PPGS_B200_FUSED_FFN=1', 'PPGS_B200_PAIR=0', 'PPGS_B200_ATTENTION=0'])
+@pytest.mark.parametrize('switch', ['PPGS_B200_FUSED_FFN=0', 'PPGS_B200_PAIR=0', 'PPGS_B200_ATTENTION=0',
+                                    'PPGS_B200_ATTN_DUAL=0', 'PPGS_B200_ATTN_QK_PLANES=2'])
 def test_alternative_kernel_paths(ppgs_b200, monkeypatch, switch):
-    """The optional kernels stay parity-checked: the fused FFN kernel, the single-CTA
-    (cta_group::1) GEMMs and the CUDA-core attention kernel (read at engine creation)."""
+    """The optional kernels stay parity-checked: linear1 / linear2 as two GEMMs instead of the
+    fused FFN kernel, the single-CTA (cta_group::1) GEMMs, the CUDA-core attention kernel, the
+    one-tile-per-CTA attention kernel and split-plane Q / K (read at engine creation)."""
     name, value = switch.split('=')
     monkeypatch.setenv(name, value)
     sd = O.random_state_dict(6, peaky=True)
