@@ -147,6 +147,8 @@ struct ppgs_engine {
     int attn_p_planes = 1;       // PPGS_B200_ATTN_P_PLANES
     int attn_dual = 1;           // head_dim 128: two query tiles per CTA (attention_dual_tc.cu; PPGS_B200_ATTN_DUAL)
     int gemm_pair = 1;           // 1 = CTA-pair (cta_group::2) GEMMs at BN = 256
+    int proj_ln = 1;             // 1 = hidden-256 projections + residual + LayerNorm through proj_ln_kernel (ffn_tc.cu);
+                                 // 0 (PPGS_B200_PROJ_LN=0) = gemm_tc's ResLN epilogue
     int fused_ffn = 1;           // 1 = one fused kernel for linear1 + ReLU + linear2 + residual + LN (ffn_tc.cu): the
                                  // hidden activation never leaves the SM; 0 (PPGS_B200_FUSED_FFN=0) = two GEMMs
     unsigned long long* trace_dev = nullptr;   // [8 kernel kinds][8] cycle counters (PPGS_B200_TRACE=1)

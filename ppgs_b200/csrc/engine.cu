@@ -412,6 +412,7 @@ int ppgs_engine_create(const ppgs_model_config* cfg, int device, ppgs_engine** o
     if (const char* v = getenv("PPGS_B200_ATTN_QK_PLANES")) e->attn_qk_planes = atoi(v) == 1 ? 1 : 2;
     if (const char* v = getenv("PPGS_B200_ATTN_P_PLANES")) e->attn_p_planes = atoi(v) == 1 ? 1 : 2;
     if (const char* v = getenv("PPGS_B200_ATTN_DUAL")) e->attn_dual = atoi(v) != 0;
+    if (const char* v = getenv("PPGS_B200_PROJ_LN")) e->proj_ln = atoi(v) != 0;
     if (const char* v = getenv("PPGS_B200_TRACE")) {
         if (atoi(v) != 0 && cudaMalloc(&e->trace_dev, 128 * sizeof(unsigned long long)) == cudaSuccess)
             cudaMemset(e->trace_dev, 0, 128 * sizeof(unsigned long long));

@@ -77,6 +77,120 @@ __device__ __forceinline__ void load_row128(uint32_t tile, int row, uint32_t (&w
                      : "r"(base + (((uint32_t)u ^ sw) << 4)));
 }
 
+
+// LayerNorm epilogue shared by the fused FFN and the projection kernel.  Thread = (row, set):
+// 128 accumulator columns [128 set, 128 set + 128) of one of the CTA's 128 rows.
+//   1. accumulator -> registers, then `release_bar` (cluster address) is signalled: the MMA
+//      warp may overwrite the TMEM columns while everything below runs from registers
+//   2. + bias + residual; the residual rows arrive by TMA in the set's 32 KB staging region
+//      (one 64-column group, hi|lo, at a time; `res_full` phases continue from `res_phase`)
+//   3. two-pass mean / variance over the 256 columns (partner thread through `ln_part`)
+//   4. normalise, zero rows outside the sequence tensor, split, stage, TMA store
+// Returns false on a barrier time-out.  All 256 epilogue threads must call it together.
+__device__ __forceinline__ bool residual_layernorm_store(
+    uint32_t t_acc, uint32_t release_bar, float scale, const float* bias, const float* gamma_p,
+    const float* beta_p, float eps, const SeqInfo* seqs, const int* tile_seq, int m_blk, int row, int set,
+    int lane, bool elected, unsigned char* stage_smem, uint64_t* res_full, uint32_t res_phase,
+    float (*ln_part)[kBM], const CUtensorMap* map_res, const CUtensorMap* map_out) {
+    const int m0 = m_blk * kBM;
+    const int64_t m = (int64_t)m0 + row;
+    bool ok = true;
+    float v[128];
+    {
+        uint32_t raw[32];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            tmem_ld_32x32(t_acc + i * 32, raw);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[i * 32 + j] = __uint_as_float(raw[j]) * scale;
+        }
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster_relaxed(release_bar);   // the next tile may overwrite the accumulator
+    // residual rows: TMA into the dead H1 tile, one 64-column group (hi|lo, 32 KB) per set
+    // at a time; y_full implies the last G2 has read H1
+    const uint32_t res_tile = smem_u32(stage_smem) + set * 2 * kTileBytes;
+    float sum = 0.f;
+#pragma unroll
+    for (int gq = 0; gq < 2; ++gq) {
+        named_bar_sync(1 + set, 128);   // previous group consumed by all rows of the set
+        if (elected) {
+            mbar_arrive_expect_tx(res_full, 2 * kTileBytes);
+            tma_load_3d(stage_smem + set * 2 * kTileBytes, map_res, res_full, set * 128 + gq * 64, m0, 0);
+        }
+        float b[32];
+        uint32_t rh[32], rl[32];
+        if (!mbar_wait(res_full, (res_phase + gq) & 1)) { ok = false; break; }
+        load_row128(res_tile, row, rh);
+        load_row128(res_tile + kTileBytes, row, rl);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            load_row32(bias + set * 128 + gq * 64 + half * 32, b);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&rh[half * 16 + j]));
+                const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&rl[half * 16 + j]));
+                const int at = gq * 64 + half * 32 + 2 * j;
+                v[at] = (v[at] + b[2 * j]) + (fh.x + fl.x);
+                v[at + 1] = (v[at + 1] + b[2 * j + 1]) + (fh.y + fl.y);
+                sum += v[at] + v[at + 1];
+            }
+        }
+    }
+    if (!ok) return false;
+    ln_part[set][row] = sum;
+    named_bar_sync(3, 256);
+    const float mean = (ln_part[0][row] + ln_part[1][row]) * (1.f / 256);
+    named_bar_sync(3, 256);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 128; ++i) {
+        const float d = v[i] - mean;
+        sq = fmaf(d, d, sq);
+    }
+    ln_part[set][row] = sq;
+    named_bar_sync(3, 256);
+    const float rstd = rsqrtf((ln_part[0][row] + ln_part[1][row]) * (1.f / 256) + eps);
+    named_bar_sync(3, 256);   // also: every row of both sets has consumed its residual tile
+    const SeqInfo s = seqs[tile_seq[m_blk]];
+    const bool in_tensor = (int)(m - s.row0) < s.tensor_len;
+    // normalise + split + stage (hi -> first 16 KB tile of the set, lo -> second) + TMA store
+#pragma unroll
+    for (int gq = 0; gq < 2; ++gq) {
+        uint32_t h[32], l[32];
+        float gamma[32], beta[32];
+        const int n0 = set * 128 + gq * 64;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            load_row32(gamma_p + n0 + half * 32, gamma);
+            load_row32(beta_p + n0 + half * 32, beta);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int at = gq * 64 + half * 32 + 2 * j;
+                const float v0 = fmaf((v[at] - mean) * rstd, gamma[2 * j], beta[2 * j]);
+                const float v1 = fmaf((v[at + 1] - mean) * rstd, gamma[2 * j + 1], beta[2 * j + 1]);
+                split2_f16(in_tensor ? v0 : 0.f, in_tensor ? v1 : 0.f, h[half * 16 + j], l[half * 16 + j]);
+            }
+        }
+        if (gq == 1) {
+            if (elected) bulk_wait_read_all();   // group 0's stores have drained the tiles
+            named_bar_sync(1 + set, 128);
+        }
+        stage_row128(res_tile, row, h);
+        stage_row128(res_tile + kTileBytes, row, l);
+        fence_proxy_async_smem();
+        named_bar_sync(1 + set, 128);
+        if (elected) {
+            tma_store_3d(map_out, stage_smem + set * 2 * kTileBytes, n0, m0, 0);
+            tma_store_3d(map_out, stage_smem + set * 2 * kTileBytes + kTileBytes, n0, m0, 1);
+            bulk_commit_group();
+        }
+    }
+    return ok;
+}
+
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_out,
@@ -326,102 +440,168 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             // ---- LayerNorm epilogue: Y -> registers (and released), + bias2 + residual
             if (!mbar_wait(&y_full, (uint32_t)(it & 1))) { ok = false; break; }
             tcgen05_fence_after();
-            float v[128];
-            {
-                uint32_t raw[32];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    tmem_ld_32x32(t_lane + kYCol + set * 128 + i * 32, raw);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[i * 32 + j] = __uint_as_float(raw[j]) * scale2;
-                }
-            }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(y_empty_remote);   // the next tile may overwrite Y
-            // residual rows: TMA into the dead H1 tile, one 64-column group (hi|lo, 32 KB) per set
-            // at a time; y_full implies the last G2 has read H1
-            const uint32_t res_tile = h1_addr + set * 2 * kTileBytes;
-            float sum = 0.f;
-#pragma unroll
-            for (int gq = 0; gq < 2; ++gq) {
-                named_bar_sync(1 + set, 128);   // previous group consumed by all rows of the set
-                if (elected) {
-                    mbar_arrive_expect_tx(&res_full[set], 2 * kTileBytes);
-                    tma_load_3d(h1_smem + set * 2 * kTileBytes, &map_res, &res_full[set], set * 128 + gq * 64, m0, 0);
-                }
-                float b[32];
-                uint32_t rh[32], rl[32];
-                if (!mbar_wait(&res_full[set], (uint32_t)((2 * it + gq) & 1))) { ok = false; break; }
-                load_row128(res_tile, row, rh);
-                load_row128(res_tile + kTileBytes, row, rl);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    load_row32(p.bias2 + set * 128 + gq * 64 + half * 32, b);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&rh[half * 16 + j]));
-                        const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&rl[half * 16 + j]));
-                        const int at = gq * 64 + half * 32 + 2 * j;
-                        v[at] = (v[at] + b[2 * j]) + (fh.x + fl.x);
-                        v[at + 1] = (v[at + 1] + b[2 * j + 1]) + (fh.y + fl.y);
-                        sum += v[at] + v[at + 1];
-                    }
-                }
-            }
-            if (!ok) break;
-            ln_part[set][row] = sum;
-            named_bar_sync(3, 256);
-            const float mean = (ln_part[0][row] + ln_part[1][row]) * (1.f / 256);
-            named_bar_sync(3, 256);
-            float sq = 0.f;
-#pragma unroll
-            for (int i = 0; i < 128; ++i) {
-                const float d = v[i] - mean;
-                sq = fmaf(d, d, sq);
-            }
-            ln_part[set][row] = sq;
-            named_bar_sync(3, 256);
-            const float rstd = rsqrtf((ln_part[0][row] + ln_part[1][row]) * (1.f / 256) + p.eps);
-            named_bar_sync(3, 256);   // also: every row of both sets has consumed its residual tile
-            const SeqInfo s = p.seqs[p.tile_seq[m_blk]];
-            const bool in_tensor = (int)(m - s.row0) < s.tensor_len;
-            // normalise + split + stage (hi -> first 16 KB tile of the set, lo -> second) + TMA store
-#pragma unroll
-            for (int gq = 0; gq < 2; ++gq) {
-                uint32_t h[32], l[32];
-                float gamma[32], beta[32];
-                const int n0 = set * 128 + gq * 64;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    load_row32(p.gamma + n0 + half * 32, gamma);
-                    load_row32(p.beta + n0 + half * 32, beta);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int at = gq * 64 + half * 32 + 2 * j;
-                        const float v0 = fmaf((v[at] - mean) * rstd, gamma[2 * j], beta[2 * j]);
-                        const float v1 = fmaf((v[at + 1] - mean) * rstd, gamma[2 * j + 1], beta[2 * j + 1]);
-                        split2_f16(in_tensor ? v0 : 0.f, in_tensor ? v1 : 0.f, h[half * 16 + j], l[half * 16 + j]);
-                    }
-                }
-                if (gq == 1) {
-                    if (elected) bulk_wait_read_all();   // group 0's stores have drained the tiles
-                    named_bar_sync(1 + set, 128);
-                }
-                stage_row128(res_tile, row, h);
-                stage_row128(res_tile + kTileBytes, row, l);
-                fence_proxy_async_smem();
-                named_bar_sync(1 + set, 128);
-                if (elected) {
-                    tma_store_3d(&map_out, h1_smem + set * 2 * kTileBytes, n0, m0, 0);
-                    tma_store_3d(&map_out, h1_smem + set * 2 * kTileBytes + kTileBytes, n0, m0, 1);
-                    bulk_commit_group();
-                }
+            if (!residual_layernorm_store(t_lane + kYCol + set * 128, y_empty_remote, scale2, p.bias2, p.gamma, p.beta,
+                                          p.eps, p.seqs, p.tile_seq, m_blk, row, set, lane, elected, h1_smem,
+                                          &res_full[set], (uint32_t)(2 * it), ln_part, &map_res, &map_out)) {
+                ok = false;
+                break;
             }
             // the staging tiles alias H1: drain the stores before the next tile's chunks
             if (elected) bulk_wait_read_all();
             named_bar_sync(3, 256);
+        }
+        if (elected) bulk_wait_all();
+        if (!ok) atomicExch(p.status, kStatusEpilogueTimeout);
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc_pair<512>(tmem_base);
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// x <- LayerNorm(x + A . W^T + b) for a hidden-256 projection (the attention out-projection,
+// K = 256; any K % 64 == 0): the CTA-pair GEMM of gemm_tc.cu with the register-resident
+// LayerNorm epilogue above.  The gemm_tc ResLN epilogue made three TMEM passes with the
+// residual fetched cooperatively through one 16 KB staging tile and took 22 k cycles per tile
+// against 6 k cycles of MMA at K = 256; here the accumulator (double-buffered, 2 x 256 TMEM
+// columns) is released after one read, so the tensor pipe runs tile i+1 under the epilogue of
+// tile i.  Ring: two 64 KB slots (A k-block hi|lo + this CTA's half of the W k-block hi|lo).
+// ---------------------------------------------------------------------------
+constexpr int kProjSlotBytes = 4 * kTileBytes;          // 64 KB
+constexpr int kProjStages = 2;
+constexpr int kProjStageOff = kProjStages * kProjSlotBytes;
+constexpr size_t kProjSmem = kProjStageOff + 4 * kTileBytes;   // 192 KB
+
+__global__ void __launch_bounds__(kFfnThreads, 1)
+proj_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
+               const FfnParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* stage_smem = smem + kProjStageOff;
+    __shared__ __align__(8) uint64_t full_bar[kProjStages], empty_bar[kProjStages];
+    __shared__ __align__(8) uint64_t y_full[2], y_empty[2], res_full[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float ln_part[2][kBM];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int worker = (int)(blockIdx.x >> 1), workers = (int)(gridDim.x >> 1);
+    const int pair_tiles = p.m_tiles / 2, KB = p.num_chunks;   // k-blocks of 64
+    if (smem_u32(smem) & 1023u) {
+        if (threadIdx.x == 0) atomicExch(p.status, kStatusBadAlignment);
+        return;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kProjStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&y_full[i], 1);
+            mbar_init(&y_empty[i], 16);
+            mbar_init(&res_full[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair<512>(&tmem_slot);
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (warp == 0) {
+            if (lane == 0) {
+                prefetch_tensormap(&map_a);
+                prefetch_tensormap(&map_w);
+                const uint32_t tx = 2u * 2u * p.planes * kTileBytes;
+                int stage = 0;
+                uint32_t phase = 0;
+                bool ok = true;
+                for (int pt = worker; pt < pair_tiles && ok; pt += workers) {
+                    const int m_blk = 2 * pt + (int)rank;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (!mbar_wait(&empty_bar[stage], phase ^ 1)) { ok = false; break; }
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
+                        unsigned char* slot = smem + stage * kProjSlotBytes;
+                        const uint32_t bar = map_to_cta(&full_bar[stage], 0);
+                        tma_load_3d_pair(slot, &map_a, bar, kb * kBK, m_blk * kBM, 0);
+                        tma_load_4d_pair(slot + 2 * kTileBytes, &map_w, bar, kb * kBK, (int)rank * 128, 0, 0);
+                        if (++stage == kProjStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+                if (!ok) atomicExch(p.status, kStatusProducerTimeout);
+            }
+        } else if (warp == 1) {
+            if (lane == 0 && rank == 0) {
+                constexpr uint32_t idesc = make_idesc_f16(2 * kBM, 256);
+                const bool two = p.planes == 2;
+                int stage = 0;
+                uint32_t phase = 0;
+                bool ok = true;
+                int it = 0;
+                for (int pt = worker; pt < pair_tiles && ok; pt += workers, ++it) {
+                    const int acc = it & 1;
+                    if (!mbar_wait(&y_empty[acc], (uint32_t)((it >> 1) & 1) ^ 1)) { ok = false; break; }
+                    tcgen05_fence_after();
+                    const uint32_t d = tmem_base + acc * 256;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (!mbar_wait(&full_bar[stage], phase)) { ok = false; break; }
+                        tcgen05_fence_after();
+                        const uint32_t a0 = smem_u32(smem + stage * kProjSlotBytes), b0 = a0 + 2 * kTileBytes;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t koff = k * 32;
+                            const uint64_t da0 = smem_desc_kmajor_sw128(a0 + koff);
+                            const uint64_t db0 = smem_desc_kmajor_sw128(b0 + koff);
+                            umma_f16_pair(d, da0, db0, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            if (two) {
+                                umma_f16_pair(d, da0, smem_desc_kmajor_sw128(b0 + kTileBytes + koff), idesc, 1);
+                                umma_f16_pair(d, smem_desc_kmajor_sw128(a0 + kTileBytes + koff), db0, idesc, 1);
+                            }
+                        }
+                        umma_commit_pair(&empty_bar[stage]);
+                        if (++stage == kProjStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    if (ok) umma_commit_pair(&y_full[acc]);
+                }
+                if (!ok) atomicExch(p.status, kStatusMmaTimeout);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        const int set = (warp - 4) >> 2, quad = warp & 3, row = quad * 32 + lane;
+        const bool elected = quad == 0 && lane == 0;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const uint32_t y_empty_remote[2] = {map_to_cta(&y_empty[0], 0), map_to_cta(&y_empty[1], 0)};
+        const float scale = *p.scale2;
+        bool ok = true;
+        int it = 0;
+        for (int pt = worker; pt < pair_tiles && ok; pt += workers, ++it) {
+            const int m_blk = 2 * pt + (int)rank, acc = it & 1;
+            if (!mbar_wait(&y_full[acc], (uint32_t)((it >> 1) & 1))) { ok = false; break; }
+            tcgen05_fence_after();
+            // the previous tile's stores have drained the staging tiles before the residual lands
+            if (elected) bulk_wait_read_all();
+            if (!residual_layernorm_store(t_lane + acc * 256 + set * 128, y_empty_remote[acc], scale, p.bias2, p.gamma,
+                                          p.beta, p.eps, p.seqs, p.tile_seq, m_blk, row, set, lane, elected,
+                                          stage_smem, &res_full[set], (uint32_t)(2 * it), ln_part, &map_res,
+                                          &map_out))
+                ok = false;
         }
         if (elected) bulk_wait_all();
         if (!ok) atomicExch(p.status, kStatusEpilogueTimeout);
@@ -469,6 +649,44 @@ int launch_ffn_fused(ppgs_engine* e, const CUtensorMap& map_x, const CUtensorMap
     {
         LaunchScope scope(e, "tc_ffn_fused_ln", stream);
         PPGS_CUDA(cudaLaunchKernelEx(&cfg, ffn_fused_kernel, map_x, map_w1, map_w2, map_out, map_res, p));
+    }
+    PPGS_CUDA(cudaGetLastError());
+    return PPGS_OK;
+}
+
+
+int launch_proj_ln(ppgs_engine* e, const char* name, const CUtensorMap& map_a, const CUtensorMap& map_w,
+                   const CUtensorMap& map_out, const CUtensorMap& map_res, const FfnParams& p,
+                   cudaStream_t stream) {
+    if (p.m_tiles <= 0 || p.m_tiles % 2 || p.num_chunks <= 0) {
+        set_error("proj_ln: needs an even number of row tiles");
+        return PPGS_E_INVALID;
+    }
+    static PerDeviceOnce attr;
+    if (attr.first(e->device)) {
+        PPGS_CUDA(cudaFuncSetAttribute(proj_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kProjSmem));
+    }
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attrs[2];
+    cfg.blockDim = dim3(kFfnThreads);
+    cfg.dynamicSmemBytes = kProjSmem;
+    cfg.stream = stream;
+    cfg.gridDim = dim3(2 * std::min(p.m_tiles / 2, e->sm_count / 2));
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 2;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    if (pdl_enabled()) {
+        attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    }
+    {
+        LaunchScope scope(e, name, stream);
+        PPGS_CUDA(cudaLaunchKernelEx(&cfg, proj_ln_kernel, map_a, map_w, map_out, map_res, p));
     }
     PPGS_CUDA(cudaGetLastError());
     return PPGS_OK;

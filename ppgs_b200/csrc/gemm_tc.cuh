@@ -112,5 +112,13 @@ int launch_ffn_fused(ppgs_engine* e, const CUtensorMap& map_x, const CUtensorMap
                      const CUtensorMap& map_w2, const CUtensorMap& map_out, const CUtensorMap& map_res,
                      const FfnParams& p, cudaStream_t stream);
 
+// x <- LayerNorm(x + A . W^T + bias2) for hidden 256 (ffn_tc.cu, proj_ln_kernel): CTA pairs, accumulator
+// released after one read, residual by TMA.  Uses FfnParams: num_chunks = K / 64, scale2 / bias2 /
+// gamma / beta / eps / seqs / tile_seq / status / planes / m_tiles.  map_a: A planes, box {64, 128,
+// planes}; map_w: weight planes, box rows 128.
+int launch_proj_ln(ppgs_engine* e, const char* name, const CUtensorMap& map_a, const CUtensorMap& map_w,
+                   const CUtensorMap& map_out, const CUtensorMap& map_res, const FfnParams& p,
+                   cudaStream_t stream);
+
 }  // namespace tc
 }  // namespace ppgs

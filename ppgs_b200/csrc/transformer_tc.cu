@@ -266,6 +266,16 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             GemmParams p = base;
             p.cblocks = cblocks; p.a_planes = planes;
             p.N = H; p.scale = wt.inv_scale; p.bias = bias; p.trace = trace(slot);
+            if (fused_ln && pair && e->proj_ln && !(split_out_proj && slot == 2)) {
+                // CTA-pair projection kernel with the register-resident LayerNorm epilogue
+                FfnParams f;
+                f.m_tiles = rows / 128; f.num_chunks = cblocks; f.planes = planes;
+                f.scale1 = wt.inv_scale; f.scale2 = wt.inv_scale;
+                f.bias1 = bias; f.bias2 = bias; f.gamma = gamma; f.beta = beta;
+                f.eps = c.layer_norm_eps; f.seqs = seqs_dev; f.tile_seq = tile_seq_dev;
+                f.status = e->status_dev; f.trace = nullptr;
+                return launch_proj_ln(e, name, map_a, wt.maps[planes - 1].bn128, out_x, map_res, f, stream);
+            }
             if (fused_ln && !(split_out_proj && slot == 2)) {
                 p.n_tiles = 1; p.trace_ln = trace(slot_ln);
                 p.residual = xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
