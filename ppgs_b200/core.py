@@ -429,7 +429,13 @@ def sparsify(
     ppg: shape=(batch, len(ppgs.PHONEMES), frames); method in ['constant', 'percentile',
     'topk'].  Like the reference, a 1-element *tensor* threshold with 'percentile' adds a
     leading axis to the result (torch.quantile keeps the q axis); 'topk' treats every batch
-    row like the reference treats a single-row batch."""
+    row like the reference treats a single-row batch.
+
+    Deviations from the reference (also listed in INTEGRATION.md): the default threshold is the
+    float 0.85, so a default call returns (batch, phonemes, frames), where the reference's
+    default `torch.Tensor([0.85])` returns (1, batch, phonemes, frames) — pass
+    `torch.tensor([0.85])` for that shape; and the result is a new tensor (the reference's
+    'topk' zeroes its input in place)."""
     import ctypes
     from . import _lib
     methods = {'constant': 0, 'percentile': 1, 'topk': 2}

@@ -58,6 +58,10 @@ struct DualParams {
     int64_t out_plane_stride;
     int q_first_tile, q_first_per_seq, q_tiles;   // query-tile window (streaming decoder)
     int* status;
+    // cycle accounting (PPGS_B200_TRACE=1), sums over CTAs: lane-0 MMA thread waits [0] q [1] s_empty
+    // [2] k_full [3] p_full [4] v_full [5] total; lane-0 softmax warp: [8] wait s_full [9] wait o_done
+    // [10] loop total [11] epilogue [12] from kernel start to first scores [14] CTAs
+    unsigned long long* trace;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -83,6 +87,7 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_kernel = clock64();
     const SeqInfo s = p.seqs[blockIdx.z];
     const int head = blockIdx.y;
     const int first = p.q_first_per_seq ? s.src_start : p.q_first_tile;
@@ -184,9 +189,17 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
             const uint32_t s_tmem = tmem_base + L * 256, o_tmem = s_tmem + 128;
             const int n = L ? nb_1 : nb_0;
             bool ok = true;
+            long long tw[5] = {0, 0, 0, 0, 0};
+            const long long t_begin = clock64();
+            auto timed = [&](uint64_t* bar, uint32_t parity, int slot) {
+                const long long t0 = clock64();
+                const bool got = mbar_wait(bar, parity);
+                tw[slot] += clock64() - t0;
+                return got;
+            };
             auto issue_s = [&](int j) -> bool {
-                if (j > 0 && !mbar_wait(&s_empty[L], (j - 1) & 1)) return false;   // scores j-1 are in registers
-                if (!mbar_wait(&k_full, j & 1)) return false;
+                if (j > 0 && !timed(&s_empty[L], (j - 1) & 1, 1)) return false;   // scores j-1 are in registers
+                if (!timed(&k_full, j & 1, 2)) return false;
                 tcgen05_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < kD / 16; ++ks) {
@@ -199,11 +212,11 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
                 return true;
             };
             if (n > 0) {
-                ok = mbar_wait(&q_full, 0);
+                ok = timed(&q_full, 0, 0);
                 if (ok) ok = issue_s(0);
                 for (int j = 0; j < n && ok; ++j) {
                     if (j + 1 < n && !issue_s(j + 1)) { ok = false; break; }
-                    if (!mbar_wait(&p_full[L], j & 1) || !mbar_wait(&v_full, j & 1)) { ok = false; break; }
+                    if (!timed(&p_full[L], j & 1, 3) || !timed(&v_full, j & 1, 4)) { ok = false; break; }
                     tcgen05_fence_after();
 #pragma unroll
                     for (int ks = 0; ks < kKeys / 16; ++ks) {
@@ -228,6 +241,10 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
                 mbar_arrive(&v_empty);
             }
             if (!ok) atomicExch(p.status, kStatusAttnTimeout);
+            if (p.trace && L == 0 && n > 0) {
+                for (int i = 0; i < 5; ++i) atomicAdd(p.trace + i, (unsigned long long)tw[i]);
+                atomicAdd(p.trace + 5, (unsigned long long)(clock64() - t_begin));
+            }
         }
     }
     } else {
@@ -255,9 +272,17 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
             const float c = p.scale_log2e;
             float m_ref = 0.f, sum = 0.f;
             bool ok = true;
+            long long t_s = 0, t_o = 0, t_first = 0;
+            const long long t_loop = clock64();
 #pragma unroll 1
             for (int j = 0; j < n && ok; ++j) {
-                if (!mbar_wait(&s_full[L], j & 1)) { ok = false; break; }
+                {
+                    const long long t0 = clock64();
+                    ok = mbar_wait(&s_full[L], j & 1);
+                    t_s += clock64() - t0;
+                    if (j == 0) t_first = clock64() - t_kernel;
+                    if (!ok) break;
+                }
                 tcgen05_fence_after();
                 uint32_t sc[4][32];
                 tmem_ld_32x32(t_row, sc[0]);
@@ -310,18 +335,30 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
                 }
                 const float mc = m_ref * c;
                 // p = exp2(s c - m c) (masked scores are -FLT_MAX: exp2 flushes to 0), rounded to
-                // fp16; the row sum is taken over the rounded values
+                // fp16 for the MMA.  The row sum is taken over the ROUNDED numerators, so the weights
+                // the P.V MMA applies sum to one exactly: with few unmasked keys (the first rows of a
+                // causal sequence) the rounding of a dominant numerator would otherwise scale the
+                // whole output row by 1 + 2^-12 (measured: the causal golden misses 1e-4 with the
+                // fp32 sum).  HADD2.F32 unpacks on the fp16 pipe, not on the MUFU pipe.
                 uint32_t h[64];
+                float sum2 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 64; ++i) {
                     const float e0 = ex2(fmaf(__uint_as_float(sc[(2 * i) >> 5][(2 * i) & 31]), c, -mc));
                     const float e1 = ex2(fmaf(__uint_as_float(sc[(2 * i + 1) >> 5][(2 * i + 1) & 31]), c, -mc));
                     h[i] = pack_f16x2(e0, e1);
                     const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
-                    sum += back.x + back.y;
+                    sum += back.x;
+                    sum2 += back.y;
                 }
+                sum += sum2;
                 // the P tile is free once P.V of block j-1 has retired (the exps above overlap it)
-                if (j > 0 && !waited && !mbar_wait(&o_done[L], (j - 1) & 1)) { ok = false; break; }
+                if (j > 0 && !waited) {
+                    const long long t0 = clock64();
+                    ok = mbar_wait(&o_done[L], (j - 1) & 1);
+                    t_o += clock64() - t0;
+                    if (!ok) break;
+                }
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
                     // 8 keys = one 16-byte unit of the 128B-swizzled row; 64 keys per tile
@@ -333,7 +370,12 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[L]);
             }
-            if (ok && !mbar_wait(&o_done[L], (n - 1) & 1)) ok = false;
+            {
+                const long long t0 = clock64();
+                if (ok && !mbar_wait(&o_done[L], (n - 1) & 1)) ok = false;
+                t_o += clock64() - t0;
+            }
+            const long long t_epi = clock64();
             tcgen05_fence_after();
             if (ok) {
                 // O / sum -> split planes, staged as [128 rows][64 cols] 128B-swizzled tiles in the
@@ -369,6 +411,15 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
                 bulk_wait_all();
             }
             if (!ok) atomicExch(p.status, kStatusAttnTimeout);
+            if (p.trace && L == 0 && quad == 0 && lane == 0) {
+                atomicAdd(p.trace + 8, (unsigned long long)t_s);
+                atomicAdd(p.trace + 9, (unsigned long long)t_o);
+                atomicAdd(p.trace + 10, (unsigned long long)(t_epi - t_loop));
+                atomicAdd(p.trace + 11, (unsigned long long)(clock64() - t_epi));
+                atomicAdd(p.trace + 12, (unsigned long long)t_first);
+                atomicAdd(p.trace + 13, (unsigned long long)(clock64() - t_kernel));
+                atomicAdd(p.trace + 14, 1ull);
+            }
         }
     }
 
@@ -412,6 +463,7 @@ int launch_attention_dual(ppgs_engine* e, const __half* qkv, __half* out, int ro
     p.q_first_per_seq = per_seq ? 1 : 0;
     p.q_tiles = q_tiles;
     p.status = e->status_dev;
+    p.trace = e->trace_dev ? e->trace_dev + 80 : nullptr;
     const int tiles = q_tiles > 0 ? q_tiles : max_pitch / 128;
     dim3 grid((tiles + 1) / 2, heads, (unsigned)nseq);
     {

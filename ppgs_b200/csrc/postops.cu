@@ -271,6 +271,7 @@ int ppgs_ppg_distance(ppgs_engine* e, const float* x_dev, const float* y_dev, in
     const int P = phonemes;
     const size_t weights_bytes = ((size_t)P * P * 4 + 255) & ~size_t(255);
     PPGS_CHECK(ensure_workspace(e, weights_bytes + (size_t)(frames > 0 ? frames : 1) * 4));
+    e->cached_plan_dev = nullptr;   // the scratch below overwrites a model engine's resident plan tables
     float* weights = static_cast<float*>(e->workspace);
     float* per_frame = reduction == 0 ? out_dev : reinterpret_cast<float*>(static_cast<char*>(e->workspace) + weights_bytes);
     if (similarity_dev) {

@@ -44,7 +44,8 @@ def save_masked(tensor, file, length):
     from .. import _lib
     length = int(length)
     if (tensor.dim() == 2 and tensor.device.type == 'cpu' and tensor.stride(-1) == 1 and
-            tensor.dtype in (torch.float16, torch.float32) and 0 <= length <= tensor.shape[-1]):
+            tensor.dtype in (torch.float16, torch.float32) and 0 <= length <= tensor.shape[-1] and
+            tensor.shape[0] * length < 2 ** 30):   # the native writer's zip fields; larger -> torch.save
         write = (_lib.lib.ppgs_pt_write_f16 if tensor.dtype == torch.float16
                  else _lib.lib.ppgs_pt_write_f32)
         _lib.check(write(os.fsencode(str(file)), ctypes.c_void_p(tensor.data_ptr()),

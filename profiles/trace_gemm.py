@@ -50,7 +50,13 @@ if c[13]:
     print('   ' + ' '.join(f'{c[8 + i] / n_cta / 1e3:8.1f}' for i in range(5)))
 
 c = [buf[80 + i] for i in range(16)]
-if c[14]:
+if c[14] and os.environ.get('PPGS_B200_ATTN_DUAL', '1') != '0':
+    n = c[14]
+    print(f'two-tile attention per CTA (cycles, {n} CTAs), lane 0: MMA waits q | s_empty | k_full | p_full | v_full | total')
+    print('   ' + ' '.join(f'{c[i] / n:8.0f}' for i in range(6)))
+    print('softmax warp: wait s_full | wait o_done | block loop | epilogue | kernel start -> first scores | kernel total')
+    print('   ' + ' '.join(f'{c[8 + i] / n:8.0f}' for i in range(6)))
+elif c[14]:
     n = c[14]
     print(f'attention per CTA (cycles, {n} CTAs): MMA waits q k p v | total')
     print('   ' + ' '.join(f'{c[i] / n:8.0f}' for i in range(5)))

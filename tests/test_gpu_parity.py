@@ -181,6 +181,26 @@ def test_alternative_kernel_paths(ppgs_b200, monkeypatch, switch):
     engine.check()
 
 
+def test_broadcast_engine_follows_live_configuration(ppgs_b200):
+    """after configure({'IS_CAUSAL': True}) the torchrun load path must build causal
+    engines (it used to capture IS_CAUSAL at import and cache a non-causal engine under the
+    causal key)."""
+    from ppgs_b200 import config, load, parallel
+    sd = O.random_state_dict(0, peaky=True)
+    feats = O.mel_from_audios(O.synthetic_audio(1, 160 * 160, 3))
+    lengths = torch.tensor([160])
+    try:
+        config.configure({'IS_CAUSAL': True})
+        engine = parallel.broadcast_engine(sd, 'mel', 0)
+        assert engine.cfg.is_causal == 1
+        assert load.cache_key('mel', None, 0)[3] is True
+        ref = O.from_features(sd, feats, lengths, is_causal=True)
+        assert (engine.transformer(feats.cuda(), lengths).cpu() - ref).abs().max() <= PPG_TOL
+    finally:
+        config.configure({'IS_CAUSAL': False})
+    assert parallel.broadcast_engine(sd, 'mel', 0).cfg.is_causal == 0
+
+
 def test_error_conventions(ppgs_b200):
     engine = make_engine(ppgs_b200, O.random_state_dict(0), 'fp32')
     feats = torch.zeros(2, 80, 100, dtype=torch.float16, device='cuda')

@@ -169,3 +169,28 @@ def test_loader_reuses_a_header_probe(tmp_path):
     assert together == [0, 1, 2, 3]
     everything = data.loader(files, num_workers=0, max_frames=120)
     assert everything.batches[0::2] == first.batches and everything.batches[1::2] == second.batches
+
+
+def test_configuration_is_read_at_call_time(tmp_path):
+    """`configure()` / `--config` after import must reach argument defaults (they
+    are `config.live(...)` placeholders resolved inside the functions), the CLI's own defaults
+    and the engine cache key — not values frozen when the modules were imported."""
+    import inspect
+    import ppgs_b200
+    from ppgs_b200 import config, core, data, engine, __main__ as cli
+    saved = {k: getattr(config, k) for k in ('REPRESENTATION', 'IS_CAUSAL', 'HIDDEN_CHANNELS', 'MAX_INFERENCE_FRAMES')}
+    try:
+        default = inspect.signature(core.from_audio).parameters['representation'].default
+        assert isinstance(default, config.Live) and config.resolve(default) == 'mel'
+        cfg = tmp_path / 'causal.py'
+        cfg.write_text("IS_CAUSAL = True\nREPRESENTATION = 'w2v2fb'\nMAX_INFERENCE_FRAMES = 12345\n")
+        args = cli.parse_args(['--audio_files', 'a.wav', '--output_files', 'a.pt', '--config', str(cfg)])
+        assert args.representation == 'w2v2fb' and args.max_frames == 12345   # defaults read AFTER --config
+        assert config.resolve(default) == 'w2v2fb' and ppgs_b200.IS_CAUSAL is True
+        for fn, name in ((core.from_features, 'representation'), (core.from_files_to_files, 'max_frames'),
+                         (data.loader, 'max_frames'), (engine.Engine.__init__, 'is_causal'),
+                         (engine.Engine.__init__, 'hidden_channels')):
+            assert isinstance(inspect.signature(fn).parameters[name].default, config.Live), (fn, name)
+        assert config.resolve(inspect.signature(engine.Engine.__init__).parameters['is_causal'].default) is True
+    finally:
+        config.configure(saved)
