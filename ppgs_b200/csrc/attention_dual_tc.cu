@@ -126,13 +126,29 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
             mbar_init(&o_done[L], 1);
         }
         fence_barrier_init();
+        // the Q tiles and the first K block are requested before TMEM allocation and the CTA
+        // barrier: their latency (2 us from a cold L2) is the longest item of the prologue
+        if (nb_max > 0) {
+            pdl_wait();   // Q / K / V of the previous kernel are needed from here on
+            const int col_q = head * kD, col_k = p.H + head * kD;
+            mbar_arrive_expect_tx(&q_full, ((nb_0 > 0) + (nb_1 > 0)) * 2 * kTile);
+            for (int dc = 0; dc < 2; ++dc) {
+                if (nb_0 > 0)
+                    tma_load_3d(smem + kQOff + dc * kTile, &map_qk, &q_full, col_q + dc * 64, s.row0 + q0_0, 0);
+                if (nb_1 > 0)
+                    tma_load_3d(smem + kQOff + (2 + dc) * kTile, &map_qk, &q_full, col_q + dc * 64, s.row0 + q0_1, 0);
+            }
+            mbar_arrive_expect_tx(&k_full, 2 * kTile);
+            for (int dc = 0; dc < 2; ++dc)
+                tma_load_3d(smem + kKOff + dc * kTile, &map_qk, &k_full, col_k + dc * 64, s.row0, 0);
+        }
     }
     if (warp == 3) tmem_alloc<512>(&tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    pdl_wait();   // Q / K / V of the previous kernel are needed from here on
+    pdl_wait();
 
     // register budget: the producer / MMA warpgroup hands its registers to the two softmax
     // warpgroups (128 scores + 64 packed numerators live per thread)
@@ -141,18 +157,9 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer: Q tiles, K blocks
         if (lane == 0 && nb_max > 0) {
-            prefetch_tensormap(&map_qk);
-            const int col_q = head * kD, col_k = p.H + head * kD;
+            const int col_k = p.H + head * kD;
             bool ok = true;
-            const int nq = (nb_0 > 0) + (nb_1 > 0);
-            mbar_arrive_expect_tx(&q_full, nq * 2 * kTile);
-            for (int dc = 0; dc < 2; ++dc) {
-                if (nb_0 > 0)
-                    tma_load_3d(smem + kQOff + dc * kTile, &map_qk, &q_full, col_q + dc * 64, s.row0 + q0_0, 0);
-                if (nb_1 > 0)
-                    tma_load_3d(smem + kQOff + (2 + dc) * kTile, &map_qk, &q_full, col_q + dc * 64, s.row0 + q0_1, 0);
-            }
-            for (int j = 0; j < nb_max && ok; ++j) {
+            for (int j = 1; j < nb_max && ok; ++j) {   // block 0 was requested in the prologue
                 if (!mbar_wait(&k_empty, (j & 1) ^ 1)) { ok = false; break; }
                 mbar_arrive_expect_tx(&k_full, 2 * kTile);
                 for (int dc = 0; dc < 2; ++dc)
@@ -303,9 +310,10 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
                         if (!allowed) sc[i >> 5][i & 31] = __float_as_uint(-FLT_MAX);
                     }
                 }
-                float bm = -FLT_MAX;
+                float bm4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};   // four independent chains
 #pragma unroll
-                for (int i = 0; i < 128; ++i) bm = fmaxf(bm, __uint_as_float(sc[i >> 5][i & 31]));
+                for (int i = 0; i < 128; ++i) bm4[i & 3] = fmaxf(bm4[i & 3], __uint_as_float(sc[i >> 5][i & 31]));
+                const float bm = fmaxf(fmaxf(bm4[0], bm4[1]), fmaxf(bm4[2], bm4[3]));
                 // lazy running max: move it only when this block exceeds it by more than 2^8
                 float factor = 1.f;
                 if (j == 0) {
@@ -408,7 +416,7 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
                     tma_store_3d(&map_out, smem + kPOff + (L * 2 + dc) * kTile, head * kD + dc * 64, (int)out_row0, 1);
                 }
                 bulk_commit_group();
-                bulk_wait_all();
+                bulk_wait_read_all();   // shared memory must outlive the reads; the writes complete with the grid
             }
             if (!ok) atomicExch(p.status, kStatusAttnTimeout);
             if (p.trace && L == 0 && quad == 0 && lane == 0) {
