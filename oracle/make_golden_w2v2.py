@@ -1,11 +1,14 @@
-"""Generate tests/golden/w2v2fb_*.npz from the REAL Hugging Face `Wav2Vec2Model`
-(the third-party model `ppgs.preprocess.w2v2fb.from_audios` calls), run in the dev
-container on seeded random weights (pretrained weights are not available offline):
+"""Generate tests/golden/w2v2fb_*.npz by calling the reference's OWN function,
+`ppgs.preprocess.w2v2fb.from_audios` (ppgs/preprocess/w2v2fb/core.py:32-75, imported
+unmodified under oracle/refshim.py), with the third-party model it would download injected
+into its cache: a seeded `transformers.Wav2Vec2Model(Wav2Vec2Config())`
+— the wav2vec2-base architecture; pretrained weights are not available offline.
 
     python -m oracle.make_golden_w2v2
 
-Stores the upsampled fp16 features that `ppgs/preprocess/w2v2fb/core.py:32-75` would return
-for that model, i.e. exactly the tensor the CUDA front-end has to reproduce."""
+Stores the upsampled fp16 features the reference returns, i.e. exactly the tensor the CUDA
+front-end has to reproduce.  `restated_features` (the same lines written out around the HF
+module, what round 1 used) must agree bit for bit — asserted here."""
 import os
 import sys
 
@@ -26,12 +29,26 @@ CASES = [
 ]
 
 
-def reference_features(sd, audio, lengths):
-    """ppgs/preprocess/w2v2fb/core.py:52-75 around the real HF module."""
+def hf_model(sd):
     from transformers import Wav2Vec2Config, Wav2Vec2Model
     model = Wav2Vec2Model(Wav2Vec2Config()).eval()
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert missing == ['masked_spec_embed'] and not unexpected
+    return model
+
+
+def reference_features(sd, audio, lengths):
+    """The reference's own `ppgs.preprocess.w2v2fb.from_audios` with the model injected."""
+    from oracle import refshim
+    ppgs = refshim.import_reference()
+    fn = ppgs.preprocess.w2v2fb.from_audios
+    fn.model, fn.device = hf_model(sd), torch.device('cpu')
+    return fn(audio, lengths, sample_rate=ppgs.SAMPLE_RATE, gpu=None)
+
+
+def restated_features(sd, audio, lengths):
+    """ppgs/preprocess/w2v2fb/core.py:52-75 written out around the real HF module."""
+    model = hf_model(sd)
     pad = W.W2V2_PAD
     padded = torch.nn.functional.pad(audio, (pad, pad)).squeeze(1)
     mask = (torch.arange(padded.shape[-1])[None] < (lengths + 2 * pad)[:, None]).long()
@@ -55,6 +72,7 @@ def main():
         sd = W.random_state_dict(wseed)
         audio, lens = case_inputs(samples, lengths, aseed)
         feats = reference_features(sd, audio, lens)
+        assert torch.equal(feats, restated_features(sd, audio, lens))
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + '.npz'), features=feats.numpy(),
                             weight_seed=wseed, audio_seed=aseed, samples=samples,
                             lengths=np.array(lengths))

@@ -41,7 +41,12 @@ def _reference():
 
 def checkpoint_for(state_dict):
     """Write `{'model': state_dict}` like the reference's trainer does and return the path."""
-    key = id(state_dict)
+    import hashlib
+    digest = hashlib.sha1()
+    for name in sorted(state_dict):
+        digest.update(name.encode())
+        digest.update(state_dict[name].detach().cpu().contiguous().numpy().tobytes())
+    key = digest.hexdigest()   # by content: `id()` of a freed dict can be reused by the next one
     if key not in _STATE:
         tmp = tempfile.NamedTemporaryFile(prefix='ppgs_ref_', suffix='.pt', delete=False)
         tmp.close()

@@ -163,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int m_blk = window_tile<PAIR>(p, m_item, (int)rank);
                 const int a_row0 = m_blk * kBM * p.row_mul - p.half + n_blk * p.a_group_rows;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks + p.cb0;
                     const long long t0 = clock64();
                     const bool got = mbar_wait(&empty_bar[stage], phase ^ 1);
                     t_wait += clock64() - t0;
@@ -209,8 +209,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             long long t_empty = 0, t_full = 0;
             const long long t_begin = clock64();
             for (int tile = worker; tile < total_tiles && ok; tile += workers, ++iter) {
-                const int acc = iter & 1;
-                const uint32_t acc_phase = (iter >> 1) & 1;
+                // split_acc: both accumulator buffers belong to ONE tile (hi.hi products in the
+                // first, the two correction products in the second; the epilogue adds them)
+                const int acc = p.split_acc ? 0 : iter & 1;
+                const uint32_t acc_phase = p.split_acc ? (iter & 1) : (iter >> 1) & 1;
                 const long long t0 = clock64();
                 const bool got = mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 t_empty += clock64() - t0;
@@ -220,7 +222,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * Shape::kAccCols;
-                uint32_t accumulate = 0;
+                const uint32_t d_corr = p.split_acc ? tmem_base + Shape::kAccCols : d_tmem;
+                uint32_t accumulate = 0, accumulate_corr = p.split_acc ? 0u : 1u;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const long long t1 = clock64();
                     const bool landed = mbar_wait(&full_bar[stage], phase);
@@ -242,10 +245,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint64_t db0 = smem_desc_kmajor_sw128(b0 + koff);
                         if (PAIR) {
                             umma_f16_pair(d_tmem, da0, db0, idesc, accumulate);
-                            if (p.b_planes == 2)
-                                umma_f16_pair(d_tmem, da0, smem_desc_kmajor_sw128(b1 + koff), idesc, 1);
-                            if (p.a_planes == 2)
-                                umma_f16_pair(d_tmem, smem_desc_kmajor_sw128(a1 + koff), db0, idesc, 1);
+                            if (p.b_planes == 2) {
+                                umma_f16_pair(d_corr, da0, smem_desc_kmajor_sw128(b1 + koff), idesc, accumulate_corr);
+                                accumulate_corr = 1;
+                            }
+                            if (p.a_planes == 2) {
+                                umma_f16_pair(d_corr, smem_desc_kmajor_sw128(a1 + koff), db0, idesc, accumulate_corr);
+                                accumulate_corr = 1;
+                            }
                         } else {
                             umma_f16(d_tmem, da0, db0, idesc, accumulate);
                             if (p.b_planes == 2)
@@ -291,8 +298,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int tile = worker; tile < total_tiles; tile += workers, ++iter) {
             const int m_item = tile / p.n_tiles, n_blk = tile - m_item * p.n_tiles;
             const int m_blk = window_tile<PAIR>(p, m_item, (int)rank);
-            const int acc = iter & 1;
-            const uint32_t acc_phase = (iter >> 1) & 1;
+            const int acc = p.split_acc ? 0 : iter & 1;
+            const uint32_t acc_phase = p.split_acc ? (iter & 1) : (iter >> 1) & 1;
             // ResLN: the residual loads of the first two column chunks are in flight while
             // this warp waits for the accumulator
             uint4 pre[2][8];
@@ -364,6 +371,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             for (int j = 0; j < 32; ++j) y[j] = 0.f;
                         } else {
                             load_params32(p.bias + n0 + half * 32, y);
+                        }
+                        if (p.split_acc) {   // + the correction accumulator (second TMEM buffer)
+                            uint32_t corr[32];
+                            tmem_ld_32x32(t_acc + Shape::kAccCols + col + half * 32, corr);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(corr[j]));
                         }
                         tmem_wait_ld();
                         if (g + 1 == kChunks / 4 && half == 1) release_tmem();   // last read

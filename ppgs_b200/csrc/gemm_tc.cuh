@@ -22,6 +22,7 @@ struct GemmParams {
     int taps = 1, half = 0;      // K loop = taps x cblocks k-blocks; A rows shift by tap - half
     int row_mul = 1;             // A row of output row m = m * row_mul + tap - half (strided conv)
     int cblocks = 0;
+    int cb0 = 0;                 // first k-block: the GEMM covers K columns [64 cb0, 64 (cb0 + cblocks)) of A and W
     // grouped GEMM (block-diagonal weights): n tile g reads A rows shifted by g * a_group_rows
     // and owns output columns [g * group_cols, (g + 1) * group_cols) (kEpiF32 only)
     int a_group_rows = 0, group_cols = 0;
@@ -48,6 +49,11 @@ struct GemmParams {
     const SeqInfo* seqs = nullptr;
     const int* tile_seq = nullptr;
     int relu = 0;                // kEpiPlanes activation: 0 none, 1 ReLU, 2 exact GELU
+    // CTA-pair kEpiPlanes only: the hi.hi products accumulate in one TMEM buffer and the two
+    // correction products in the other (no tile overlap).  tcgen05 accumulation truncates, so the
+    // error of an accumulator grows with its number of MMA steps; the large sum then sees one
+    // third of them.  Used where K is long and the tolerance is a flip of an fp16 feature.
+    int split_acc = 0;
     int hi_only_cols = 0;        // kEpiPlanes: output columns [0, hi_only_cols) keep only their hi plane (multiple of 64)
     float* ppg = nullptr;   // kEpiConvOut
     int T = 0, O = 0, softmax = 1;

@@ -334,9 +334,9 @@ __global__ void to_planes_kernel(const float* __restrict__ x, int64_t count, __h
 // ---- x <- LayerNorm(x + y) over split planes (one warp per row), optional fp32 copy
 template <int H>
 __global__ void __launch_bounds__(256)
-add_layernorm_planes_kernel(__half* __restrict__ x, const __half* __restrict__ y, int64_t plane_stride,
-                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                            int rows, float* __restrict__ out_f32) {
+add_layernorm_planes_kernel(__half* __restrict__ x, const __half* __restrict__ y, const __half* __restrict__ y2,
+                            int64_t plane_stride, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, float eps, int rows, float* __restrict__ out_f32) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     constexpr int PER = H / 64;   // half2 per lane
@@ -350,8 +350,15 @@ add_layernorm_planes_kernel(__half* __restrict__ x, const __half* __restrict__ y
         const float2 xl = __half22float2(*reinterpret_cast<const __half2*>(x + plane_stride + at));
         const float2 yh = __half22float2(*reinterpret_cast<const __half2*>(y + at));
         const float2 yl = __half22float2(*reinterpret_cast<const __half2*>(y + plane_stride + at));
-        v[2 * i] = (xh.x + xl.x) + (yh.x + yl.x);
-        v[2 * i + 1] = (xh.y + xl.y) + (yh.y + yl.y);
+        float y0 = yh.x + yl.x, y1 = yh.y + yl.y;
+        if (y2) {   // second partial sum of a K-split projection (fp32 add: round to nearest)
+            const float2 zh = __half22float2(*reinterpret_cast<const __half2*>(y2 + at));
+            const float2 zl = __half22float2(*reinterpret_cast<const __half2*>(y2 + plane_stride + at));
+            y0 += zh.x + zl.x;
+            y1 += zh.y + zl.y;
+        }
+        v[2 * i] = (xh.x + xl.x) + y0;
+        v[2 * i + 1] = (xh.y + xl.y) + y1;
         sum += v[2 * i] + v[2 * i + 1];
     }
 #pragma unroll
@@ -664,6 +671,7 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
         seqs[b] = s;
     }
     static const bool use_tc = [] { const char* v = getenv("PPGS_B200_W2V2_TC"); return !v || atoi(v) != 0; }();
+    static const int split_acc = [] { const char* v = getenv("PPGS_B200_W2V2_SPLIT_ACC"); return v ? atoi(v) : 1; }();
 
     // workspace: two conv activation buffers (fp32 rows, or split-fp16 planes: same bytes
     // per element) + encoder buffers (fp32).  512 slack rows: GEMM tiles round M up.
@@ -756,6 +764,7 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
             p.bias = w.zero_bias;
             p.relu = 2;   // GELU
             p.status = e->status_dev;
+            p.split_acc = split_acc;
             PPGS_CHECK(launch_gemm_tc(e, "w2v2_tc_conv", 256, kEpiPlanes, map_a, wt.maps[1].bn128, &map_out,
                                       p, stream));
             cur ^= 1;
@@ -897,12 +906,16 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
             LaunchScope scope(e, "w2v2_to_planes", stream);
             to_planes_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(h, count, xh);
         }
+        // K split (`parts` launches over K ranges, partial sums added in fp32 by the LayerNorm
+        // pass): tcgen05 accumulation TRUNCATES, so an accumulator's error grows with its number
+        // of MMA steps; the K = 3072 projection is the longest chain of the encoder
         auto gemm = [&](const char* name, const CUtensorMap& a, TcWeight& wt, const CUtensorMap& out_map,
-                        const float* bias, int act) -> int {
+                        const float* bias, int act, int part = 0, int parts = 1) -> int {
             GemmParams p;
             p.m_tiles = (int)(M / 128);
             p.n_tiles = wt.N / 256;
-            p.cblocks = wt.C / 64;
+            p.cblocks = wt.C / 64 / parts;
+            p.cb0 = part * p.cblocks;
             p.a_planes = 2;
             p.b_planes = 2;
             p.pair = 1;
@@ -911,13 +924,18 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
             p.bias = bias;
             p.relu = act;
             p.status = e->status_dev;
+            p.split_acc = split_acc;
             return launch_gemm_tc(e, name, 256, kEpiPlanes, a, wt.maps[1].bn128, &out_map, p, stream);
         };
-        auto add_ln = [&](const float* g, const float* b2, float* f32) {
+        auto add_ln = [&](const float* g, const float* b2, float* f32, const __half* y2 = nullptr) {
             LaunchScope scope(e, "w2v2_add_layernorm_planes", stream);
             add_layernorm_planes_kernel<kHidden><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>(
-                xh, yh, M * kHidden, g, b2, 1e-5f, (int)M, f32);
+                xh, yh, y2, M * kHidden, g, b2, 1e-5f, (int)M, f32);
         };
+        // second partial sum of the K-split FFN projection: the QKV planes are dead by then
+        CUtensorMap s_y2;
+        PPGS_CHECK(make_store_map(&s_y2, qh, kHidden, M, (uint64_t)M * kHidden));
+        const int ffn2_parts = split_acc ? 2 : 1;
         for (int l = 0; l < kLayers; ++l) {
             const W2v2Layer& L = w.layers[l];
             W2v2TcLayer& T = e->w2v2->tc[l];
@@ -927,8 +945,9 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
             PPGS_CHECK(gemm("w2v2_tc_out_proj", a_att, T.out, s_y, L.out_b, 0));
             add_ln(L.ln1_w, L.ln1_b, nullptr);
             PPGS_CHECK(gemm("w2v2_tc_ffn1", a_x, T.ff1, s_ff, L.ff1_b, 2));
-            PPGS_CHECK(gemm("w2v2_tc_ffn2", a_ff, T.ff2, s_y, L.ff2_b, 0));
-            add_ln(L.ln2_w, L.ln2_b, l == kLayers - 1 ? h : nullptr);
+            PPGS_CHECK(gemm("w2v2_tc_ffn2", a_ff, T.ff2, s_y, L.ff2_b, 0, 0, ffn2_parts));
+            if (ffn2_parts == 2) PPGS_CHECK(gemm("w2v2_tc_ffn2", a_ff, T.ff2, s_y2, w.zero_bias, 0, 1, 2));
+            add_ln(L.ln2_w, L.ln2_b, l == kLayers - 1 ? h : nullptr, ffn2_parts == 2 ? qh : nullptr);
             PPGS_CUDA(cudaGetLastError());
         }
     } else
