@@ -355,6 +355,104 @@ def measure_other_workload(workload_name, steps, warmup):
     return line
 
 
+def run_files_workload(args, rank, world, local_rank):
+    """BASELINE configs[4]: `from_files_to_files` over a synthetic corpus of 10 s 16 kHz int16
+    WAVE files, batch-sharded over the ranks (ppgs_b200.parallel.from_files_to_files: every
+    rank takes batches rank::world of the same deterministic batch list, no collective).  Weak
+    scaling: `--files-per-gpu` files per rank (4500 x 8 ranks = 36 000 files = the 100 h corpus).
+    Files live on tmpfs (/dev/shm) spread over 64 directories; outputs likewise.  Wall clock
+    between barriers (a host pipeline: file reads, PCIe, kernels and .pt writes all count), max
+    over ranks.  PPGS_B200_FILES_NULL_GPU=1 gives the host ceiling (kernels skipped)."""
+    import shutil
+    import wave
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ppgs_b200
+    from ppgs_b200 import parallel
+    from oracle import ppg_oracle as O   # synthetic weights only
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        parallel.init('nccl')
+    per_gpu = args.files_per_gpu
+    total = per_gpu * world
+    root = os.path.join('/dev/shm' if os.path.isdir('/dev/shm') else '/tmp', f'ppgs_b200_files_{args.run_id}')
+    dirs = 64
+    audio_files = [os.path.join(root, f'in{i % dirs:02d}', f'{i:06d}.wav') for i in range(total)]
+    output_files = [os.path.join(root, f'out{i % dirs:02d}', f'{i:06d}-ppg.pt') for i in range(total)]
+    if rank == 0:
+        shutil.rmtree(root, ignore_errors=True)
+        for d in range(dirs):
+            os.makedirs(os.path.join(root, f'in{d:02d}'))
+            os.makedirs(os.path.join(root, f'out{d:02d}'))
+        torch.save({'model': O.random_state_dict(0, peaky=True)}, os.path.join(root, 'ckpt.pt'))
+    if world > 1:
+        dist.barrier()
+    rng = np.random.default_rng(rank)
+    base = (rng.uniform(-0.5, 0.5, SAMPLES + per_gpu) * 32767).astype(np.int16)
+    for j, i in enumerate(range(rank, total, world)):        # every rank writes its share of the corpus
+        with wave.open(audio_files[i], 'wb') as f:
+            f.setnchannels(1)
+            f.setsampwidth(2)
+            f.setframerate(SAMPLE_RATE)
+            f.writeframes(base[j:j + SAMPLES].tobytes())
+    if world > 1:
+        dist.barrier()
+    checkpoint = os.path.join(root, 'ckpt.pt')
+    workers = args.file_workers
+    try:
+        warm = 256 * world
+        parallel.from_files_to_files(audio_files[:warm], output_files[:warm], 'mel', checkpoint,
+                                     num_workers=workers, max_frames=BATCH * FRAMES)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        passes = []
+        for _ in range(max(args.file_repeats, 1)):   # whole-corpus passes; sub-second each, so repeated
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            parallel.from_files_to_files(audio_files, output_files, 'mel', checkpoint, num_workers=workers,
+                                         max_frames=BATCH * FRAMES)
+            torch.cuda.synchronize()
+            elapsed = torch.tensor([time.perf_counter() - t0], device='cuda')
+            if world > 1:
+                dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+            passes.append(elapsed.item())
+        seconds = statistics.median(passes)
+        if rank == 0:
+            sample = torch.load(output_files[-1])
+            assert sample.shape == (O_OUT, FRAMES) and bool(torch.isfinite(sample).all())
+            engine = ppgs_b200.load.model(checkpoint, 'mel', local_rank)
+            null_gpu = os.environ.get('PPGS_B200_FILES_NULL_GPU', '0') not in ('', '0')
+            line = {
+                'metric': METRIC, 'value': total * FRAMES / seconds, 'unit': UNIT, 'n_gpus': world,
+                'steps': 1, 'warmup': 1, 'ms_per_step': seconds * 1e3, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f16x2-split tcgen05 MMA, f32 accumulate', 'data': 'synthetic',
+                'config': {'workload': 'from_files_to_files, synthetic corpus of 10 s 16 kHz int16 WAVE files '
+                                       f'({total} files = {total * SECONDS / 3600:.1f} h), max_frames=64000, '
+                                       'batch-sharded over the ranks', 'files_per_gpu': per_gpu,
+                           'files': total, 'storage': root.split('/')[1] + ' (tmpfs), 64 input + 64 output directories',
+                           'host_cores': os.cpu_count(), 'reader_writer_threads_per_rank': workers,
+                           'null_gpu_host_ceiling': null_gpu, 'precision': engine.precision},
+                'files_per_sec': total / seconds, 'audio_hours_per_hour': total * SECONDS / seconds,
+                'seconds': seconds, 'passes_seconds': [round(x, 4) for x in passes], 'statistic': 'median pass',
+                'e2e': {'value': total * FRAMES / seconds, 'unit': UNIT,
+                        'h2d_bytes_per_step': total * SAMPLES * 2, 'd2h_bytes_per_step': total * O_OUT * FRAMES * 4,
+                        'api': 'ppgs_b200.parallel.from_files_to_files (files on tmpfs in, .pt files out)'},
+                'gpu_launches': int(engine.launches),
+            }
+            print(json.dumps(line), flush=True)
+    finally:
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            shutil.rmtree(root, ignore_errors=True)
+        if world > 1:
+            dist.destroy_process_group()
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
@@ -367,9 +465,16 @@ def main():
     parser.add_argument('--no-other-configs', action='store_true')
     parser.add_argument('--windows', type=int, default=10,
                         help='repeats of the K-step timed window (median reported, min / max in "spread")')
-    parser.add_argument('--workload', default='mel', choices=['mel', 'w2v2fb', 'causal-stream'],
+    parser.add_argument('--workload', default='mel', choices=['mel', 'w2v2fb', 'causal-stream', 'files'],
                         help="mel = BASELINE configs[1] (the headline; default); w2v2fb = configs[2]; "
-                             "causal-stream = configs[3] with state (extra lines, N=1 only)")
+                             "causal-stream = configs[3] with state (extra lines, N=1 only); "
+                             "files = configs[4], from_files_to_files over a synthetic corpus (any N)")
+    parser.add_argument('--files-per-gpu', type=int, default=4500,
+                        help='files workload: 10 s files per rank (4500 x 8 = the 100 h corpus)')
+    parser.add_argument('--file-workers', type=int, default=16,
+                        help='files workload: num_workers per rank (half readers, half writers)')
+    parser.add_argument('--file-repeats', type=int, default=5, help='files workload: timed passes over the corpus')
+    parser.add_argument('--run-id', default=os.environ.get('MASTER_PORT', 'single'))
     args = parser.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -378,6 +483,9 @@ def main():
 
     if args.impl == 'reference':
         run_reference(args, rank)
+        return
+    if args.workload == 'files':
+        run_files_workload(args, rank, world, local_rank)
         return
     if args.workload != 'mel':
         if rank == 0:

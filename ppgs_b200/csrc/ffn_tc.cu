@@ -78,6 +78,14 @@ __device__ __forceinline__ void load_row128(uint32_t tile, int row, uint32_t (&w
 }
 
 
+// pair-tile index -> row tile of this CTA (identity unless a row-tile window is set)
+__device__ __forceinline__ int pair_row_tile(const FfnParams& p, int pt, int rank) {
+    if (p.win_size == 0) return 2 * pt + rank;
+    const int per_seq = p.win_size / 2;
+    const int seq = pt / per_seq, u = pt - seq * per_seq;
+    return seq * p.win_stride + p.seqs[seq].src_start + 2 * u + rank;
+}
+
 // LayerNorm epilogue shared by the fused FFN and the projection kernel.  Thread = (row, set):
 // 128 accumulator columns [128 set, 128 set + 128) of one of the CTA's 128 rows.
 //   1. accumulator -> registers, then `release_bar` (cluster address) is signalled: the MMA
@@ -264,7 +272,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     }
                 };
                 for (int pt = worker; pt < pair_tiles && ok; pt += workers) {
-                    const int m_blk = 2 * pt + (int)rank;
+                    const int m_blk = pair_row_tile(p, pt, (int)rank);
                     auto load_g1 = [&](int c) {
                         for (int kb = 0; kb < 4 && ok; ++kb) {
                             unsigned char* slot = acquire(g1_tx);
@@ -398,7 +406,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         int it = 0;
         uint32_t g = 0;
         for (int pt = worker; pt < pair_tiles && ok; pt += workers, ++it) {
-            const int m_blk = 2 * pt + (int)rank;
+            const int m_blk = pair_row_tile(p, pt, (int)rank);
             const int m0 = m_blk * kBM;
             const int64_t m = (int64_t)m0 + row;
             // ---- hidden chunks: Hacc -> relu -> split -> H1 (A operand of G2); this thread owns
@@ -527,7 +535,7 @@ proj_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 uint32_t phase = 0;
                 bool ok = true;
                 for (int pt = worker; pt < pair_tiles && ok; pt += workers) {
-                    const int m_blk = 2 * pt + (int)rank;
+                    const int m_blk = pair_row_tile(p, pt, (int)rank);
                     for (int kb = 0; kb < KB; ++kb) {
                         if (!mbar_wait(&empty_bar[stage], phase ^ 1)) { ok = false; break; }
                         if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
@@ -592,7 +600,7 @@ proj_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         bool ok = true;
         int it = 0;
         for (int pt = worker; pt < pair_tiles && ok; pt += workers, ++it) {
-            const int m_blk = 2 * pt + (int)rank, acc = it & 1;
+            const int m_blk = pair_row_tile(p, pt, (int)rank), acc = it & 1;
             if (!mbar_wait(&y_full[acc], (uint32_t)((it >> 1) & 1))) { ok = false; break; }
             tcgen05_fence_after();
             // the previous tile's stores have drained the staging tiles before the residual lands

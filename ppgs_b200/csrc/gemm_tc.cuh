@@ -95,6 +95,9 @@ int launch_gemm_tc(ppgs_engine* e, const char* name, int bn, int epilogue,
 // Fused linear1 + ReLU + linear2 + residual + LayerNorm (ffn_tc.cu), CTA pairs.
 struct FfnParams {
     int m_tiles, num_chunks, planes;
+    // row-tile window (streaming decoder, same meaning as GemmParams::win_*): m_tiles = sequences x
+    // win_size, the first tile of sequence s is seqs[s].src_start; 0 = all rows
+    int win_size = 0, win_stride = 0;
     const float* scale1;
     const float* scale2;
     const float* bias1;

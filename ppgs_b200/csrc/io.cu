@@ -982,8 +982,13 @@ int ppgs_files_to_files(ppgs_engine* e, int n_batches, const int32_t* batch_size
         res.pinned.push_back(*out);
         return PPGS_OK;
     };
-    auto event = [&](cudaEvent_t* out) -> int {
-        PPGS_CUDA(cudaEventCreateWithFlags(out, cudaEventDisableTiming));
+    auto event = [&](cudaEvent_t* out, bool blocking = false) -> int {
+        // blocking sync for the events the WRITER threads wait on: they sleep in
+        // cudaEventSynchronize instead of spinning — eight spinning writers per GPU starve the
+        // readers and the launch thread as soon as ranks share a host (measured: 2 ranks on 24
+        // cores ran at half speed).  The pipeline thread keeps spinning on its own events: its
+        // wake-up latency is GPU idle time.
+        PPGS_CUDA(cudaEventCreateWithFlags(out, cudaEventDisableTiming | (blocking ? cudaEventBlockingSync : 0)));
         res.events.push_back(*out);
         return PPGS_OK;
     };
@@ -1017,7 +1022,7 @@ int ppgs_files_to_files(ppgs_engine* e, int n_batches, const int32_t* batch_size
     for (auto& ev : h2d_done) PPGS_CHECK(event(&ev));
     for (auto& ev : compute_done) PPGS_CHECK(event(&ev));
     for (auto& ev : dev_free) PPGS_CHECK(event(&ev));
-    for (auto& ev : p.d2h_done) PPGS_CHECK(event(&ev));
+    for (auto& ev : p.d2h_done) PPGS_CHECK(event(&ev, true));
 
     p.in_pending.assign(n_batches, -1);
     p.out_pending.assign(n_batches, 0);
@@ -1068,8 +1073,13 @@ int ppgs_files_to_files(ppgs_engine* e, int n_batches, const int32_t* batch_size
                                                                                       (int64_t)count);
         }
         if (!cuda_ok(cudaGetLastError(), "pcm16_to_f32 launch")) break;
-        rc = ppgs_detail_from_audio_device(e, audio_dev, B, max_samples, stride, lengths.data(), 1, legacy_mode, out_dev,
-                               mel_dev, stream);
+        // PPGS_B200_FILES_NULL_GPU=1 (measurement only): skip the mel + Transformer kernels and keep
+        // everything else (file reads, H2D, D2H of the unwritten buffer, crop, .pt writes) — the
+        // host-side ceiling of this pipeline on a given box
+        static const bool null_gpu = [] { const char* v = getenv("PPGS_B200_FILES_NULL_GPU"); return v && atoi(v) != 0; }();
+        if (!null_gpu)
+            rc = ppgs_detail_from_audio_device(e, audio_dev, B, max_samples, stride, lengths.data(), 1, legacy_mode,
+                                               out_dev, mel_dev, stream);
         if (rc != PPGS_OK) break;
         if (!cuda_ok(cudaEventRecord(compute_done[b % 2], stream), "cudaEventRecord")) break;
         if (!cuda_ok(cudaStreamWaitEvent(copy_out, compute_done[b % 2], 0), "cudaStreamWaitEvent")) break;

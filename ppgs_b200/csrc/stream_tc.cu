@@ -431,6 +431,8 @@ int ppgs_stream_push_ragged(ppgs_stream* s, const void* features_dev, int max_fr
     PPGS_CHECK(make_plane_map(&map_ff, s->ff, false, F, rows, 1, 2, F, 0, (uint64_t)rows * F, 128, planes));
     PPGS_CHECK(make_store_map(&out_x, s->xh, H, rows, (uint64_t)rows * H));
     PPGS_CHECK(make_store_map(&out_ff, s->ff, F, rows, (uint64_t)rows * F));
+    CUtensorMap map_res;   // residual rows of the LayerNorm epilogues: both planes of x
+    PPGS_CHECK(make_plane_map(&map_res, s->xh, false, H, rows, 1, 2, H, 0, (uint64_t)rows * H, 128, 2));
 
     GemmParams base;
     base.m_tiles = B * win_tiles;
@@ -465,13 +467,32 @@ int ppgs_stream_push_ragged(ppgs_stream* s, const void* features_dev, int max_fr
         PPGS_CHECK(launch_attention_any(e, s->qkv[layer], s->att, rows, H, c.num_heads, kStreamPitch, B,
                                         s->seqs_dev, 1, planes, stream, -1, win_tiles, e->attn_qk_planes,
                                         e->attn_p_planes));
-        {
+        // the batch path's fused kernels over the same row-tile window (ffn_tc.cu)
+        FfnParams f;
+        f.m_tiles = B * win_tiles; f.planes = planes;
+        f.win_size = win_tiles; f.win_stride = tiles_per_seq;
+        f.eps = c.layer_norm_eps; f.seqs = s->seqs_dev; f.tile_seq = s->tile_seq_dev;
+        f.status = e->status_dev; f.trace = nullptr;
+        if (e->proj_ln && H == 256) {
+            f.num_chunks = H / 64;
+            f.scale1 = T.out_w.inv_scale; f.scale2 = T.out_w.inv_scale;
+            f.bias1 = Lw.out_b; f.bias2 = Lw.out_b; f.gamma = Lw.n1_w; f.beta = Lw.n1_b;
+            PPGS_CHECK(launch_proj_ln(e, "tc_out_proj_ln", map_att, wmap(T.out_w), out_x, map_res, f, stream));
+        } else {
             GemmParams p = base;
             p.n_tiles = 1; p.cblocks = H / 64; p.a_planes = planes;
             p.N = H; p.scale = T.out_w.inv_scale; p.bias = Lw.out_b;
             p.residual = s->xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
             p.gamma = Lw.n1_w; p.beta = Lw.n1_b;
             PPGS_CHECK(launch_gemm_tc(e, "tc_out_proj_ln", 256, kEpiResLN, map_att, wmap(T.out_w), &out_x, p, stream));
+        }
+        if (e->fused_ffn && H == 256 && F % 128 == 0) {
+            f.num_chunks = F / 128;
+            f.scale1 = T.l1_w.inv_scale; f.scale2 = T.l2_w.inv_scale;
+            f.bias1 = Lw.l1_b; f.bias2 = Lw.l2_b; f.gamma = Lw.n2_w; f.beta = Lw.n2_b;
+            PPGS_CHECK(launch_ffn_fused(e, map_x, T.l1_w.maps[planes - 1].bn64, T.l2_w.maps[planes - 1].bn128, out_x,
+                                        map_res, f, stream));
+            continue;
         }
         {
             GemmParams p = base;

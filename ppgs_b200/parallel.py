@@ -91,11 +91,14 @@ def from_files_to_files(audio_files, output_files, representation=config.live('R
     representation = config.resolve(representation)
     rank, world = init()
     gpu = local_device()
-    if world > 1:
+    key = load.cache_key(representation, checkpoint, gpu)
+    with load._lock:
+        cached = key in load._engines
+    if world > 1 and not cached:   # one broadcast per (representation, checkpoint, device), like load.model
         state = load.state_dict(checkpoint, representation) if rank == 0 else None
         engine = broadcast_engine(state, representation, gpu)
         with load._lock:
-            load._engines[load.cache_key(representation, checkpoint, gpu)] = engine
+            load._engines[key] = engine
     dataloader = data.loader(
         audio_files, num_workers=max(num_workers // 2, 1), max_frames=max_frames,
         shard=(rank, world), device=gpu)
