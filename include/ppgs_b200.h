@@ -245,6 +245,18 @@ int ppgs_pt_write_f32(const char* path, const float* data_host, int64_t rows, in
 int ppgs_pt_write_f16(const char* path, const void* data_host, int64_t rows, int64_t cols,
                       int64_t row_stride);
 
+/* torch.load of a feature cache (ppgs/data/dataset.py:98-101: `torch.load(cache /
+ * f'{stem}-{feature}.pt')`) without Python: probe / read a torch.save archive that holds ONE
+ * whole contiguous fp16 or fp32 CPU tensor of 1..3 dimensions (what ppgs.preprocess and this
+ * library write).  ppgs_pt_info: dims3 = the sizes right-aligned in 3 slots (leading slots 1).
+ * ppgs_pt_read: copies the tensor viewed as (rows, cols) = (dims3[0]*dims3[1], dims3[2]) into
+ * `dst_host` with row stride `dst_row_stride` elements (a row of a padded batch).  Archives the
+ * native reader does not understand (legacy format, zip64, other dtypes, views) return
+ * PPGS_E_UNSUPPORTED: callers fall back to torch.load. */
+int ppgs_pt_info(const char* path, int* ndim, int64_t* dims3, int* elem_bytes);
+int ppgs_pt_read(const char* path, void* dst_host, int64_t rows, int64_t cols, int elem_bytes,
+                 int64_t dst_row_stride);
+
 /* The batching loop of ppgs.from_files_to_files / from_dataloader (ppgs/core.py:207-391)
  * for the mel representation as ONE call: `reader_threads` threads decode 16-bit PCM
  * 16 kHz WAVE files straight into pinned zero-padded int16 batches, the calling thread

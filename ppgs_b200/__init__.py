@@ -13,7 +13,7 @@ from .engine import Engine  # noqa: F401
 from .streaming import LongStreamer, Streamer  # noqa: F401
 from .core import (  # noqa: F401
     from_audio, from_features, from_file, from_file_to_file, from_files_to_files,
-    from_dataloader, infer, resample, representation_file_extension,
+    from_feature_files_to_files, from_dataloader, infer, resample, representation_file_extension,
     distance, interpolate, sparsify)
 from . import edit  # noqa: F401
 

@@ -76,6 +76,8 @@ SYMBOLS = {
     'ppgs_resample_taps': (_i, [_i, _i, _vp, _i64, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
     'ppgs_pt_write_f32': (_i, [_c.c_char_p, _vp, _i64, _i64, _i64]),
     'ppgs_pt_write_f16': (_i, [_c.c_char_p, _vp, _i64, _i64, _i64]),
+    'ppgs_pt_info': (_i, [_c.c_char_p, _c.POINTER(_i), _c.POINTER(_i64), _c.POINTER(_i)]),
+    'ppgs_pt_read': (_i, [_c.c_char_p, _vp, _i64, _i64, _i, _i64]),
     'ppgs_files_to_files': (_i, [_vp, _i, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_char_p),
                                  _c.POINTER(_c.c_char_p), _c.POINTER(_i64), _i, _i, _i, _vp,
                                  _c.POINTER(_i64)]),

@@ -268,6 +268,70 @@ def from_dataloader(
         writer.close()
 
 
+def from_feature_files_to_files(
+    feature_files: List[Union[str, bytes, os.PathLike]],
+    output_files: List[Union[str, bytes, os.PathLike]],
+    representation: str = config.live('REPRESENTATION'),
+    checkpoint: Optional[Union[str, bytes, os.PathLike]] = None,
+    num_workers: int = 0,
+    gpu: Optional[int] = None,
+    max_frames: int = config.live('MAX_INFERENCE_FRAMES'),
+    legacy_mode: bool = False,
+    container: Optional[Union[str, bytes, os.PathLike]] = None
+) -> None:
+    """Infer ppgs from cached input features (the `<stem>-mel.pt` / `<stem>-w2v2fb.pt` files
+    `python -m ppgs.preprocess` writes and ppgs/data/dataset.py:98-101 reads back with
+    torch.load): each file holds a (channels, frames) fp16 tensor.  Files are read by the native
+    `.pt` reader straight into pinned padded batches (frame-budget batches like the audio path),
+    run through `ppgs_transformer_forward`, and written cropped, one `.pt` per input.
+
+    `container`: write ONE file per batch instead, `<container>.<batch:05d>.pt` =
+    {'files': [output names], 'lengths': int64 (B,), 'ppgs': float32 (B, 40, max_frames)} — the
+    sharded / batched output option for corpora where 10^5 small files are the bottleneck."""
+    representation = config.resolve(representation)
+    max_frames = config.resolve(max_frames)
+    if len(feature_files) != len(output_files):
+        raise ValueError('feature_files and output_files must have equal lengths')
+    engine = load.model(checkpoint, representation, gpu)
+    channels = engine.cfg.input_channels
+    shapes = []
+    for file in feature_files:
+        info = load.tensor_info(file)
+        shape = info[0] if info is not None else tuple(torch.load(file, map_location='cpu').shape)
+        if len(shape) != 2 or shape[0] != channels:
+            raise ValueError(f'{file}: expected features of shape ({channels}, frames), got {shape}')
+        shapes.append(shape)
+    lengths = [shape[-1] for shape in shapes]
+    budget = data.bounded_max_frames(max_frames, engine.device)
+    batches = data.frame_budget_batches(lengths, budget)
+    writer = _Writer(max(num_workers // 2, 1) if num_workers else 0)
+    readers = max(num_workers - num_workers // 2, 1)
+    import concurrent.futures
+    pool = concurrent.futures.ThreadPoolExecutor(readers)
+    try:
+        for index, batch in enumerate(batches):
+            frames = max(lengths[i] for i in batch)
+            host = torch.zeros(len(batch), channels, frames, dtype=torch.float16, pin_memory=True)
+            list(pool.map(lambda item: load.features(feature_files[item[1]], out=host[item[0]]),
+                          enumerate(batch)))
+            batch_lengths = torch.tensor([lengths[i] for i in batch], dtype=torch.long)
+            result = engine.transformer(host.to(engine.device, non_blocking=True), batch_lengths,
+                                        softmax=True, legacy_mode=legacy_mode)
+            out_host = torch.empty(result.shape, dtype=result.dtype, pin_memory=True)
+            out_host.copy_(result, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(engine.device))
+            names = [output_files[i] for i in batch]
+            if container is None:
+                writer.put(done, out_host, names, batch_lengths.tolist())
+            else:
+                writer.put_container(done, out_host, [str(name) for name in names], batch_lengths,
+                                     f'{os.fspath(container)}.{index:05d}.pt')
+    finally:
+        pool.shutdown()
+        writer.close()
+
+
 class _Writer:
     """Bounded queue + `workers` saver threads (0 = save synchronously).
     Replaces the spawn Pool + qsize back-pressure of ppgs/core.py:311-314,358-365."""
@@ -295,7 +359,7 @@ class _Writer:
             if item is None:
                 return
             try:
-                self._save(*item)
+                (self._save_container if len(item) == 5 else self._save)(*item)
             except Exception as error:   # surfaced by close()
                 self.errors.append(error)
 
@@ -304,6 +368,19 @@ class _Writer:
             self.queue.put((done, host, filenames, frames))
         else:
             self._save(done, host, filenames, frames)
+
+    @staticmethod
+    def _save_container(done, host, filenames, lengths, file):
+        done.synchronize()
+        torch.save({'files': filenames, 'lengths': lengths, 'ppgs': host.clone()}, file)
+
+    def put_container(self, done, host, filenames, lengths, file):
+        """One file for the whole batch (padded tensor + lengths + names)."""
+        item = (done, host, filenames, lengths, file)
+        if self.workers:
+            self.queue.put(item)
+        else:
+            self._save_container(*item)
 
     def close(self):
         if self.workers:

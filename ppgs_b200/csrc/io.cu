@@ -435,6 +435,209 @@ static int pt_write(const char* path, const void* data_, int64_t rows, int64_t c
 }
 
 // ---------------------------------------------------------------------------
+// .pt reader: one contiguous 1..3-D fp16 / fp32 CPU tensor saved by torch.save (zip container,
+// stored entries) — the feature caches `data/cache/<dataset>/<stem>-mel.pt` that
+// ppgs/data/dataset.py:98-101 loads with torch.load, and this library's own outputs.
+// ---------------------------------------------------------------------------
+struct PtInfo {
+    int64_t dims[3] = {1, 1, 1};
+    int ndim = 0, elem = 0;
+    int64_t data_offset = 0, data_bytes = 0;
+};
+
+
+// Walks the pickle of `torch.save(tensor)`: the storage class names the element type, the ints
+// after BINPERSID are (storage offset, size tuple, stride tuple).  Only the opcodes torch's
+// pickler emits for a plain tensor are understood; anything else is "unsupported" and the
+// caller falls back to torch.load.
+static int parse_tensor_pickle(const unsigned char* b, size_t n, PtInfo* info, const char* path) {
+    std::vector<int64_t> ints;
+    std::vector<std::vector<int64_t>> tuples;
+    bool after_persid = false, first_object = true;
+    int64_t storage_offset = -1;
+    size_t i = 0;
+    auto need = [&](size_t k) { return i + k <= n; };
+    while (i < n) {
+        const unsigned char op = b[i++];
+        if (first_object && op != 0x80 && op != 0x95) {
+            // the pickled object must BE a tensor (not a dict / list that contains one)
+            static const char kRebuild[] = "torch._utils\n_rebuild_tensor_v2\n";
+            if (op != 'c' || !need(sizeof(kRebuild) - 1) || memcmp(b + i, kRebuild, sizeof(kRebuild) - 1) != 0) {
+                set_error("%s: the file does not hold a bare tensor", path);
+                return PPGS_E_UNSUPPORTED;
+            }
+            first_object = false;
+        }
+        switch (op) {
+            case 0x80: if (!need(1)) goto bad; i += 1; break;                         // PROTO
+            case 0x95: if (!need(8)) goto bad; i += 8; break;                         // FRAME
+            case 'c': {                                                               // GLOBAL module\nname\n
+                const size_t start = i;
+                int newlines = 0;
+                while (i < n && newlines < 2) newlines += b[i++] == '\n';
+                if (newlines < 2) goto bad;
+                const std::string g(reinterpret_cast<const char*>(b + start), i - start);
+                if (g.find("HalfStorage") != std::string::npos) info->elem = 2;
+                else if (g.find("FloatStorage") != std::string::npos) info->elem = 4;
+                else if (g.find("Storage") != std::string::npos) {
+                    set_error("%s: tensor storage %s is not fp16 / fp32", path, g.c_str());
+                    return PPGS_E_UNSUPPORTED;
+                }
+                break;
+            }
+            case 'X': case 'T': if (!need(4)) goto bad; { const uint32_t len = rd32(b + i); i += 4; if (!need(len)) goto bad; i += len; } break;
+            case 0x8c: case 'U': if (!need(1)) goto bad; { const size_t len = b[i]; i += 1; if (!need(len)) goto bad; i += len; } break;
+            case 'K': if (!need(1)) goto bad; if (after_persid) ints.push_back(b[i]); i += 1; break;
+            case 'M': if (!need(2)) goto bad; if (after_persid) ints.push_back(rd16(b + i)); i += 2; break;
+            case 'J': if (!need(4)) goto bad; if (after_persid) ints.push_back((int32_t)rd32(b + i)); i += 4; break;
+            case 0x8a: {                                                              // LONG1
+                if (!need(1)) goto bad;
+                const size_t len = b[i]; i += 1;
+                if (!need(len) || len > 8) goto bad;
+                int64_t v = 0;
+                for (size_t k = 0; k < len; ++k) v |= (int64_t)b[i + k] << (8 * k);
+                if (after_persid) ints.push_back(v);
+                i += len;
+                break;
+            }
+            case 'q': case 'h': if (!need(1)) goto bad; i += 1; break;               // BINPUT / BINGET
+            case 'r': case 'j': if (!need(4)) goto bad; i += 4; break;               // LONG_BINPUT / LONG_BINGET
+            case 'Q': after_persid = true; ints.clear(); break;                       // BINPERSID
+            case 0x85: case 0x86: case 0x87: {                                        // TUPLE1..3
+                const size_t k = op - 0x84;
+                if (after_persid && tuples.size() < 2) {
+                    if (ints.size() < k) goto bad;
+                    if (tuples.empty()) {
+                        if (ints.size() != k + 1) goto bad;   // storage offset, then the sizes
+                        storage_offset = ints[0];
+                    }
+                    tuples.emplace_back(ints.end() - k, ints.end());
+                    ints.clear();
+                }
+                break;
+            }
+            case ')': if (after_persid && tuples.size() < 2) { tuples.emplace_back(); ints.clear(); } break;   // 0-d
+            case '(': case 't': case 'R': case '}': case ']': case 'N': case 0x88: case 0x89: case 'b':
+            case 'u': case 's': case 0x94: case 'a': case 'e':
+                break;
+            case '.': i = n; break;
+            default:
+                set_error("%s: pickle opcode 0x%02x is not part of a plain tensor file", path, op);
+                return PPGS_E_UNSUPPORTED;
+        }
+        if (tuples.size() == 2 && info->ndim == 0 && !tuples[0].empty()) {
+            const std::vector<int64_t>&size = tuples[0], &stride = tuples[1];
+            if (size.size() != stride.size() || size.size() > 3 || storage_offset != 0) {
+                set_error("%s: not a whole contiguous tensor (storage offset %lld)", path, (long long)storage_offset);
+                return PPGS_E_UNSUPPORTED;
+            }
+            int64_t expect = 1;
+            for (int d = (int)size.size() - 1; d >= 0; --d) {
+                if (size[d] < 0 || (size[d] > 1 && stride[d] != expect)) {
+                    set_error("%s: tensor is not contiguous", path);
+                    return PPGS_E_UNSUPPORTED;
+                }
+                expect *= size[d];
+            }
+            info->ndim = (int)size.size();
+            for (size_t d = 0; d < size.size(); ++d) info->dims[3 - size.size() + d] = size[d];
+        }
+    }
+    if (info->ndim == 0 || info->elem == 0) {
+        set_error("%s: no fp16 / fp32 tensor found in data.pkl", path);
+        return PPGS_E_UNSUPPORTED;
+    }
+    return PPGS_OK;
+bad:
+    set_error("%s: truncated or unexpected pickle stream", path);
+    return PPGS_E_UNSUPPORTED;
+}
+
+static int pt_probe(int fd, const char* path, PtInfo* info) {
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 22) {
+        set_error("%s: not a torch.save archive", path);
+        return PPGS_E_INVALID;
+    }
+    const size_t tail = (size_t)std::min<int64_t>(st.st_size, 65536 + 22);
+    std::vector<unsigned char> buf(tail);
+    if (pread(fd, buf.data(), tail, st.st_size - (int64_t)tail) != (ssize_t)tail) {
+        set_error("%s: read failed: %s", path, strerror(errno));
+        return PPGS_E_INVALID;
+    }
+    int64_t eocd = -1;
+    for (int64_t i = (int64_t)tail - 22; i >= 0; --i)
+        if (rd32(&buf[i]) == 0x06054b50) { eocd = i; break; }
+    if (eocd < 0) {
+        set_error("%s: not a zip archive (legacy torch.save format is not supported)", path);
+        return PPGS_E_UNSUPPORTED;
+    }
+    const uint32_t entries = rd16(&buf[eocd + 10]), cd_size = rd32(&buf[eocd + 12]), cd_off = rd32(&buf[eocd + 16]);
+    if (cd_off == 0xFFFFFFFFu || entries == 0xFFFF) {
+        set_error("%s: zip64 archives are not supported by the native reader", path);
+        return PPGS_E_UNSUPPORTED;
+    }
+    std::vector<unsigned char> cd(cd_size);
+    if (pread(fd, cd.data(), cd_size, cd_off) != (ssize_t)cd_size) {
+        set_error("%s: central directory read failed", path);
+        return PPGS_E_INVALID;
+    }
+    int64_t pkl_local = -1, pkl_size = 0, data_local = -1, data_size = 0;
+    size_t at = 0;
+    for (uint32_t k = 0; k < entries && at + 46 <= cd.size(); ++k) {
+        if (rd32(&cd[at]) != 0x02014b50) break;
+        const uint16_t method = rd16(&cd[at + 10]), name_len = rd16(&cd[at + 28]), extra_len = rd16(&cd[at + 30]),
+                       comment_len = rd16(&cd[at + 32]);
+        const uint32_t comp = rd32(&cd[at + 20]), local = rd32(&cd[at + 42]);
+        const std::string name(reinterpret_cast<const char*>(&cd[at + 46]), name_len);
+        auto ends_with = [&](const char* suffix) {
+            const size_t m = strlen(suffix);
+            return name.size() >= m && name.compare(name.size() - m, m, suffix) == 0;
+        };
+        if (ends_with("/data.pkl") || ends_with("/data/0")) {
+            if (method != 0) {
+                set_error("%s: entry %s is compressed", path, name.c_str());
+                return PPGS_E_UNSUPPORTED;
+            }
+            if (ends_with("/data.pkl")) { pkl_local = local; pkl_size = comp; }
+            else { data_local = local; data_size = comp; }
+        } else if (name.find("/data/") != std::string::npos) {
+            set_error("%s: more than one tensor storage in the archive", path);
+            return PPGS_E_UNSUPPORTED;
+        }
+        at += 46 + name_len + extra_len + comment_len;
+    }
+    if (pkl_local < 0 || data_local < 0) {
+        set_error("%s: data.pkl / data/0 not found", path);
+        return PPGS_E_UNSUPPORTED;
+    }
+    auto payload_offset = [&](int64_t local, int64_t* out) -> bool {
+        unsigned char h[30];
+        if (pread(fd, h, 30, local) != 30 || rd32(h) != 0x04034b50) return false;
+        *out = local + 30 + rd16(h + 26) + rd16(h + 28);
+        return true;
+    };
+    int64_t pkl_at = 0;
+    if (!payload_offset(pkl_local, &pkl_at) || !payload_offset(data_local, &info->data_offset)) {
+        set_error("%s: bad local file header", path);
+        return PPGS_E_INVALID;
+    }
+    std::vector<unsigned char> pkl((size_t)pkl_size);
+    if (pread(fd, pkl.data(), pkl.size(), pkl_at) != (ssize_t)pkl.size()) {
+        set_error("%s: data.pkl read failed", path);
+        return PPGS_E_INVALID;
+    }
+    PPGS_CHECK(parse_tensor_pickle(pkl.data(), pkl.size(), info, path));
+    info->data_bytes = info->dims[0] * info->dims[1] * info->dims[2] * info->elem;
+    if (info->data_bytes != data_size) {
+        set_error("%s: storage holds %lld bytes, the tensor needs %lld", path, (long long)data_size,
+                  (long long)info->data_bytes);
+        return PPGS_E_UNSUPPORTED;
+    }
+    return PPGS_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Device kernels
 // ---------------------------------------------------------------------------
 // int16 PCM -> fp32 / 32768: 8 samples per thread (16-byte load, two 16-byte stores)
@@ -775,6 +978,61 @@ int ppgs_pt_write_f16(const char* path, const void* data, int64_t rows, int64_t 
     std::vector<float> contiguous;
     ByteSink head;
     return pt_write(path, data, rows, cols, row_stride, contiguous, head, 2);
+}
+
+int ppgs_pt_info(const char* path, int* ndim, int64_t* dims3, int* elem_bytes) {
+    if (!path || !ndim || !dims3 || !elem_bytes) {
+        set_error("pt_info: NULL argument");
+        return PPGS_E_INVALID;
+    }
+    Fd in(path, O_RDONLY);
+    if (in.fd < 0) {
+        set_error("%s: cannot open: %s", path, strerror(errno));
+        return PPGS_E_INVALID;
+    }
+    PtInfo info;
+    PPGS_CHECK(pt_probe(in.fd, path, &info));
+    *ndim = info.ndim;
+    for (int d = 0; d < 3; ++d) dims3[d] = info.dims[d];
+    *elem_bytes = info.elem;
+    return PPGS_OK;
+}
+
+int ppgs_pt_read(const char* path, void* dst_host, int64_t rows, int64_t cols, int elem_bytes,
+                 int64_t dst_row_stride) {
+    if (!path || !dst_host || rows < 0 || cols < 0 || dst_row_stride < cols) {
+        set_error("pt_read: bad argument");
+        return PPGS_E_INVALID;
+    }
+    Fd in(path, O_RDONLY);
+    if (in.fd < 0) {
+        set_error("%s: cannot open: %s", path, strerror(errno));
+        return PPGS_E_INVALID;
+    }
+    PtInfo info;
+    PPGS_CHECK(pt_probe(in.fd, path, &info));
+    if (info.elem != elem_bytes || info.dims[0] * info.dims[1] != rows || info.dims[2] != cols) {
+        set_error("%s: holds (%lld, %lld) x %d bytes, the caller expects (%lld, %lld) x %d", path,
+                  (long long)(info.dims[0] * info.dims[1]), (long long)info.dims[2], info.elem, (long long)rows,
+                  (long long)cols, elem_bytes);
+        return PPGS_E_INVALID;
+    }
+    char* dst = static_cast<char*>(dst_host);
+    const size_t row_bytes = (size_t)cols * elem_bytes;
+    if (dst_row_stride == cols) {
+        if (pread(in.fd, dst, row_bytes * rows, info.data_offset) != (ssize_t)(row_bytes * rows)) {
+            set_error("%s: payload read failed: %s", path, strerror(errno));
+            return PPGS_E_INVALID;
+        }
+        return PPGS_OK;
+    }
+    for (int64_t r = 0; r < rows; ++r)   // rows land in a padded batch tensor
+        if (pread(in.fd, dst + r * dst_row_stride * elem_bytes, row_bytes, info.data_offset + r * (int64_t)row_bytes) !=
+            (ssize_t)row_bytes) {
+            set_error("%s: payload read failed: %s", path, strerror(errno));
+            return PPGS_E_INVALID;
+        }
+    return PPGS_OK;
 }
 
 int64_t ppgs_resample_length(int64_t samples, int orig_rate, int target_rate) {

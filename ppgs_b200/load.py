@@ -112,6 +112,51 @@ def wav_num_frames(file):
     return waveform.shape[-1], config.SAMPLE_RATE
 
 
+def tensor_info(file):
+    """(shape, dtype) of a `.pt` file holding one whole contiguous fp16 / fp32 CPU tensor, from
+    the archive's directory and pickle header only (native: ppgs_pt_info); None when the native
+    reader does not understand the file (callers then use torch.load)."""
+    import ctypes
+    ndim, elem = ctypes.c_int(), ctypes.c_int()
+    dims = (ctypes.c_int64 * 3)()
+    if _lib.lib.ppgs_pt_info(os.fsencode(str(file)), ctypes.byref(ndim), dims, ctypes.byref(elem)) != 0:
+        return None
+    shape = tuple(dims[3 - ndim.value:3])
+    return shape, torch.float16 if elem.value == 2 else torch.float32
+
+
+def features(file, out=None):
+    """Load cached input features, `torch.load(cache / f'{stem}-{feature}.pt')` of
+    ppgs/data/dataset.py:98-101, through the native reader (no unpickling in Python, no GIL
+    while the payload is read).  `out`: optional (channels, >= frames) slice of a padded batch
+    tensor the rows are read into directly.  Falls back to torch.load for anything the native
+    reader does not cover (legacy archives, other dtypes, views)."""
+    import ctypes
+    info = tensor_info(file)
+    if info is None or len(info[0]) < 2:
+        tensor = torch.load(file, map_location='cpu')
+        if out is not None:
+            out[..., :tensor.shape[-1]].copy_(tensor)
+            return out[..., :tensor.shape[-1]]
+        return tensor
+    shape, dtype = info
+    rows, cols = 1, shape[-1]
+    for n in shape[:-1]:
+        rows *= n
+    if out is None:
+        out = torch.empty(shape, dtype=dtype)
+        stride = cols
+    else:
+        if out.dtype != dtype or out.device.type != 'cpu' or out.stride(-1) != 1 or out.shape[-1] < cols \
+                or out.numel() // out.shape[-1] != rows or out.dim() != 2:
+            raise ValueError(f'features: `out` must be a CPU {dtype} (rows, >= {cols}) view, got {tuple(out.shape)}')
+        stride = out.stride(0)
+    _lib.check(_lib.lib.ppgs_pt_read(
+        os.fsencode(str(file)), ctypes.c_void_p(out.data_ptr()), rows, cols, 2 if dtype == torch.float16 else 4,
+        stride))
+    return out[..., :cols] if out.shape[-1] != cols else out
+
+
 def state_dict(checkpoint=None, representation=None):
     """Resolve + read a checkpoint (ppgs/load.py:59-79).  Unlike the reference,
     `checkpoint=` is honoured for w2v2fb too."""

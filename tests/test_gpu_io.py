@@ -261,3 +261,41 @@ def test_preprocess_from_files_to_files(ppgs_b200, tmp_path):
     assert seen == len(files)
     with pytest.raises(ValueError, match='not supported'):
         preprocess.from_files_to_files(files, outputs, ['bottleneck'], gpu=0)
+
+
+def test_from_feature_files_to_files_and_container(ppgs_b200, tmp_path):
+    """cached `<stem>-mel.pt` features (what `python -m ppgs.preprocess` writes and
+    ppgs/data/dataset.py:98-101 loads) -> posteriorgrams, read by the native `.pt` reader into
+    padded batches; one `.pt` per input, or one container file per batch.  Results equal the
+    per-utterance `from_features` of the same cached features."""
+    import torch
+    from oracle import ppg_oracle as O
+    sd = O.random_state_dict(5)
+    ckpt = tmp_path / 'ckpt.pt'
+    torch.save({'model': sd}, ckpt)
+    frames = [400, 333, 1000, 57]
+    feature_files, output_files, cached = [], [], []
+    for i, n in enumerate(frames):
+        feats = O.mel_from_audios(O.synthetic_audio(1, n * 160, 20 + i))[0]
+        file = tmp_path / f'utt{i}-mel.pt'
+        torch.save(feats, file)                                  # torch's own writer
+        feature_files.append(file)
+        output_files.append(tmp_path / f'utt{i}-ppg.pt')
+        cached.append(feats)
+    ppgs_b200.from_feature_files_to_files(feature_files, output_files, checkpoint=ckpt, gpu=0, num_workers=4,
+                                          max_frames=1500)
+    for feats, file, n in zip(cached, output_files, frames):
+        out = torch.load(file)
+        assert out.shape == (40, n)
+        ref = O.from_features(sd, feats[None], torch.tensor([n]))[0]
+        assert (out - ref).abs().max() <= 1e-4
+    ppgs_b200.from_feature_files_to_files(feature_files, output_files, checkpoint=ckpt, gpu=0, max_frames=1500,
+                                          container=tmp_path / 'shard')
+    seen = {}
+    for file in sorted(tmp_path.glob('shard.*.pt')):
+        shard = torch.load(file)
+        for name, n, ppg in zip(shard['files'], shard['lengths'].tolist(), shard['ppgs']):
+            seen[name] = ppg[:, :n]
+    assert len(seen) == len(frames)
+    for file, n in zip(output_files, frames):
+        assert torch.equal(seen[str(file)], torch.load(file))

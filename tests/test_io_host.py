@@ -206,3 +206,43 @@ def test_pt_writer_fp16_and_save_masked(library, tmp_path):
         path = tmp_path / 'masked.pt'
         preprocess.save_masked(tensor, path, 3)         # native for 2-D fp16 / fp32, torch.save otherwise
         assert torch.equal(torch.load(path), tensor[..., :3])
+
+
+def test_native_pt_reader_roundtrip_and_torch_files(tmp_path):
+    """ppgs_pt_info / ppgs_pt_read (the feature-cache reader, ppgs/data/dataset.py:98-101): files
+    written by torch.save itself (fp16 / fp32, 1-D .. 3-D) and by the library's own writer come
+    back bit for bit, also into a row of a padded batch; anything else reports 'unsupported'
+    through tensor_info() -> None so that callers fall back to torch.load."""
+    import torch
+    from ppgs_b200 import load, preprocess
+    g = torch.Generator().manual_seed(0)
+    cases = {
+        'mel': torch.randn(80, 333, generator=g).half(),
+        'ppg': torch.rand(40, 1000, generator=g),
+        'vec': torch.randn(17, generator=g),
+        'cube': torch.randn(2, 3, 5, generator=g).half(),
+    }
+    for name, tensor in cases.items():
+        file = tmp_path / f'{name}.pt'
+        torch.save(tensor, file)
+        shape, dtype = load.tensor_info(file)
+        assert shape == tuple(tensor.shape) and dtype == tensor.dtype
+        assert torch.equal(load.features(file), tensor)
+    # the library's own writer (save_masked crops a padded row)
+    padded = torch.zeros(80, 400, dtype=torch.float16)
+    padded[:, :333] = cases['mel']
+    preprocess.save_masked(padded, tmp_path / 'own.pt', 333)
+    assert load.tensor_info(tmp_path / 'own.pt') == ((80, 333), torch.float16)
+    assert torch.equal(load.features(tmp_path / 'own.pt'), cases['mel'])
+    # straight into a row of a padded batch
+    batch = torch.zeros(3, 80, 512, dtype=torch.float16)
+    view = load.features(tmp_path / 'mel.pt', out=batch[1])
+    assert view.shape == (80, 333) and torch.equal(batch[1, :, :333], cases['mel'])
+    assert not batch[1, :, 333:].any() and not batch[0].any() and not batch[2].any()
+    # not covered natively: views, other dtypes, dicts -> None, and features() still loads them
+    torch.save(cases['ppg'][:, 10:20], tmp_path / 'view.pt')     # storage larger than the tensor
+    torch.save(torch.arange(6).reshape(2, 3), tmp_path / 'int.pt')
+    torch.save({'model': cases['vec']}, tmp_path / 'dict.pt')
+    for name in ('view', 'int', 'dict'):
+        assert load.tensor_info(tmp_path / f'{name}.pt') is None
+    assert torch.equal(load.features(tmp_path / 'view.pt'), cases['ppg'][:, 10:20])
