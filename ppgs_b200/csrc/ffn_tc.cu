@@ -99,7 +99,8 @@ __device__ __forceinline__ bool residual_layernorm_store(
     uint32_t t_acc, uint32_t release_bar, float scale, const float* bias, const float* gamma_p,
     const float* beta_p, float eps, const SeqInfo* seqs, const int* tile_seq, int m_blk, int row, int set,
     int lane, bool elected, unsigned char* stage_smem, uint64_t* res_full, uint32_t res_phase,
-    float (*ln_part)[kBM], const CUtensorMap* map_res, const CUtensorMap* map_out) {
+    float (*ln_part)[kBM], const CUtensorMap* map_res, const CUtensorMap* map_out,
+    bool res0_issued = false) {
     const int m0 = m_blk * kBM;
     const int64_t m = (int64_t)m0 + row;
     bool ok = true;
@@ -123,10 +124,13 @@ __device__ __forceinline__ bool residual_layernorm_store(
     float sum = 0.f;
 #pragma unroll
     for (int gq = 0; gq < 2; ++gq) {
-        named_bar_sync(1 + set, 128);   // previous group consumed by all rows of the set
-        if (elected) {
-            mbar_arrive_expect_tx(res_full, 2 * kTileBytes);
-            tma_load_3d(stage_smem + set * 2 * kTileBytes, map_res, res_full, set * 128 + gq * 64, m0, 0);
+        // (the caller may have requested group 0 already, under the wait for the accumulator)
+        if (gq > 0 || !res0_issued) {
+            named_bar_sync(1 + set, 128);   // previous group consumed by all rows of the set
+            if (elected) {
+                mbar_arrive_expect_tx(res_full, 2 * kTileBytes);
+                tma_load_3d(stage_smem + set * 2 * kTileBytes, map_res, res_full, set * 128 + gq * 64, m0, 0);
+            }
         }
         float b[32];
         uint32_t rh[32], rl[32];
@@ -601,14 +605,21 @@ proj_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int it = 0;
         for (int pt = worker; pt < pair_tiles && ok; pt += workers, ++it) {
             const int m_blk = pair_row_tile(p, pt, (int)rank), acc = it & 1;
+            // the first residual group of this tile is requested BEFORE the wait for the accumulator
+            // (it depends on x only): its latency hides behind the tile's MMAs.  The staging tiles are
+            // free once the previous tile's stores have read them and every row of the set is past them.
+            named_bar_sync(1 + set, 128);
+            if (elected) {
+                bulk_wait_read_all();
+                mbar_arrive_expect_tx(&res_full[set], 2 * kTileBytes);
+                tma_load_3d(stage_smem + set * 2 * kTileBytes, &map_res, &res_full[set], set * 128, m_blk * kBM, 0);
+            }
             if (!mbar_wait(&y_full[acc], (uint32_t)((it >> 1) & 1))) { ok = false; break; }
             tcgen05_fence_after();
-            // the previous tile's stores have drained the staging tiles before the residual lands
-            if (elected) bulk_wait_read_all();
             if (!residual_layernorm_store(t_lane + acc * 256 + set * 128, y_empty_remote[acc], scale, p.bias2, p.gamma,
                                           p.beta, p.eps, p.seqs, p.tile_seq, m_blk, row, set, lane, elected,
                                           stage_smem, &res_full[set], (uint32_t)(2 * it), ln_part, &map_res,
-                                          &map_out))
+                                          &map_out, true))
                 ok = false;
         }
         if (elected) bulk_wait_all();
