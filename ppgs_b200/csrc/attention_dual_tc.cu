@@ -126,8 +126,11 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
             mbar_init(&o_done[L], 1);
         }
         fence_barrier_init();
-        // the Q tiles and the first K block are requested before TMEM allocation and the CTA
-        // barrier: their latency (2 us from a cold L2) is the longest item of the prologue
+    }
+    __syncthreads();   // every barrier is initialised before any thread (or the async proxy) touches one
+    if (threadIdx.x == 0) {
+        // the Q tiles and the first K block are requested before TMEM allocation and the second
+        // CTA barrier: their latency (2 us from a cold L2) is the longest item of the prologue
         if (nb_max > 0) {
             pdl_wait();   // Q / K / V of the previous kernel are needed from here on
             const int col_q = head * kD, col_k = p.H + head * kD;

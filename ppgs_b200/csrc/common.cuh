@@ -150,7 +150,8 @@ struct ppgs_engine {
     int proj_ln = 1;             // 1 = hidden-256 projections + residual + LayerNorm through proj_ln_kernel (ffn_tc.cu);
                                  // 0 (PPGS_B200_PROJ_LN=0) = gemm_tc's ResLN epilogue
     int fused_ffn = 1;           // 1 = one fused kernel for linear1 + ReLU + linear2 + residual + LN (ffn_tc.cu): the
-                                 // hidden activation never leaves the SM; 0 (PPGS_B200_FUSED_FFN=0) = two GEMMs
+                                 // hidden activation never leaves the SM (used from sm_count / 8 row-tile pairs up;
+                                 // 2 = always); 0 (PPGS_B200_FUSED_FFN=0) = two GEMMs
     unsigned long long* trace_dev = nullptr;   // [8 kernel kinds][8] cycle counters (PPGS_B200_TRACE=1)
 
     // wav2vec2-base front-end of the `w2v2fb` representation (optional)

@@ -302,7 +302,11 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
         };
         PPGS_CHECK(project_ln(fused_ln ? "tc_out_proj_ln" : "tc_out_proj", map_att, T.out_w, H / 64, L.out_b,
                               L.n1_w, L.n1_b, 2, 6));
-        if (pair && e->fused_ffn && fused_ln && F % 128 == 0) {
+        // The fused kernel walks the 16 hidden chunks of a row-tile pair on ONE CTA pair; with
+        // fewer pair tiles than half of the CTA-pair slots the two-GEMM form is shorter (its
+        // linear1 spreads the same tile over 8 CTA pairs): 37 pair tiles = 9 472 rows on a B200.
+        const bool enough_tiles = rows / 256 >= e->sm_count / 4 || e->fused_ffn == 2;
+        if (pair && e->fused_ffn && enough_tiles && fused_ln && F % 128 == 0) {
             FfnParams f;
             f.m_tiles = rows / 128; f.num_chunks = F / 128; f.planes = planes;
             f.scale1 = T.l1_w.inv_scale; f.scale2 = T.l2_w.inv_scale;
