@@ -2,9 +2,9 @@
 the reference's ppgs.distance / sparsify / interpolate / edit.grid.sample and the oracle.
 
 Tolerances: interpolate / grid sample bit-exact (products and sums are not fused);
-sparsify <= 1e-6 (logf / expf); distance <= 5e-4 absolute per frame on values of O(1) — the
-square root of near-zero fp32 divergences amplifies last-bit differences of logf (the
-reference's own fp32 result is as far from an fp64 evaluation)."""
+sparsify <= 1e-6 (logf / expf); distance <= 1e-4 per frame with the similarity weights and <= 5e-6
+without them, on values of O(1) (measured 6.6e-5 / 2.4e-6; the reference's own fp32 result is farther
+from an fp64 evaluation of its formula than this kernel's)."""
 import pytest
 import torch
 
@@ -14,7 +14,15 @@ from oracle import postops_oracle as P
 pytestmark = pytest.mark.gpu
 
 CASES = ['postops_s0', 'postops_s1']
-DISTANCE_TOL = 5e-4
+# measured on the goldens (distances of 0.6 .. 1.5): 6.6e-5 with the similarity weights (the reference's
+# own fp32 result is 1.6e-4 from an fp64 evaluation of the same formula in the divergence, ours 7.5e-5),
+# 2.4e-6 without them
+DISTANCE_TOL = 1e-4
+RAW_DISTANCE_TOL = 5e-6
+
+
+def close_distance(got, ref, tol=DISTANCE_TOL):
+    return bool((got.double().cpu() - ref.double().cpu()).abs().max() <= tol)
 
 
 @pytest.fixture(scope='module')
@@ -36,26 +44,26 @@ def test_distance_vs_reference_golden(ppgs_b200, name):
         a, b = x.to(device), y.to(device)
         got = ppgs_b200.distance(a, b, reduction='none', similarity=similarity)
         assert got.device.type == device and got.shape == (frames,)
-        assert (got.cpu() - g['distance_none']).abs().max() <= DISTANCE_TOL
+        assert close_distance(got, g['distance_none'])
         got = ppgs_b200.distance(a, b, reduction='none', normalize=False)
-        assert (got.cpu() - g['distance_raw_none']).abs().max() <= DISTANCE_TOL
+        assert close_distance(got, g['distance_raw_none'], RAW_DISTANCE_TOL)
     for reduction, scale in (('mean', 1), ('sum', frames)):
         got = ppgs_b200.distance(x.cuda(), y.cuda(), reduction=reduction, similarity=similarity)
         assert got.dim() == 0
         assert abs(got.item() - g[f'distance_{reduction}'].item()) <= DISTANCE_TOL * scale
         got = ppgs_b200.distance(x, y, reduction=reduction, normalize=False)
-        assert abs(got.item() - g[f'distance_raw_{reduction}'].item()) <= DISTANCE_TOL * scale
+        assert abs(got.item() - g[f'distance_raw_{reduction}'].item()) <= RAW_DISTANCE_TOL * scale
     got = ppgs_b200.distance(x, y, exponent=2.0, similarity=similarity)
     assert abs(got.item() - g['distance_exp2'].item()) <= DISTANCE_TOL
     # fp64 ground truth: as close as the reference's own fp32 evaluation
     truth = P.distance(x.double(), y.double(), 'none', similarity=similarity.double())
     mine = ppgs_b200.distance(x, y, reduction='none', similarity=similarity).double()
-    assert (mine - truth).abs().max() <= DISTANCE_TOL
+    assert close_distance(mine, truth)
     # identical PPGs are at distance ~0, strided inputs are accepted
     assert ppgs_b200.distance(x, x, normalize=False).item() <= 1e-3
     wide = torch.cat((x, y), dim=-1).cuda()
     strided = ppgs_b200.distance(wide[:, :frames], wide[:, frames:], 'none', normalize=False)
-    assert (strided.cpu() - g['distance_raw_none']).abs().max() <= DISTANCE_TOL
+    assert close_distance(strided, g['distance_raw_none'], RAW_DISTANCE_TOL)
 
 
 def test_distance_errors_and_config_path(ppgs_b200, tmp_path):

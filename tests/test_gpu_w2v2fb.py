@@ -13,12 +13,16 @@ from test_w2v2_oracle import CASES
 
 
 def close_fp16(a, b):
-    """GPU front-end vs the reference features (both fp16).  The default encoder runs its
-    projections as split-fp16 tensor-core GEMMs whose fp32 TMEM accumulation is ~5e-5 off a
-    CPU fp32 evaluation after 12 layers: at most one fp16 step of the value away (two of the
-    finer steps just below a power of two), ~5 % of the elements differ by that step."""
-    a, b = a.astype(np.float32), b.astype(np.float32)
-    return np.abs(a - b) <= 1e-4 + 2.0 ** -9 * np.abs(b)
+    """GPU front-end vs the reference features (both fp16): at most ONE fp16 step apart (the step of
+    the larger magnitude, so a pair that straddles a power of two counts as one step), the same tier as
+    the mel front-end.  With split accumulators in the encoder GEMMs (tcgen05 accumulation truncates,
+    DESIGN.md §4) about 4 % of the elements differ by that step; round 1's single accumulator: 8 %."""
+    a16, b16 = a.astype(np.float16), b.astype(np.float16)
+    step = np.spacing(np.maximum(np.abs(a16), np.abs(b16))).astype(np.float32)
+    return np.abs(a16.astype(np.float32) - b16.astype(np.float32)) <= np.maximum(step, 2.0 ** -14)
+
+
+MAX_FLIPS = 0.06
 
 pytestmark = pytest.mark.gpu
 
@@ -43,7 +47,7 @@ def test_features_vs_hf_golden(ppgs_b200, name):
     engine.check()
     assert feats.shape == g['features'].shape and feats.dtype == np.float16
     assert close_fp16(feats, g['features']).all()
-    assert (feats != g['features']).mean() <= 0.1
+    assert (feats != g['features']).mean() <= MAX_FLIPS
 
 
 def test_features_ragged_batch_vs_oracle(ppgs_b200):
@@ -133,7 +137,7 @@ def test_w2v2fb_peaky_head_end_to_end(tc):
     per setting), ragged lengths."""
     result = run_e2e(tc, wseed=3, pseed=4, samples=48000, lengths=[48000, 31000], aseed=5)
     assert result['err'] <= 1e-4, result
-    assert result['flips'] <= (0.1 if tc else 0.03), result
+    assert result['flips'] <= (MAX_FLIPS if tc else 0.03), result
 
 
 def test_w2v2fb_full_size_rows_vs_oracle():
