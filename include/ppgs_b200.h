@@ -215,6 +215,14 @@ int ppgs_wav_info_many(const char* const* paths, int64_t count, int threads, int
 int ppgs_wav_read_f32(const char* path, float* dst_host, int64_t capacity, int64_t* frames,
                       int* sample_rate);
 
+/* torchaudio.info / torchaudio.load (ppgs/data/dataset.py:187, ppgs/load.py:17-30) for FLAC
+ * files: STREAMINFO probe, and a verifying decode (frame CRC-8 / CRC-16, STREAMINFO MD5) of ALL
+ * channels to fp32 = sample / 2^(bits-1), channel-major with row stride `capacity` frames.
+ * PPGS_E_UNSUPPORTED: not a FLAC stream.  Any out pointer may be NULL. */
+int ppgs_flac_info(const char* path, int64_t* frames, int* sample_rate, int* channels, int* bits);
+int ppgs_flac_read_f32(const char* path, float* dst_host, int64_t capacity, int64_t* frames,
+                       int* sample_rate, int* channels);
+
 /* The /32768 normalisation of torchaudio.load on the device: `count` int16 samples ->
  * fp32 (both buffers 16-byte aligned), so that file batches cross PCIe as 2-byte PCM. */
 int ppgs_pcm16_to_f32(ppgs_engine* engine, const void* pcm_dev, int64_t count,

@@ -70,6 +70,8 @@ SYMBOLS = {
                                 _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32),
                                 _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
     'ppgs_wav_read_f32': (_i, [_c.c_char_p, _vp, _i64, _c.POINTER(_i64), _c.POINTER(_i)]),
+    'ppgs_flac_info': (_i, [_c.c_char_p, _c.POINTER(_i64), _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
+    'ppgs_flac_read_f32': (_i, [_c.c_char_p, _vp, _i64, _c.POINTER(_i64), _c.POINTER(_i), _c.POINTER(_i)]),
     'ppgs_pcm16_to_f32': (_i, [_vp, _vp, _i64, _vp, _vp]),
     'ppgs_resample_length': (_i64, [_i64, _i, _i]),
     'ppgs_resample': (_i, [_vp, _vp, _i, _i64, _i64, _i, _i, _vp, _i64, _vp]),

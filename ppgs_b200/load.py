@@ -55,16 +55,38 @@ def wav_info_many(files, threads=16):
     return infos
 
 
+def flac_info(file):
+    """STREAMINFO of a FLAC file (ppgs_flac_info): dict(samples, sample_rate, channels, bits), or
+    None when the file is not a FLAC stream."""
+    frames, rate, channels, bits = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    code = _lib.lib.ppgs_flac_info(
+        os.fsencode(str(file)), ctypes.byref(frames), ctypes.byref(rate), ctypes.byref(channels),
+        ctypes.byref(bits))
+    if code == _lib.E_UNSUPPORTED:
+        return None
+    _lib.check(code)
+    return {'samples': frames.value, 'sample_rate': rate.value, 'channels': channels.value,
+            'bits': bits.value}
+
+
 def audio(file, device=None):
     """Load audio from disk as (channels, samples) fp32 at 16 kHz
-    (ppgs/load.py:17-30).  Mono PCM / float WAVE files are decoded by the native
-    reader (ppgs_wav_read_f32; torchaudio.load needs torchcodec) and
-    resampled on the GPU; multi-channel WAVE files by scipy; other containers go
-    through torchaudio when it can decode them.  `device`: return the waveform on
-    that CUDA device instead of the CPU (saves a round trip after resampling)."""
+    (ppgs/load.py:17-30).  Mono PCM / float WAVE files and FLAC files are decoded by the
+    native readers (ppgs_wav_read_f32 / ppgs_flac_read_f32; torchaudio.load needs
+    torchcodec, SURVEY.md F9) and resampled on the GPU; multi-channel WAVE files by scipy;
+    other containers go through torchaudio when it can decode them.  `device`: return the
+    waveform on that CUDA device instead of the CPU (saves a round trip after resampling)."""
     path = Path(file)
     info = wav_info(path) if path.suffix.lower() == '.wav' else None
-    if info is not None and info['channels'] == 1:
+    flac = flac_info(path) if path.suffix.lower() == '.flac' else None
+    if flac is not None:
+        waveform = torch.empty(flac['channels'], flac['samples'], dtype=torch.float32)
+        frames, rate, channels = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(_lib.lib.ppgs_flac_read_f32(
+            os.fsencode(str(path)), ctypes.c_void_p(waveform.data_ptr()), flac['samples'],
+            ctypes.byref(frames), ctypes.byref(rate), ctypes.byref(channels)))
+        sample_rate = rate.value
+    elif info is not None and info['channels'] == 1:
         waveform = torch.empty(1, info['samples'], dtype=torch.float32)
         frames, rate = ctypes.c_int64(), ctypes.c_int()
         _lib.check(_lib.lib.ppgs_wav_read_f32(
@@ -106,6 +128,8 @@ def wav_num_frames(file):
     """(samples, sample_rate) from the header only (torchaudio.info at
     ppgs/data/dataset.py:187)."""
     info = wav_info(file)
+    if info is None and str(file).lower().endswith('.flac'):
+        info = flac_info(file)
     if info is not None:
         return info['samples'], info['sample_rate']
     waveform = audio(file)

@@ -191,6 +191,31 @@ def test_non_native_files_take_the_python_path(ppgs_b200, tmp_path):
         assert (torch.load(out) - row).abs().max() <= 1e-4
 
 
+def test_flac_files_through_the_file_api(ppgs_b200, tmp_path):
+    """FLAC corpora (f2): a 16 kHz mono and a 22.05 kHz stereo FLAC file through
+    from_files_to_files (native verifying decoder -> GPU resampler -> engine) against the
+    oracle on the same samples; channel 0 is what ppgs/data/collate.py:27 keeps."""
+    import torchaudio
+    import flac_writer
+    sd = O.random_state_dict(6, peaky=True)
+    checkpoint = tmp_path / 'ckpt.pt'
+    torch.save({'model': sd}, checkpoint)
+    a = (O.synthetic_audio(1, 22050, 3)[0, 0] * 32768).round().clamp(-32768, 32767)
+    b = (O.synthetic_audio(1, 16000, 4)[0, 0] * 32768).round().clamp(-32768, 32767)
+    fa, fb = tmp_path / 'a.flac', tmp_path / 'b.flac'
+    stereo = np.stack([a.numpy(), -a.numpy().clip(-32767, 32767)]).astype(np.int64)
+    fa.write_bytes(flac_writer.encode(stereo, 22050, 16, blocks=4096, stereo='mid_side',
+                                      specs=[dict(kind='lpc', order=8, partition_order=3)]))
+    fb.write_bytes(flac_writer.encode(b.numpy()[None].astype(np.int64), 16000, 16, blocks=1152,
+                                      specs=[dict(kind='fixed', order=2, partition_order=2)]))
+    outs = [str(tmp_path / 'a.pt'), str(tmp_path / 'b.pt')]
+    ppgs_b200.from_files_to_files([str(fa), str(fb)], outs, checkpoint=checkpoint, num_workers=2, gpu=0)
+    resampled = torchaudio.transforms.Resample(22050, 16000)(a[None] / 32768)
+    expected = O.from_audio(sd, torch.stack([resampled, b[None] / 32768]))
+    for out, row in zip(outs, expected):
+        assert (torch.load(out) - row).abs().max() <= 1e-4
+
+
 def test_files_sharded_over_a_gpu_list(ppgs_b200, tmp_path):
     """`gpu=[...]`: one pipeline thread per listed device over batches i::n of the same batch
     list (here the same device twice = two engines sharing a blob copy): results equal the
