@@ -144,6 +144,7 @@ struct ppgs_engine {
     // softmax numerators P enter their MMAs as one fp16 plane (S in one pass, P.V in two; measured
     // +1e-5 on the posteriorgram, profiles/r02_attn_planes.jsonl); 2 = hi + lo like every other operand
     int attn_qk_planes = 1;      // PPGS_B200_ATTN_QK_PLANES
+    int qk_gemm_passes = 3;      // PPGS_B200_QK_GEMM_PASSES: MMA passes of the Q / K columns of the QKV GEMM when they are kept as one plane
     int attn_p_planes = 1;       // PPGS_B200_ATTN_P_PLANES
     int attn_dual = 1;           // head_dim 128: two query tiles per CTA (attention_dual_tc.cu; PPGS_B200_ATTN_DUAL)
     int gemm_pair = 1;           // 1 = CTA-pair (cta_group::2) GEMMs at BN = 256

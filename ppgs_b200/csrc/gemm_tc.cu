@@ -224,6 +224,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t d_tmem = tmem_base + acc * Shape::kAccCols;
                 const uint32_t d_corr = p.split_acc ? tmem_base + Shape::kAccCols : d_tmem;
                 uint32_t accumulate = 0, accumulate_corr = p.split_acc ? 0u : 1u;
+                // N blocks whose outputs are kept as one fp16 plane may run fewer passes
+                const int n_blk_mma = tile - (tile / p.n_tiles) * p.n_tiles;
+                const int passes = (n_blk_mma + 1) * BN <= p.hi_only_cols && !p.split_acc ? p.hi_only_passes : 3;
+                const bool pass_b_lo = p.b_planes == 2 && passes >= 3;
+                const bool pass_a_lo = p.a_planes == 2 && passes >= 2;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const long long t1 = clock64();
                     const bool landed = mbar_wait(&full_bar[stage], phase);
@@ -245,19 +250,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint64_t db0 = smem_desc_kmajor_sw128(b0 + koff);
                         if (PAIR) {
                             umma_f16_pair(d_tmem, da0, db0, idesc, accumulate);
-                            if (p.b_planes == 2) {
+                            if (pass_b_lo) {
                                 umma_f16_pair(d_corr, da0, smem_desc_kmajor_sw128(b1 + koff), idesc, accumulate_corr);
                                 accumulate_corr = 1;
                             }
-                            if (p.a_planes == 2) {
+                            if (pass_a_lo) {
                                 umma_f16_pair(d_corr, smem_desc_kmajor_sw128(a1 + koff), db0, idesc, accumulate_corr);
                                 accumulate_corr = 1;
                             }
                         } else {
                             umma_f16(d_tmem, da0, db0, idesc, accumulate);
-                            if (p.b_planes == 2)
+                            if (pass_b_lo)
                                 umma_f16(d_tmem, da0, smem_desc_kmajor_sw128(b1 + koff), idesc, 1);
-                            if (p.a_planes == 2)
+                            if (pass_a_lo)
                                 umma_f16(d_tmem, smem_desc_kmajor_sw128(a1 + koff), db0, idesc, 1);
                         }
                         accumulate = 1;

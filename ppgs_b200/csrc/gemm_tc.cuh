@@ -54,6 +54,7 @@ struct GemmParams {
     // error of an accumulator grows with its number of MMA steps; the large sum then sees one
     // third of them.  Used where K is long and the tolerance is a flip of an fp16 feature.
     int split_acc = 0;
+    int hi_only_passes = 3;      // MMA passes for the N blocks that lie below hi_only_cols: 3 (hi.hi + both corrections), 2 (hi.hi + a_lo.b_hi) or 1
     int hi_only_cols = 0;        // kEpiPlanes: output columns [0, hi_only_cols) keep only their hi plane (multiple of 64)
     float* ppg = nullptr;   // kEpiConvOut
     int T = 0, O = 0, softmax = 1;

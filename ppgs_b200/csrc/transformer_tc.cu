@@ -254,7 +254,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             if (planes == 2 && e->attn_qk_planes == 1 && e->attention_impl == 1 &&
                 (H / c.num_heads == 128 ? e->attn_dual != 0 || plan.max_pitch <= 512 : plan.max_pitch <= 512) &&
                 plan.max_pitch % 128 == 0)
-                p.hi_only_cols = 2 * H;
+                p.hi_only_cols = 2 * H, p.hi_only_passes = e->qk_gemm_passes;
             PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, wmap(T.in_w), &out_qkv,
                                       p, stream));
         }
