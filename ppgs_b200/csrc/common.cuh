@@ -71,9 +71,12 @@ struct MelTables {
     float* window = nullptr;      // [1024] periodic hann
     float2* tw512 = nullptr;      // [512] exp(-2 pi i m / 512)
     float2* tw1024 = nullptr;     // [513] exp(-2 pi i k / 1024)
-    int32_t* band_meta = nullptr; // [80][3] first bin, count, weight offset
-    float* band_weights = nullptr;
-    int band_weight_count = 0;
+    // filterbank cut into pieces of kFbPiece bins (mel_math.cuh: FilterbankLayout)
+    float* fb_w = nullptr;          // [rounds][kFbPiece][32]
+    int32_t* fb_base = nullptr;     // [rounds][32]
+    int32_t* band_slot = nullptr;   // [80]
+    int32_t* band_pieces = nullptr; // [80]
+    int fb_rounds = 0;
 };
 
 // Split-fp16 operand planes: plane 0 = hi, plane 1 = lo (rows stacked).

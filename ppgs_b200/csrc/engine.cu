@@ -448,8 +448,10 @@ void ppgs_engine_destroy(ppgs_engine* e) {
     cudaFree(e->mel.window);
     cudaFree(e->mel.tw512);
     cudaFree(e->mel.tw1024);
-    cudaFree(e->mel.band_meta);
-    cudaFree(e->mel.band_weights);
+    cudaFree(e->mel.fb_w);
+    cudaFree(e->mel.fb_base);
+    cudaFree(e->mel.band_slot);
+    cudaFree(e->mel.band_pieces);
     drain_stats(e);
     for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
     delete e;

@@ -23,7 +23,6 @@ constexpr int kTileFrames = 32;
 constexpr int kMelWarps = 8;
 constexpr int kMelThreads = kMelWarps * 32;
 constexpr int kTileSamples = (kTileFrames - 1) * kHop + kNfft;   // 5984
-constexpr int kMaxBandWeights = 2048;
 
 struct MelSmem {
     alignas(16) float audio[kTileSamples];
@@ -32,8 +31,9 @@ struct MelSmem {
     alignas(16) cf tw_pass2[7 * 64];    // [r - 1][k]      = tw512[k r]
     alignas(16) cf tw1024[kBins + 3];
     alignas(16) cf zb[kMelWarps][kZPad];
-    alignas(16) float band_weights[kMaxBandWeights];
-    int32_t band_meta[kMels * 3];
+    alignas(16) float fb_w[kFbMaxRounds * kFbPiece * 32];
+    int32_t fb_base[kFbMaxRounds * 32];
+    int32_t band_slot[kMels], band_pieces[kMels];
     // rows padded to 34 halves (68 B): the per-frame column store out[m][f] of lanes m = 0..31
     // then hits 32 different banks (17 m mod 32) instead of two
     alignas(16) __half out[kMels][kTileFrames + 2];
@@ -77,7 +77,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
 // One frame by one warp.  `a` points at the frame's first (padded-signal) sample
 // in the shared audio tile.
 __device__ __forceinline__ void frame_to_mel(const float* a, MelSmem& s, cf* zb, int lane,
-                                             int frame_in_tile) {
+                                             int frame_in_tile, int fb_rounds) {
     cf v0[8], v1[8];
     // ---- pass 0: window + pack (z[n] = x[2n] + i x[2n+1]) + radix-8, Ns = 1
     {
@@ -139,32 +139,45 @@ __device__ __forceinline__ void frame_to_mel(const float* a, MelSmem& s, cf* zb,
         zb[zpad(lane + 32 + 64 * r)] = v1[r];
     }
     __syncwarp();
-    // ---- unpack to 513 one-sided bins, magnitude, fp16 round
-    float mag[17];
+    // ---- unpack to 513 one-sided bins, magnitude, fp16 round: bins k and 512 - k share one
+    // pair of FFT outputs (lane 0 also takes the three self-paired bins 0, 256 and 512)
+    float mlo[8], mhi[8], mid = 0.f;
 #pragma unroll
-    for (int i = 0; i < 17; ++i) {
-        int k = lane + 32 * i;
-        float m = 0.f;
-        if (k < kBins) m = __half2float(__float2half_rn(sqrtf(bin_power(zb, k, s.tw1024))));
-        mag[i] = m;
+    for (int i = 0; i < 8; ++i) {
+        const int k = lane + 32 * i;
+        float plo, phi;
+        if (k == 0) {
+            plo = bin_power(zb, 0, s.tw1024);
+            phi = bin_power(zb, kHalf, s.tw1024);
+            mid = __half2float(__float2half_rn(sqrtf(bin_power(zb, kHalf / 2, s.tw1024))));
+        } else {
+            bin_power_pair(zb, k, s.tw1024, plo, phi);
+        }
+        mlo[i] = __half2float(__float2half_rn(sqrtf(plo)));
+        mhi[i] = __half2float(__float2half_rn(sqrtf(phi)));
     }
     __syncwarp();
     float* spec = reinterpret_cast<float*>(zb);   // reuse the FFT buffer: [513] floats
 #pragma unroll
-    for (int i = 0; i < 17; ++i) {
-        int k = lane + 32 * i;
-        if (k < kBins) spec[k] = mag[i];
+    for (int i = 0; i < 8; ++i) {
+        const int k = lane + 32 * i;
+        spec[k] = mlo[i];
+        spec[kHalf - k] = mhi[i];
     }
+    if (lane == 0) spec[kHalf / 2] = mid;
     __syncwarp();
-    // ---- sparse triangular filterbank, ascending-k fmaf chain per band
+    // ---- triangular filterbank: one piece of kFbPiece bins per lane and round, then the
+    // bands add their pieces' partial sums (mel_math.cuh)
+    float* partial = spec + kFbPartialOffset;
+    for (int r = 0; r < fb_rounds; ++r)
+        partial[r * 32 + lane] =
+            filterbank_piece(s.fb_w + r * kFbPiece * 32, s.fb_base + r * 32, lane, spec);
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         int m = lane + 32 * i;
         if (m < kMels) {
-            int first = s.band_meta[3 * m], count = s.band_meta[3 * m + 1];
-            const float* w = s.band_weights + s.band_meta[3 * m + 2];
-            float acc = 0.f;
-            for (int j = 0; j < count; ++j) acc = fmaf(w[j], spec[first + j], acc);
+            const float acc = filterbank_band(partial, s.band_slot[m], s.band_pieces[m]);
             s.out[m][frame_in_tile] = __float2half_rn(logf(fmaxf(acc, 1e-5f)));
         }
     }
@@ -188,9 +201,12 @@ mel_kernel(const float* __restrict__ audio, int64_t samples, int64_t stride, int
         s.tw_pass2[i] = {t.tw512[k * r].x, t.tw512[k * r].y};
     }
     for (int i = tid; i < kBins; i += kMelThreads) s.tw1024[i] = {t.tw1024[i].x, t.tw1024[i].y};
-    for (int i = tid; i < kMels * 3; i += kMelThreads) s.band_meta[i] = t.band_meta[i];
-    for (int i = tid; i < t.band_weight_count; i += kMelThreads)
-        s.band_weights[i] = t.band_weights[i];
+    for (int i = tid; i < t.fb_rounds * kFbPiece * 32; i += kMelThreads) s.fb_w[i] = t.fb_w[i];
+    for (int i = tid; i < t.fb_rounds * 32; i += kMelThreads) s.fb_base[i] = t.fb_base[i];
+    for (int i = tid; i < kMels; i += kMelThreads) {
+        s.band_slot[i] = t.band_slot[i];
+        s.band_pieces[i] = t.band_pieces[i];
+    }
     if (tid == 0) {
         mbar_init(&s.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -228,7 +244,7 @@ mel_kernel(const float* __restrict__ audio, int64_t samples, int64_t stride, int
         }
 
         for (int f = warp; f < nf; f += kMelWarps)
-            frame_to_mel(s.audio + f * kHop, s, s.zb[warp], lane, f);
+            frame_to_mel(s.audio + f * kHop, s, s.zb[warp], lane, f, t.fb_rounds);
         __syncthreads();
 
         // (80, nf) tile -> mel[b][m][f0 + f], contiguous along f
@@ -309,24 +325,10 @@ int build_mel_tables(ppgs_engine* e, const float* basis_host) {
         double a = -2.0 * M_PI * k / kNfft;
         tw1024[k] = make_float2((float)cos(a), (float)sin(a));
     }
-    std::vector<int32_t> meta(kMels * 3);
-    std::vector<float> weights;
-    for (int m = 0; m < kMels; ++m) {
-        int first = -1, last = -1;
-        for (int k = 0; k < kBins; ++k)
-            if (basis[(size_t)m * kBins + k] != 0.f) {
-                if (first < 0) first = k;
-                last = k;
-            }
-        int count = first < 0 ? 0 : last - first + 1;
-        meta[3 * m] = first < 0 ? 0 : first;
-        meta[3 * m + 1] = count;
-        meta[3 * m + 2] = (int32_t)weights.size();
-        for (int j = 0; j < count; ++j) weights.push_back(basis[(size_t)m * kBins + first + j]);
-    }
-    if ((int)weights.size() > kMaxBandWeights) {
-        set_error("mel basis has %zu non-zeros, more than the kernel's %d", weights.size(),
-                  kMaxBandWeights);
+    std::vector<FilterbankLayout> layout(1);
+    if (!build_filterbank_layout(basis.data(), layout.data())) {
+        set_error("mel basis needs more than %d pieces of %d bins, more than the kernel holds",
+                  kFbMaxRounds * 32, kFbPiece);
         return PPGS_E_INVALID;
     }
     MelTables& t = e->mel;
@@ -339,9 +341,12 @@ int build_mel_tables(ppgs_engine* e, const float* basis_host) {
     PPGS_CHECK(upload((void**)&t.window, window.data(), window.size() * 4));
     PPGS_CHECK(upload((void**)&t.tw512, tw512.data(), tw512.size() * 8));
     PPGS_CHECK(upload((void**)&t.tw1024, tw1024.data(), tw1024.size() * 8));
-    PPGS_CHECK(upload((void**)&t.band_meta, meta.data(), meta.size() * 4));
-    PPGS_CHECK(upload((void**)&t.band_weights, weights.data(), weights.size() * 4));
-    t.band_weight_count = (int)weights.size();
+    const FilterbankLayout& fb = layout[0];
+    PPGS_CHECK(upload((void**)&t.fb_w, fb.w, sizeof(fb.w)));
+    PPGS_CHECK(upload((void**)&t.fb_base, fb.base, sizeof(fb.base)));
+    PPGS_CHECK(upload((void**)&t.band_slot, fb.band_slot, sizeof(fb.band_slot)));
+    PPGS_CHECK(upload((void**)&t.band_pieces, fb.band_pieces, sizeof(fb.band_pieces)));
+    t.fb_rounds = fb.rounds;
     return PPGS_OK;
 }
 

@@ -124,4 +124,84 @@ PPGS_HD float bin_power(const cf* zb, int k, const cf* tw1024) {
     return p + 1e-6f;
 }
 
+// Bins k and 512 - k (1 <= k <= 255) from the one pair (Z[k], Z[512 - k]) they share: with
+// t = W^k O, bin k is E + t and bin 512 - k is conj(E - t) (tw1024[512 - k] == -conj(tw1024[k])
+// bit for bit for these k), so both powers equal bin_power()'s to the last bit at half the loads.
+PPGS_HD void bin_power_pair(const cf* zb, int k, const cf* tw1024, float& p_lo, float& p_hi) {
+    cf zk = zb[zpad(k)];
+    cf zn = zb[zpad(kHalf - k)];
+    cf e = {0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y)};
+    cf o = {0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x)};
+    cf t = cmul(tw1024[k], o);
+    cf x = cadd(e, t), y = csub(e, t);
+    float a = x.x * x.x + x.y * x.y;
+    float b = y.x * y.x + y.y * y.y;
+    p_lo = a + 1e-6f;
+    p_hi = b + 1e-6f;
+}
+
+// ---- triangular filterbank as balanced pieces ------------------------------------------------
+// Band m is a run of `count` consecutive bins; one lane per band leaves most of the warp idle
+// (5 bins at the bottom, 60 at the top).  The runs are cut into pieces of kFbPiece bins, piece s
+// goes to (round s / 32, lane s % 32), every lane reduces one piece per round with an ascending-k
+// fmaf chain, and band m then adds its pieces' partial sums in order.  kFbPiece is odd so that
+// the lanes of a round, whose pieces start kFbPiece bins apart inside a wide band, read 32
+// different shared-memory banks.
+constexpr int kFbPiece = 7;
+constexpr int kFbMaxRounds = 9;
+constexpr int kFbPartialOffset = 520;     // floats: partial sums sit behind the 513 + 6 spectrum slots
+
+struct FilterbankLayout {
+    int rounds;
+    float w[kFbMaxRounds * kFbPiece * 32];     // [round][j][lane], zero beyond a piece's bins
+    int32_t base[kFbMaxRounds * 32];           // [round][lane] first bin of the piece
+    int32_t band_slot[kMels];                  // first piece of band m
+    int32_t band_pieces[kMels];
+};
+
+// basis: [kMels][kBins] row-major.  False when the basis needs more pieces than the kernel holds.
+inline bool build_filterbank_layout(const float* basis, FilterbankLayout* layout) {
+    for (int i = 0; i < kFbMaxRounds * kFbPiece * 32; ++i) layout->w[i] = 0.f;
+    for (int i = 0; i < kFbMaxRounds * 32; ++i) layout->base[i] = 0;
+    int slot = 0;
+    for (int m = 0; m < kMels; ++m) {
+        int first = -1, last = -1;
+        for (int k = 0; k < kBins; ++k)
+            if (basis[m * kBins + k] != 0.f) {
+                if (first < 0) first = k;
+                last = k;
+            }
+        const int count = first < 0 ? 0 : last - first + 1;
+        const int pieces = (count + kFbPiece - 1) / kFbPiece;
+        layout->band_slot[m] = slot;
+        layout->band_pieces[m] = pieces;
+        if (slot + pieces > kFbMaxRounds * 32) return false;
+        for (int p = 0; p < pieces; ++p, ++slot) {
+            const int round = slot / 32, lane = slot % 32, k0 = first + p * kFbPiece;
+            layout->base[round * 32 + lane] = k0;
+            for (int j = 0; j < kFbPiece && k0 + j <= last; ++j)
+                layout->w[(round * kFbPiece + j) * 32 + lane] = basis[m * kBins + k0 + j];
+        }
+    }
+    layout->rounds = (slot + 31) / 32;
+    return true;
+}
+
+// One lane's piece of one round; spec[] holds the 513 magnitudes (+ 6 finite slots behind them).
+PPGS_HD float filterbank_piece(const float* w_round, const int32_t* base_round, int lane, const float* spec) {
+    const int k0 = base_round[lane];
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < kFbPiece; ++j) acc = fmaf(w_round[j * 32 + lane], spec[k0 + j], acc);
+    return acc;
+}
+
+// Band m from the partial sums of its pieces, in piece order.
+PPGS_HD float filterbank_band(const float* partial, int slot, int pieces) {
+    float acc = 0.f;
+    if (pieces > 0) acc = partial[slot];
+    for (int p = 1; p < pieces; ++p) acc = acc + partial[slot + p];
+    return acc;
+}
+
 }  // namespace ppgs

@@ -50,15 +50,25 @@ static float half_to_float(uint16_t h) {
     return f;
 }
 
+// Pieces the filterbank is cut into for `basis` ([80][513]); -1 when it does not fit the kernel.
+extern "C" int mel_filterbank_rounds(const float* basis) {
+    std::vector<FilterbankLayout> layout(1);
+    return build_filterbank_layout(basis, layout.data()) ? layout[0].rounds : -1;
+}
+
 extern "C" int mel_emul(const float* audio, int batch, long samples, const float* window,
-                        const float* tw512f, const float* tw1024f, const int32_t* band_meta,
-                        const float* band_weights, uint16_t* mel_out) {
+                        const float* tw512f, const float* tw1024f, const float* basis,
+                        uint16_t* mel_out) {
+    std::vector<FilterbankLayout> layout(1);
+    if (!build_filterbank_layout(basis, layout.data())) return -1;
+    const FilterbankLayout& fb = layout[0];
+    std::vector<float> partial(kFbMaxRounds * 32);
     const long frames = samples / kHop;
     const cf* tw512 = reinterpret_cast<const cf*>(tw512f);
     const cf* tw1024 = reinterpret_cast<const cf*>(tw1024f);
     std::vector<float> frame(kNfft);
     std::vector<cf> zb(kZPad), tmp(kHalf);
-    std::vector<float> spec(kBins);
+    std::vector<float> spec(kFbPartialOffset, 0.f);   // the kernel's slots 513..519 hold finite leftovers: weight 0
     for (int b = 0; b < batch; ++b) {
         const float* row = audio + (long)b * samples;
         for (long f = 0; f < frames; ++f) {
@@ -99,11 +109,12 @@ extern "C" int mel_emul(const float* audio, int batch, long samples, const float
             for (int i = 0; i < kHalf; ++i) zb[zpad(i)] = tmp[i];
             for (int k = 0; k < kBins; ++k)
                 spec[k] = half_to_float(float_to_half_rn(sqrtf(bin_power(zb.data(), k, tw1024))));
+            for (int r = 0; r < fb.rounds; ++r)
+                for (int lane = 0; lane < 32; ++lane)
+                    partial[r * 32 + lane] = filterbank_piece(fb.w + r * kFbPiece * 32, fb.base + r * 32,
+                                                              lane, spec.data());
             for (int m = 0; m < kMels; ++m) {
-                int first = band_meta[3 * m], count = band_meta[3 * m + 1];
-                const float* w = band_weights + band_meta[3 * m + 2];
-                float acc = 0.f;
-                for (int j = 0; j < count; ++j) acc = fmaf(w[j], spec[first + j], acc);
+                const float acc = filterbank_band(partial.data(), fb.band_slot[m], fb.band_pieces[m]);
                 mel_out[((long)b * kMels + m) * frames + f] =
                     float_to_half_rn(logf(fmaxf(acc, 1e-5f)));
             }

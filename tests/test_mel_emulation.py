@@ -22,12 +22,7 @@ def kernel_tables():
     tw512 = np.stack([np.cos(a), np.sin(a)], 1).astype(np.float32)
     a = -2 * np.pi * np.arange(513) / 1024
     tw1024 = np.stack([np.cos(a), np.sin(a)], 1).astype(np.float32)
-    meta, weights = np.zeros((80, 3), np.int32), []
-    for band in range(80):
-        nz = np.nonzero(basis[band])[0]
-        meta[band] = (nz[0], nz[-1] - nz[0] + 1, len(weights))
-        weights.extend(basis[band, nz[0]:nz[-1] + 1])
-    return window, tw512, tw1024, meta, np.asarray(weights, np.float32)
+    return window, tw512, tw1024, np.ascontiguousarray(basis, dtype=np.float32)
 
 
 def emulate(lib, audio):
@@ -54,6 +49,10 @@ def test_kernel_arithmetic_vs_reference_mel(mel_emul_lib, name):
     assert (dist > 0).mean() <= 1e-3
 
 
-def test_slaney_weights_fit_kernel_table():
-    *_, weights = kernel_tables()
-    assert len(weights) <= 2048   # kMaxBandWeights in mel.cu
+def test_slaney_filterbank_fits_kernel_table(mel_emul_lib):
+    """The Slaney basis cut into pieces of 7 bins: 6 rounds of 32 pieces (kFbMaxRounds = 9 in
+    mel_math.cuh); a dense basis is refused."""
+    *_, basis = kernel_tables()
+    ptr = lambda x: x.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    assert 0 < mel_emul_lib.mel_filterbank_rounds(ptr(basis)) <= 9
+    assert mel_emul_lib.mel_filterbank_rounds(ptr(np.ones((80, 513), np.float32))) == -1
