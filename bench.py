@@ -655,7 +655,7 @@ def main():
     whole = FLOPS_PER_UTT * BATCH / (device_ms / steps * 1e-3) / 1e12
     roofline['whole_step'] = {'achieved_tflops': whole, 'frac': whole / peaks['tflops_sustained'],
                               'algorithmic_flops_per_step': FLOPS_PER_UTT * BATCH}
-    mel_stat = stats.get('mel_stft_fbank')
+    mel_stat = stats.get('mel_stft_fbank_rows') or stats.get('mel_stft_fbank')
     if mel_stat:
         mel_ms = mel_stat[0] / max(mel_stat[1], 1)
         gbs = BATCH * FRAMES * 800 / (mel_ms * 1e-3) / 1e9

@@ -147,6 +147,7 @@ struct ppgs_engine {
     // softmax numerators P enter their MMAs as one fp16 plane (S in one pass, P.V in two; measured
     // +1e-5 on the posteriorgram, profiles/r02_attn_planes.jsonl); 2 = hi + lo like every other operand
     int attn_qk_planes = 1;      // PPGS_B200_ATTN_QK_PLANES
+    int mel_rows = 1;            // PPGS_B200_MEL_ROWS: from_audio's mel kernel writes the input convolution's operand rows itself (no fold pass)
     int qk_gemm_passes = 3;      // PPGS_B200_QK_GEMM_PASSES: MMA passes of the Q / K columns of the QKV GEMM when they are kept as one plane
     int attn_p_planes = 1;       // PPGS_B200_ATTN_P_PLANES
     int attn_dual = 1;           // head_dim 128: two query tiles per CTA (attention_dual_tc.cu; PPGS_B200_ATTN_DUAL)
@@ -282,6 +283,11 @@ bool tensor_core_shape(const ppgs_model_config& c);   // model shapes the tcgen0
 int build_weight_maps(ppgs_engine* e);
 int transformer_forward_tc(ppgs_engine* e, const __half* features, const ForwardPlan& plan,
                            int softmax, float* out, cudaStream_t stream);
+int launch_mel_rows(ppgs_engine* e, const float* audio, int batch, int64_t samples, int64_t stride,
+                    const ForwardPlan& plan, int legacy_mode, __half* x0, const SeqInfo* seqs_dev,
+                    cudaStream_t stream);   // mel.cu
+int transformer_tc_input_rows(ppgs_engine* e, const ForwardPlan& plan, cudaStream_t stream, __half** x0,
+                              const SeqInfo** seqs_dev);
 int check_status(ppgs_engine* e, cudaStream_t stream);
 
 }  // namespace ppgs

@@ -410,6 +410,7 @@ int ppgs_engine_create(const ppgs_model_config* cfg, int device, ppgs_engine** o
     if (const char* v = getenv("PPGS_B200_ATTENTION")) e->attention_impl = atoi(v) != 0;
     if (const char* v = getenv("PPGS_B200_FUSED_FFN")) e->fused_ffn = atoi(v);   // 0 off, 1 auto, 2 always
     if (const char* v = getenv("PPGS_B200_ATTN_QK_PLANES")) e->attn_qk_planes = atoi(v) == 1 ? 1 : 2;
+    if (const char* v = getenv("PPGS_B200_MEL_ROWS")) e->mel_rows = atoi(v) != 0;
     if (const char* v = getenv("PPGS_B200_QK_GEMM_PASSES")) e->qk_gemm_passes = std::min(3, std::max(1, atoi(v)));
     if (const char* v = getenv("PPGS_B200_ATTN_P_PLANES")) e->attn_p_planes = atoi(v) == 1 ? 1 : 2;
     if (const char* v = getenv("PPGS_B200_ATTN_DUAL")) e->attn_dual = atoi(v) != 0;
@@ -739,6 +740,14 @@ static int from_audio_device_launch(ppgs_engine* e, const float* audio, int batc
         for (int b = 0; b < batch; ++b) frame_lengths[b] = lengths[b] / kHopSamples;
     ForwardPlan plan;
     PPGS_CHECK(build_plan(e, batch, frames, frame_lengths.data(), legacy_mode, &plan));
+    if (e->mel_rows && e->precision != PPGS_PRECISION_FP32 && e->cfg.input_channels == 80 &&
+        tensor_core_shape(e->cfg)) {
+        __half* x0 = nullptr;
+        const SeqInfo* seqs_dev = nullptr;
+        PPGS_CHECK(transformer_tc_input_rows(e, plan, stream, &x0, &seqs_dev));
+        PPGS_CHECK(launch_mel_rows(e, audio, batch, samples, stride, plan, legacy_mode, x0, seqs_dev, stream));
+        return transformer_forward_tc(e, nullptr, plan, softmax, out, stream);
+    }
     PPGS_CHECK(launch_mel(e, audio, batch, samples, stride, mel, stream));
     return run_transformer(e, mel, plan, softmax, out, stream);
 }

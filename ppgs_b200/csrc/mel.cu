@@ -23,6 +23,7 @@ constexpr int kTileFrames = 32;
 constexpr int kMelWarps = 8;
 constexpr int kMelThreads = kMelWarps * 32;
 constexpr int kTileSamples = (kTileFrames - 1) * kHop + kNfft;   // 5984
+constexpr int kRowPitch = 88;      // halves per frame row of the transposed output tile
 
 struct MelSmem {
     alignas(16) float audio[kTileSamples];
@@ -34,9 +35,13 @@ struct MelSmem {
     alignas(16) float fb_w[kFbMaxRounds * kFbPiece * 32];
     int32_t fb_base[kFbMaxRounds * 32];
     int32_t band_slot[kMels], band_pieces[kMels];
-    // rows padded to 34 halves (68 B): the per-frame column store out[m][f] of lanes m = 0..31
-    // then hits 32 different banks (17 m mod 32) instead of two
-    alignas(16) __half out[kMels][kTileFrames + 2];
+    // (B, 80, T) output: rows padded to 34 halves (68 B) so that the per-frame column store
+    // out[m][f] of lanes m = 0..31 hits 32 different banks (17 m mod 32) instead of two.
+    // Operand-row output: out_t[f][m], rows of 88 halves (176 B, 16-byte segments for the stores).
+    union {
+        alignas(16) __half out[kMels][kTileFrames + 2];
+        alignas(16) __half out_t[kTileFrames][kRowPitch];
+    };
     alignas(8) unsigned long long mbar;
 };
 
@@ -76,6 +81,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
 
 // One frame by one warp.  `a` points at the frame's first (padded-signal) sample
 // in the shared audio tile.
+template <bool ROWS>
 __device__ __forceinline__ void frame_to_mel(const float* a, MelSmem& s, cf* zb, int lane,
                                              int frame_in_tile, int fb_rounds) {
     cf v0[8], v1[8];
@@ -178,15 +184,29 @@ __device__ __forceinline__ void frame_to_mel(const float* a, MelSmem& s, cf* zb,
         int m = lane + 32 * i;
         if (m < kMels) {
             const float acc = filterbank_band(partial, s.band_slot[m], s.band_pieces[m]);
-            s.out[m][frame_in_tile] = __float2half_rn(logf(fmaxf(acc, 1e-5f)));
+            const __half v = __float2half_rn(logf(fmaxf(acc, 1e-5f)));
+            if (ROWS) s.out_t[frame_in_tile][m] = v;
+            else s.out[m][frame_in_tile] = v;
         }
     }
 }
 
+// Destination of the operand-row output: the input convolution's A operand of the tensor-core
+// Transformer ([rows][80] fp16, time-major) with the chunk bookkeeping of transformer.py:49-64
+// folded in — frame g of utterance b lands in every chunk tensor that holds it (at most two:
+// chunks overlap by 2 x 50 frames), frame 0 also in the 50 replicate-padding rows of chunk 0.
+struct MelRows {
+    __half* x0 = nullptr;
+    const SeqInfo* seqs = nullptr;   // chunk-major: sequence of (chunk i, utterance b) = i * batch + b
+    int batch = 0;
+    int chunked = 0, blocks = 1, stride = 0, overlap = 0;
+};
+
+template <bool ROWS>
 __global__ void __launch_bounds__(kMelThreads, 2)
 mel_kernel(const float* __restrict__ audio, int64_t samples, int64_t stride, int frames,
            int tiles_per_row, int total_tiles, MelTables t, __half* __restrict__ mel,
-           int bulk_ok) {
+           MelRows rows, int bulk_ok) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MelSmem& s = *reinterpret_cast<MelSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -244,9 +264,39 @@ mel_kernel(const float* __restrict__ audio, int64_t samples, int64_t stride, int
         }
 
         for (int f = warp; f < nf; f += kMelWarps)
-            frame_to_mel(s.audio + f * kHop, s, s.zb[warp], lane, f, t.fb_rounds);
+            frame_to_mel<ROWS>(s.audio + f * kHop, s, s.zb[warp], lane, f, t.fb_rounds);
         __syncthreads();
 
+        if (ROWS) {
+            // (nf, 80) tile -> operand rows, ten 16-byte segments per frame and destination
+            for (int idx = tid; idx < 2 * nf * 10; idx += kMelThreads) {
+                const int d = idx / (nf * 10), rem = idx - d * nf * 10;
+                const int f = rem / 10, u = rem - f * 10, g = f0 + f;
+                int seq = b, local = g;
+                if (rows.chunked) {
+                    const int chunk = min((g + rows.overlap) / rows.stride, rows.blocks - 1) - d;
+                    if (chunk < 0) continue;
+                    seq = chunk * rows.batch + b;
+                    local = g + rows.overlap - chunk * rows.stride;
+                } else if (d) {
+                    break;
+                }
+                const int row0 = rows.seqs[seq].row0, len = rows.seqs[seq].tensor_len;
+                if (local < len)
+                    *reinterpret_cast<uint4*>(rows.x0 + (int64_t)(row0 + local) * kMels + 8 * u) =
+                        *reinterpret_cast<const uint4*>(&s.out_t[f][8 * u]);
+            }
+            if (rows.chunked && f0 == 0) {   // replicate padding in front of chunk 0 = frame 0
+                const int row0 = rows.seqs[b].row0;
+                for (int idx = tid; idx < rows.overlap * 10; idx += kMelThreads) {
+                    const int local = idx / 10, u = idx - local * 10;
+                    *reinterpret_cast<uint4*>(rows.x0 + (int64_t)(row0 + local) * kMels + 8 * u) =
+                        *reinterpret_cast<const uint4*>(&s.out_t[0][8 * u]);
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         // (80, nf) tile -> mel[b][m][f0 + f], contiguous along f
         __half* dst = mel + ((int64_t)b * kMels) * frames + f0;
         if (nf == kTileFrames && (frames & 1) == 0) {
@@ -350,8 +400,8 @@ int build_mel_tables(ppgs_engine* e, const float* basis_host) {
     return PPGS_OK;
 }
 
-int launch_mel(ppgs_engine* e, const float* audio, int batch, int64_t samples, int64_t stride,
-               __half* mel, cudaStream_t stream) {
+static int launch_mel_any(ppgs_engine* e, const float* audio, int batch, int64_t samples, int64_t stride,
+                          __half* mel, const MelRows* rows, cudaStream_t stream) {
     if (batch <= 0) return PPGS_OK;
     if (samples <= kReflect) {
         // torch reflection_pad1d: "padding size should be less than the input size"
@@ -369,7 +419,9 @@ int launch_mel(ppgs_engine* e, const float* audio, int batch, int64_t samples, i
     }
     static PerDeviceOnce attr_set;
     if (attr_set.first(e->device)) {
-        PPGS_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PPGS_CUDA(cudaFuncSetAttribute(mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(MelSmem)));
+        PPGS_CUDA(cudaFuncSetAttribute(mel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(MelSmem)));
     }
     // bulk copies need 16-byte aligned sources: base, row stride and tile offset
@@ -377,12 +429,44 @@ int launch_mel(ppgs_engine* e, const float* audio, int batch, int64_t samples, i
     const int bulk_ok = ((reinterpret_cast<uintptr_t>(audio) & 15) == 0) && (stride % 4 == 0);
     const int grid = (int)std::min<int64_t>(total, 2 * (int64_t)e->sm_count);
     {
-        LaunchScope scope(e, "mel_stft_fbank", stream);
-        mel_kernel<<<grid, kMelThreads, sizeof(MelSmem), stream>>>(
-            audio, samples, stride, frames, tiles_per_row, (int)total, e->mel, mel, bulk_ok);
+        LaunchScope scope(e, rows ? "mel_stft_fbank_rows" : "mel_stft_fbank", stream);
+        if (rows)
+            mel_kernel<true><<<grid, kMelThreads, sizeof(MelSmem), stream>>>(
+                audio, samples, stride, frames, tiles_per_row, (int)total, e->mel, nullptr, *rows, bulk_ok);
+        else
+            mel_kernel<false><<<grid, kMelThreads, sizeof(MelSmem), stream>>>(
+                audio, samples, stride, frames, tiles_per_row, (int)total, e->mel, mel, MelRows(), bulk_ok);
     }
     PPGS_CUDA(cudaGetLastError());
     return PPGS_OK;
+}
+
+int launch_mel(ppgs_engine* e, const float* audio, int batch, int64_t samples, int64_t stride,
+               __half* mel, cudaStream_t stream) {
+    return launch_mel_any(e, audio, batch, samples, stride, mel, nullptr, stream);
+}
+
+// The mel front-end writing the tensor-core Transformer's input rows directly (no (B, 80, T)
+// tensor, no fold pass): `x0` / `seqs_dev` from transformer_tc_input_rows for `plan`.
+int launch_mel_rows(ppgs_engine* e, const float* audio, int batch, int64_t samples, int64_t stride,
+                    const ForwardPlan& plan, int legacy_mode, __half* x0, const SeqInfo* seqs_dev,
+                    cudaStream_t stream) {
+    const ppgs_model_config& c = e->cfg;
+    if (c.input_channels != kMels || plan.frames != (int)(samples / kHop) || plan.batch != batch) {
+        set_error("mel rows: plan does not match the audio batch");
+        return PPGS_E_INVALID;
+    }
+    MelRows rows;
+    rows.x0 = x0;
+    rows.seqs = seqs_dev;
+    rows.batch = batch;
+    rows.overlap = c.chunk_overlap;
+    rows.stride = c.chunk_length - 2 * c.chunk_overlap;
+    rows.chunked = (!legacy_mode && plan.frames > c.chunk_length) ? 1 : 0;
+    rows.blocks = rows.chunked ? (plan.frames + rows.stride - 1) / rows.stride : 1;
+    // rows behind each chunk tensor (and the pad sequence) are zero operands of the convolution
+    PPGS_CUDA(cudaMemsetAsync(x0, 0, (size_t)plan.rows * kMels * sizeof(__half), stream));
+    return launch_mel_any(e, audio, batch, samples, stride, nullptr, &rows, stream);
 }
 
 }  // namespace ppgs

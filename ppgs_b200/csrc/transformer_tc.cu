@@ -154,6 +154,52 @@ __global__ void fold_half_kernel(const __half* __restrict__ feats, int C, int T,
     }
 }
 
+static bool split_out_proj_experiment() {
+    // experiment (PPGS_B200_SPLIT_OUT_PROJ_LN=1): the K = 256 out-projection is epilogue-bound
+    // with the fused LayerNorm; run it with the plain epilogue + the standalone LayerNorm pass
+    static const bool on = [] { const char* v = getenv("PPGS_B200_SPLIT_OUT_PROJ_LN"); return v && atoi(v) != 0; }();
+    return on;
+}
+
+// Workspace of one forward: offsets of the activation buffers and plan tables.
+struct TcWorkspace {
+    size_t o_x0, o_xh, o_qkv, o_att, o_ff, o_y, o_seqs, o_tiles, bytes;
+};
+static TcWorkspace tc_workspace(const ppgs_model_config& c, const ForwardPlan& plan) {
+    const size_t rows = (size_t)plan.rows, C = c.input_channels, H = c.hidden_channels, F = c.ffn_channels;
+    Carver w;
+    TcWorkspace t;
+    t.o_x0 = w.take(rows * C * 2);
+    t.o_xh = w.take(2 * rows * H * 2);
+    t.o_qkv = w.take(2 * rows * 3 * H * 2);
+    t.o_att = w.take(2 * rows * H * 2);
+    t.o_ff = w.take(2 * rows * F * 2);
+    t.o_y = w.take(H == 256 && !split_out_proj_experiment() ? 0 : 2 * rows * H * 2);
+    t.o_seqs = w.take(plan.seqs.size() * sizeof(SeqInfo));
+    t.o_tiles = w.take((rows / 128) * 4);
+    t.bytes = w.off;
+    return t;
+}
+
+// The input convolution's operand rows ([rows][C] fp16, time-major, zero beyond each chunk
+// tensor) and the device plan table, for a producer that writes them itself (the mel kernel)
+// and then calls transformer_forward_tc with features == nullptr.
+int transformer_tc_input_rows(ppgs_engine* e, const ForwardPlan& plan, cudaStream_t stream, __half** x0,
+                              const SeqInfo** seqs_dev) {
+    if (!tensor_core_shape(e->cfg)) {
+        set_error("tensor-core path does not cover this model shape");
+        return PPGS_E_UNSUPPORTED;
+    }
+    const TcWorkspace w = tc_workspace(e->cfg, plan);
+    PPGS_CHECK(ensure_workspace(e, w.bytes));
+    char* ws = static_cast<char*>(e->workspace);
+    PPGS_CHECK(upload_plan(e, plan, reinterpret_cast<SeqInfo*>(ws + w.o_seqs),
+                           reinterpret_cast<int*>(ws + w.o_tiles), stream));
+    *x0 = reinterpret_cast<__half*>(ws + w.o_x0);
+    *seqs_dev = reinterpret_cast<const SeqInfo*>(ws + w.o_seqs);
+    return PPGS_OK;
+}
+
 int transformer_forward_tc(ppgs_engine* e, const __half* features, const ForwardPlan& plan,
                            int softmax, float* out, cudaStream_t stream) {
     const ppgs_model_config& c = e->cfg;
@@ -168,31 +214,21 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     // hidden 256: one GEMM tile spans a full row and the residual + LayerNorm live in the
     // epilogue; wider models store the projection and normalise in a separate pass
     const bool fused_ln = H == 256;
-    // experiment (PPGS_B200_SPLIT_OUT_PROJ_LN=1): the K = 256 out-projection is epilogue-bound
-    // with the fused LayerNorm; run it with the plain epilogue + the standalone LayerNorm pass
-    static const bool split_out_proj = [] { const char* v = getenv("PPGS_B200_SPLIT_OUT_PROJ_LN"); return v && atoi(v) != 0; }();
+    const bool split_out_proj = split_out_proj_experiment();
     PPGS_CHECK(build_weight_maps(e));
     const int planes = e->precision == PPGS_PRECISION_F16X2 ? 2 : 1;
 
-    Carver w;
-    const size_t o_x0 = w.take((size_t)rows * C * 2);
-    const size_t o_xh = w.take((size_t)2 * rows * H * 2);
-    const size_t o_qkv = w.take((size_t)2 * rows * 3 * H * 2);
-    const size_t o_att = w.take((size_t)2 * rows * H * 2);
-    const size_t o_ff = w.take((size_t)2 * rows * F * 2);
-    const size_t o_y = w.take(fused_ln && !split_out_proj ? 0 : (size_t)2 * rows * H * 2);
-    const size_t o_seqs = w.take(plan.seqs.size() * sizeof(SeqInfo));
-    const size_t o_tiles = w.take((size_t)(rows / 128) * 4);
-    PPGS_CHECK(ensure_workspace(e, w.off));
+    const TcWorkspace w = tc_workspace(c, plan);
+    PPGS_CHECK(ensure_workspace(e, w.bytes));
     char* ws = static_cast<char*>(e->workspace);
-    __half* x0 = reinterpret_cast<__half*>(ws + o_x0);
-    __half* xh = reinterpret_cast<__half*>(ws + o_xh);
-    __half* qkv = reinterpret_cast<__half*>(ws + o_qkv);
-    __half* att = reinterpret_cast<__half*>(ws + o_att);
-    __half* ff = reinterpret_cast<__half*>(ws + o_ff);
-    __half* yh = reinterpret_cast<__half*>(ws + o_y);
-    SeqInfo* seqs_dev = reinterpret_cast<SeqInfo*>(ws + o_seqs);
-    int* tile_seq_dev = reinterpret_cast<int*>(ws + o_tiles);
+    __half* x0 = reinterpret_cast<__half*>(ws + w.o_x0);
+    __half* xh = reinterpret_cast<__half*>(ws + w.o_xh);
+    __half* qkv = reinterpret_cast<__half*>(ws + w.o_qkv);
+    __half* att = reinterpret_cast<__half*>(ws + w.o_att);
+    __half* ff = reinterpret_cast<__half*>(ws + w.o_ff);
+    __half* yh = reinterpret_cast<__half*>(ws + w.o_y);
+    SeqInfo* seqs_dev = reinterpret_cast<SeqInfo*>(ws + w.o_seqs);
+    int* tile_seq_dev = reinterpret_cast<int*>(ws + w.o_tiles);
     PPGS_CHECK(upload_plan(e, plan, seqs_dev, tile_seq_dev, stream));
 
     // activation tensor maps (A operands): {K, rows, planes}
@@ -211,7 +247,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     PPGS_CHECK(make_store_map(&out_qkv, qkv, 3 * H, rows, (uint64_t)rows * 3 * H));
     PPGS_CHECK(make_store_map(&out_ff, ff, F, rows, (uint64_t)rows * F));
 
-    {
+    if (features) {   // nullptr: the mel kernel already wrote x0 (transformer_tc_input_rows)
         dim3 grid(rows / 32, (C + 31) / 32);
         LaunchScope scope(e, "fold_chunks", stream);
         fold_half_kernel<<<grid, dim3(32, 8), 0, stream>>>(features, C, plan.frames, seqs_dev,

@@ -162,11 +162,13 @@ def test_single_pass_f16_mode_is_the_autocast_numerics_class(ppgs_b200):
 
 
 @pytest.mark.parametrize('switch', ['PPGS_B200_FUSED_FFN=0', 'PPGS_B200_FUSED_FFN=2', 'PPGS_B200_PAIR=0', 'PPGS_B200_ATTENTION=0',
-                                    'PPGS_B200_ATTN_DUAL=0', 'PPGS_B200_ATTN_QK_PLANES=2', 'PPGS_B200_PROJ_LN=0'])
+                                    'PPGS_B200_ATTN_DUAL=0', 'PPGS_B200_ATTN_QK_PLANES=2', 'PPGS_B200_PROJ_LN=0',
+                                    'PPGS_B200_MEL_ROWS=0'])
 def test_alternative_kernel_paths(ppgs_b200, monkeypatch, switch):
     """The optional kernels stay parity-checked: linear1 / linear2 as two GEMMs instead of the
     fused FFN kernel, the single-CTA (cta_group::1) GEMMs, the CUDA-core attention kernel, the
-    one-tile-per-CTA attention kernel and split-plane Q / K (read at engine creation)."""
+    one-tile-per-CTA attention kernel, split-plane Q / K and the (B, 80, T) mel tensor + fold pass
+    instead of the mel kernel writing the operand rows (read at engine creation)."""
     name, value = switch.split('=')
     monkeypatch.setenv(name, value)
     sd = O.random_state_dict(6, peaky=True)
@@ -179,6 +181,31 @@ def test_alternative_kernel_paths(ppgs_b200, monkeypatch, switch):
         for row, n in enumerate(lengths):
             assert np.abs(out[row, :, :n] - ref[row, :, :n]).max() <= PPG_TOL
     engine.check()
+
+
+@pytest.mark.parametrize('frames,lengths,legacy', [
+    (400, [400, 250, 31], False), (500, [500], False), (501, [501, 77], False), (1000, [1000, 640], False),
+    (1237, [1237, 1200, 801, 399, 5], False), (2003, [2003], False), (33, [33, 1], False),
+    (4000, [4000, 123], True)])
+def test_mel_operand_rows_equal_the_fold_pass(ppgs_b200, frames, lengths, legacy):
+    """from_audio's mel kernel writes the input convolution's operand rows itself (chunk
+    overlap, replicate padding of chunk 0, zero rows behind every chunk tensor); the result must
+    be BITWISE that of ppgs_mel_forward -> (B, 80, T) -> fold pass -> Transformer, for chunked,
+    unchunked, ragged, odd-sized and legacy (one long sequence) batches."""
+    sd = O.random_state_dict(3, peaky=True)
+    engine = make_engine(ppgs_b200, sd, 'f16x2')
+    audio = O.synthetic_audio(len(lengths), frames * 160 + 37, seed=frames).cuda()
+    sample_lengths = torch.tensor(lengths) * 160 + 37
+    direct = engine.from_audio(audio, lengths=sample_lengths, legacy_mode=legacy).clone()
+    engine.check()
+    feats = engine.mel(audio)
+    folded = engine.transformer(feats, torch.tensor(lengths), legacy_mode=legacy)
+    assert torch.equal(direct, folded)
+    engine.set_profiling(True)
+    engine.from_audio(audio, lengths=sample_lengths, legacy_mode=legacy)
+    names = set(engine.kernel_stats())
+    engine.set_profiling(False)
+    assert 'mel_stft_fbank_rows' in names and 'fold_chunks' not in names
 
 
 def test_broadcast_engine_follows_live_configuration(ppgs_b200):
