@@ -734,5 +734,16 @@ def main():
         dist.destroy_process_group()
 
 
+def stdout_is_the_json_line_only():
+    """The driver reads ONE JSON line from stdout: send everything else written to file descriptor 1
+    (NCCL's version banner, library chatter from C code) to stderr and keep the real stdout for
+    print()."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, 'w', buffering=1)
+
+
 if __name__ == '__main__':
+    stdout_is_the_json_line_only()
     main()
