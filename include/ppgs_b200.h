@@ -267,7 +267,8 @@ int ppgs_pt_read(const char* path, void* dst_host, int64_t rows, int64_t cols, i
 
 /* The batching loop of ppgs.from_files_to_files / from_dataloader (ppgs/core.py:207-391)
  * for the mel representation as ONE call: `reader_threads` threads decode 16-bit PCM
- * 16 kHz WAVE files straight into pinned zero-padded int16 batches, the calling thread
+ * 16 kHz WAVE files (and 16 kHz FLAC files of <= 16 bits, by extension `.flac`, verified
+ * like ppgs_flac_read_f32) straight into pinned zero-padded int16 batches, the calling thread
  * runs H2D -> pcm16_to_f32 -> mel + Transformer + softmax -> D2H on two device slots
  * (copies on private streams, kernels on `stream`), `writer_threads` threads crop every
  * row to samples/160 frames and write `<output>.pt`.  The threads live for the duration
@@ -275,7 +276,7 @@ int ppgs_pt_read(const char* path, void* dst_host, int64_t rows, int64_t cols, i
  *   batch_sizes  : files per batch, n_batches entries (batch composition is the
  *                  caller's: ppgs/data/sampler.py:46-82 semantics live in Python)
  *   audio_files / output_files / file_samples : flat, in batch order; file_samples are
- *                  the per-file sample counts from ppgs_wav_info
+ *                  the per-file sample counts from ppgs_wav_info / ppgs_flac_info
  *   frames_done  : out, posteriorgram frames written
  * PPGS_E_UNSUPPORTED when a file is not 16-bit PCM at 16 kHz (callers fall back to the
  * per-batch API with ppgs_wav_read_f32 + ppgs_resample). */

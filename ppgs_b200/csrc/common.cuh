@@ -283,6 +283,8 @@ bool tensor_core_shape(const ppgs_model_config& c);   // model shapes the tcgen0
 int build_weight_maps(ppgs_engine* e);
 int transformer_forward_tc(ppgs_engine* e, const __half* features, const ForwardPlan& plan,
                            int softmax, float* out, cudaStream_t stream);
+// flac.cu
+int flac_read_pcm16(const char* path, int16_t* dst, int64_t capacity, int64_t expect_frames);
 int launch_mel_rows(ppgs_engine* e, const float* audio, int batch, int64_t samples, int64_t stride,
                     const ForwardPlan& plan, int legacy_mode, __half* x0, const SeqInfo* seqs_dev,
                     cudaStream_t stream);   // mel.cu

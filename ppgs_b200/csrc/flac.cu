@@ -30,46 +30,85 @@ struct Md5 {
     static uint32_t rotl(uint32_t x, int s) { return (x << s) | (x >> (32 - s)); }
 
     void compress(const uint8_t* p) {
-        static const uint32_t K[64] = {
-            0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501,
-            0x698098d8, 0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821,
-            0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8,
-            0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a,
-            0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70,
-            0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665,
-            0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1,
-            0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
-        static const int S[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22,
-                                  5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20,
-                                  4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23,
-                                  6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
         uint32_t m[16];
-        for (int i = 0; i < 16; ++i)
-            m[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) |
-                   ((uint32_t)p[4 * i + 3] << 24);
+        memcpy(m, p, 64);                        // little-endian host (x86-64 / aarch64)
         uint32_t A = a, B = b, C = c, D = d;
-        for (int i = 0; i < 64; ++i) {
-            uint32_t f;
-            int g;
-            if (i < 16) {
-                f = (B & C) | (~B & D);
-                g = i;
-            } else if (i < 32) {
-                f = (D & B) | (~D & C);
-                g = (5 * i + 1) & 15;
-            } else if (i < 48) {
-                f = B ^ C ^ D;
-                g = (3 * i + 5) & 15;
-            } else {
-                f = C ^ (B | ~D);
-                g = (7 * i) & 15;
-            }
-            const uint32_t next = B + rotl(A + f + K[i] + m[g], S[i]);
-            A = D;
-            D = C;
-            C = B;
-            B = next;
-        }
+#define PPGS_MD5_STEP(f, w, x, y, z, g, k, s) \
+    w += f(x, y, z) + m[g] + k;               \
+    w = rotl(w, s) + x;
+#define PPGS_MD5_F(x, y, z) (z ^ (x & (y ^ z)))
+#define PPGS_MD5_G(x, y, z) (y ^ (z & (x ^ y)))
+#define PPGS_MD5_H(x, y, z) (x ^ y ^ z)
+#define PPGS_MD5_I(x, y, z) (y ^ (x | ~z))
+        PPGS_MD5_STEP(PPGS_MD5_F, A, B, C, D, 0, 0xd76aa478u, 7)
+        PPGS_MD5_STEP(PPGS_MD5_F, D, A, B, C, 1, 0xe8c7b756u, 12)
+        PPGS_MD5_STEP(PPGS_MD5_F, C, D, A, B, 2, 0x242070dbu, 17)
+        PPGS_MD5_STEP(PPGS_MD5_F, B, C, D, A, 3, 0xc1bdceeeu, 22)
+        PPGS_MD5_STEP(PPGS_MD5_F, A, B, C, D, 4, 0xf57c0fafu, 7)
+        PPGS_MD5_STEP(PPGS_MD5_F, D, A, B, C, 5, 0x4787c62au, 12)
+        PPGS_MD5_STEP(PPGS_MD5_F, C, D, A, B, 6, 0xa8304613u, 17)
+        PPGS_MD5_STEP(PPGS_MD5_F, B, C, D, A, 7, 0xfd469501u, 22)
+        PPGS_MD5_STEP(PPGS_MD5_F, A, B, C, D, 8, 0x698098d8u, 7)
+        PPGS_MD5_STEP(PPGS_MD5_F, D, A, B, C, 9, 0x8b44f7afu, 12)
+        PPGS_MD5_STEP(PPGS_MD5_F, C, D, A, B, 10, 0xffff5bb1u, 17)
+        PPGS_MD5_STEP(PPGS_MD5_F, B, C, D, A, 11, 0x895cd7beu, 22)
+        PPGS_MD5_STEP(PPGS_MD5_F, A, B, C, D, 12, 0x6b901122u, 7)
+        PPGS_MD5_STEP(PPGS_MD5_F, D, A, B, C, 13, 0xfd987193u, 12)
+        PPGS_MD5_STEP(PPGS_MD5_F, C, D, A, B, 14, 0xa679438eu, 17)
+        PPGS_MD5_STEP(PPGS_MD5_F, B, C, D, A, 15, 0x49b40821u, 22)
+        PPGS_MD5_STEP(PPGS_MD5_G, A, B, C, D, 1, 0xf61e2562u, 5)
+        PPGS_MD5_STEP(PPGS_MD5_G, D, A, B, C, 6, 0xc040b340u, 9)
+        PPGS_MD5_STEP(PPGS_MD5_G, C, D, A, B, 11, 0x265e5a51u, 14)
+        PPGS_MD5_STEP(PPGS_MD5_G, B, C, D, A, 0, 0xe9b6c7aau, 20)
+        PPGS_MD5_STEP(PPGS_MD5_G, A, B, C, D, 5, 0xd62f105du, 5)
+        PPGS_MD5_STEP(PPGS_MD5_G, D, A, B, C, 10, 0x02441453u, 9)
+        PPGS_MD5_STEP(PPGS_MD5_G, C, D, A, B, 15, 0xd8a1e681u, 14)
+        PPGS_MD5_STEP(PPGS_MD5_G, B, C, D, A, 4, 0xe7d3fbc8u, 20)
+        PPGS_MD5_STEP(PPGS_MD5_G, A, B, C, D, 9, 0x21e1cde6u, 5)
+        PPGS_MD5_STEP(PPGS_MD5_G, D, A, B, C, 14, 0xc33707d6u, 9)
+        PPGS_MD5_STEP(PPGS_MD5_G, C, D, A, B, 3, 0xf4d50d87u, 14)
+        PPGS_MD5_STEP(PPGS_MD5_G, B, C, D, A, 8, 0x455a14edu, 20)
+        PPGS_MD5_STEP(PPGS_MD5_G, A, B, C, D, 13, 0xa9e3e905u, 5)
+        PPGS_MD5_STEP(PPGS_MD5_G, D, A, B, C, 2, 0xfcefa3f8u, 9)
+        PPGS_MD5_STEP(PPGS_MD5_G, C, D, A, B, 7, 0x676f02d9u, 14)
+        PPGS_MD5_STEP(PPGS_MD5_G, B, C, D, A, 12, 0x8d2a4c8au, 20)
+        PPGS_MD5_STEP(PPGS_MD5_H, A, B, C, D, 5, 0xfffa3942u, 4)
+        PPGS_MD5_STEP(PPGS_MD5_H, D, A, B, C, 8, 0x8771f681u, 11)
+        PPGS_MD5_STEP(PPGS_MD5_H, C, D, A, B, 11, 0x6d9d6122u, 16)
+        PPGS_MD5_STEP(PPGS_MD5_H, B, C, D, A, 14, 0xfde5380cu, 23)
+        PPGS_MD5_STEP(PPGS_MD5_H, A, B, C, D, 1, 0xa4beea44u, 4)
+        PPGS_MD5_STEP(PPGS_MD5_H, D, A, B, C, 4, 0x4bdecfa9u, 11)
+        PPGS_MD5_STEP(PPGS_MD5_H, C, D, A, B, 7, 0xf6bb4b60u, 16)
+        PPGS_MD5_STEP(PPGS_MD5_H, B, C, D, A, 10, 0xbebfbc70u, 23)
+        PPGS_MD5_STEP(PPGS_MD5_H, A, B, C, D, 13, 0x289b7ec6u, 4)
+        PPGS_MD5_STEP(PPGS_MD5_H, D, A, B, C, 0, 0xeaa127fau, 11)
+        PPGS_MD5_STEP(PPGS_MD5_H, C, D, A, B, 3, 0xd4ef3085u, 16)
+        PPGS_MD5_STEP(PPGS_MD5_H, B, C, D, A, 6, 0x04881d05u, 23)
+        PPGS_MD5_STEP(PPGS_MD5_H, A, B, C, D, 9, 0xd9d4d039u, 4)
+        PPGS_MD5_STEP(PPGS_MD5_H, D, A, B, C, 12, 0xe6db99e5u, 11)
+        PPGS_MD5_STEP(PPGS_MD5_H, C, D, A, B, 15, 0x1fa27cf8u, 16)
+        PPGS_MD5_STEP(PPGS_MD5_H, B, C, D, A, 2, 0xc4ac5665u, 23)
+        PPGS_MD5_STEP(PPGS_MD5_I, A, B, C, D, 0, 0xf4292244u, 6)
+        PPGS_MD5_STEP(PPGS_MD5_I, D, A, B, C, 7, 0x432aff97u, 10)
+        PPGS_MD5_STEP(PPGS_MD5_I, C, D, A, B, 14, 0xab9423a7u, 15)
+        PPGS_MD5_STEP(PPGS_MD5_I, B, C, D, A, 5, 0xfc93a039u, 21)
+        PPGS_MD5_STEP(PPGS_MD5_I, A, B, C, D, 12, 0x655b59c3u, 6)
+        PPGS_MD5_STEP(PPGS_MD5_I, D, A, B, C, 3, 0x8f0ccc92u, 10)
+        PPGS_MD5_STEP(PPGS_MD5_I, C, D, A, B, 10, 0xffeff47du, 15)
+        PPGS_MD5_STEP(PPGS_MD5_I, B, C, D, A, 1, 0x85845dd1u, 21)
+        PPGS_MD5_STEP(PPGS_MD5_I, A, B, C, D, 8, 0x6fa87e4fu, 6)
+        PPGS_MD5_STEP(PPGS_MD5_I, D, A, B, C, 15, 0xfe2ce6e0u, 10)
+        PPGS_MD5_STEP(PPGS_MD5_I, C, D, A, B, 6, 0xa3014314u, 15)
+        PPGS_MD5_STEP(PPGS_MD5_I, B, C, D, A, 13, 0x4e0811a1u, 21)
+        PPGS_MD5_STEP(PPGS_MD5_I, A, B, C, D, 4, 0xf7537e82u, 6)
+        PPGS_MD5_STEP(PPGS_MD5_I, D, A, B, C, 11, 0xbd3af235u, 10)
+        PPGS_MD5_STEP(PPGS_MD5_I, C, D, A, B, 2, 0x2ad7d2bbu, 15)
+        PPGS_MD5_STEP(PPGS_MD5_I, B, C, D, A, 9, 0xeb86d391u, 21)
+#undef PPGS_MD5_STEP
+#undef PPGS_MD5_F
+#undef PPGS_MD5_G
+#undef PPGS_MD5_H
+#undef PPGS_MD5_I
         a += A;
         b += B;
         c += C;
@@ -78,6 +117,8 @@ struct Md5 {
 
     void update(const uint8_t* p, size_t n) {
         bytes += n;
+        if (fill == 0)
+            for (; n >= 64; p += 64, n -= 64) compress(p);
         while (n) {
             const size_t take = n < 64 - fill ? n : 64 - fill;
             memcpy(block + fill, p, take);
@@ -107,7 +148,7 @@ struct Md5 {
 // ---- CRCs of the frame layer ------------------------------------------------------------------
 struct CrcTables {
     uint8_t crc8[256];
-    uint16_t crc16[256];
+    uint16_t crc16[8][256];     // slice-by-8: crc16[k][x] = CRC of byte x followed by k zero bytes
     CrcTables() {
         for (int i = 0; i < 256; ++i) {
             uint8_t c8 = (uint8_t)i;
@@ -117,8 +158,11 @@ struct CrcTables {
                 c16 = (uint16_t)((c16 << 1) ^ ((c16 & 0x8000) ? 0x8005 : 0));       // x^16 + x^15 + x^2 + 1
             }
             crc8[i] = c8;
-            crc16[i] = c16;
+            crc16[0][i] = c16;
         }
+        for (int k = 1; k < 8; ++k)
+            for (int i = 0; i < 256; ++i)
+                crc16[k][i] = (uint16_t)((crc16[k - 1][i] << 8) ^ crc16[0][crc16[k - 1][i] >> 8]);
     }
 };
 const CrcTables& crc_tables() {
@@ -134,11 +178,16 @@ uint8_t crc8(const uint8_t* p, size_t n) {
 uint16_t crc16(const uint8_t* p, size_t n) {
     const CrcTables& t = crc_tables();
     uint16_t c = 0;
-    for (size_t i = 0; i < n; ++i) c = (uint16_t)((c << 8) ^ t.crc16[(c >> 8) ^ p[i]]);
+    for (; n >= 8; p += 8, n -= 8)
+        c = (uint16_t)(t.crc16[7][p[0] ^ (c >> 8)] ^ t.crc16[6][p[1] ^ (c & 0xff)] ^ t.crc16[5][p[2]] ^
+                       t.crc16[4][p[3]] ^ t.crc16[3][p[4]] ^ t.crc16[2][p[5]] ^ t.crc16[1][p[6]] ^
+                       t.crc16[0][p[7]]);
+    for (size_t i = 0; i < n; ++i) c = (uint16_t)((c << 8) ^ t.crc16[0][(c >> 8) ^ p[i]]);
     return c;
 }
 
 // ---- MSB-first bit reader over the file image ------------------------------------------------
+// The image it reads must be followed by >= 8 readable zero bytes (load_file pads).
 struct BitReader {
     const uint8_t* data;
     size_t size;
@@ -148,12 +197,13 @@ struct BitReader {
 
     BitReader(const uint8_t* d, size_t n, size_t start) : data(d), size(n), next(start) {}
 
-    void refill() {
-        while (bits <= 56) {
-            const uint64_t byte = next < size ? data[next] : 0;
-            ++next;
-            window |= byte << (56 - bits);
-            bits += 8;
+    void refill() {      // >= 33 valid bits afterwards
+        if (bits <= 32) {
+            uint32_t word = 0;
+            if (next + 4 <= size + 8) memcpy(&word, data + next, 4);
+            window |= (uint64_t)__builtin_bswap32(word) << (32 - bits);
+            next += 4;
+            bits += 32;
         }
     }
     uint32_t read(int count) {                    // 0..32 bits
@@ -194,6 +244,22 @@ struct BitReader {
             return true;
         }
     }
+    // One Rice-coded residual with parameter k (< 31): unary quotient, k-bit remainder, zig-zag.
+    bool read_rice(int k, int64_t* value) {
+        refill();
+        uint32_t quotient;
+        if (window >> 32) {                        // the terminating 1 is within the next 32 bits
+            const int lead = __builtin_clzll(window);
+            window <<= lead + 1;
+            bits -= lead + 1;
+            quotient = (uint32_t)lead;
+        } else if (!read_unary(&quotient)) {
+            return false;
+        }
+        const uint64_t folded = ((uint64_t)quotient << k) | read(k);
+        *value = (int64_t)(folded >> 1) ^ -(int64_t)(folded & 1);
+        return true;
+    }
     size_t bit_position() const { return next * 8 - bits; }
     bool overrun() const { return bit_position() > size * 8; }
     void align() {
@@ -213,6 +279,9 @@ struct StreamInfo {
     size_t audio_offset = 0;
 };
 
+constexpr size_t kImagePad = 16;
+
+// The file followed by kImagePad zero bytes (image->size() - kImagePad is the file size).
 bool load_file(const char* path, std::vector<uint8_t>* image) {
     const int fd = open(path, O_RDONLY);
     if (fd < 0) {
@@ -225,16 +294,17 @@ bool load_file(const char* path, std::vector<uint8_t>* image) {
         close(fd);
         return false;
     }
-    image->resize((size_t)st.st_size);
+    const size_t size = (size_t)st.st_size;
+    image->assign(size + kImagePad, 0);          // zero bytes behind the file for the bit reader
     size_t done = 0;
-    while (done < image->size()) {
-        const ssize_t got = read(fd, image->data() + done, image->size() - done);
+    while (done < size) {
+        const ssize_t got = read(fd, image->data() + done, size - done);
         if (got < 0 && errno == EINTR) continue;
         if (got <= 0) break;
         done += (size_t)got;
     }
     close(fd);
-    if (done != image->size()) {
+    if (done != size) {
         set_error("%s: short read", path);
         return false;
     }
@@ -294,7 +364,8 @@ int parse_stream(const char* path, const uint8_t* p, size_t n, StreamInfo* si) {
     return PPGS_OK;
 }
 
-const char* decode_residual(BitReader& br, int order, int block, int64_t* out) {
+template <typename T>
+const char* decode_residual(BitReader& br, int order, int block, T* out) {
     const int method = (int)br.read(2);
     if (method > 1) return "reserved residual coding method";
     const int param_bits = method == 0 ? 4 : 5;
@@ -304,19 +375,18 @@ const char* decode_residual(BitReader& br, int order, int block, int64_t* out) {
     if (partition_order > 0 && (block & (partitions - 1))) return "block size not divisible into partitions";
     const int per_partition = block >> partition_order;
     if (per_partition < order) return "partition shorter than the predictor order";
-    int64_t* dst = out + order;
+    T* dst = out + order;
     for (int part = 0; part < partitions; ++part) {
         const int count = per_partition - (part == 0 ? order : 0);
         const uint32_t k = br.read(param_bits);
         if (k == escape) {
             const int raw_bits = (int)br.read(5);
-            for (int i = 0; i < count; ++i) dst[i] = br.read_signed(raw_bits);
+            for (int i = 0; i < count; ++i) dst[i] = (T)br.read_signed(raw_bits);
         } else {
             for (int i = 0; i < count; ++i) {
-                uint32_t quotient;
-                if (!br.read_unary(&quotient)) return "truncated residual";
-                const uint64_t folded = ((uint64_t)quotient << k) | br.read((int)k);
-                dst[i] = (int64_t)(folded >> 1) ^ -(int64_t)(folded & 1);
+                int64_t value;
+                if (!br.read_rice((int)k, &value)) return "truncated residual";
+                dst[i] = (T)value;
             }
         }
         dst += count;
@@ -325,7 +395,38 @@ const char* decode_residual(BitReader& br, int order, int block, int64_t* out) {
     return nullptr;
 }
 
-const char* decode_subframe(BitReader& br, int bits, int block, int64_t* out) {
+// out[i] += (sum_j coefficient[j] * out[i - 1 - j]) >> shift, products and sum in 64 bits.
+template <typename T, int ORDER>
+void lpc_restore_fixed_order(T* out, int block, const int32_t* coefficient, int shift) {
+    int64_t c[ORDER];
+    for (int j = 0; j < ORDER; ++j) c[j] = coefficient[j];
+    for (int i = ORDER; i < block; ++i) {
+        int64_t sum = 0;
+#pragma GCC unroll 32
+        for (int j = ORDER - 1; j >= 0; --j) sum += c[j] * (int64_t)out[i - 1 - j];   // newest sample last
+        out[i] = (T)(out[i] + (sum >> shift));
+    }
+}
+
+template <typename T>
+void lpc_restore(T* out, int block, int order, const int32_t* coefficient, int shift) {
+    switch (order) {
+#define PPGS_LPC_CASE(n) case n: lpc_restore_fixed_order<T, n>(out, block, coefficient, shift); return;
+        PPGS_LPC_CASE(1) PPGS_LPC_CASE(2) PPGS_LPC_CASE(3) PPGS_LPC_CASE(4) PPGS_LPC_CASE(5) PPGS_LPC_CASE(6)
+        PPGS_LPC_CASE(7) PPGS_LPC_CASE(8) PPGS_LPC_CASE(9) PPGS_LPC_CASE(10) PPGS_LPC_CASE(11) PPGS_LPC_CASE(12)
+#undef PPGS_LPC_CASE
+        default:
+            for (int i = order; i < block; ++i) {
+                int64_t sum = 0;
+                for (int j = 0; j < order; ++j) sum += (int64_t)coefficient[j] * (int64_t)out[i - 1 - j];
+                out[i] = (T)(out[i] + (sum >> shift));
+            }
+    }
+}
+
+// T = int32_t holds streams of <= 24 bits (25 with the side channel), int64_t the rest.
+template <typename T>
+const char* decode_subframe(BitReader& br, int bits, int block, T* out) {
     if (br.read(1)) return "subframe padding bit set";
     const int type = (int)br.read(6);
     int wasted = 0;
@@ -337,14 +438,14 @@ const char* decode_subframe(BitReader& br, int bits, int block, int64_t* out) {
         bits -= wasted;
     }
     if (type == 0) {
-        const int64_t value = br.read_signed(bits);
+        const T value = (T)br.read_signed(bits);
         for (int i = 0; i < block; ++i) out[i] = value;
     } else if (type == 1) {
-        for (int i = 0; i < block; ++i) out[i] = br.read_signed(bits);
+        for (int i = 0; i < block; ++i) out[i] = (T)br.read_signed(bits);
     } else if (type >= 8 && type <= 12) {
         const int order = type - 8;
         if (order > block) return "predictor order exceeds the block";
-        for (int i = 0; i < order; ++i) out[i] = br.read_signed(bits);
+        for (int i = 0; i < order; ++i) out[i] = (T)br.read_signed(bits);
         if (const char* err = decode_residual(br, order, block, out)) return err;
         switch (order) {
             case 1:
@@ -366,35 +467,33 @@ const char* decode_subframe(BitReader& br, int bits, int block, int64_t* out) {
     } else if (type >= 32) {
         const int order = (type & 31) + 1;
         if (order > block) return "predictor order exceeds the block";
-        for (int i = 0; i < order; ++i) out[i] = br.read_signed(bits);
+        for (int i = 0; i < order; ++i) out[i] = (T)br.read_signed(bits);
         const int precision = (int)br.read(4) + 1;
         if (precision == 16) return "reserved predictor precision";
         const int shift = (int)br.read_signed(5);
         if (shift < 0) return "negative predictor shift";
-        int64_t coefficient[32];
-        for (int i = 0; i < order; ++i) coefficient[i] = br.read_signed(precision);
+        int32_t coefficient[32];
+        for (int i = 0; i < order; ++i) coefficient[i] = (int32_t)br.read_signed(precision);
         if (const char* err = decode_residual(br, order, block, out)) return err;
-        for (int i = order; i < block; ++i) {
-            int64_t sum = 0;
-            for (int j = 0; j < order; ++j) sum += coefficient[j] * out[i - 1 - j];
-            out[i] += sum >> shift;
-        }
+        lpc_restore(out, block, order, coefficient, shift);
     } else {
         return "reserved subframe type";
     }
     if (wasted)
-        for (int i = 0; i < block; ++i) out[i] *= (int64_t)1 << wasted;
+        for (int i = 0; i < block; ++i) out[i] = (T)(out[i] * ((T)1 << wasted));
     return br.overrun() ? "truncated subframe" : nullptr;
 }
 
 // Decodes every frame; dst (may be null: count / verify only) is channel-major with row stride
-// `capacity`.
-int decode_stream(const char* path, const uint8_t* p, size_t n, const StreamInfo& si, float* dst,
-                  int64_t capacity, int64_t* frames_out) {
+// `capacity`; dst16 (may be null; streams of <= 16 bits) takes channel 0 on the int16 scale, the
+// form the file pipeline ships to the device.
+template <typename T>
+int decode_stream_as(const char* path, const uint8_t* p, size_t n, const StreamInfo& si, float* dst,
+                     int16_t* dst16, int64_t capacity, int64_t* frames_out) {
     static const int kBlock[16] = {0, 192, 576, 1152, 2304, 4608, 0, 0, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768};
     static const int kRate[12] = {0, 88200, 176400, 192000, 8000, 16000, 22050, 24000, 32000, 44100, 48000, 96000};
     static const int kBits[8] = {0, 8, 12, -1, 16, 20, 24, 32};
-    std::vector<int64_t> channel[8];
+    std::vector<T> channel[8];
     std::vector<uint8_t> pcm;
     Md5 md5;
     const int sample_bytes = (si.bits + 7) / 8;
@@ -476,8 +575,8 @@ int decode_stream(const char* path, const uint8_t* p, size_t n, const StreamInfo
                 set_error("%s: frame CRC mismatch (frame at byte %zu)", path, pos);
                 return PPGS_E_INVALID;
             }
-            int64_t* a = channel[0].data();
-            int64_t* b = channels > 1 ? channel[1].data() : nullptr;
+            T* a = channel[0].data();
+            T* b = channels > 1 ? channel[1].data() : nullptr;
             if (assignment == 8) {
                 for (int i = 0; i < block; ++i) b[i] = a[i] - b[i];
             } else if (assignment == 9) {
@@ -485,13 +584,22 @@ int decode_stream(const char* path, const uint8_t* p, size_t n, const StreamInfo
             } else if (assignment == 10) {
                 for (int i = 0; i < block; ++i) {
                     const int64_t side = b[i];
-                    const int64_t mid = a[i] * 2 + (side & 1);
-                    a[i] = (mid + side) >> 1;
-                    b[i] = (mid - side) >> 1;
+                    const int64_t mid = (int64_t)a[i] * 2 + (side & 1);
+                    a[i] = (T)((mid + side) >> 1);
+                    b[i] = (T)((mid - side) >> 1);
                 }
             }
             int keep = block;
             if (si.total > 0 && done + keep > si.total) keep = (int)(si.total - done);
+            if (dst16) {
+                if (done + keep > capacity) {
+                    set_error("%s: more than %lld frames; the buffer is too small", path, (long long)capacity);
+                    return PPGS_E_INVALID;
+                }
+                const int up = 16 - si.bits;
+                const T* src = channel[0].data();
+                for (int i = 0; i < keep; ++i) dst16[done + i] = (int16_t)(src[i] * ((T)1 << up));
+            }
             if (dst) {
                 if (done + keep > capacity) {
                     set_error("%s: more than %lld frames; the buffer is too small", path, (long long)capacity);
@@ -499,18 +607,26 @@ int decode_stream(const char* path, const uint8_t* p, size_t n, const StreamInfo
                 }
                 for (int c = 0; c < channels; ++c) {
                     float* row = dst + (int64_t)c * capacity + done;
-                    const int64_t* src = channel[c].data();
+                    const T* src = channel[c].data();
                     for (int i = 0; i < keep; ++i) row[i] = (float)src[i] * scale;
                 }
             }
             if (si.has_md5) {
                 pcm.resize((size_t)block * channels * sample_bytes);
                 uint8_t* w = pcm.data();
-                for (int i = 0; i < block; ++i)
-                    for (int c = 0; c < channels; ++c) {
-                        const int64_t v = channel[c][(size_t)i];
-                        for (int byte = 0; byte < sample_bytes; ++byte) *w++ = (uint8_t)(v >> (8 * byte));
+                if (channels == 1 && sample_bytes == 2) {
+                    const T* src = channel[0].data();
+                    for (int i = 0; i < block; ++i) {
+                        const int16_t v = (int16_t)src[i];
+                        memcpy(w + 2 * i, &v, 2);       // little-endian host
                     }
+                } else {
+                    for (int i = 0; i < block; ++i)
+                        for (int c = 0; c < channels; ++c) {
+                            const int64_t v = channel[c][(size_t)i];
+                            for (int byte = 0; byte < sample_bytes; ++byte) *w++ = (uint8_t)(v >> (8 * byte));
+                        }
+                }
                 md5.update(pcm.data(), pcm.size());
             }
             done += keep;
@@ -537,7 +653,64 @@ int decode_stream(const char* path, const uint8_t* p, size_t n, const StreamInfo
     return PPGS_OK;
 }
 
+int decode_stream(const char* path, const uint8_t* p, size_t n, const StreamInfo& si, float* dst,
+                  int16_t* dst16, int64_t capacity, int64_t* frames_out) {
+    if (si.bits <= 24) return decode_stream_as<int32_t>(path, p, n, si, dst, dst16, capacity, frames_out);
+    return decode_stream_as<int64_t>(path, p, n, si, dst, dst16, capacity, frames_out);
+}
+
+// STREAMINFO from the first bytes of the file only (header probes of a corpus must not read it).
+int probe_streaminfo(const char* path, StreamInfo* si) {
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) {
+        set_error("%s: cannot open: %s", path, strerror(errno));
+        return PPGS_E_INVALID;
+    }
+    uint8_t head[10 + 42];
+    ssize_t got = pread(fd, head, 10, 0);
+    off_t at = 0;
+    if (got == 10 && memcmp(head, "ID3", 3) == 0)
+        at = 10 + (((off_t)(head[6] & 0x7f) << 21) | ((off_t)(head[7] & 0x7f) << 14) |
+                   ((off_t)(head[8] & 0x7f) << 7) | (off_t)(head[9] & 0x7f)) + ((head[5] & 0x10) ? 10 : 0);
+    got = pread(fd, head, 42, at);
+    close(fd);
+    if (got < 4 || memcmp(head, "fLaC", 4) != 0) {
+        set_error("%s: not a FLAC stream", path);
+        return PPGS_E_UNSUPPORTED;
+    }
+    if (got < 42) {
+        set_error("%s: truncated FLAC metadata", path);
+        return PPGS_E_INVALID;
+    }
+    // a complete one-block stream for parse_stream: mark STREAMINFO as the last block
+    head[4] |= 0x80;
+    return parse_stream(path, head, 42, si);
+}
+
 }  // namespace
+
+// File pipeline (io.cu): channel 0 of a 16 kHz FLAC file of <= 16 bits as int16, zero padded to
+// `capacity`; the stream must hold exactly `expect_frames` frames.
+int flac_read_pcm16(const char* path, int16_t* dst, int64_t capacity, int64_t expect_frames) {
+    std::vector<uint8_t> image;
+    if (!load_file(path, &image)) return PPGS_E_INVALID;
+    StreamInfo si;
+    PPGS_CHECK(parse_stream(path, image.data(), image.size() - kImagePad, &si));
+    if (si.bits > 16 || si.sample_rate != 16000) {
+        set_error("%s: the native file pipeline takes FLAC of <= 16 bits at 16 kHz (got %d bits, %d Hz)", path,
+                  si.bits, si.sample_rate);
+        return PPGS_E_UNSUPPORTED;
+    }
+    int64_t total = 0;
+    PPGS_CHECK(decode_stream(path, image.data(), image.size() - kImagePad, si, nullptr, dst, capacity, &total));
+    if (total != expect_frames) {
+        set_error("%s: %lld frames, expected %lld", path, (long long)total, (long long)expect_frames);
+        return PPGS_E_UNSUPPORTED;
+    }
+    if (total < capacity) memset(dst + total, 0, (size_t)(capacity - total) * sizeof(int16_t));
+    return PPGS_OK;
+}
+
 }  // namespace ppgs
 
 using namespace ppgs;
@@ -549,13 +722,16 @@ int ppgs_flac_info(const char* path, int64_t* frames, int* sample_rate, int* cha
         set_error("flac_info: bad argument");
         return PPGS_E_INVALID;
     }
-    std::vector<uint8_t> image;
-    if (!load_file(path, &image)) return PPGS_E_INVALID;
     StreamInfo si;
-    PPGS_CHECK(parse_stream(path, image.data(), image.size(), &si));
+    std::vector<uint8_t> image;
+    int rc = probe_streaminfo(path, &si);
+    if (rc != PPGS_OK) return rc;
     int64_t total = si.total;
-    if (total == 0)      // length not recorded (streamed encoder): count by decoding
-        PPGS_CHECK(decode_stream(path, image.data(), image.size(), si, nullptr, 0, &total));
+    if (total == 0) {    // length not recorded (streamed encoder): count by decoding
+        if (!load_file(path, &image)) return PPGS_E_INVALID;
+        PPGS_CHECK(parse_stream(path, image.data(), image.size() - kImagePad, &si));
+        PPGS_CHECK(decode_stream(path, image.data(), image.size() - kImagePad, si, nullptr, nullptr, 0, &total));
+    }
     if (frames) *frames = total;
     if (sample_rate) *sample_rate = si.sample_rate;
     if (channels) *channels = si.channels;
@@ -572,9 +748,9 @@ int ppgs_flac_read_f32(const char* path, float* dst, int64_t capacity, int64_t* 
     std::vector<uint8_t> image;
     if (!load_file(path, &image)) return PPGS_E_INVALID;
     StreamInfo si;
-    PPGS_CHECK(parse_stream(path, image.data(), image.size(), &si));
+    PPGS_CHECK(parse_stream(path, image.data(), image.size() - kImagePad, &si));
     int64_t total = 0;
-    PPGS_CHECK(decode_stream(path, image.data(), image.size(), si, dst, capacity, &total));
+    PPGS_CHECK(decode_stream(path, image.data(), image.size() - kImagePad, si, dst, nullptr, capacity, &total));
     if (frames) *frames = total;
     if (sample_rate) *sample_rate = si.sample_rate;
     if (channels) *channels = si.channels;

@@ -15,6 +15,7 @@
 #include <fcntl.h>
 #include <math.h>
 #include <string.h>
+#include <strings.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -795,7 +796,10 @@ static void reader_main(Pipeline* p, int64_t total_files) {
         int16_t* dst = p->in_host[batch % p->n_in] + (int64_t)row * max_samples;
         const char* path = p->audio_files[f];
         int rc = PPGS_OK;
-        {
+        const size_t path_len = strlen(path);
+        if (path_len > 5 && strcasecmp(path + path_len - 5, ".flac") == 0) {
+            rc = flac_read_pcm16(path, dst, max_samples, p->file_samples[f]);
+        } else {
             Fd in(path, O_RDONLY);
             WavHeader h;
             if (in.fd < 0) {

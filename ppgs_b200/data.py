@@ -27,13 +27,19 @@ class Metadata:
     def __init__(self, audio_files, max_frames=config.live('MAX_INFERENCE_FRAMES')):
         max_frames = config.resolve(max_frames)
         self.audio_files, self.lengths, self.samples = [], [], {}
-        # every file is 16-bit PCM at 16 kHz: eligible for ppgs_files_to_files
+        # every file is 16-bit PCM WAVE or <= 16-bit FLAC at 16 kHz: eligible for ppgs_files_to_files
         self.native = True
         audio_files = list(audio_files)
         for audio_file, info in zip(audio_files, load.wav_info_many(audio_files)):
             if info is None:
-                samples, sample_rate = load.wav_num_frames(audio_file)
-                self.native = False
+                flac = load.flac_info(audio_file) if str(audio_file).lower().endswith('.flac') else None
+                if flac is not None:     # the native pipeline decodes <= 16-bit FLAC at 16 kHz too
+                    samples, sample_rate = flac['samples'], flac['sample_rate']
+                    if flac['bits'] > 16 or sample_rate != config.SAMPLE_RATE:
+                        self.native = False
+                else:
+                    samples, sample_rate = load.wav_num_frames(audio_file)
+                    self.native = False
             else:
                 samples, sample_rate = info['samples'], info['sample_rate']
                 if info['bits'] != 16 or info['is_float'] or sample_rate != config.SAMPLE_RATE:

@@ -124,6 +124,57 @@ def test_native_file_pipeline_equals_per_batch_api(ppgs_b200, tmp_path, monkeypa
         assert (got - row[:, :n // 160]).abs().max() <= 1e-4
 
 
+def test_native_file_pipeline_takes_flac(ppgs_b200, tmp_path, monkeypatch):
+    """A corpus of 16 kHz FLAC files (16-bit mono, 16-bit mid-side stereo, 12-bit) next to WAVE
+    files runs inside ppgs_files_to_files (FLAC decoded by the reader threads straight to the int16
+    batch): bitwise the Python reader path, which decodes through ppgs_flac_read_f32."""
+    import flac_writer
+    sd = O.random_state_dict(6, peaky=True)
+    checkpoint = tmp_path / 'ckpt.pt'
+    torch.save({'model': sd}, checkpoint)
+    rng = np.random.default_rng(0)
+    files, lengths = [], [16000, 24000, 8000, 40000, 12345]
+    for i, n in enumerate(lengths):
+        pcm = (O.synthetic_audio(1, n, 60 + i)[0, 0].numpy() * 32768).round().clip(-32768, 32767).astype(np.int64)
+        path = tmp_path / f'{i}.flac'
+        if i == 1:      # stereo: channel 0 is what the pipeline keeps
+            other = rng.integers(-2000, 2000, n)
+            path.write_bytes(flac_writer.encode(np.stack([pcm, other]), 16000, 16, blocks=4096, stereo='mid_side',
+                                                specs=[dict(kind='lpc', order=8, partition_order=3)]))
+        elif i == 2:    # 12-bit samples
+            path.write_bytes(flac_writer.encode((pcm >> 4)[None], 16000, 12, blocks=1152,
+                                                specs=[dict(kind='fixed', order=2, partition_order=2)]))
+        elif i == 3:    # a WAVE file in the same list
+            path = tmp_path / f'{i}.wav'
+            wavfile.write(path, 16000, pcm.astype(np.int16))
+        else:
+            path.write_bytes(flac_writer.encode(pcm[None], 16000, 16, blocks=4096,
+                                                specs=[dict(kind='lpc', order=12, partition_order=4)]))
+        files.append(str(path))
+    native = [str(tmp_path / f'{i}-native.pt') for i in range(len(files))]
+    python = [str(tmp_path / f'{i}-python.pt') for i in range(len(files))]
+    calls = []
+    original = ppgs_b200.Engine.files_to_files
+    monkeypatch.setattr(ppgs_b200.Engine, 'files_to_files',
+                        lambda self, *a, **k: calls.append(1) or original(self, *a, **k))
+    ppgs_b200.from_files_to_files(files, native, checkpoint=checkpoint, num_workers=4, gpu=0, max_frames=600)
+    assert calls, 'the native pipeline was not used'
+    monkeypatch.setenv('PPGS_B200_NATIVE_FILES', '0')
+    ppgs_b200.from_files_to_files(files, python, checkpoint=checkpoint, num_workers=4, gpu=0, max_frames=600)
+    assert len(calls) == 1
+    for a, b, n in zip(native, python, lengths):
+        x, y = torch.load(a), torch.load(b)
+        assert x.shape == (40, n // 160)
+        assert torch.equal(x, y)
+    # a damaged FLAC file fails the call with the decoder's message
+    data = bytearray(open(files[0], 'rb').read())
+    data[len(data) // 2] ^= 0x55
+    open(files[0], 'wb').write(bytes(data))
+    monkeypatch.delenv('PPGS_B200_NATIVE_FILES')
+    with pytest.raises((RuntimeError, ValueError), match='CRC|sync|residual|MD5|subframe'):
+        ppgs_b200.from_files_to_files(files, native, checkpoint=checkpoint, num_workers=4, gpu=0, max_frames=600)
+
+
 def test_native_file_pipeline_many_batches(ppgs_b200, tmp_path):
     """More batches than staging slots, one reader / one writer thread and many."""
     sd = O.random_state_dict(6)
