@@ -585,7 +585,7 @@ def representation_file_extension():
 
 def _native_pipeline(dataloader, representation):
     """The whole loop runs inside libppgs_b200 (ppgs_files_to_files) when the
-    representation is mel and every file is 16-bit PCM at 16 kHz; otherwise the
+    representation is mel and every file is 16-bit PCM WAVE or <= 16-bit FLAC at 16 kHz; otherwise the
     batches come from the Python reader threads (same batches, same kernels).
     PPGS_B200_NATIVE_FILES=0 forces the latter."""
     if os.environ.get('PPGS_B200_NATIVE_FILES', '1') == '0':
