@@ -53,6 +53,7 @@ constexpr float kRescaleLog2 = 8.f;          // running max lags the true max by
 struct DualParams {
     const SeqInfo* seqs;
     int H, causal, v_planes;
+    int reverse;                 // sequences from the last to the first (serpentine order, GemmParams::reverse)
     float scale_log2e;
     __half* out;
     int64_t out_plane_stride;
@@ -88,7 +89,7 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long t_kernel = clock64();
-    const SeqInfo s = p.seqs[blockIdx.z];
+    const SeqInfo s = p.seqs[p.reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z];
     const int head = blockIdx.y;
     const int first = p.q_first_per_seq ? s.src_start : p.q_first_tile;
     // lane L owns query tile first + 2 x + L; a lane is idle when its tile lies outside the
@@ -466,6 +467,7 @@ int launch_attention_dual(ppgs_engine* e, const __half* qkv, __half* out, int ro
     p.seqs = seqs_dev;
     p.H = H;
     p.causal = causal;
+    p.reverse = per_seq ? 0 : e->attn_reverse;
     p.v_planes = planes;
     p.scale_log2e = 1.4426950408889634f / sqrtf((float)kD);
     p.out = out;

@@ -147,6 +147,8 @@ struct ppgs_engine {
     // softmax numerators P enter their MMAs as one fp16 plane (S in one pass, P.V in two; measured
     // +1e-5 on the posteriorgram, profiles/r02_attn_planes.jsonl); 2 = hi + lo like every other operand
     int attn_qk_planes = 1;      // PPGS_B200_ATTN_QK_PLANES
+    int serpentine = 1;          // PPGS_B200_SERPENTINE: consecutive kernels of a forward walk the row tiles in opposite directions
+    int attn_reverse = 0;        // direction of the next attention launch (set by the forward)
     int mel_rows = 1;            // PPGS_B200_MEL_ROWS: from_audio's mel kernel writes the input convolution's operand rows itself (no fold pass)
     int qk_gemm_passes = 3;      // PPGS_B200_QK_GEMM_PASSES: MMA passes of the Q / K columns of the QKV GEMM when they are kept as one plane
     int attn_p_planes = 1;       // PPGS_B200_ATTN_P_PLANES

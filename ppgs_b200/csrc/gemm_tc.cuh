@@ -19,6 +19,7 @@ enum GemmEpilogue : int {
 
 struct GemmParams {
     int m_tiles = 0, n_tiles = 0;
+    int reverse = 0;             // walk the row tiles from the last to the first (serpentine order across the kernels of a forward: start where the previous kernel's data is still in L2)
     int taps = 1, half = 0;      // K loop = taps x cblocks k-blocks; A rows shift by tap - half
     int row_mul = 1;             // A row of output row m = m * row_mul + tap - half (strided conv)
     int cblocks = 0;
@@ -96,6 +97,7 @@ int launch_gemm_tc(ppgs_engine* e, const char* name, int bn, int epilogue,
 // Fused linear1 + ReLU + linear2 + residual + LayerNorm (ffn_tc.cu), CTA pairs.
 struct FfnParams {
     int m_tiles, num_chunks, planes;
+    int reverse = 0;             // as GemmParams::reverse
     // row-tile window (streaming decoder, same meaning as GemmParams::win_*): m_tiles = sequences x
     // win_size, the first tile of sequence s is seqs[s].src_start; 0 = all rows
     int win_size = 0, win_stride = 0;

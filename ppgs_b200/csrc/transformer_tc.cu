@@ -271,8 +271,17 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
     // cycle accounting slots: 0 conv_in, 1 qkv, 2 out_proj, 3 ffn1, 4 ffn2, 5 conv_out
     auto trace = [&](int slot) { return e->trace_dev ? e->trace_dev + 8 * slot : nullptr; };
 
+    // Serpentine order: every kernel walks the row tiles in the direction opposite to its
+    // predecessor's, so it starts on the rows that kernel wrote last (still in L2).
+    int direction = 0;
+    auto next_direction = [&]() {
+        const int d = e->serpentine ? direction : 0;
+        direction ^= 1;
+        return d;
+    };
     {   // input conv: features are exact fp16 -> one A plane
         GemmParams p = base;
+        p.reverse = next_direction();
         p.n_tiles = H / 256; p.taps = k; p.half = k / 2; p.cblocks = (C + 63) / 64; p.a_planes = 1;
         p.N = H; p.scale = e->tc_conv_in.inv_scale; p.bias = e->conv_in_b; p.pe = e->pe;
         p.trace = trace(0);
@@ -286,6 +295,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             GemmParams p = base;
             p.n_tiles = 3 * H / 256; p.cblocks = H / 64; p.a_planes = planes;
             p.N = 3 * H; p.scale = T.in_w.inv_scale; p.bias = L.in_b; p.trace = trace(1);
+            p.reverse = next_direction();
             // Q / K enter the attention MMAs as their hi planes only: skip the lo-plane stores
             if (planes == 2 && e->attn_qk_planes == 1 && e->attention_impl == 1 &&
                 (H / c.num_heads == 128 ? e->attn_dual != 0 || plan.max_pitch <= 512 : plan.max_pitch <= 512) &&
@@ -294,6 +304,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, wmap(T.in_w), &out_qkv,
                                       p, stream));
         }
+        e->attn_reverse = next_direction();
         PPGS_CHECK(launch_attention_tc(e, qkv, att, rows, plan, seqs_dev, planes, stream));
         // x <- LayerNorm(x + projection): epilogue of the GEMM (hidden 256) or its own pass
         auto project_ln = [&](const char* name, const CUtensorMap& map_a, TcWeight& wt, int cblocks,
@@ -302,6 +313,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             GemmParams p = base;
             p.cblocks = cblocks; p.a_planes = planes;
             p.N = H; p.scale = wt.inv_scale; p.bias = bias; p.trace = trace(slot);
+            p.reverse = next_direction();
             if (fused_ln && pair && e->proj_ln && !(split_out_proj && slot == 2)) {
                 // CTA-pair projection kernel with the register-resident LayerNorm epilogue
                 FfnParams f;
@@ -309,7 +321,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
                 f.scale1 = wt.inv_scale; f.scale2 = wt.inv_scale;
                 f.bias1 = bias; f.bias2 = bias; f.gamma = gamma; f.beta = beta;
                 f.eps = c.layer_norm_eps; f.seqs = seqs_dev; f.tile_seq = tile_seq_dev;
-                f.status = e->status_dev; f.trace = nullptr;
+                f.status = e->status_dev; f.trace = nullptr; f.reverse = p.reverse;
                 return launch_proj_ln(e, name, map_a, wt.maps[planes - 1].bn128, out_x, map_res, f, stream);
             }
             if (fused_ln && !(split_out_proj && slot == 2)) {
@@ -350,6 +362,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             f.eps = c.layer_norm_eps; f.seqs = seqs_dev; f.tile_seq = tile_seq_dev;
             f.status = e->status_dev;
             f.trace = e->trace_dev ? e->trace_dev + 64 : nullptr;   // counters 64..79
+            f.reverse = next_direction();
             PPGS_CHECK(launch_ffn_fused(e, map_x, T.l1_w.maps[planes - 1].bn64, T.l2_w.maps[planes - 1].bn128, out_x,
                                         map_res, f, stream));
         } else {
@@ -357,6 +370,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
                 GemmParams p = base;
                 p.n_tiles = F / 256; p.cblocks = H / 64; p.a_planes = planes;
                 p.N = F; p.scale = T.l1_w.inv_scale; p.bias = L.l1_b; p.relu = 1; p.trace = trace(3);
+                p.reverse = next_direction();
                 PPGS_CHECK(launch_gemm_tc(e, "tc_ffn1", 256, kEpiPlanes, map_x, wmap(T.l1_w), &out_ff,
                                           p, stream));
             }
@@ -369,9 +383,11 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
         p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = H / 64; p.a_planes = planes;
         p.N = O; p.O = O; p.scale = e->tc_conv_out.inv_scale; p.bias = e->conv_out_b;
         p.ppg = out; p.T = plan.frames; p.softmax = softmax; p.pair = 0;
+        p.reverse = next_direction();
         PPGS_CHECK(launch_gemm_tc(e, "tc_conv_out_softmax", 64, kEpiConvOut, map_x,
                                   e->tc_conv_out.maps[planes - 1].bn64, nullptr, p, stream));
     }
+    e->attn_reverse = 0;
     return PPGS_OK;
 }
 
