@@ -53,6 +53,7 @@ constexpr float kRescaleLog2 = 8.f;          // running max lags the true max by
 struct DualParams {
     const SeqInfo* seqs;
     int H, causal, v_planes;
+    uint64_t dead_policy;        // L2 policy of the Q / K / V loads: qkv is dead after this kernel
     int reverse;                 // sequences from the last to the first (serpentine order, GemmParams::reverse)
     float scale_log2e;
     __half* out;
@@ -138,13 +139,13 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
             mbar_arrive_expect_tx(&q_full, ((nb_0 > 0) + (nb_1 > 0)) * 2 * kTile);
             for (int dc = 0; dc < 2; ++dc) {
                 if (nb_0 > 0)
-                    tma_load_3d(smem + kQOff + dc * kTile, &map_qk, &q_full, col_q + dc * 64, s.row0 + q0_0, 0);
+                    tma_load_3d_hint(smem + kQOff + dc * kTile, &map_qk, &q_full, col_q + dc * 64, s.row0 + q0_0, 0, p.dead_policy);
                 if (nb_1 > 0)
-                    tma_load_3d(smem + kQOff + (2 + dc) * kTile, &map_qk, &q_full, col_q + dc * 64, s.row0 + q0_1, 0);
+                    tma_load_3d_hint(smem + kQOff + (2 + dc) * kTile, &map_qk, &q_full, col_q + dc * 64, s.row0 + q0_1, 0, p.dead_policy);
             }
             mbar_arrive_expect_tx(&k_full, 2 * kTile);
             for (int dc = 0; dc < 2; ++dc)
-                tma_load_3d(smem + kKOff + dc * kTile, &map_qk, &k_full, col_k + dc * 64, s.row0, 0);
+                tma_load_3d_hint(smem + kKOff + dc * kTile, &map_qk, &k_full, col_k + dc * 64, s.row0, 0, p.dead_policy);
         }
     }
     if (warp == 3) tmem_alloc<512>(&tmem_slot);
@@ -167,8 +168,8 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
                 if (!mbar_wait(&k_empty, (j & 1) ^ 1)) { ok = false; break; }
                 mbar_arrive_expect_tx(&k_full, 2 * kTile);
                 for (int dc = 0; dc < 2; ++dc)
-                    tma_load_3d(smem + kKOff + dc * kTile, &map_qk, &k_full, col_k + dc * 64,
-                                s.row0 + j * kKeys, 0);
+                    tma_load_3d_hint(smem + kKOff + dc * kTile, &map_qk, &k_full, col_k + dc * 64,
+                                s.row0 + j * kKeys, 0, p.dead_policy);
             }
             if (!ok) atomicExch(p.status, kStatusAttnTimeout);
         }
@@ -183,8 +184,8 @@ attention_dual_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_c
                 if (!mbar_wait(&v_empty, (j & 1) ^ 1)) { ok = false; break; }
                 mbar_arrive_expect_tx(&v_full, p.v_planes * 2 * kTile);
                 for (int dh = 0; dh < 2; ++dh)
-                    tma_load_3d(smem + kVOff + dh * 2 * kTile, &map_v, &v_full, col_v + dh * 64,
-                                s.row0 + j * kKeys, 0);
+                    tma_load_3d_hint(smem + kVOff + dh * 2 * kTile, &map_v, &v_full, col_v + dh * 64,
+                                s.row0 + j * kKeys, 0, p.dead_policy);
             }
             if (!ok) atomicExch(p.status, kStatusAttnTimeout);
         }
@@ -468,6 +469,7 @@ int launch_attention_dual(ppgs_engine* e, const __half* qkv, __half* out, int ro
     p.H = H;
     p.causal = causal;
     p.reverse = per_seq ? 0 : e->attn_reverse;
+    p.dead_policy = (e->l2_hints && !per_seq) ? kL2EvictFirst : kL2EvictNormal;   // the streaming decoder re-reads its K / V caches
     p.v_planes = planes;
     p.scale_log2e = 1.4426950408889634f / sqrtf((float)kD);
     p.out = out;

@@ -147,6 +147,7 @@ struct ppgs_engine {
     // softmax numerators P enter their MMAs as one fp16 plane (S in one pass, P.V in two; measured
     // +1e-5 on the posteriorgram, profiles/r02_attn_planes.jsonl); 2 = hi + lo like every other operand
     int attn_qk_planes = 1;      // PPGS_B200_ATTN_QK_PLANES
+    int l2_hints = 0;            // PPGS_B200_L2_HINTS: evict-first loads of operands that die with the kernel (measured: slightly slower, off)
     int serpentine = 1;          // PPGS_B200_SERPENTINE: consecutive kernels of a forward walk the row tiles in opposite directions
     int attn_reverse = 0;        // direction of the next attention launch (set by the forward)
     int mel_rows = 1;            // PPGS_B200_MEL_ROWS: from_audio's mel kernel writes the input convolution's operand rows itself (no fold pass)

@@ -412,6 +412,7 @@ int ppgs_engine_create(const ppgs_model_config* cfg, int device, ppgs_engine** o
     if (const char* v = getenv("PPGS_B200_ATTN_QK_PLANES")) e->attn_qk_planes = atoi(v) == 1 ? 1 : 2;
     if (const char* v = getenv("PPGS_B200_MEL_ROWS")) e->mel_rows = atoi(v) != 0;
     if (const char* v = getenv("PPGS_B200_SERPENTINE")) e->serpentine = atoi(v) != 0;
+    if (const char* v = getenv("PPGS_B200_L2_HINTS")) e->l2_hints = atoi(v) != 0;
     if (const char* v = getenv("PPGS_B200_QK_GEMM_PASSES")) e->qk_gemm_passes = std::min(3, std::max(1, atoi(v)));
     if (const char* v = getenv("PPGS_B200_ATTN_P_PLANES")) e->attn_p_planes = atoi(v) == 1 ? 1 : 2;
     if (const char* v = getenv("PPGS_B200_ATTN_DUAL")) e->attn_dual = atoi(v) != 0;

@@ -100,7 +100,7 @@ __device__ __forceinline__ bool residual_layernorm_store(
     const float* beta_p, float eps, const SeqInfo* seqs, const int* tile_seq, int m_blk, int row, int set,
     int lane, bool elected, unsigned char* stage_smem, uint64_t* res_full, uint32_t res_phase,
     float (*ln_part)[kBM], const CUtensorMap* map_res, const CUtensorMap* map_out,
-    bool res0_issued = false) {
+    bool res0_issued = false, uint64_t res_policy = kL2EvictNormal) {
     const int m0 = m_blk * kBM;
     const int64_t m = (int64_t)m0 + row;
     bool ok = true;
@@ -129,7 +129,8 @@ __device__ __forceinline__ bool residual_layernorm_store(
             named_bar_sync(1 + set, 128);   // previous group consumed by all rows of the set
             if (elected) {
                 mbar_arrive_expect_tx(res_full, 2 * kTileBytes);
-                tma_load_3d(stage_smem + set * 2 * kTileBytes, map_res, res_full, set * 128 + gq * 64, m0, 0);
+                tma_load_3d_hint(stage_smem + set * 2 * kTileBytes, map_res, res_full, set * 128 + gq * 64, m0, 0,
+                                 res_policy);
             }
         }
         float b[32];
@@ -454,7 +455,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             tcgen05_fence_after();
             if (!residual_layernorm_store(t_lane + kYCol + set * 128, y_empty_remote, scale2, p.bias2, p.gamma, p.beta,
                                           p.eps, p.seqs, p.tile_seq, m_blk, row, set, lane, elected, h1_smem,
-                                          &res_full[set], (uint32_t)(2 * it), ln_part, &map_res, &map_out)) {
+                                          &res_full[set], (uint32_t)(2 * it), ln_part, &map_res, &map_out, false,
+                                          p.dead_policy)) {
                 ok = false;
                 break;
             }
@@ -545,7 +547,7 @@ proj_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
                         unsigned char* slot = smem + stage * kProjSlotBytes;
                         const uint32_t bar = map_to_cta(&full_bar[stage], 0);
-                        tma_load_3d_pair(slot, &map_a, bar, kb * kBK, m_blk * kBM, 0);
+                        tma_load_3d_pair_hint(slot, &map_a, bar, kb * kBK, m_blk * kBM, 0, p.dead_policy);
                         tma_load_4d_pair(slot + 2 * kTileBytes, &map_w, bar, kb * kBK, (int)rank * 128, 0, 0);
                         if (++stage == kProjStages) {
                             stage = 0;
@@ -612,14 +614,15 @@ proj_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (elected) {
                 bulk_wait_read_all();
                 mbar_arrive_expect_tx(&res_full[set], 2 * kTileBytes);
-                tma_load_3d(stage_smem + set * 2 * kTileBytes, &map_res, &res_full[set], set * 128, m_blk * kBM, 0);
+                tma_load_3d_hint(stage_smem + set * 2 * kTileBytes, &map_res, &res_full[set], set * 128, m_blk * kBM, 0,
+                                 p.dead_policy);
             }
             if (!mbar_wait(&y_full[acc], (uint32_t)((it >> 1) & 1))) { ok = false; break; }
             tcgen05_fence_after();
             if (!residual_layernorm_store(t_lane + acc * 256 + set * 128, y_empty_remote[acc], scale, p.bias2, p.gamma,
                                           p.beta, p.eps, p.seqs, p.tile_seq, m_blk, row, set, lane, elected,
                                           stage_smem, &res_full[set], (uint32_t)(2 * it), ln_part, &map_res,
-                                          &map_out, true))
+                                          &map_out, true, p.dead_policy))
                 ok = false;
         }
         if (elected) bulk_wait_all();

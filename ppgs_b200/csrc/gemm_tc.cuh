@@ -98,6 +98,7 @@ int launch_gemm_tc(ppgs_engine* e, const char* name, int bn, int epilogue,
 struct FfnParams {
     int m_tiles, num_chunks, planes;
     int reverse = 0;             // as GemmParams::reverse
+    unsigned long long dead_policy = 0x1000000000000000ull;   // L2 policy of loads whose source is dead after the kernel (residual rows; the projection's A operand): tc_common.cuh kL2Evict*
     // row-tile window (streaming decoder, same meaning as GemmParams::win_*): m_tiles = sequences x
     // win_size, the first tile of sequence s is seqs[s].src_start; 0 = all rows
     int win_size = 0, win_stride = 0;

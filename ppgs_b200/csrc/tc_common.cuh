@@ -113,6 +113,30 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// L2 eviction policies for the `_hint` loads (the encodings CUTLASS uses for createpolicy results):
+// operands that are dead after this kernel are loaded evict-first so that they do not push the
+// kernel's own outputs (the next kernel's inputs) out of L2.
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                                 int c0, int c1, int c2, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
+        "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair_hint(void* dst, const CUtensorMap* map,
+                                                      uint32_t leader_bar, int c0, int c1, int c2,
+                                                      uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1),
+        "r"(c2), "l"(policy)
+        : "memory");
+}
 // CTA-pair (cta_group::2) variants: both CTAs of the pair load into their own
 // shared memory, the transaction bytes are credited to the LEADER CTA's mbarrier
 // (`leader_bar` = shared::cluster address of the barrier in CTA rank 0).

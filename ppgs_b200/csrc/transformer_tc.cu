@@ -322,6 +322,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
                 f.bias1 = bias; f.bias2 = bias; f.gamma = gamma; f.beta = beta;
                 f.eps = c.layer_norm_eps; f.seqs = seqs_dev; f.tile_seq = tile_seq_dev;
                 f.status = e->status_dev; f.trace = nullptr; f.reverse = p.reverse;
+                if (e->l2_hints) f.dead_policy = 0x12F0000000000000ull;   // attention output + old x: dead after this kernel
                 return launch_proj_ln(e, name, map_a, wt.maps[planes - 1].bn128, out_x, map_res, f, stream);
             }
             if (fused_ln && !(split_out_proj && slot == 2)) {
@@ -363,6 +364,7 @@ int transformer_forward_tc(ppgs_engine* e, const __half* features, const Forward
             f.status = e->status_dev;
             f.trace = e->trace_dev ? e->trace_dev + 64 : nullptr;   // counters 64..79
             f.reverse = next_direction();
+            if (e->l2_hints) f.dead_policy = 0x12F0000000000000ull;   // residual rows are overwritten by the outputs
             PPGS_CHECK(launch_ffn_fused(e, map_x, T.l1_w.maps[planes - 1].bn64, T.l2_w.maps[planes - 1].bn128, out_x,
                                         map_res, f, stream));
         } else {

@@ -163,7 +163,7 @@ def test_single_pass_f16_mode_is_the_autocast_numerics_class(ppgs_b200):
 
 @pytest.mark.parametrize('switch', ['PPGS_B200_FUSED_FFN=0', 'PPGS_B200_FUSED_FFN=2', 'PPGS_B200_PAIR=0', 'PPGS_B200_ATTENTION=0',
                                     'PPGS_B200_ATTN_DUAL=0', 'PPGS_B200_ATTN_QK_PLANES=2', 'PPGS_B200_PROJ_LN=0',
-                                    'PPGS_B200_MEL_ROWS=0', 'PPGS_B200_SERPENTINE=0'])
+                                    'PPGS_B200_MEL_ROWS=0', 'PPGS_B200_SERPENTINE=0', 'PPGS_B200_L2_HINTS=1'])
 def test_alternative_kernel_paths(ppgs_b200, monkeypatch, switch):
     """The optional kernels stay parity-checked: linear1 / linear2 as two GEMMs instead of the
     fused FFN kernel, the single-CTA (cta_group::1) GEMMs, the CUDA-core attention kernel, the
