@@ -212,3 +212,43 @@ def test_load_audio_reads_flac(tmp_path):
     assert audio.shape == (2, 16000) and audio.dtype == torch.float32
     assert np.array_equal(audio.numpy(), (samples / 32768.0).astype(np.float32))
     assert load.wav_num_frames(path) == (16000, 16000)
+
+
+def test_damaged_streams_never_crash_the_decoder(tmp_path):
+    """Files are untrusted input: random byte damage, truncation and insertions into valid streams
+    must end in a status code (almost always an error: CRC-8 / CRC-16 / MD5 / structure checks),
+    never in a crash or a write outside the caller's buffer (guard rows stay untouched)."""
+    import random
+    random.seed(0)
+    streams = [
+        F.encode(signal(2, 3000, 16, 1), 16000, 16, blocks=1024, stereo='mid_side',
+                 specs=[dict(kind='lpc', order=8, partition_order=3)]),
+        F.encode(signal(1, 2500, 24, 2), 48000, 24, blocks=576,
+                 specs=[dict(kind='fixed', order=3, method=1, partition_order=2, escape=(1,))]),
+        F.encode(signal(3, 1500, 8, 3), 8000, 8, blocks=[192, 16, 1000], variable=True, specs=[dict(kind='verbatim')]),
+        F.encode(signal(2, 900, 32, 4), 48000, 32, blocks=256, stereo='left_side',
+                 specs=[dict(kind='lpc', order=32, precision=14)]),
+    ]
+    capacity = 4000
+    out = torch.full((9, capacity), 7.0)            # 8 channels at most + one guard row
+    path = tmp_path / 'fuzz.flac'
+    rejected = 0
+    for _ in range(1500):
+        data = bytearray(random.choice(streams))
+        mode = random.random()
+        if mode < 0.6:
+            for _ in range(random.randint(1, 4)):
+                data[random.randrange(len(data))] = random.randrange(256)
+        elif mode < 0.8:
+            data = data[:random.randrange(1, len(data))]
+        else:
+            at = random.randrange(len(data))
+            data[at:at] = bytes(random.randrange(256) for _ in range(random.randint(1, 8)))
+        path.write_bytes(bytes(data))
+        frames, rate, channels = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int()
+        _lib.lib.ppgs_flac_info(str(path).encode(), ctypes.byref(frames), ctypes.byref(rate), ctypes.byref(channels), None)
+        code = _lib.lib.ppgs_flac_read_f32(str(path).encode(), ctypes.c_void_p(out.data_ptr()), capacity,
+                                           ctypes.byref(frames), ctypes.byref(rate), ctypes.byref(channels))
+        rejected += code != 0
+        assert bool((out[8] == 7.0).all())
+    assert rejected >= 1400
