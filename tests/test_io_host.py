@@ -246,3 +246,63 @@ def test_native_pt_reader_roundtrip_and_torch_files(tmp_path):
     for name in ('view', 'int', 'dict'):
         assert load.tensor_info(tmp_path / f'{name}.pt') is None
     assert torch.equal(load.features(tmp_path / 'view.pt'), cases['ppg'][:, 10:20])
+
+
+def test_damaged_wav_and_pt_files_never_crash_the_readers(tmp_path):
+    """Untrusted files: random damage / truncation / insertions into valid WAVE and `.pt` files end in
+    a status code (or a successful read of in-range data), never in a crash or a write past the buffer."""
+    import ctypes
+    import io
+    import random
+    from scipy.io import wavfile
+    from ppgs_b200 import _lib, load
+    random.seed(1)
+
+    def damaged(pool, head=None):
+        data = bytearray(random.choice(pool))
+        span = min(len(data), head) if head else len(data)
+        mode = random.random()
+        if mode < 0.6:
+            for _ in range(random.randint(1, 4)):
+                data[random.randrange(span)] = random.randrange(256)
+        elif mode < 0.8:
+            data = data[:random.randrange(1, len(data))]
+        else:
+            at = random.randrange(span)
+            data[at:at] = bytes(random.randrange(256) for _ in range(random.randint(1, 8)))
+        return bytes(data)
+
+    wavs = []
+    for array, rate in ((np.random.default_rng(0).integers(-3000, 3000, 5000).astype(np.int16), 16000),
+                        (np.random.default_rng(1).standard_normal((3000, 2)).astype(np.float32), 22050)):
+        buffer = io.BytesIO()
+        wavfile.write(buffer, rate, array)
+        wavs.append(buffer.getvalue())
+    out = torch.full((2, 6000), 7.0)                 # row 1 is the guard
+    path = tmp_path / 'fuzz.wav'
+    for _ in range(800):
+        path.write_bytes(damaged(wavs, head=80))
+        frames, rate = ctypes.c_int64(), ctypes.c_int()
+        _lib.lib.ppgs_wav_read_f32(str(path).encode(), ctypes.c_void_p(out.data_ptr()), 6000,
+                                   ctypes.byref(frames), ctypes.byref(rate))
+        assert bool((out[1] == 7.0).all())
+
+    tensors = []
+    for tensor in (torch.randn(80, 137).half(), torch.randn(40, 55), torch.randn(2, 3, 17).half()):
+        buffer = io.BytesIO()
+        torch.save(tensor, buffer)
+        tensors.append(buffer.getvalue())
+    path = tmp_path / 'fuzz.pt'
+    for _ in range(800):
+        path.write_bytes(damaged(tensors))
+        info = load.tensor_info(path)
+        if info is None or len(info[0]) < 2:
+            continue
+        shape, dtype = info
+        rows, cols = int(np.prod(shape[:-1])), int(shape[-1])
+        if not 0 < rows * cols <= 1 << 16:
+            continue
+        buffer = torch.full((rows * cols + 64,), 7.0, dtype=dtype)
+        _lib.lib.ppgs_pt_read(str(path).encode(), ctypes.c_void_p(buffer.data_ptr()), rows, cols,
+                              2 if dtype == torch.float16 else 4, cols)
+        assert bool((buffer[rows * cols:] == 7.0).all())
