@@ -910,8 +910,9 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
         // pass): tcgen05 accumulation TRUNCATES, so an accumulator's error grows with its number
         // of MMA steps; the K = 3072 projection is the longest chain of the encoder
         auto gemm = [&](const char* name, const CUtensorMap& a, TcWeight& wt, const CUtensorMap& out_map,
-                        const float* bias, int act, int part = 0, int parts = 1) -> int {
+                        const float* bias, int act, int reverse, int part = 0, int parts = 1) -> int {
             GemmParams p;
+            p.reverse = e->serpentine ? reverse : 0;   // serpentine row order across the kernels
             p.m_tiles = (int)(M / 128);
             p.n_tiles = wt.N / 256;
             p.cblocks = wt.C / 64 / parts;
@@ -939,14 +940,16 @@ int w2v2fb_forward(ppgs_engine* e, const float* audio, int batch, int64_t sample
         for (int l = 0; l < kLayers; ++l) {
             const W2v2Layer& L = w.layers[l];
             W2v2TcLayer& T = e->w2v2->tc[l];
-            PPGS_CHECK(gemm("w2v2_tc_qkv", a_x, T.qkv, s_qkv, L.qkv_b, 0));
+            // row direction per kernel: each starts where its predecessor (GEMM, attention or the
+            // ascending LayerNorm pass) ended
+            PPGS_CHECK(gemm("w2v2_tc_qkv", a_x, T.qkv, s_qkv, L.qkv_b, 0, 1));
             PPGS_CHECK(launch_attention_any(e, qh, ah, (int)M, kHidden, kHeads, (int)P, batch, seqs_dev, 0,
                                             2, stream));
-            PPGS_CHECK(gemm("w2v2_tc_out_proj", a_att, T.out, s_y, L.out_b, 0));
+            PPGS_CHECK(gemm("w2v2_tc_out_proj", a_att, T.out, s_y, L.out_b, 0, 1));
             add_ln(L.ln1_w, L.ln1_b, nullptr);
-            PPGS_CHECK(gemm("w2v2_tc_ffn1", a_x, T.ff1, s_ff, L.ff1_b, 2));
-            PPGS_CHECK(gemm("w2v2_tc_ffn2", a_ff, T.ff2, s_y, L.ff2_b, 0, 0, ffn2_parts));
-            if (ffn2_parts == 2) PPGS_CHECK(gemm("w2v2_tc_ffn2", a_ff, T.ff2, s_y2, w.zero_bias, 0, 1, 2));
+            PPGS_CHECK(gemm("w2v2_tc_ffn1", a_x, T.ff1, s_ff, L.ff1_b, 2, 1));
+            PPGS_CHECK(gemm("w2v2_tc_ffn2", a_ff, T.ff2, s_y, L.ff2_b, 0, 0, 0, ffn2_parts));
+            if (ffn2_parts == 2) PPGS_CHECK(gemm("w2v2_tc_ffn2", a_ff, T.ff2, s_y2, w.zero_bias, 0, 1, 1, 2));
             add_ln(L.ln2_w, L.ln2_b, l == kLayers - 1 ? h : nullptr, ffn2_parts == 2 ? qh : nullptr);
             PPGS_CUDA(cudaGetLastError());
         }
