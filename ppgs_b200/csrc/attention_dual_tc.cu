@@ -468,7 +468,7 @@ int launch_attention_dual(ppgs_engine* e, const __half* qkv, __half* out, int ro
     p.seqs = seqs_dev;
     p.H = H;
     p.causal = causal;
-    p.reverse = per_seq ? 0 : e->attn_reverse;
+    p.reverse = e->attn_reverse;
     p.dead_policy = (e->l2_hints && !per_seq) ? kL2EvictFirst : kL2EvictNormal;   // the streaming decoder re-reads its K / V caches
     p.v_planes = planes;
     p.scale_log2e = 1.4426950408889634f / sqrtf((float)kD);

@@ -80,7 +80,8 @@ __device__ __forceinline__ void load_row128(uint32_t tile, int row, uint32_t (&w
 
 // pair-tile index -> row tile of this CTA (identity unless a row-tile window is set)
 __device__ __forceinline__ int pair_row_tile(const FfnParams& p, int pt, int rank) {
-    if (p.win_size == 0) return 2 * (p.reverse ? p.m_tiles / 2 - 1 - pt : pt) + rank;
+    if (p.reverse) pt = p.m_tiles / 2 - 1 - pt;
+    if (p.win_size == 0) return 2 * pt + rank;
     const int per_seq = p.win_size / 2;
     const int seq = pt / per_seq, u = pt - seq * per_seq;
     return seq * p.win_stride + p.seqs[seq].src_start + 2 * u + rank;

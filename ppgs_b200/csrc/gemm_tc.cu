@@ -86,10 +86,8 @@ __device__ __forceinline__ void split32(const float (&y)[32], uint32_t (&h)[32],
 // it need not start at an even tile.
 template <bool PAIR>
 __device__ __forceinline__ int window_tile(const GemmParams& p, int item, int rank) {
-    if (p.win_size == 0) {
-        if (p.reverse) item = (PAIR ? p.m_tiles / 2 : p.m_tiles) - 1 - item;
-        return PAIR ? 2 * item + rank : item;
-    }
+    if (p.reverse) item = (PAIR ? p.m_tiles / 2 : p.m_tiles) - 1 - item;
+    if (p.win_size == 0) return PAIR ? 2 * item + rank : item;
     const int per_seq = PAIR ? p.win_size / 2 : p.win_size;
     const int seq = item / per_seq, u = item - seq * per_seq;
     const int first = p.win_per_seq ? p.seqs[seq].src_start : p.win_first;

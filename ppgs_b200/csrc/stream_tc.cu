@@ -446,9 +446,17 @@ int ppgs_stream_push_ragged(ppgs_stream* s, const void* features_dev, int max_fr
     base.win_stride = tiles_per_seq;
     base.win_per_seq = 1;
     auto wmap = [&](TcWeight& w) -> const CUtensorMap& { return w.maps[planes - 1].bn128; };
+    // serpentine order over the (session, window tile) items, as in the batch path
+    int direction = 0;
+    auto next_direction = [&]() {
+        const int d = e->serpentine ? direction : 0;
+        direction ^= 1;
+        return d;
+    };
 
     {
         GemmParams p = base;
+        p.reverse = next_direction();
         p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = (C + 63) / 64; p.a_planes = 1;
         p.N = H; p.scale = e->tc_conv_in.inv_scale; p.bias = e->conv_in_b; p.pe = e->pe;
         PPGS_CHECK(launch_gemm_tc(e, "tc_conv_in", 256, kEpiConvIn, map_x0, wmap(e->tc_conv_in), &out_x, p, stream));
@@ -462,8 +470,10 @@ int ppgs_stream_push_ragged(ppgs_stream* s, const void* features_dev, int max_fr
             GemmParams p = base;
             p.n_tiles = 3 * H / 256; p.cblocks = H / 64; p.a_planes = planes;
             p.N = 3 * H; p.scale = T.in_w.inv_scale; p.bias = Lw.in_b;
+            p.reverse = next_direction();
             PPGS_CHECK(launch_gemm_tc(e, "tc_qkv", 256, kEpiPlanes, map_x, wmap(T.in_w), &out_qkv, p, stream));
         }
+        e->attn_reverse = next_direction();
         PPGS_CHECK(launch_attention_any(e, s->qkv[layer], s->att, rows, H, c.num_heads, kStreamPitch, B,
                                         s->seqs_dev, 1, planes, stream, -1, win_tiles, e->attn_qk_planes,
                                         e->attn_p_planes));
@@ -473,6 +483,8 @@ int ppgs_stream_push_ragged(ppgs_stream* s, const void* features_dev, int max_fr
         f.win_size = win_tiles; f.win_stride = tiles_per_seq;
         f.eps = c.layer_norm_eps; f.seqs = s->seqs_dev; f.tile_seq = s->tile_seq_dev;
         f.status = e->status_dev; f.trace = nullptr;
+        e->attn_reverse = 0;
+        f.reverse = next_direction();
         if (e->proj_ln && H == 256) {
             f.num_chunks = H / 64;
             f.scale1 = T.out_w.inv_scale; f.scale2 = T.out_w.inv_scale;
@@ -483,13 +495,14 @@ int ppgs_stream_push_ragged(ppgs_stream* s, const void* features_dev, int max_fr
             p.n_tiles = 1; p.cblocks = H / 64; p.a_planes = planes;
             p.N = H; p.scale = T.out_w.inv_scale; p.bias = Lw.out_b;
             p.residual = s->xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
-            p.gamma = Lw.n1_w; p.beta = Lw.n1_b;
+            p.gamma = Lw.n1_w; p.beta = Lw.n1_b; p.reverse = f.reverse;
             PPGS_CHECK(launch_gemm_tc(e, "tc_out_proj_ln", 256, kEpiResLN, map_att, wmap(T.out_w), &out_x, p, stream));
         }
         if (e->fused_ffn && H == 256 && F % 128 == 0) {
             f.num_chunks = F / 128;
             f.scale1 = T.l1_w.inv_scale; f.scale2 = T.l2_w.inv_scale;
             f.bias1 = Lw.l1_b; f.bias2 = Lw.l2_b; f.gamma = Lw.n2_w; f.beta = Lw.n2_b;
+            f.reverse = next_direction();
             PPGS_CHECK(launch_ffn_fused(e, map_x, T.l1_w.maps[planes - 1].bn64, T.l2_w.maps[planes - 1].bn128, out_x,
                                         map_res, f, stream));
             continue;
@@ -498,6 +511,7 @@ int ppgs_stream_push_ragged(ppgs_stream* s, const void* features_dev, int max_fr
             GemmParams p = base;
             p.n_tiles = F / 256; p.cblocks = H / 64; p.a_planes = planes;
             p.N = F; p.scale = T.l1_w.inv_scale; p.bias = Lw.l1_b; p.relu = 1;
+            p.reverse = next_direction();
             PPGS_CHECK(launch_gemm_tc(e, "tc_ffn1", 256, kEpiPlanes, map_x, wmap(T.l1_w), &out_ff, p, stream));
         }
         {
@@ -505,7 +519,7 @@ int ppgs_stream_push_ragged(ppgs_stream* s, const void* features_dev, int max_fr
             p.n_tiles = 1; p.cblocks = F / 64; p.a_planes = planes;
             p.N = H; p.scale = T.l2_w.inv_scale; p.bias = Lw.l2_b;
             p.residual = s->xh; p.res_ld = H; p.res_plane_stride = (int64_t)rows * H;
-            p.gamma = Lw.n2_w; p.beta = Lw.n2_b;
+            p.gamma = Lw.n2_w; p.beta = Lw.n2_b; p.reverse = next_direction();
             PPGS_CHECK(launch_gemm_tc(e, "tc_ffn2_ln", 256, kEpiResLN, map_ff, wmap(T.l2_w), &out_x, p, stream));
         }
     }
@@ -514,7 +528,7 @@ int ppgs_stream_push_ragged(ppgs_stream* s, const void* features_dev, int max_fr
         p.pair = 0;                       // the BN = 64 kernel is single-CTA
         p.n_tiles = 1; p.taps = k; p.half = k / 2; p.cblocks = H / 64; p.a_planes = planes;
         p.N = O; p.O = O; p.scale = e->tc_conv_out.inv_scale; p.bias = e->conv_out_b;
-        p.ppg = out_dev; p.T = out_capacity; p.softmax = softmax;
+        p.ppg = out_dev; p.T = out_capacity; p.softmax = softmax; p.reverse = next_direction();
         PPGS_CHECK(launch_gemm_tc(e, "tc_conv_out_softmax", 64, kEpiConvOut, map_x,
                                   e->tc_conv_out.maps[planes - 1].bn64, nullptr, p, stream));
     }
